@@ -1,0 +1,98 @@
+/* vpn_b200 - C ABI of the B200 (sm_100a) primitive-assembly + loss kernels.
+ *
+ * Drop-in boundary for the hot path of hank-kuo-cs/Volumetric-Primitives-Net.
+ * The reference has no FFI layer for this path - its boundary is the Python call surface of
+ * modules/{transform,sampling,loss,render,meshing} - so the convention copied here is the one of its
+ * only native op (modules/loss/emd/emd_module.py:32-59, emd.cpp:6-23): the caller allocates every output
+ * and scratch buffer, native code only fills them and returns an int status.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 / int32 data unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, stream ordered, never
+ *     allocate, never synchronise (vpn_fp32_peak_probe excepted) and keep no global state;
+ *   - return 0 on success, negative on error (VPN_ERR_*); vpn_last_error_string() describes the last
+ *     error of the calling thread;
+ *   - "nprim" is B*K: one pose (v,q,t) per primitive, primitives laid out sample-major (b*K + k).
+ */
+#ifndef VPN_B200_H
+#define VPN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPN_OK 0
+#define VPN_ERR_CUDA (-1)
+#define VPN_ERR_SHAPE (-2)
+#define VPN_ERR_ARG (-3)
+#define VPN_ERR_WORKSPACE (-4)
+
+/* kinds for vpn_pose_points_* */
+#define VPN_KIND_SPHERE 0   /* src = uniforms (nprim, N, 2): [elev draw, azim draw]  (sampling/sphere.py:26-27) */
+#define VPN_KIND_CUBOID 1   /* src = uniforms (nprim, N, 3)                           (sampling/cuboid.py:66)     */
+#define VPN_KIND_TEMPLATE 2 /* src = template vertices (N, 3), shared by all primitives (meshing/sphere.py:17)   */
+#define VPN_KIND_POINTS 3   /* src = caller points (nprim, N, 3); v ignored          (transform/transform.py:6)  */
+
+const char* vpn_last_error_string(void);
+int vpn_abi_version(void);
+int vpn_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+
+/* ---- primitive instantiation: canonical sample -> scale -> rotate -> translate, one kernel ------------
+ * Replaces Sampling.{sphere,cuboid}_sampling (modules/sampling/sampling.py:12-38), transform_points /
+ * rotate_points / translate_points (modules/transform/transform.py:6-18, rotate.py:7-25, translate.py:4-8)
+ * and Meshing.{sphere,cuboid}_meshing's vertex math (modules/meshing/sphere.py:8-27, cuboid.py:8-27).
+ * v (nprim,3), q (nprim,4) = (axis, turn fraction), t (nprim,3) or NULL (rotate only), out (nprim,N,3). */
+int vpn_pose_points_fwd(int kind, const float* v, const float* q, const float* t, const float* src,
+                        float* out, int nprim, int N, void* stream);
+int vpn_pose_bwd_workspace_floats(int nprim, int N, size_t* floats);
+/* grad_out (nprim,N,3) -> grad_v (nprim,3), grad_q (nprim,4), grad_t (nprim,3); any may be NULL.
+ * grad_points (nprim,N,3) is written for VPN_KIND_POINTS only (may be NULL). */
+int vpn_pose_points_bwd(int kind, const float* v, const float* q, const float* src, const float* grad_out,
+                        float* grad_v, float* grad_q, float* grad_t, float* grad_points,
+                        float* workspace, size_t workspace_floats, int nprim, int N, void* stream);
+/* get_faces_points (modules/sampling/cuboid.py:30-53): counts (nprim,6) int32. */
+int vpn_cuboid_face_counts(const float* v, int* counts, int nprim, int N, void* stream);
+
+/* ---- camera frame changes: view_to_obj_points / obj_to_view_points (modules/transform/transform.py:21-73)
+ * mode 0 = view_to_obj (angles required), 1 = obj_to_view.  transpose 1 = gradient w.r.t. the points. */
+int vpn_view_workspace_bytes(int B, size_t* bytes);
+int vpn_view_points(int mode, int transpose, const float* in, const float* dists, const float* elevs,
+                    const float* azims, const float* angles, float* out, void* workspace,
+                    size_t workspace_bytes, int B, int n, void* stream);
+
+/* ---- Chamfer nearest neighbours, both directions (modules/loss/chamfer_distance.py:14-23) ------------
+ * p1 (B,P,3), p2 (B,M,3) -> min1 (B,P) = min_j sqrt(d_ij), idx1 (B,P) int32 = first arg-min, min2 (B,M),
+ * idx2 (B,M).  Arg-mins are bit-exact to torch.min over the reference's dense distance tensor.
+ * impl: 0 auto, 1 generic kernel, 2 tiled kernel / exact hot-loop arithmetic, 3 tiled / FMA filter. */
+int vpn_chamfer_workspace_bytes(int B, int P, int M, int impl, size_t* bytes);
+int vpn_chamfer_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
+                    int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, void* stream);
+/* g1 (B,P), g2 (B,M): upstream gradients of min1 / min2.  grad_p1 (B,P,3) overwritten; grad_p2 (B,M,3)
+ * overwritten when not NULL.  Same result as autograd through the reference's dense graph. */
+int vpn_chamfer_bwd(const float* p1, const float* p2, const float* min1, const int* idx1,
+                    const float* min2, const int* idx2, const float* g1, const float* g2,
+                    float* grad_p1, float* grad_p2, int B, int P, int M, void* stream);
+
+/* ---- soft silhouette (modules/loss/silhouette.py:13-23 -> render/vertex_renderer.py:15-26 -> kaolin DIB-R)
+ * verts (B,V,3), faces (F,3) int32 shared topology, cam_rot (B,3,3), cam_pos (B,3), proj = (px,py,pz).
+ * alpha (B,H,W); covered (B,H,W) uint8; normals (B,F,3) or NULL.  bwd needs the workspace as fwd left it. */
+int vpn_silhouette_workspace_bytes(int B, int V, int F, size_t* bytes);
+int vpn_silhouette_fwd(const float* verts, const int* faces, const float* cam_rot, const float* cam_pos,
+                       float proj_x, float proj_y, float proj_z, float expand, int knum, float multiplier,
+                       float delta, float* alpha, unsigned char* covered, float* normals,
+                       void* workspace, size_t workspace_bytes, int B, int V, int F, int H, int W, void* stream);
+int vpn_silhouette_bwd(const int* faces, const float* cam_rot, float proj_x, float proj_y, float proj_z,
+                       float expand, int knum, float multiplier, float delta, const float* grad_alpha,
+                       const unsigned char* covered, float* grad_verts, void* workspace, size_t workspace_bytes,
+                       int B, int V, int F, int H, int W, void* stream);
+
+/* ---- measurement helper: achieved FP32 FMA throughput (the Chamfer roofline denominator) ----------------
+ * scratch: >= 64 device floats, the first 16 finite and near 1.0.  Synchronises the stream. */
+int vpn_fp32_peak_probe(float* scratch, int reps, double* tflops_ffma, double* tflops_ffma2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPN_B200_H */

@@ -1,0 +1,186 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own modules on CPU.
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+The vectors travel to the GPU box with the repo; the reference does not.  Everything stored under a
+`ref_` key was produced by reference code (oracle/ref_import.py documents the two arithmetic-neutral
+accommodations); `in_` keys are the seeded inputs.  Template meshes are the reference's OBJ assets
+parsed to arrays (modules/meshing/objects/{sphere,cuboid}.obj, /386.obj).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+
+from oracle import ref_import  # noqa: E402
+from oracle.vpn_oracle import parse_obj  # noqa: E402
+
+OUT = os.path.join(REPO, "tests", "golden")
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def main():
+    R = ref_import.load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    g = torch.Generator().manual_seed(1234)      # config.py:20 MANUAL_SEED
+    rn = lambda *s: torch.randn(*s, generator=g)
+    ru = lambda *s: torch.rand(*s, generator=g)
+    d = {}
+
+    # ---- transform -----------------------------------------------------------------------
+    B, n = 4, 19
+    pts = rn(B, n, 3)
+    q = torch.cat([rn(B, 3), torch.tensor([[0.3], [-0.25], [1.75], [0.0]])], dim=1)   # w<0, w>1, w=0
+    t = rn(B, 3)
+    d["in_tf_points"], d["in_tf_q"], d["in_tf_t"] = npy(pts), npy(q), npy(t)
+    d["ref_tf_refine"] = npy(R.rotate.refine_quaternions(q))
+    d["ref_tf_matrices"] = npy(R.rotate.get_rotation_matrices(R.rotate.refine_quaternions(q)))
+    d["ref_tf_rotate"] = npy(R.rotate.rotate_points(pts, q))
+    d["ref_tf_transform"] = npy(R.transform.transform_points(pts, q, t))
+    dists, elevs, azims, angles = ru(B) + 0.5, ru(B) * 80 - 20, ru(B) * 360, ru(B) * 360
+    d["in_tf_dists"], d["in_tf_elevs"], d["in_tf_azims"], d["in_tf_angles"] = map(npy, (dists, elevs, azims, angles))
+    d["ref_tf_view_to_obj"] = npy(R.transform.view_to_obj_points(pts, dists, elevs, azims, angles))
+    d["ref_tf_obj_to_view"] = npy(R.transform.obj_to_view_points(pts, dists, elevs, azims))
+    d["ref_tf_rotate_x"] = npy(R.transform.rotate_points_forward_x_axis(pts, angles))
+    # gradient of a scalar through transform_points w.r.t. points, q, t
+    pg, qg, tg = pts.clone().requires_grad_(), q.clone().requires_grad_(), t.clone().requires_grad_()
+    wgt = rn(B, n, 3)
+    (R.transform.transform_points(pg, qg, tg) * wgt).sum().backward()
+    d["in_tf_upstream"] = npy(wgt)
+    d["ref_tf_grad_points"], d["ref_tf_grad_q"], d["ref_tf_grad_t"] = npy(pg.grad), npy(qg.grad), npy(tg.grad)
+    pg = pts.clone().requires_grad_()
+    (R.transform.view_to_obj_points(pg, dists, elevs, azims, angles) * wgt).sum().backward()
+    d["ref_tf_view_to_obj_grad_points"] = npy(pg.grad)
+
+    # ---- sampling ------------------------------------------------------------------------
+    B, N = 3, 96
+    v = (torch.sigmoid(rn(B, 3)) + 0.1) / torch.tensor([8.0, 10.0, 10.0])
+    q = torch.sigmoid(rn(B, 4)); t = torch.tanh(rn(B, 3))
+    ue, ua = ru(B, N, 1), ru(B, N, 1)
+    d["in_sp_v"], d["in_sp_q"], d["in_sp_t"], d["in_sp_ue"], d["in_sp_ua"] = map(npy, (v, q, t, ue, ua))
+    with ref_import.forced_uniforms([ue, ua]):
+        d["ref_sp_canonical"] = npy(R.sphere.sphere_sampling(v, N))
+    vg, qg, tg = v.clone().requires_grad_(), q.clone().requires_grad_(), t.clone().requires_grad_()
+    with ref_import.forced_uniforms([ue, ua]):
+        out = R.Sampling.sphere_sampling(vg, qg, tg, N)
+    wgt = rn(B, N, 3)
+    (out * wgt).sum().backward()
+    d["ref_sp_points"], d["in_sp_upstream"] = npy(out), npy(wgt)
+    d["ref_sp_grad_v"], d["ref_sp_grad_q"], d["ref_sp_grad_t"] = npy(vg.grad), npy(qg.grad), npy(tg.grad)
+
+    B, N = 5, 100
+    v = (torch.sigmoid(rn(B, 3)) + 0.1) / torch.tensor([8.0, 10.0, 10.0])
+    v[3] = torch.tensor([0.5, 0.5, 1e-4])        # nearly flat: faces 0..3 get ~0 points
+    v[4] = torch.tensor([0.125, 0.125, 0.125])   # cube: N*w = 16.67 each, remainder face
+    q = torch.sigmoid(rn(B, 4)); t = torch.tanh(rn(B, 3))
+    u = ru(B, N, 3)
+    d["in_cb_v"], d["in_cb_q"], d["in_cb_t"], d["in_cb_u"] = map(npy, (v, q, t, u))
+    w, h, dd = v[:, 0:1], v[:, 1:2], v[:, 2:3]
+    d["ref_cb_counts"] = npy(R.cuboid.get_faces_points(w, h, dd, N))
+    with ref_import.forced_uniforms([u]):
+        d["ref_cb_canonical"] = npy(R.cuboid.cuboid_sampling(v, N))
+    vg, qg, tg = v.clone().requires_grad_(), q.clone().requires_grad_(), t.clone().requires_grad_()
+    with ref_import.forced_uniforms([u]):
+        out = R.Sampling.cuboid_sampling(vg, qg, tg, N)
+    wgt = rn(B, N, 3)
+    (out * wgt).sum().backward()
+    d["ref_cb_points"], d["in_cb_upstream"] = npy(out), npy(wgt)
+    d["ref_cb_grad_v"], d["ref_cb_grad_q"], d["ref_cb_grad_t"] = npy(vg.grad), npy(qg.grad), npy(tg.grad)
+    # N=1000 counts on many random boxes (rounding rule incl. half-even)
+    vv = (torch.sigmoid(rn(64, 3)) + 0.1) / torch.tensor([8.0, 10.0, 10.0])
+    d["in_cb_counts_v"] = npy(vv)
+    d["ref_cb_counts_1000"] = npy(R.cuboid.get_faces_points(vv[:, 0:1], vv[:, 1:2], vv[:, 2:3], 1000))
+    d["ref_cb_counts_4096"] = npy(R.cuboid.get_faces_points(vv[:, 0:1], vv[:, 1:2], vv[:, 2:3], 4096))
+
+    # ---- Chamfer -------------------------------------------------------------------------
+    B, P, M = 3, 160, 72
+    p1, p2 = rn(B, P, 3) * 0.3, rn(B, M, 3) * 0.3
+    p2[0, 10] = p2[0, 3]; p2[0, 40] = p2[0, 3]           # duplicate targets: first index must win
+    p1[1, 100] = p1[1, 7]                                 # duplicate predicted points
+    p1[2, :27] = torch.stack(torch.meshgrid(*[torch.arange(3.0)] * 3, indexing="ij"), -1).reshape(-1, 3) * 0.25
+    p2[2, :8] = torch.stack(torch.meshgrid(*[torch.arange(2.0)] * 3, indexing="ij"), -1).reshape(-1, 3) * 0.25 + 0.125
+    d["in_cd_p1"], d["in_cd_p2"] = npy(p1), npy(p2)
+    cd = R.ChamferDistanceLoss()
+    a, b_ = p1.clone().requires_grad_(), p2.clone().requires_grad_()
+    loss = cd(a, b_)
+    loss.backward()
+    d["ref_cd_loss"], d["ref_cd_grad_p1"], d["ref_cd_grad_p2"] = npy(loss), npy(a.grad), npy(b_.grad)
+    d["ref_cd_loss_each"] = npy(cd(p1, p2, each_batch=True))
+    d["ref_cd_loss_w"] = npy(cd(p1, p2, w1=0.5, w2=1.0))
+    # the arg-mins the reference's torch.min picks (chamfer_distance.py:14-23 re-run to keep them)
+    diff = p1[:, :, None, :] - p2[:, None, :, :]
+    dist = torch.sum(diff * diff, dim=3)
+    m1, i1 = torch.min(torch.sqrt(dist), dim=2)
+    m2, i2 = torch.min(torch.sqrt(torch.transpose(dist, 1, 2)), dim=2)
+    d["ref_cd_min1"], d["ref_cd_idx1"], d["ref_cd_min2"], d["ref_cd_idx2"] = npy(m1), npy(i1), npy(m2), npy(i2)
+
+    # ---- VP diverse ----------------------------------------------------------------------
+    K = R.config.VP_NUM
+    tr = [torch.tanh(rn(2, 3)) for _ in range(K)]
+    gt = rn(2, 64, 3) * 0.3
+    d["in_vd_translates"], d["in_vd_gt"] = npy(torch.stack(tr, 1)), npy(gt)
+    d["ref_vd_loss"] = npy(R.VPDiverseLoss()(tr, gt))
+
+    # ---- end to end: sample_predict_points (train.py:105-120) + Chamfer, grads to v,q,t ----
+    for kind in ("sphere", "cuboid"):
+        B, K, N, M = 2, 3, 64, 80
+        v = ((torch.sigmoid(rn(B, K, 3)) + 0.1) / torch.tensor([8.0, 10.0, 10.0])).requires_grad_()
+        q = torch.sigmoid(rn(B, K, 4)).requires_grad_()
+        t = (torch.tanh(rn(B, K, 3)) * 0.3).requires_grad_()
+        tgt = rn(B, M, 3) * 0.2
+        if kind == "sphere":
+            u = ru(B, K, N, 2)
+            draws = [x for i in range(K) for x in (u[:, i, :, 0:1].contiguous(), u[:, i, :, 1:2].contiguous())]
+            fn = R.Sampling.sphere_sampling
+        else:
+            u = ru(B, K, N, 3)
+            draws = [u[:, i].contiguous() for i in range(K)]
+            fn = R.Sampling.cuboid_sampling
+        with ref_import.forced_uniforms(draws):
+            pred = torch.cat([fn(v[:, i], q[:, i], t[:, i], N) for i in range(K)], dim=1)
+        loss = cd(pred, tgt)
+        loss.backward()
+        for name, val in (("v", v), ("q", q), ("t", t)):
+            d[f"in_e2e_{kind}_{name}"] = npy(val)
+            d[f"ref_e2e_{kind}_grad_{name}"] = npy(val.grad)
+        d[f"in_e2e_{kind}_u"], d[f"in_e2e_{kind}_target"] = npy(u), npy(tgt)
+        d[f"ref_e2e_{kind}_points"], d[f"ref_e2e_{kind}_loss"] = npy(pred), npy(loss)
+
+    # ---- meshing (reference arithmetic over the stubbed TriangleMesh container) ------------
+    B = 2
+    v = (torch.sigmoid(rn(B, 3)) + 0.1) / torch.tensor([8.0, 10.0, 10.0])
+    q = torch.sigmoid(rn(B, 4)); t = torch.tanh(rn(B, 3))
+    d["in_ms_v"], d["in_ms_q"], d["in_ms_t"] = map(npy, (v, q, t))
+    sm = R.Meshing.sphere_meshing(v, q, t)
+    cm = R.Meshing.cuboid_meshing(v, q, t)
+    d["ref_ms_sphere_vertices"] = npy(torch.stack([m.vertices for m in sm]))
+    d["ref_ms_cuboid_vertices"] = npy(torch.stack([m.vertices for m in cm]))
+    comp = R.Meshing.compose_meshes([sm[0], cm[0], sm[1]])
+    d["ref_ms_compose_vertices"], d["ref_ms_compose_faces"] = npy(comp.vertices), npy(comp.faces)
+
+    np.savez_compressed(os.path.join(OUT, "hotpath_golden.npz"), **d)
+
+    # ---- template meshes -------------------------------------------------------------------
+    tm = {}
+    for key, rel in (("sphere", "modules/meshing/objects/sphere.obj"),
+                     ("cuboid", "modules/meshing/objects/cuboid.obj"),
+                     ("sphere386", "386.obj")):
+        with open(os.path.join(R.root, rel)) as fh:
+            vv, ff = parse_obj(fh.read())
+        tm[key + "_vertices"], tm[key + "_faces"] = vv, ff.astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "templates.npz"), **tm)
+    tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
+    print("wrote", sorted(os.listdir(OUT)), "total bytes", tot)
+
+
+if __name__ == "__main__":
+    main()

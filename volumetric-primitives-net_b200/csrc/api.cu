@@ -1,0 +1,90 @@
+// C-ABI glue: error reporting, device info, Chamfer forward dispatch.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void vpn_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int vpn_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { vpn_set_error("%s: %s", what, cudaGetErrorString(e)); return VPN_ERR_CUDA; }
+  return VPN_OK;
+}
+
+namespace vpn {
+int chamfer_simple_direction(const float* A, const float* Bp, float* mn, int* idx, u64* key,
+                             int B, int nA, int nB, int sm_count, cudaStream_t s);
+int chamfer_tiled_supported(int B, int P, int M);
+size_t chamfer_tiled_workspace_bytes(int B, int P, int M);
+int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
+                      int B, int P, int M, void* ws, size_t ws_bytes, int sm_count, int mode, cudaStream_t s);
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_sm_count = n;
+    else g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+extern "C" const char* vpn_last_error_string(void) { return g_err; }
+
+extern "C" int vpn_abi_version(void) { return 1; }
+
+extern "C" int vpn_device_info(int* sms, int* cc_major, int* cc_minor, int* clock_khz) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { vpn_set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
+  cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
+  cudaDeviceGetAttribute(clock_khz, cudaDevAttrClockRate, dev);
+  return VPN_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// impl: 0 = auto (tiled kernel, FMA-filter arithmetic, when the shape allows, else generic),
+//       1 = generic kernel only, 2 = tiled kernel with the reference's exact arithmetic in the hot loop,
+//       3 = tiled kernel with FMA-filter arithmetic.  2 and 3 fail on shapes the tiled kernel rejects.
+extern "C" int vpn_chamfer_workspace_bytes(int B, int P, int M, int impl, size_t* bytes) {
+  if (B < 0 || P <= 0 || M <= 0 || !bytes) { vpn_set_error("chamfer workspace: bad arguments"); return VPN_ERR_ARG; }
+  size_t simple = align256((size_t)B * P * 8) + align256((size_t)B * M * 8);
+  size_t tiled = (impl != 1 && vpn::chamfer_tiled_supported(B, P, M)) ? vpn::chamfer_tiled_workspace_bytes(B, P, M) : 0;
+  *bytes = simple > tiled ? simple : tiled;
+  return VPN_OK;
+}
+
+extern "C" int vpn_chamfer_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
+                               int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  if (B < 0 || P <= 0 || M <= 0) { vpn_set_error("chamfer fwd: bad shape B=%d P=%d M=%d", B, P, M); return VPN_ERR_SHAPE; }
+  if (B == 0) return VPN_OK;
+  if (B > 65535) { vpn_set_error("chamfer fwd: batch > 65535 unsupported"); return VPN_ERR_SHAPE; }
+  if (!p1 || !p2 || !min1 || !idx1 || !min2 || !idx2 || !workspace) { vpn_set_error("chamfer fwd: null pointer"); return VPN_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  bool tiled_ok = vpn::chamfer_tiled_supported(B, P, M) != 0;
+  if (impl < 0 || impl > 3) { vpn_set_error("chamfer fwd: bad impl %d", impl); return VPN_ERR_ARG; }
+  if (impl >= 2 && !tiled_ok) { vpn_set_error("chamfer fwd: tiled kernel does not support this shape"); return VPN_ERR_SHAPE; }
+  if (impl != 1 && tiled_ok) {
+    int mode = impl == 2 ? 0 : (impl == 3 ? 1 : -1);
+    return vpn::chamfer_tiled_fwd(p1, p2, min1, idx1, min2, idx2, B, P, M, workspace, workspace_bytes, sm_count(), mode, s);
+  }
+  size_t need = align256((size_t)B * P * 8) + align256((size_t)B * M * 8);
+  if (workspace_bytes < need) { vpn_set_error("chamfer fwd: workspace too small (%zu < %zu)", workspace_bytes, need); return VPN_ERR_WORKSPACE; }
+  vpn::u64* key1 = reinterpret_cast<vpn::u64*>(workspace);
+  vpn::u64* key2 = reinterpret_cast<vpn::u64*>(reinterpret_cast<char*>(workspace) + align256((size_t)B * P * 8));
+  int rc = vpn::chamfer_simple_direction(p1, p2, min1, idx1, key1, B, P, M, sm_count(), s);
+  if (rc) return rc;
+  return vpn::chamfer_simple_direction(p2, p1, min2, idx2, key2, B, M, P, sm_count(), s);
+}

@@ -1,0 +1,180 @@
+// Chamfer nearest-neighbour search, generic path + backward.
+//
+// Reference arithmetic (modules/loss/chamfer_distance.py:14-23), per pair:
+//   d = fl(fl(fl(dx*dx) + fl(dy*dy)) + fl(dz*dz)),  dx = fl(p.x - t.x) ...   (no FMA contraction)
+//   v = sqrt(d);  min over the other cloud;  ties -> FIRST index (torch.min).
+// This file holds the shape-agnostic kernel (any P, M >= 1): used for small or ragged clouds
+// (VP-diverse: P = K = 16, modules/loss/vp_diverse.py:12-18) and as the on-device cross-check of
+// the tiled kernel in chamfer_tiled.cu.  Both directions are the same kernel with the clouds
+// swapped.  Results are combined across column segments with a 64-bit atomicMin on
+// (float_bits(v) << 32 | index): for non-negative floats that orders by value, then by lowest
+// index, which is exactly the reference's tie rule, independent of scheduling.
+#include "common.cuh"
+
+namespace vpn {
+
+constexpr int kSimpleThreads = 128;
+constexpr int kSimpleRows = 2;            // rows per thread
+constexpr int kSimpleTile = 1024;         // columns staged in shared memory per step
+
+__device__ __forceinline__ float exact_d2(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// rows: cloud A (B, nA, 3) ; cols: cloud B (B, nB, 3).  key (B, nA) u64, pre-filled with 0xFF..FF.
+// grid: x = row block, y = column segment, z = sample.
+__global__ void __launch_bounds__(kSimpleThreads)
+chamfer_simple_kernel(const float* __restrict__ A, const float* __restrict__ Bp, u64* __restrict__ key,
+                      int nA, int nB, int seg_len) {
+  __shared__ float4 tile[kSimpleTile];
+  const int b = blockIdx.z;
+  const float* a = A + (size_t)b * nA * 3;
+  const float* t = Bp + (size_t)b * nB * 3;
+  const int row0 = (blockIdx.x * kSimpleThreads + threadIdx.x) * kSimpleRows;
+  float px[kSimpleRows], py[kSimpleRows], pz[kSimpleRows];
+  float best_d[kSimpleRows], best_v[kSimpleRows];
+  int best_j[kSimpleRows];
+#pragma unroll
+  for (int r = 0; r < kSimpleRows; ++r) {
+    int i = min(row0 + r, nA - 1);
+    px[r] = a[3 * (size_t)i]; py[r] = a[3 * (size_t)i + 1]; pz[r] = a[3 * (size_t)i + 2];
+    best_d[r] = __int_as_float(0x7f800000); best_v[r] = best_d[r]; best_j[r] = 0;
+  }
+  const int c_begin = blockIdx.y * seg_len;
+  const int c_end = min(nB, c_begin + seg_len);
+  for (int c0 = c_begin; c0 < c_end; c0 += kSimpleTile) {
+    const int cnt = min(kSimpleTile, c_end - c0);
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt; k += kSimpleThreads) {
+      const float* s = t + 3 * (size_t)(c0 + k);
+      tile[k] = make_float4(s[0], s[1], s[2], 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < cnt; ++k) {
+      float4 q = tile[k];
+#pragma unroll
+      for (int r = 0; r < kSimpleRows; ++r) {
+        float d = exact_d2(px[r], py[r], pz[r], q.x, q.y, q.z);
+        if (d < best_d[r]) {
+          // Rare path.  d improves the squared distance; the index only moves if the ROUNDED sqrt
+          // improves too, because the reference minimises sqrt(d) and keeps the first index of a tie.
+          float v = sqrtf(d);
+          if (v < best_v[r]) { best_v[r] = v; best_j[r] = c0 + k; }
+          best_d[r] = d;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kSimpleRows; ++r) {
+    int i = row0 + r;
+    if (i < nA && c_begin < c_end) {
+      u64 kv = ((u64)__float_as_uint(best_v[r]) << 32) | (unsigned)best_j[r];
+      atomicMin(&key[(size_t)b * nA + i], kv);
+    }
+  }
+}
+
+__global__ void chamfer_unpack_kernel(const u64* __restrict__ key, float* __restrict__ mn, int* __restrict__ idx, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 k = key[i];
+  mn[i] = __uint_as_float((unsigned)(k >> 32));
+  idx[i] = (int)(unsigned)(k & 0xffffffffu);
+}
+
+// Backward (what autograd does through chamfer_distance.py:14-23 given the arg-mins):
+//   row term : dL/dp1[i] = (g1[i] / (2 v1[i])) * 2 (p1[i] - p2[idx1[i]])          -> plain store
+//   col term : dL/dp1[idx2[j]] += (g2[j] / (2 v2[j])) * 2 (p1[idx2[j]] - p2[j])    -> atomic scatter
+// and the negatives into dL/dp2 when requested.  v == 0 gives inf * 0 = NaN, as in the reference.
+__global__ void chamfer_bwd_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                                        const float* __restrict__ min1, const int* __restrict__ idx1,
+                                        const float* __restrict__ g1, float* __restrict__ gp1,
+                                        float* __restrict__ gp2, int P, int M) {
+  const int b = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  size_t ri = (size_t)b * P + i;
+  int j = idx1[ri];
+  const float* a = p1 + 3 * ri;
+  const float* t = p2 + 3 * ((size_t)b * M + j);
+  float coef = g1[ri] / (2.0f * min1[ri]);
+  float cx = coef * (2.0f * (a[0] - t[0])), cy = coef * (2.0f * (a[1] - t[1])), cz = coef * (2.0f * (a[2] - t[2]));
+  gp1[3 * ri] = cx; gp1[3 * ri + 1] = cy; gp1[3 * ri + 2] = cz;
+  if (gp2) {
+    float* o = gp2 + 3 * ((size_t)b * M + j);
+    atomicAdd(o, -cx); atomicAdd(o + 1, -cy); atomicAdd(o + 2, -cz);
+  }
+}
+
+__global__ void chamfer_bwd_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                                        const float* __restrict__ min2, const int* __restrict__ idx2,
+                                        const float* __restrict__ g2, float* __restrict__ gp1,
+                                        float* __restrict__ gp2, int P, int M) {
+  const int b = blockIdx.y;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  size_t cj = (size_t)b * M + j;
+  int i = idx2[cj];
+  const float* a = p1 + 3 * ((size_t)b * P + i);
+  const float* t = p2 + 3 * cj;
+  float coef = g2[cj] / (2.0f * min2[cj]);
+  float cx = coef * (2.0f * (a[0] - t[0])), cy = coef * (2.0f * (a[1] - t[1])), cz = coef * (2.0f * (a[2] - t[2]));
+  float* o = gp1 + 3 * ((size_t)b * P + i);
+  atomicAdd(o, cx); atomicAdd(o + 1, cy); atomicAdd(o + 2, cz);
+  if (gp2) {
+    float* o2 = gp2 + 3 * cj;
+    atomicAdd(o2, -cx); atomicAdd(o2 + 1, -cy); atomicAdd(o2 + 2, -cz);
+  }
+}
+
+// one direction: for every row of A the nearest column of Bp
+int chamfer_simple_direction(const float* A, const float* Bp, float* mn, int* idx, u64* key,
+                             int B, int nA, int nB, int sm_count, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(key, 0xFF, (size_t)B * nA * sizeof(u64), s);
+  if (e != cudaSuccess) { vpn_set_error("chamfer: memset failed: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
+  int row_blocks = (nA + kSimpleThreads * kSimpleRows - 1) / (kSimpleThreads * kSimpleRows);
+  // split the columns so that small row counts (VP-diverse: 16 rows) still fill the SMs
+  long long want = 4LL * sm_count;
+  int segs = (int)((want + (long long)row_blocks * B - 1) / ((long long)row_blocks * B));
+  int max_segs = (nB + kSimpleTile - 1) / kSimpleTile;
+  if (segs > max_segs) segs = max_segs;
+  if (segs < 1) segs = 1;
+  int seg_len = (nB + segs - 1) / segs;
+  seg_len = ((seg_len + 31) / 32) * 32;
+  segs = (nB + seg_len - 1) / seg_len;
+  dim3 grid(row_blocks, segs, B);
+  chamfer_simple_kernel<<<grid, kSimpleThreads, 0, s>>>(A, Bp, key, nA, nB, seg_len);
+  int rc = vpn_check_launch("chamfer_simple_kernel");
+  if (rc) return rc;
+  size_t n = (size_t)B * nA;
+  chamfer_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(key, mn, idx, n);
+  return vpn_check_launch("chamfer_unpack_kernel");
+}
+
+}  // namespace vpn
+
+using namespace vpn;
+
+extern "C" int vpn_chamfer_bwd(const float* p1, const float* p2, const float* min1, const int* idx1,
+                               const float* min2, const int* idx2, const float* g1, const float* g2,
+                               float* grad_p1, float* grad_p2, int B, int P, int M, void* stream) {
+  if (B < 0 || P <= 0 || M <= 0) { vpn_set_error("chamfer bwd: bad shape"); return VPN_ERR_SHAPE; }
+  if (B == 0) return VPN_OK;
+  if (B > 65535) { vpn_set_error("chamfer bwd: batch > 65535 unsupported"); return VPN_ERR_SHAPE; }
+  if (!p1 || !p2 || !min1 || !idx1 || !min2 || !idx2 || !g1 || !g2 || !grad_p1) {
+    vpn_set_error("chamfer bwd: null pointer"); return VPN_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (grad_p2) {
+    cudaError_t e = cudaMemsetAsync(grad_p2, 0, (size_t)B * M * 3 * sizeof(float), s);
+    if (e != cudaSuccess) { vpn_set_error("chamfer bwd: memset failed: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
+  }
+  chamfer_bwd_rows_kernel<<<dim3((P + 255) / 256, B), 256, 0, s>>>(p1, p2, min1, idx1, g1, grad_p1, grad_p2, P, M);
+  int rc = vpn_check_launch("chamfer_bwd_rows_kernel");
+  if (rc) return rc;
+  chamfer_bwd_cols_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(p1, p2, min2, idx2, g2, grad_p1, grad_p2, P, M);
+  return vpn_check_launch("chamfer_bwd_cols_kernel");
+}

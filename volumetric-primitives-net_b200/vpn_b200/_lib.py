@@ -1,0 +1,88 @@
+"""ctypes binding of libvpn_b200.so (include/vpn_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a tensor is not a contiguous CUDA
+tensor of the expected dtype, the call raises.  torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_size_t, c_void_p, POINTER
+
+import torch
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.environ.get("VPN_B200_LIB", os.path.join(_PKG_ROOT, "lib", "libvpn_b200.so"))
+
+_lib = None
+
+_SIGNATURES = {
+    "vpn_last_error_string": (c_char_p, []),
+    "vpn_abi_version": (c_int, []),
+    "vpn_device_info": (c_int, [POINTER(c_int)] * 4),
+    "vpn_pose_points_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "vpn_pose_bwd_workspace_floats": (c_int, [c_int, c_int, POINTER(c_size_t)]),
+    "vpn_pose_points_bwd": (c_int, [c_int] + [c_void_p] * 9 + [c_size_t, c_int, c_int, c_void_p]),
+    "vpn_cuboid_face_counts": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "vpn_view_workspace_bytes": (c_int, [c_int, POINTER(c_size_t)]),
+    "vpn_view_points": (c_int, [c_int, c_int] + [c_void_p] * 7 + [c_size_t, c_int, c_int, c_void_p]),
+    "vpn_chamfer_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_size_t)]),
+    "vpn_chamfer_fwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "vpn_chamfer_bwd": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_void_p]),
+    "vpn_silhouette_workspace_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
+    "vpn_silhouette_fwd": (c_int, [c_void_p] * 4 + [c_float] * 4 + [c_int, c_float, c_float] + [c_void_p] * 4
+                           + [c_size_t] + [c_int] * 5 + [c_void_p]),
+    "vpn_silhouette_bwd": (c_int, [c_void_p] * 2 + [c_float] * 4 + [c_int, c_float, c_float] + [c_void_p] * 4
+                           + [c_size_t] + [c_int] * 5 + [c_void_p]),
+    "vpn_fp32_peak_probe": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_double), c_void_p]),
+}
+
+
+def exported_symbols():
+    """Names include/vpn_b200.h declares (tests check that the library exports each one)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"vpn_b200: CUDA library not found at {LIB_PATH}. Build it with "
+                "`make -C volumetric-primitives-net_b200/csrc` (or __graft_entry__.build()). "
+                "There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class VpnError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().vpn_last_error_string()
+        raise VpnError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require(t: torch.Tensor, dtype, name: str):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise VpnError(f"{name}: expected a CUDA tensor (vpn_b200 has no CPU path), got "
+                       f"{type(t).__name__ if not isinstance(t, torch.Tensor) else t.device}")
+    if t.dtype != dtype:
+        raise VpnError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise VpnError(f"{name}: expected a contiguous tensor")
+    return t

@@ -1,0 +1,318 @@
+"""torch.autograd.Functions over the C ABI (include/vpn_b200.h).
+
+Each Function follows the ownership convention of the reference's only native op
+(modules/loss/emd/emd_module.py:32-59): Python allocates outputs and scratch with torch, the native
+call fills them on the current CUDA stream.  No CPU path exists; CPU tensors raise VpnError.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import VpnError, check, ptr, require, stream_ptr
+
+KIND_SPHERE, KIND_CUBOID, KIND_TEMPLATE, KIND_POINTS = 0, 1, 2, 3
+CHAMFER_AUTO, CHAMFER_GENERIC, CHAMFER_TILED_EXACT, CHAMFER_TILED_FMA = 0, 1, 2, 3
+
+f32 = torch.float32
+
+
+def _scratch_bytes(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------
+# primitive instantiation
+# --------------------------------------------------------------------------------------
+class _PosePoints(torch.autograd.Function):
+    """out[p, n] = R(q[p]) (canonical(kind, src)[p, n] * v[p]) + t[p]   for nprim primitives."""
+
+    @staticmethod
+    def forward(ctx, kind, v, q, t, src, n_points):
+        lib = _lib.load()
+        q = require(q, f32, "q")
+        nprim = q.shape[0]
+        dev = q.device
+        if kind != KIND_POINTS:
+            v = require(v, f32, "v")
+        if t is not None:
+            t = require(t, f32, "t")
+        src = require(src, f32, "src")
+        out = torch.empty((nprim, n_points, 3), dtype=f32, device=dev)
+        check(lib.vpn_pose_points_fwd(kind, ptr(v) if kind != KIND_POINTS else None, ptr(q), ptr(t), ptr(src),
+                                      ptr(out), nprim, n_points, stream_ptr(dev)), "vpn_pose_points_fwd")
+        ctx.kind, ctx.n_points, ctx.has_t = kind, n_points, t is not None
+        ctx.save_for_backward(v if kind != KIND_POINTS else q, q, src)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        v, q, src = ctx.saved_tensors
+        kind, n = ctx.kind, ctx.n_points
+        nprim, dev = q.shape[0], q.device
+        grad_out = grad_out.contiguous()
+        need_v = kind != KIND_POINTS and ctx.needs_input_grad[1]
+        need_q, need_t = ctx.needs_input_grad[2], ctx.has_t and ctx.needs_input_grad[3]
+        need_p = kind == KIND_POINTS and ctx.needs_input_grad[4]
+        gv = torch.empty((nprim, 3), dtype=f32, device=dev) if need_v else None
+        gq = torch.empty((nprim, 4), dtype=f32, device=dev) if need_q else None
+        gt = torch.empty((nprim, 3), dtype=f32, device=dev) if need_t else None
+        gp = torch.empty((nprim, n, 3), dtype=f32, device=dev) if need_p else None
+        nfl = ctypes.c_size_t(0)
+        check(lib.vpn_pose_bwd_workspace_floats(nprim, n, ctypes.byref(nfl)), "vpn_pose_bwd_workspace_floats")
+        ws = torch.empty(max(nfl.value, 16), dtype=f32, device=dev)
+        check(lib.vpn_pose_points_bwd(kind, ptr(v) if kind != KIND_POINTS else None, ptr(q), ptr(src), ptr(grad_out),
+                                      ptr(gv), ptr(gq), ptr(gt), ptr(gp), ptr(ws), nfl.value, nprim, n,
+                                      stream_ptr(dev)), "vpn_pose_points_bwd")
+        return None, gv, gq, gt, gp, None
+
+
+def _flat_prims(v, q, t):
+    if q.dim() != 3 or q.size(-1) != 4:
+        raise AssertionError("q must be (B, K, 4)")
+    b, k = q.shape[:2]
+    assert v.shape == (b, k, 3) and t.shape == (b, k, 3), "v, t must be (B, K, 3)"
+    return b, k, v.reshape(b * k, 3).contiguous(), q.reshape(b * k, 4).contiguous(), t.reshape(b * k, 3).contiguous()
+
+
+def sample_primitives(kind: str, v: torch.Tensor, q: torch.Tensor, t: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """Fused sampling + pose of K primitives per sample (train.py:105-120 in one launch).
+
+    v (B,K,3), q (B,K,4), t (B,K,3); u uniforms in [0,1): sphere (B,K,N,2) = [elev draw, azim draw]
+    (sampling/sphere.py:26-27), cuboid (B,K,N,3) (sampling/cuboid.py:66).  Returns (B, K*N, 3),
+    primitive-major along dim 1 exactly like the reference's torch.cat(dim=1)."""
+    b, k, vf, qf, tf = _flat_prims(v, q, t)
+    kid = {"sphere": KIND_SPHERE, "cuboid": KIND_CUBOID}[kind]
+    width = 2 if kid == KIND_SPHERE else 3
+    assert u.dim() == 4 and u.shape[:2] == (b, k) and u.size(-1) == width, "bad uniforms shape"
+    n = u.size(2)
+    out = _PosePoints.apply(kid, vf, qf, tf, u.reshape(b * k, n, width).contiguous(), n)
+    return out.view(b, k * n, 3)
+
+
+def mesh_vertices(template: torch.Tensor, v: torch.Tensor, q: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """Template vertices (V,3) scaled by v and posed per primitive: (B, K*V, 3)
+    (meshing/sphere.py:8-27, cuboid.py:8-27, then compose order of meshing.py:28-46)."""
+    b, k, vf, qf, tf = _flat_prims(v, q, t)
+    assert template.dim() == 2 and template.size(1) == 3
+    nv = template.size(0)
+    out = _PosePoints.apply(KIND_TEMPLATE, vf, qf, tf, template.contiguous(), nv)
+    return out.view(b, k * nv, 3)
+
+
+def transform_points(points: torch.Tensor, q: torch.Tensor, t: Optional[torch.Tensor]) -> torch.Tensor:
+    """translate(rotate(points, q), t)  (transform/transform.py:6-9); t=None -> rotate only."""
+    assert points.dim() == 3 and points.size(-1) == 3
+    b, n = points.shape[:2]
+    assert q.shape == (b, 4) and (t is None or t.shape == (b, 3))
+    if n == 0:
+        return points.clone()
+    return _PosePoints.apply(KIND_POINTS, None, q.contiguous(), None if t is None else t.contiguous(),
+                             points.contiguous(), n)
+
+
+def cuboid_face_counts(v: torch.Tensor, num_points: int) -> torch.Tensor:
+    """get_faces_points (sampling/cuboid.py:30-53): (..., 6) int32."""
+    lib = _lib.load()
+    vf = require(v.reshape(-1, 3).contiguous(), f32, "v")
+    out = torch.empty((vf.shape[0], 6), dtype=torch.int32, device=vf.device)
+    check(lib.vpn_cuboid_face_counts(ptr(vf), ptr(out), vf.shape[0], int(num_points), stream_ptr(vf.device)),
+          "vpn_cuboid_face_counts")
+    return out.view(*v.shape[:-1], 6)
+
+
+# --------------------------------------------------------------------------------------
+# camera frame changes
+# --------------------------------------------------------------------------------------
+class _ViewPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mode, points, dists, elevs, azims, angles):
+        out = _ViewPoints._run(mode, 0, points, dists, elevs, azims, angles)
+        ctx.mode = mode
+        ctx.save_for_backward(dists, elevs, azims, angles if angles is not None else dists)
+        return out
+
+    @staticmethod
+    def _run(mode, transpose, x, dists, elevs, azims, angles):
+        lib = _lib.load()
+        x = require(x.contiguous(), f32, "points")
+        b, n = x.shape[:2]
+        dev = x.device
+        args = [require(a.contiguous(), f32, nm) for a, nm in ((dists, "dists"), (elevs, "elevs"), (azims, "azims"))]
+        ang = require(angles.contiguous(), f32, "angles") if mode == 0 else None
+        out = torch.empty_like(x)
+        nb = ctypes.c_size_t(0)
+        check(lib.vpn_view_workspace_bytes(b, ctypes.byref(nb)), "vpn_view_workspace_bytes")
+        ws = _scratch_bytes(nb.value, dev)
+        check(lib.vpn_view_points(mode, transpose, ptr(x), ptr(args[0]), ptr(args[1]), ptr(args[2]), ptr(ang), ptr(out),
+                                  ptr(ws), nb.value, b, n, stream_ptr(dev)), "vpn_view_points")
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dists, elevs, azims, angles = ctx.saved_tensors
+        g = _ViewPoints._run(ctx.mode, 1, grad_out, dists, elevs, azims, angles)
+        return None, g, None, None, None, None
+
+
+def view_to_obj_points(points, dists, elevs, azims, angles):
+    """transform/transform.py:21-47."""
+    assert points.dim() == 3
+    assert dists.dim() == elevs.dim() == azims.dim() == 1
+    return _ViewPoints.apply(0, points, dists, elevs, azims, angles)
+
+
+def obj_to_view_points(points, dists, elevs, azims):
+    """transform/transform.py:50-73."""
+    assert points.dim() == 3
+    assert dists.dim() == elevs.dim() == azims.dim() == 1
+    return _ViewPoints.apply(1, points, dists, elevs, azims, None)
+
+
+# --------------------------------------------------------------------------------------
+# Chamfer
+# --------------------------------------------------------------------------------------
+class _ChamferNN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p1, p2, impl):
+        lib = _lib.load()
+        p1 = require(p1.contiguous(), f32, "points1")
+        p2 = require(p2.contiguous(), f32, "points2")
+        b, p, _ = p1.shape
+        m = p2.shape[1]
+        dev = p1.device
+        min1 = torch.empty((b, p), dtype=f32, device=dev); idx1 = torch.empty((b, p), dtype=torch.int32, device=dev)
+        min2 = torch.empty((b, m), dtype=f32, device=dev); idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+        nb = ctypes.c_size_t(0)
+        check(lib.vpn_chamfer_workspace_bytes(b, p, m, impl, ctypes.byref(nb)), "vpn_chamfer_workspace_bytes")
+        ws = _scratch_bytes(nb.value, dev)
+        check(lib.vpn_chamfer_fwd(ptr(p1), ptr(p2), ptr(min1), ptr(idx1), ptr(min2), ptr(idx2), b, p, m,
+                                  ptr(ws), nb.value, impl, stream_ptr(dev)), "vpn_chamfer_fwd")
+        ctx.save_for_backward(p1, p2, min1, idx1, min2, idx2)
+        ctx.mark_non_differentiable(idx1, idx2)
+        return min1, idx1, min2, idx2
+
+    @staticmethod
+    def backward(ctx, g1, _gi1, g2, _gi2):
+        lib = _lib.load()
+        p1, p2, min1, idx1, min2, idx2 = ctx.saved_tensors
+        b, p, _ = p1.shape
+        m = p2.shape[1]
+        dev = p1.device
+        g1 = torch.zeros_like(min1) if g1 is None else g1.contiguous()
+        g2 = torch.zeros_like(min2) if g2 is None else g2.contiguous()
+        gp1 = torch.empty_like(p1)
+        gp2 = torch.empty_like(p2) if ctx.needs_input_grad[1] else None
+        check(lib.vpn_chamfer_bwd(ptr(p1), ptr(p2), ptr(min1), ptr(idx1), ptr(min2), ptr(idx2), ptr(g1), ptr(g2),
+                                  ptr(gp1), ptr(gp2), b, p, m, stream_ptr(dev)), "vpn_chamfer_bwd")
+        return (gp1 if ctx.needs_input_grad[0] else None), gp2, None
+
+
+def chamfer_nn(points1: torch.Tensor, points2: torch.Tensor, impl: int = CHAMFER_AUTO):
+    """Nearest neighbours in both directions: (min1 (B,P), idx1 (B,P) int32, min2 (B,M), idx2 (B,M) int32).
+    min* are differentiable w.r.t. both clouds; arithmetic and tie rule of chamfer_distance.py:14-23."""
+    assert points1.dim() == 3 and points1.size(-1) == 3          # chamfer_distance.py:33-35
+    assert points2.dim() == 3 and points2.size(-1) == 3
+    assert points1.size(0) == points2.size(0)
+    return _ChamferNN.apply(points1, points2, impl)
+
+
+def chamfer_distance(points1, points2, each_batch=False, w1=1.0, w2=1.0, impl: int = CHAMFER_AUTO):
+    """ChamferDistanceLoss.forward (chamfer_distance.py:10-30)."""
+    min1, _, min2, _ = chamfer_nn(points1, points2, impl)
+    loss = w1 * min1.mean(1) + w2 * min2.mean(1)
+    return loss if each_batch else loss.mean()
+
+
+# --------------------------------------------------------------------------------------
+# soft silhouette
+# --------------------------------------------------------------------------------------
+DIBR_FOVY_DEG = 49.13434207744484
+DIBR_EXPAND, DIBR_KNUM, DIBR_MULTIPLIER, DIBR_DELTA = 0.02, 30, 1000.0, 7000.0
+
+
+def projection_vector() -> Tuple[float, float, float]:
+    tf = math.tan(math.radians(DIBR_FOVY_DEG) / 2.0)
+    return 1.0 / tf, 1.0 / tf, -1.0
+
+
+def look_at_cameras(azims: torch.Tensor, elevs: torch.Tensor, dists: torch.Tensor):
+    """kaolin compute_camera_params for a batch, on the tensors' device, no host sync:
+    rot (B,3,3) rows = unit X = Y0 x Z, Y = Z x X, Z = cam_pos; pos (B,3)."""
+    theta, phi = torch.deg2rad(azims.double()), torch.deg2rad(elevs.double())
+    d = dists.double()
+    pos = torch.stack([d * torch.cos(phi) * torch.cos(theta), d * torch.sin(phi), d * torch.cos(phi) * torch.sin(theta)], 1)
+    az = pos
+    ay0 = torch.tensor([0.0, 1.0, 0.0], dtype=torch.float64, device=pos.device).expand_as(pos)
+    ax = torch.cross(ay0, az, dim=1)
+    ay = torch.cross(az, ax, dim=1)
+    unit = lambda x: x / torch.linalg.norm(x, dim=1, keepdim=True)
+    rot = torch.stack([unit(ax), unit(ay), unit(az)], dim=1)
+    return rot.float().contiguous(), pos.float().contiguous()
+
+
+class _SoftSilhouette(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, faces, rot, pos, height, width, want_normals):
+        lib = _lib.load()
+        verts = require(verts.contiguous(), f32, "verts")
+        faces = require(faces.contiguous(), torch.int32, "faces")
+        rot = require(rot.contiguous(), f32, "cam_rot")
+        pos = require(pos.contiguous(), f32, "cam_pos")
+        b, v, _ = verts.shape
+        f = faces.shape[0]
+        dev = verts.device
+        alpha = torch.empty((b, height, width), dtype=f32, device=dev)
+        covered = torch.empty((b, height, width), dtype=torch.uint8, device=dev)
+        normals = torch.empty((b, f, 3), dtype=f32, device=dev) if want_normals else None
+        nb = ctypes.c_size_t(0)
+        check(lib.vpn_silhouette_workspace_bytes(b, v, f, ctypes.byref(nb)), "vpn_silhouette_workspace_bytes")
+        ws = _scratch_bytes(nb.value, dev)
+        px, py, pz = projection_vector()
+        check(lib.vpn_silhouette_fwd(ptr(verts), ptr(faces), ptr(rot), ptr(pos), px, py, pz, DIBR_EXPAND, DIBR_KNUM,
+                                     DIBR_MULTIPLIER, DIBR_DELTA, ptr(alpha), ptr(covered), ptr(normals), ptr(ws),
+                                     nb.value, b, v, f, height, width, stream_ptr(dev)), "vpn_silhouette_fwd")
+        ctx.save_for_backward(faces, rot, covered, ws)
+        ctx.dims = (b, v, f, height, width, nb.value)
+        ctx.mark_non_differentiable(covered)
+        if normals is None:
+            normals = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(normals)
+        return alpha, covered, normals
+
+    @staticmethod
+    def backward(ctx, galpha, _gc, _gn):
+        lib = _lib.load()
+        faces, rot, covered, ws = ctx.saved_tensors
+        b, v, f, h, w, nbytes = ctx.dims
+        dev = rot.device
+        galpha = galpha.contiguous()
+        gverts = torch.empty((b, v, 3), dtype=f32, device=dev)
+        px, py, pz = projection_vector()
+        check(lib.vpn_silhouette_bwd(ptr(faces), ptr(rot), px, py, pz, DIBR_EXPAND, DIBR_KNUM, DIBR_MULTIPLIER, DIBR_DELTA,
+                                     ptr(galpha), ptr(covered), ptr(gverts), ptr(ws), nbytes, b, v, f, h, w,
+                                     stream_ptr(dev)), "vpn_silhouette_bwd")
+        return gverts, None, None, None, None, None, None
+
+
+def soft_silhouette(verts, faces, rot, pos, height: int, width: int, want_normals: bool = False):
+    """Batched DIB-R soft alpha: verts (B,V,3), faces (F,3) int32 (shared topology), cameras (B,3,3)/(B,3).
+    Returns (alpha (B,H,W), covered (B,H,W) uint8, face_normals (B,F,3) or empty)."""
+    assert verts.dim() == 3 and verts.size(-1) == 3 and faces.dim() == 2 and faces.size(-1) == 3
+    return _SoftSilhouette.apply(verts, faces, rot, pos, int(height), int(width), bool(want_normals))
+
+
+def fp32_peak_tflops(device=None, reps: int = 3):
+    """Achieved FP32 FMA throughput (TFLOP/s) of scalar FFMA and packed FFMA2 streams on this GPU."""
+    lib = _lib.load()
+    dev = torch.device("cuda" if device is None else device)
+    scratch = torch.ones(64, dtype=f32, device=dev)
+    a, b = ctypes.c_double(0), ctypes.c_double(0)
+    check(lib.vpn_fp32_peak_probe(ptr(scratch), reps, ctypes.byref(a), ctypes.byref(b), stream_ptr(dev)),
+          "vpn_fp32_peak_probe")
+    return {"ffma": a.value, "ffma2": b.value}
