@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Headline benchmark: primitive-loss forward+backward samples/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c1]
+
+A step = one pass of the hot path over one synthetic batch: draw uniforms -> fused sample+pose of K
+primitives -> Chamfer NN (both directions) vs the targets (+ VP-diverse Chamfer, + mesh vertices ->
+soft silhouette -> L1 when the workload has a render term) -> backward to (v, q, t).
+Default workload = BASELINE.json configs[1] ("c2": B=32/GPU, 16 cuboids x 4096 samples, 8192 targets).
+Multi-GPU: one process per GPU under torchrun, batch sharded (weak scaling, 32 samples per GPU), plus one
+NCCL all-reduce of a VPNetOneRes-sized gradient buffer (22 875 848 fp32) per step.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "volumetric-primitives-net_b200")
+for p in (REPO, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (kind, B per GPU, K, N, M, render resolution or 0)
+    "c1": ("sphere", 1, 16, 1024, 2048, 64),
+    "c2": ("cuboid", 32, 16, 4096, 8192, 0),
+    "c3": ("cuboid", 32, 32, 4096, 8192, 128),
+}
+GRAD_NUMEL = 22_875_848          # VPNetOneRes parameters at K = 16
+METRIC = "primitive-loss fwd+bwd samples/sec"
+
+
+def synthetic(workload, device, seed=1234, sets=1):
+    """Network-output-shaped primitives + ShapeNet-shaped targets, fp32."""
+    kind, b, k, n, m, res = WORKLOADS[workload]
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(sets):
+        v = (torch.sigmoid(torch.randn(b, k, 3, generator=g)) + 0.1) / torch.tensor([8.0, 10.0, 10.0])
+        q = torch.sigmoid(torch.randn(b, k, 4, generator=g))
+        t = torch.tanh(torch.randn(b, k, 3, generator=g)) * 0.4
+        # targets: points on the surface of a random union of boxes inside [-0.5, 0.5]^3
+        centre = (torch.rand(b, 8, 3, generator=g) - 0.5) * 0.7
+        half = torch.rand(b, 8, 3, generator=g) * 0.12 + 0.03
+        which = torch.randint(0, 8, (b, m), generator=g)
+        p = (torch.rand(b, m, 3, generator=g) * 2 - 1)
+        axis = torch.randint(0, 3, (b, m), generator=g)
+        sign = torch.randint(0, 2, (b, m), generator=g).float() * 2 - 1
+        p.scatter_(2, axis[..., None], sign[..., None])
+        bi = torch.arange(b)[:, None]
+        tgt = centre[bi, which] + p * half[bi, which]
+        sil = (torch.rand(b, 1, res, res, generator=g) > 0.5).float() if res else None
+        out.append(dict(v=v, q=q, t=t, target=tgt.contiguous(), sil=sil))
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent clock / throttle sampling (NVML) during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_step(workload, rows_per_sample, threads):
+    """The reference's own formulation on the host (oracle port, op for op: dense (B,P,M,3) broadcast,
+    modules/loss/chamfer_distance.py:14-23), fwd + bwd to (v,q,t), on a bounded slice of the workload:
+    one sample, `rows_per_sample` of its K*N predicted points (whole primitives)."""
+    from oracle import vpn_oracle as O
+    kind, b, k, n, m, res = WORKLOADS[workload]
+    kk = max(1, rows_per_sample // n)
+    torch.set_num_threads(threads)
+    data = synthetic(workload, "cpu")[0]
+    v, q, t = (data[x][:1, :kk].clone().requires_grad_() for x in ("v", "q", "t"))
+    tgt = data["target"][:1]
+    g = torch.Generator().manual_seed(1)
+    u = torch.rand(1, kk, n, 2 if kind == "sphere" else 3, generator=g)
+    t0 = time.perf_counter()
+    pts = O.sample_predict_points(kind, v, q, t, u)
+    loss = O.chamfer_dense(pts, tgt) + 0.1 * O.chamfer_dense(t, tgt, w1=0.5, w2=1.0)
+    loss.backward()
+    dt = time.perf_counter() - t0
+    frac = (kk * n) / float(k * n)          # share of one sample's pair work that was timed
+    return dt, frac, kk * n
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path (oracle port) on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    kind, b, k, n, m, res = WORKLOADS[args.workload]
+    rows = min(k * n, 8192)
+    for _ in range(args.warmup):
+        cpu_reference_step(args.workload, rows, threads)
+    times = []
+    for _ in range(args.steps):
+        dt, frac, used = cpu_reference_step(args.workload, rows, threads)
+        times.append(dt)
+    mean = sum(times) / len(times)
+    per_sample = mean / frac
+    value = 1.0 / per_sample
+    sample = (f"1 sample, {used} of {k * n} predicted points x {m} targets per step (dense torch-CPU formulation of the "
+              f"reference, fwd+bwd), scaled linearly to a full sample; render term not included")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": describe(args.workload)},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def describe(workload):
+    kind, b, k, n, m, res = WORKLOADS[workload]
+    s = f"{workload}: B={b}/GPU, {k} {kind} primitives x {n} samples (P={k * n}), Chamfer vs M={m} targets + VP-diverse"
+    if res:
+        s += f" + {res}x{res} soft-silhouette L1"
+    return s + ", fwd+bwd to (v,q,t)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chamfer-impl", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import vpn_b200
+    from vpn_b200 import _lib, dist as vdist
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    kind, b, k, n, m, res = WORKLOADS[args.workload]
+    width = 2 if kind == "sphere" else 3
+    nsets = 4
+    host = synthetic(args.workload, "cpu", seed=1234 + rank, sets=nsets)
+    devsets = [{kk: (vv.to(dev) if vv is not None else None) for kk, vv in s.items()} for s in host]
+    pinned = [{kk: (vv.pin_memory() if vv is not None else None) for kk, vv in s.items()} for s in host]
+    cfg = vpn_b200.PrimitiveLossConfig(kind=kind, l_sil=(1.0 if res else 0.0), chamfer_impl=args.chamfer_impl)
+    step_fn = vpn_b200.PrimitiveLoss(cfg)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    sync = vdist.GradientAllReduce(GRAD_NUMEL, dev) if world > 1 else None
+
+    def one_step(s, grads_out=None):
+        v, q, t = (s[x].detach().requires_grad_() for x in ("v", "q", "t"))
+        u = torch.rand((b, k, n, width), device=dev)               # drawn on device, like the reference
+        out = step_fn(v, q, t, u, s["target"], silhouettes=s["sil"])
+        out["total"].backward()
+        if sync is not None:
+            sync.launch()
+        return out["total"], v.grad, q.grad, t.grad
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------
+    for i in range(args.warmup):
+        one_step(devsets[i % nsets])
+    if sync is not None:
+        sync.join()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = lib.vpn_launch_count()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                               # L2 flush between timed iterations
+        evs[i][0].record()
+        one_step(devsets[i % nsets])
+        if sync is not None:
+            sync.join()
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = (lib.vpn_launch_count() - launches0) // args.steps
+    sampler.stop_flag = True
+    step_ms = [a.elapsed_time(bb) for a, bb in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * b * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers ("e2e") ------------------------------
+    def e2e_step(ps):
+        s = {kk: (vv.to(dev, non_blocking=True) if vv is not None else None) for kk, vv in ps.items()}
+        loss, gv, gq, gt = one_step(s)
+        if sync is not None:
+            sync.join()
+        return loss.cpu(), gv.cpu(), gq.cpu(), gt.cpu()
+
+    for i in range(2):
+        e2e_step(pinned[i % nsets])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(pinned[i % nsets])
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), e2e_wall * 1e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * b * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    h2d = sum(vv.numel() * vv.element_size() for vv in pinned[0].values() if vv is not None)
+    d2h = 4 + b * k * 10 * 4
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel group: Chamfer forward (FP32 pipe) ----------------------
+        s = devsets[0]
+        with torch.no_grad():
+            u = torch.rand((b, k, n, width), device=dev)
+            pts = vpn_b200.sample_primitives(kind, s["v"], s["q"], s["t"], u)
+            reps = 10
+            ce = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for i in range(3):
+                vpn_b200.chamfer_nn(pts, s["target"], args.chamfer_impl)
+            for i in range(reps):
+                flush.zero_()
+                ce[i][0].record()
+                vpn_b200.chamfer_nn(pts, s["target"], args.chamfer_impl)
+                ce[i][1].record()
+            torch.cuda.synchronize()
+            cham_ms = sum(a.elapsed_time(bb) for a, bb in ce) / reps
+            se = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for i in range(reps):
+                flush.zero_()
+                se[i][0].record()
+                vpn_b200.sample_primitives(kind, s["v"], s["q"], s["t"], u)
+                se[i][1].record()
+            torch.cuda.synchronize()
+            samp_ms = sum(a.elapsed_time(bb) for a, bb in se) / reps
+        peak = vpn_b200.fp32_peak_tflops(dev)
+        flops = 8.0 * b * (k * n) * m                      # 8 flop per (predicted, target) pair, both directions
+        achieved = flops / (cham_ms * 1e-3) / 1e12
+        sm_mhz_max = sampler.summary()["sm_max_mhz"] or 1965
+        nominal = 148 * 128 * 2 * sm_mhz_max * 1e6 / 1e12
+        peak_tf = max(peak["ffma2"], peak["ffma"])
+        roofline = {"kernel": "vpn_chamfer_fwd (chamfer_tiled_kernel + 2 recovery kernels)", "bound": "fp32",
+                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "peak_source": "live FFMA2 probe (vpn_fp32_peak_probe); MEASURED_PEAKS.json has no FP32 entry",
+                    "peak_nominal": nominal, "frac_of_nominal": achieved / nominal, "ms": cham_ms,
+                    "algorithmic_flops": flops, "traffic": None}
+        hbm_peak = 6536.7
+        try:
+            hbm_peak = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            hbm_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback"
+        sbytes = b * k * n * (12 + 4 * width)
+        roof_s = {"kernel": "pose_fwd_kernel (fused sample+pose)", "bound": "hbm",
+                  "achieved": sbytes / (samp_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                  "frac": sbytes / (samp_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms": samp_ms,
+                  "algorithmic_bytes": sbytes, "traffic": None}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rows = min(k * n, 8192)
+            cpu_reference_step(args.workload, min(rows, n), threads)      # warm-up on one primitive
+            dt, frac, used = cpu_reference_step(args.workload, rows, threads)
+            cpu = {"value": 1.0 / (dt / frac), "unit": "samples/s", "cores": threads, "kind": "port",
+                   "sample": f"1 sample, {used} of {k * n} predicted points x {m} targets, dense torch-CPU formulation "
+                             f"of the reference (fwd+bwd, no render term), {dt:.1f} s, scaled linearly to a full sample"}
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": describe(args.workload), "global_batch": world * b,
+                           "parallelism": f"dp{world}", "l2": "256 MB L2 flush between timed iterations, outside the "
+                           "per-step CUDA-event pairs; 4 rotating input sets",
+                           "allreduce_numel": GRAD_NUMEL if world > 1 else 0,
+                           "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps},
+                "clocks": sampler.summary(), "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "steps": e2e_steps},
+                "roofline": roofline, "roofline_sampling": roof_s, "cpu_baseline": cpu,
+                "fp32_peak_probe_tflops": peak}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,8 @@ extern "C" {
 const char* vpn_last_error_string(void);
 int vpn_abi_version(void);
 int vpn_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+/* kernels launched by this library in this process so far (bench.py reports the per-step delta) */
+unsigned long long vpn_launch_count(void);
 
 /* ---- primitive instantiation: canonical sample -> scale -> rotate -> translate, one kernel ------------
  * Replaces Sampling.{sphere,cuboid}_sampling (modules/sampling/sampling.py:12-38), transform_points /

@@ -1,0 +1,116 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/vpn_b200.h declares, the
+product refuses to run without CUDA (no CPU fallback), never touches oracle/, and the drop-ins keep the
+reference's AssertionError behaviour.  No compute calls are made here."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "volumetric-primitives-net_b200")
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    path = os.path.join(PKG, "lib", "libvpn_b200.so")
+    if not os.path.isfile(path):
+        subprocess.check_call(["make", "-C", os.path.join(PKG, "csrc"), "-j8"])
+    return path
+
+
+def header_functions():
+    text = open(os.path.join(REPO, "include", "vpn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vpn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    names = header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vpn_b200.h but not exported"
+    lib.vpn_abi_version.restype = ctypes.c_int
+    assert lib.vpn_abi_version() == 1
+
+
+def test_python_binding_covers_header(lib_path):
+    from vpn_b200 import _lib
+    assert _lib.exported_symbols() == header_functions()
+    _lib.load()
+
+
+def test_library_is_sm100a_only(lib_path):
+    out = subprocess.run(["cuobjdump", "-lelf", lib_path], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback(lib_path):
+    import vpn_b200
+    with pytest.raises(vpn_b200.VpnError):
+        vpn_b200.chamfer_nn(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+    with pytest.raises(vpn_b200.VpnError):
+        vpn_b200.sample_primitives("sphere", torch.zeros(1, 1, 3), torch.zeros(1, 1, 4), torch.zeros(1, 1, 3),
+                                   torch.zeros(1, 1, 8, 2))
+
+
+def test_missing_library_fails_loudly(lib_path, monkeypatch):
+    from vpn_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libvpn_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for root, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "vpn_oracle" in txt:
+                    bad.append(os.path.join(root, f))
+    assert not bad, bad
+
+
+def test_dropin_shape_asserts_match_reference(lib_path):
+    """transform.py:12-18, sampling.py:48-52, chamfer_distance.py:33-35, meshing.py:49-55 raise AssertionError."""
+    import modules.loss as ml
+    import modules.meshing as mm
+    import modules.sampling as ms
+    import modules.transform as mt
+    z = torch.zeros
+    with pytest.raises(AssertionError):
+        mt.transform_points(z(2, 5, 3), z(2, 3), z(2, 3))
+    with pytest.raises(AssertionError):
+        mt.transform_points(z(2, 5, 2), z(2, 4), z(2, 3))
+    with pytest.raises(AssertionError):
+        mt.rotate_points(z(2, 5), z(2, 4))
+    with pytest.raises(AssertionError):
+        mt.view_to_obj_points(z(2, 5, 3), z(2, 1), z(2), z(2), z(2))
+    with pytest.raises(AssertionError):
+        ms.Sampling.cuboid_sampling(z(2, 3), z(2, 4), z(3, 3), 10)
+    with pytest.raises(AssertionError):
+        ms.Sampling.sphere_sampling(z(2, 3), z(2, 4), z(2, 3), 0)
+    with pytest.raises(AssertionError):
+        ml.ChamferDistanceLoss()(z(2, 5, 2), z(2, 5, 3))
+    with pytest.raises(AssertionError):
+        ml.VPDiverseLoss()([z(2, 3)] * 3, z(2, 5, 3))          # len != VP_NUM
+    with pytest.raises(AssertionError):
+        mm.Meshing.sphere_meshing(z(2, 3), z(2, 4), z(3, 3))
+    assert ms.Sampling.cone_sampling(z(2, 3), z(2, 4), z(2, 3)) is None
+
+
+def test_templates_match_reference_assets(golden_templates):
+    from vpn_b200 import templates
+    from oracle import vpn_oracle as O
+    for name in ("sphere", "cuboid", "sphere386"):
+        v, f = templates.raw_template(name)
+        assert (v == golden_templates[name + "_vertices"]).all() and (f == golden_templates[name + "_faces"]).all()
+    tv, _ = templates.template("sphere", "cpu")
+    ref = O.sphere_template(torch.from_numpy(golden_templates["sphere_vertices"]))
+    assert torch.equal(tv, ref)

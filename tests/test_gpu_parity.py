@@ -1,0 +1,367 @@
+"""GPU parity tests: every call goes product API -> ctypes -> C ABI -> sm_100a kernel, and is compared
+with the CPU oracle (oracle/vpn_oracle.py, oracle/chamfer_oracle.c) and with the golden vectors the
+reference itself produced (tests/golden/).  Bars: arg-min indices and integer outputs bit-exact;
+floating point within 1e-4 relative (BASELINE.json north_star), tolerance written at each assert.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4   # north_star: "losses, silhouettes and gradients within 1e-4 relative in FP32"
+
+
+@pytest.fixture(scope="module")
+def vpn():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import vpn_b200
+    return vpn_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import vpn_oracle
+    return vpn_oracle
+
+
+def C(a):
+    return torch.as_tensor(np.asarray(a)).cuda()
+
+
+def close(a, b, rtol=RTOL, atol=1e-6, what=""):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=what)
+
+
+def same(a, b, what=""):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_array_equal(a, b, err_msg=what)
+
+
+# ------------------------------------------------------------------------------------------------
+# transform
+# ------------------------------------------------------------------------------------------------
+def test_transform_golden(vpn, golden):
+    g = golden
+    import modules.transform as mt
+    pts, q, t = C(g["in_tf_points"]), C(g["in_tf_q"]), C(g["in_tf_t"])
+    close(mt.rotate_points(pts, q), g["ref_tf_rotate"], atol=1e-6)
+    close(mt.transform_points(pts, q, t), g["ref_tf_transform"], atol=1e-6)
+    d, e, a, ang = (C(g["in_tf_" + k]) for k in ("dists", "elevs", "azims", "angles"))
+    close(mt.view_to_obj_points(pts, d, e, a, ang), g["ref_tf_view_to_obj"], atol=2e-6)
+    close(mt.obj_to_view_points(pts, d, e, a), g["ref_tf_obj_to_view"], atol=2e-6)
+    close(mt.rotate_points_forward_x_axis(pts, ang), g["ref_tf_rotate_x"], atol=1e-6)
+    close(mt.translate_points(pts, t), g["in_tf_points"] + g["in_tf_t"][:, None, :], atol=0, rtol=0)
+    # gradients
+    pts, q, t = (x.clone().requires_grad_() for x in (pts, q, t))
+    (mt.transform_points(pts, q, t) * C(g["in_tf_upstream"])).sum().backward()
+    close(pts.grad, g["ref_tf_grad_points"], atol=1e-6)
+    close(q.grad, g["ref_tf_grad_q"], atol=2e-5)
+    close(t.grad, g["ref_tf_grad_t"], atol=1e-6)
+    pg = C(g["in_tf_points"]).requires_grad_()
+    (mt.view_to_obj_points(pg, d, e, a, ang) * C(g["in_tf_upstream"])).sum().backward()
+    close(pg.grad, g["ref_tf_view_to_obj_grad_points"], atol=2e-6)
+
+
+def test_transform_random_vs_oracle(vpn, O):
+    gen = torch.Generator().manual_seed(7)
+    for b, n in ((1, 1), (3, 5), (2, 1000), (5, 4099)):
+        pts = torch.randn(b, n, 3, generator=gen); q = torch.randn(b, 4, generator=gen) * 2; t = torch.randn(b, 3, generator=gen)
+        w = torch.randn(b, n, 3, generator=gen)
+        po, qo, to = (x.clone().requires_grad_() for x in (pts, q, t))
+        (O.transform_points(po, qo, to) * w).sum().backward()
+        pc, qc, tc = (x.cuda().requires_grad_() for x in (pts, q, t))
+        out = vpn.transform_points(pc, qc, tc)
+        close(out, O.transform_points(pts, q, t), atol=2e-6)
+        (out * w.cuda()).sum().backward()
+        close(pc.grad, po.grad, atol=2e-6)
+        close(tc.grad, to.grad, atol=1e-5 * max(1, n ** 0.5))
+        close(qc.grad, qo.grad, rtol=2e-4, atol=2e-5 * max(1.0, float(qo.grad.abs().max())))
+
+
+# ------------------------------------------------------------------------------------------------
+# sampling
+# ------------------------------------------------------------------------------------------------
+def test_sphere_sampling_golden(vpn, golden):
+    g = golden
+    v, q, t = (C(g["in_sp_" + k]).requires_grad_() for k in ("v", "q", "t"))
+    u = torch.cat([C(g["in_sp_ue"]), C(g["in_sp_ua"])], dim=2)[:, None]       # (B,1,N,2)
+    out = vpn.sample_primitives("sphere", v[:, None], q[:, None], t[:, None], u)
+    close(out, g["ref_sp_points"], atol=1e-6)
+    (out * C(g["in_sp_upstream"])).sum().backward()
+    close(v.grad, g["ref_sp_grad_v"], atol=1e-5); close(q.grad, g["ref_sp_grad_q"], atol=1e-5); close(t.grad, g["ref_sp_grad_t"], atol=1e-5)
+
+
+def test_cuboid_sampling_golden(vpn, golden):
+    g = golden
+    v, q, t = (C(g["in_cb_" + k]).requires_grad_() for k in ("v", "q", "t"))
+    u = C(g["in_cb_u"])[:, None]
+    same(vpn.cuboid_face_counts(v.detach(), u.shape[2]), g["ref_cb_counts"], "face counts must be bit-exact")
+    same(vpn.cuboid_face_counts(C(g["in_cb_counts_v"]), 1000), g["ref_cb_counts_1000"])
+    same(vpn.cuboid_face_counts(C(g["in_cb_counts_v"]), 4096), g["ref_cb_counts_4096"])
+    out = vpn.sample_primitives("cuboid", v[:, None], q[:, None], t[:, None], u)
+    close(out, g["ref_cb_points"], atol=1e-6)
+    (out * C(g["in_cb_upstream"])).sum().backward()
+    close(v.grad, g["ref_cb_grad_v"], atol=1e-5); close(q.grad, g["ref_cb_grad_q"], atol=1e-5); close(t.grad, g["ref_cb_grad_t"], atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["sphere", "cuboid"])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 3, 7), (2, 16, 128), (3, 2, 1026), (1, 2, 4096)])
+def test_sampling_random_vs_oracle(vpn, O, kind, shape):
+    b, k, n = shape
+    v, q, t = O.synthetic_primitives(b, k, seed=11)
+    gen = torch.Generator().manual_seed(5)
+    u = torch.rand(b, k, n, 2 if kind == "sphere" else 3, generator=gen)
+    w = torch.randn(b, k * n, 3, generator=gen)
+    vo, qo, to = (x.clone().requires_grad_() for x in (v, q, t))
+    ref = O.sample_predict_points(kind, vo, qo, to, u)
+    (ref * w).sum().backward()
+    vc, qc, tc = (x.cuda().requires_grad_() for x in (v, q, t))
+    out = vpn.sample_primitives(kind, vc, qc, tc, u.cuda())
+    assert out.shape == (b, k * n, 3)
+    close(out, ref, atol=1e-6)
+    (out * w.cuda()).sum().backward()
+    scale = max(1.0, n ** 0.5)
+    close(vc.grad, vo.grad, rtol=2e-4, atol=2e-5 * scale)
+    close(tc.grad, to.grad, rtol=2e-4, atol=2e-5 * scale)
+    close(qc.grad, qo.grad, rtol=2e-4, atol=2e-5 * scale)
+
+
+def test_mesh_vertices_golden(vpn, golden, golden_templates):
+    g = golden
+    from vpn_b200 import templates
+    v, q, t = C(g["in_ms_v"]), C(g["in_ms_q"]), C(g["in_ms_t"])
+    for name in ("sphere", "cuboid"):
+        tv, tf = templates.template(name, "cuda")
+        out = vpn.mesh_vertices(tv, v[:, None], q[:, None], t[:, None])
+        close(out, g[f"ref_ms_{name}_vertices"], atol=1e-6)
+        same(tf, golden_templates[name + "_faces"])
+    import modules.meshing as mm
+    sm, cm = mm.Meshing.sphere_meshing(v, q, t), mm.Meshing.cuboid_meshing(v, q, t)
+    comp = mm.Meshing.compose_meshes([sm[0], cm[0], sm[1]])
+    close(comp.vertices, g["ref_ms_compose_vertices"], atol=1e-6)
+    same(comp.faces, g["ref_ms_compose_faces"])
+    assert comp.faces.dtype == torch.int64
+
+
+# ------------------------------------------------------------------------------------------------
+# Chamfer
+# ------------------------------------------------------------------------------------------------
+IMPLS = {"generic": 1, "tiled_exact": 2, "tiled_fma": 3, "auto": 0}
+
+
+def run_nn(vpn, p1, p2, impl):
+    m1, i1, m2, i2 = vpn.chamfer_nn(torch.as_tensor(p1).cuda(), torch.as_tensor(p2).cuda(), impl)
+    return m1.cpu().numpy(), i1.cpu().numpy().astype(np.int64), m2.cpu().numpy(), i2.cpu().numpy().astype(np.int64)
+
+
+def test_chamfer_golden(vpn, golden):
+    g = golden
+    m1, i1, m2, i2 = run_nn(vpn, g["in_cd_p1"], g["in_cd_p2"], 1)
+    same(i1, g["ref_cd_idx1"], "idx1 bit-exact vs reference torch.min"); same(i2, g["ref_cd_idx2"])
+    # golden values carry torch-CPU's VML sqrt (<= 1 ulp off); IEEE values are checked against the oracle below
+    close(m1, g["ref_cd_min1"], rtol=1.3e-7, atol=0); close(m2, g["ref_cd_min2"], rtol=1.3e-7, atol=0)
+    import modules.loss as ml
+    p1, p2 = C(g["in_cd_p1"]).requires_grad_(), C(g["in_cd_p2"]).requires_grad_()
+    loss = ml.ChamferDistanceLoss()(p1, p2)
+    close(loss, g["ref_cd_loss"], atol=0)
+    loss.backward()
+    close(p1.grad, g["ref_cd_grad_p1"], atol=1e-8); close(p2.grad, g["ref_cd_grad_p2"], atol=1e-8)
+    close(ml.ChamferDistanceLoss()(p1.detach(), p2.detach(), each_batch=True), g["ref_cd_loss_each"], atol=0)
+    close(ml.ChamferDistanceLoss()(p1.detach(), p2.detach(), w1=0.5, w2=1.0), g["ref_cd_loss_w"], atol=0)
+    tr = C(g["in_vd_translates"])
+    close(ml.VPDiverseLoss()([tr[:, i] for i in range(tr.shape[1])], C(g["in_vd_gt"])), g["ref_vd_loss"], atol=0)
+
+
+def adversarial_clouds(name, b, p, m, gen):
+    r = lambda *s: torch.rand(*s, generator=gen)
+    if name == "uniform":
+        return r(b, p, 3) - 0.5, r(b, m, 3) - 0.5
+    if name == "lattice":          # many exact ties in d and in sqrt(d)
+        return torch.floor(r(b, p, 3) * 6) / 4, torch.floor(r(b, m, 3) * 6) / 4 + 0.125
+    if name == "duplicates":       # every target appears ~4 times -> first index must win
+        base = r(b, (m + 3) // 4, 3)
+        return r(b, p, 3), base.repeat(1, 4, 1)[:, :m].contiguous()
+    if name == "offset":           # far from the origin: differences lose low bits, near ties abound
+        return r(b, p, 3) * 0.05 + 100.0, r(b, m, 3) * 0.05 + 100.0
+    if name == "identical":        # all distances zero
+        return torch.zeros(b, p, 3) + 0.25, torch.zeros(b, m, 3) + 0.25
+    if name == "surface":          # clustered like primitive samples vs shape samples
+        c = r(b, 1, 3)
+        return c + 0.05 * torch.nn.functional.normalize(torch.randn(b, p, 3, generator=gen), dim=2), \
+            c + 0.05 * torch.nn.functional.normalize(torch.randn(b, m, 3, generator=gen), dim=2)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("impl", ["generic", "tiled_exact", "tiled_fma"])
+@pytest.mark.parametrize("case", ["uniform", "lattice", "duplicates", "offset", "identical", "surface"])
+def test_chamfer_nn_bit_exact(vpn, c_oracle, impl, case):
+    gen = torch.Generator().manual_seed(sum(map(ord, case)))
+    shapes = [(2, 1500, 700), (1, 4100, 130), (3, 1024, 128), (1, 9000, 2500)]
+    if impl == "generic":
+        shapes += [(2, 16, 300), (2, 1, 1), (1, 5, 3), (2, 300, 16)]
+    for (b, p, m) in shapes:
+        p1, p2 = adversarial_clouds(case, b, p, m, gen)
+        ref = c_oracle(p1.numpy(), p2.numpy())
+        got = run_nn(vpn, p1, p2, IMPLS[impl])
+        for name, r_, g_ in zip(("min1", "idx1", "min2", "idx2"), ref, got):
+            same(g_, r_, f"{impl}/{case}/{(b, p, m)}/{name}")
+
+
+def test_chamfer_full_size_slice(vpn, c_oracle):
+    """BASELINE config 2 cloud sizes (P=65536, M=8192) on a 2-sample slice, bit-exact vs the C oracle."""
+    gen = torch.Generator().manual_seed(1234)
+    p1, p2 = torch.rand(2, 65536, 3, generator=gen) - 0.5, torch.rand(2, 8192, 3, generator=gen) - 0.5
+    ref = c_oracle(p1.numpy(), p2.numpy())
+    for impl in ("auto", "tiled_exact", "generic"):
+        got = run_nn(vpn, p1, p2, IMPLS[impl])
+        for name, r_, g_ in zip(("min1", "idx1", "min2", "idx2"), ref, got):
+            same(g_, r_, f"{impl}/{name}")
+
+
+def test_chamfer_properties_full_batch(vpn):
+    """Size-independent properties at BASELINE config 2's full size (B=32, P=65536, M=8192)."""
+    gen = torch.Generator().manual_seed(3)
+    p1, p2 = (torch.rand(32, 65536, 3, generator=gen) - 0.5).cuda(), (torch.rand(32, 8192, 3, generator=gen) - 0.5).cuda()
+    m1, i1, m2, i2 = vpn.chamfer_nn(p1, p2)
+    # (1) the reported minimum is the distance to the reported arg-min, recomputed with the reference's arithmetic
+    bi = torch.arange(32, device="cuda")[:, None]
+    d = p1 - p2[bi, i1.long()]
+    d = torch.sqrt((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2])
+    assert torch.equal(d, m1)
+    d = p1[bi, i2.long()] - p2
+    d = torch.sqrt((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2])
+    assert torch.equal(d, m2)
+    # (2) swapping the clouds swaps the outputs
+    s1, j1, s2, j2 = vpn.chamfer_nn(p2, p1)
+    assert torch.equal(s1, m2) and torch.equal(j1, i2) and torch.equal(s2, m1) and torch.equal(j2, i1)
+    # (3) permuting the targets leaves min1 unchanged and idx1 still points at a target at that distance
+    perm = torch.randperm(8192, generator=gen).cuda()
+    p2p = p2[:, perm].contiguous()
+    q1, k1, q2, k2 = vpn.chamfer_nn(p1, p2p)
+    assert torch.equal(q1, m1) and torch.equal(q2, m2[:, perm])
+    d = p1 - p2p[bi, k1.long()]
+    d = torch.sqrt((d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2])
+    assert torch.equal(d, m1)
+    assert (perm[k1.long()] == i1.long()).float().mean() > 0.9999
+    # (4) both kernels agree
+    g1, gi1, g2, gi2 = vpn.chamfer_nn(p1[:4].contiguous(), p2[:4].contiguous(), 1)
+    assert torch.equal(g1, m1[:4]) and torch.equal(gi1, i1[:4]) and torch.equal(g2, m2[:4]) and torch.equal(gi2, i2[:4])
+
+
+def test_chamfer_backward_vs_oracle(vpn, O):
+    gen = torch.Generator().manual_seed(9)
+    for (b, p, m) in ((2, 300, 200), (1, 2048, 1024)):
+        p1, p2 = torch.rand(b, p, 3, generator=gen), torch.rand(b, m, 3, generator=gen)
+        g1, g2 = torch.rand(b, p, generator=gen), torch.rand(b, m, generator=gen)
+        m1, i1, m2, i2 = O.chamfer_nn(p1, p2)
+        gp1, gp2 = O.chamfer_grad_from_nn(p1, p2, m1, i1, m2, i2, g1, g2)
+        a, c = p1.cuda().requires_grad_(), p2.cuda().requires_grad_()
+        o1, _, o2, _ = vpn.chamfer_nn(a, c)
+        ((o1 * g1.cuda()).sum() + (o2 * g2.cuda()).sum()).backward()
+        close(a.grad, gp1, atol=1e-6); close(c.grad, gp2, atol=1e-6)
+
+
+def test_chamfer_zero_distance_gives_nan_like_reference(vpn):
+    p = torch.rand(1, 8, 3).cuda().requires_grad_()
+    vpn.chamfer_distance(p, p.detach().clone()).backward()
+    assert torch.isnan(p.grad).all()        # sqrt'(0) * 0 = inf * 0, as autograd through the reference
+
+
+# ------------------------------------------------------------------------------------------------
+# end to end (train.py:105-120 + Chamfer) against the reference's own autograd
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["sphere", "cuboid"])
+def test_end_to_end_golden(vpn, golden, kind):
+    g = golden
+    v, q, t = (C(g[f"in_e2e_{kind}_{k}"]).requires_grad_() for k in ("v", "q", "t"))
+    step = vpn.PrimitiveLoss(vpn.PrimitiveLossConfig(kind=kind, l_vp_div=0.0))
+    out = step(v, q, t, C(g[f"in_e2e_{kind}_u"]), C(g[f"in_e2e_{kind}_target"]))
+    close(out["points"], g[f"ref_e2e_{kind}_points"], atol=1e-6)
+    close(out["total"], g[f"ref_e2e_{kind}_loss"], atol=0)
+    out["total"].backward()
+    for k, x in (("v", v), ("q", q), ("t", t)):
+        ref = g[f"ref_e2e_{kind}_grad_{k}"]
+        close(x.grad, ref, atol=1e-4 * float(np.abs(ref).max()), what=f"grad_{k}")
+
+
+# ------------------------------------------------------------------------------------------------
+# soft silhouette (oracle = the DIB-R restatement; parity unpinned, see oracle/vpn_oracle.py)
+# ------------------------------------------------------------------------------------------------
+def _sil_case(O, kind, b, k, seed):
+    from vpn_b200 import templates
+    v, q, t = O.synthetic_primitives(b, k, seed=seed)
+    t = t * 0.25
+    v = v * 1.5
+    tv, tf = templates.template(kind, "cpu")
+    return v, q, t, tv, tf
+
+
+@pytest.mark.parametrize("kind,b,k,res", [("sphere", 2, 3, 32), ("cuboid", 1, 2, 48), ("sphere", 1, 16, 64)])
+def test_silhouette_vs_oracle(vpn, O, kind, b, k, res):
+    v, q, t, tv, tf = _sil_case(O, kind, b, k, seed=21)
+    verts_ref, faces_ref = O.compose_primitive_meshes(tv, tf.long(), v, q, t)
+    verts_ref = verts_ref.clone().requires_grad_()
+    cams = [O.look_at_camera(0.0, 0.0, 1.0) for _ in range(b)]
+    rot, pos = torch.stack([c[0] for c in cams]), torch.stack([c[1] for c in cams])
+    ref = O.soft_silhouette(verts_ref, faces_ref, rot, pos, res, res)
+    gen = torch.Generator().manual_seed(4)
+    w = torch.rand(b, res, res, generator=gen)
+    (ref * w).sum().backward()
+    verts = vpn.mesh_vertices(tv.cuda(), v.cuda(), q.cuda(), t.cuda()).detach().requires_grad_()
+    faces = torch.cat([tf + i * tv.shape[0] for i in range(k)]).cuda()
+    zero, one = torch.zeros(b).cuda(), torch.ones(b).cuda()
+    r_c, p_c = vpn.look_at_cameras(zero, zero, one)
+    close(r_c, rot, atol=1e-7); close(p_c, pos, atol=1e-7)
+    alpha, covered, _ = vpn.soft_silhouette(verts, faces, r_c, p_c, res, res)
+    # 1e-4 relative plus an absolute floor: alpha = 1 - prod(1 - p) cancels for faint pixels
+    close(alpha, ref, rtol=RTOL, atol=2e-6)
+    assert ((alpha.detach().cpu() == 1.0) == (ref.detach() == 1.0)).all()
+    (alpha * w.cuda()).sum().backward()
+    gref = verts_ref.grad
+    close(verts.grad, gref, rtol=1e-3, atol=1e-4 * float(gref.abs().max()))
+
+
+def test_silhouette_loss_dropin(vpn, O):
+    import modules.loss as ml
+    import modules.meshing as mm
+    b, k, res = 2, 4, 128
+    v, q, t, tv, tf = _sil_case(O, "sphere", b, k, seed=8)
+    meshes_k = [mm.Meshing.sphere_meshing(v[:, i].cuda(), q[:, i].cuda(), t[:, i].cuda()) for i in range(k)]
+    meshes = [mm.Meshing.compose_meshes([meshes_k[i][s] for i in range(k)]) for s in range(b)]
+    gt = (torch.rand(b, 1, res, res, generator=torch.Generator().manual_seed(1)) > 0.5).float()
+    dists, elevs, azims = torch.ones(b), torch.zeros(b), torch.zeros(b)
+    loss = ml.SilhouetteLoss()(meshes, gt.cuda(), dists.cuda(), elevs.cuda(), azims.cuda())
+    verts_ref, faces_ref = O.compose_primitive_meshes(tv, tf.long(), v, q, t)
+    ref = O.silhouette_loss(verts_ref, faces_ref, gt, dists, elevs, azims)
+    close(loss, ref, atol=1e-7)
+    import modules.render as mr
+    rgb, alpha, normals = mr.VertexRenderer.render(meshes[0], dists[0], elevs[0], azims[0])
+    assert rgb.shape == (1, 128, 128, 3) and alpha.shape == (1, 128, 128, 1) and normals.shape == (1, k * 252, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-in surface
+# ------------------------------------------------------------------------------------------------
+def test_sampling_dropin_consumes_reference_rng_stream(vpn, O):
+    import modules.sampling as ms
+    v, q, t = (x[:, 0].cuda() for x in O.synthetic_primitives(3, 1, seed=2))
+    for kind in ("sphere", "cuboid"):
+        torch.manual_seed(1234)
+        fn = ms.Sampling.sphere_sampling if kind == "sphere" else ms.Sampling.cuboid_sampling
+        out = fn(v, q, t, 200)
+        torch.manual_seed(1234)
+        if kind == "sphere":
+            ue, ua = torch.rand((3, 200, 1), device="cuda"), torch.rand((3, 200, 1), device="cuda")
+            ref = O.sphere_sampling(v.cpu(), q.cpu(), t.cpu(), ue.cpu(), ua.cpu())
+        else:
+            u = torch.rand((3, 200, 3), dtype=torch.float, device="cuda")
+            ref = O.cuboid_sampling(v.cpu(), q.cpu(), t.cpu(), u.cpu())
+        assert out.shape == (3, 200, 3)
+        close(out, ref, atol=1e-6)
+    assert ms.Sampling.cone_sampling(v, q, t, 10) is None
+    with pytest.raises(AssertionError):
+        ms.Sampling.sphere_sampling(v, q[:, :3], t, 10)

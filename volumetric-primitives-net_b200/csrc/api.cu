@@ -12,7 +12,10 @@ void vpn_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+
 int vpn_check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { vpn_set_error("%s: %s", what, cudaGetErrorString(e)); return VPN_ERR_CUDA; }
   return VPN_OK;
@@ -41,6 +44,9 @@ static int sm_count() {
 extern "C" const char* vpn_last_error_string(void) { return g_err; }
 
 extern "C" int vpn_abi_version(void) { return 1; }
+
+// Number of kernels this library has launched in this process (bench.py reports the per-step delta).
+extern "C" unsigned long long vpn_launch_count(void) { return g_launches; }
 
 extern "C" int vpn_device_info(int* sms, int* cc_major, int* cc_minor, int* clock_khz) {
   int dev = 0;

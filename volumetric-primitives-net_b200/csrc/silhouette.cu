@@ -11,8 +11,8 @@
 //   backward : same binning; per uncovered pixel the <= knum recorded faces are differentiated and
 //              scattered with atomics into a per-face screen-space gradient buffer (B,F,6), which a
 //              last kernel chains through the projection into vertex gradients.
-// Arithmetic follows oracle/vpn_oracle.py::soft_silhouette operation by operation (explicit
-// round-to-nearest intrinsics, no FMA contraction): the algorithm works on coordinates scaled by
+// Arithmetic follows DIB-R's expression order operation by operation (explicit
+// round-to-nearest intrinsics, no FMA contraction; the order is written out in DESIGN.md): the algorithm works on coordinates scaled by
 // 1000 and is cancellation prone, so a different rounding sequence moves alpha by ~1e-3.
 #include "common.cuh"
 

@@ -19,6 +19,7 @@ _lib = None
 _SIGNATURES = {
     "vpn_last_error_string": (c_char_p, []),
     "vpn_abi_version": (c_int, []),
+    "vpn_launch_count": (ctypes.c_ulonglong, []),
     "vpn_device_info": (c_int, [POINTER(c_int)] * 4),
     "vpn_pose_points_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vpn_pose_bwd_workspace_floats": (c_int, [c_int, c_int, POINTER(c_size_t)]),
