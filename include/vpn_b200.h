@@ -67,10 +67,16 @@ int vpn_view_points(int mode, int transpose, const float* in, const float* dists
 /* ---- Chamfer nearest neighbours, both directions (modules/loss/chamfer_distance.py:14-23) ------------
  * p1 (B,P,3), p2 (B,M,3) -> min1 (B,P) = min_j sqrt(d_ij), idx1 (B,P) int32 = first arg-min, min2 (B,M),
  * idx2 (B,M).  Arg-mins are bit-exact to torch.min over the reference's dense distance tensor.
- * impl: 0 auto, 1 generic kernel, 2 tiled kernel / exact hot-loop arithmetic, 3 tiled / FMA filter. */
+ * impl: 0 auto, 1 generic kernel, 2/3/4 tiled kernel with exact / FMA-difference / centred-expansion
+ * hot-loop arithmetic (identical results; the hot loop only selects candidates, the recovery is exact). */
 int vpn_chamfer_workspace_bytes(int B, int P, int M, int impl, size_t* bytes);
 int vpn_chamfer_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                     int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, void* stream);
+/* Measurement variant: `reps` forwards with CUDA events between the stages; stage_ms is a HOST float[4]
+ * (main kernel, fall-back launch, row recovery, column recovery), mean ms per stage.  Synchronises. */
+int vpn_chamfer_fwd_timed(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
+                          int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, int reps,
+                          float* stage_ms, void* stream);
 /* g1 (B,P), g2 (B,M): upstream gradients of min1 / min2.  grad_p1 (B,P,3) overwritten; grad_p2 (B,M,3)
  * overwritten when not NULL.  Same result as autograd through the reference's dense graph. */
 int vpn_chamfer_bwd(const float* p1, const float* p2, const float* min1, const int* idx1,

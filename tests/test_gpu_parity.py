@@ -150,7 +150,7 @@ def test_mesh_vertices_golden(vpn, golden, golden_templates):
 # ------------------------------------------------------------------------------------------------
 # Chamfer
 # ------------------------------------------------------------------------------------------------
-IMPLS = {"generic": 1, "tiled_exact": 2, "tiled_fma": 3, "auto": 0}
+IMPLS = {"generic": 1, "tiled_exact": 2, "tiled_fma": 3, "tiled_expand": 4, "auto": 0}
 
 
 def run_nn(vpn, p1, p2, impl):
@@ -196,7 +196,7 @@ def adversarial_clouds(name, b, p, m, gen):
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("impl", ["generic", "tiled_exact", "tiled_fma"])
+@pytest.mark.parametrize("impl", ["generic", "tiled_exact", "tiled_fma", "tiled_expand"])
 @pytest.mark.parametrize("case", ["uniform", "lattice", "duplicates", "offset", "identical", "surface"])
 def test_chamfer_nn_bit_exact(vpn, c_oracle, impl, case):
     gen = torch.Generator().manual_seed(sum(map(ord, case)))
@@ -216,7 +216,7 @@ def test_chamfer_full_size_slice(vpn, c_oracle):
     gen = torch.Generator().manual_seed(1234)
     p1, p2 = torch.rand(2, 65536, 3, generator=gen) - 0.5, torch.rand(2, 8192, 3, generator=gen) - 0.5
     ref = c_oracle(p1.numpy(), p2.numpy())
-    for impl in ("auto", "tiled_exact", "generic"):
+    for impl in ("auto", "tiled_exact", "tiled_fma", "tiled_expand", "generic"):
         got = run_nn(vpn, p1, p2, IMPLS[impl])
         for name, r_, g_ in zip(("min1", "idx1", "min2", "idx2"), ref, got):
             same(g_, r_, f"{impl}/{name}")

@@ -27,7 +27,7 @@ int chamfer_simple_direction(const float* A, const float* Bp, float* mn, int* id
 int chamfer_tiled_supported(int B, int P, int M);
 size_t chamfer_tiled_workspace_bytes(int B, int P, int M);
 int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
-                      int B, int P, int M, void* ws, size_t ws_bytes, int sm_count, int mode, cudaStream_t s);
+                      int B, int P, int M, void* ws, size_t ws_bytes, int mode, cudaStream_t s, cudaEvent_t* ev);
 }
 
 static int g_sm_count = 0;
@@ -61,9 +61,10 @@ extern "C" int vpn_device_info(int* sms, int* cc_major, int* cc_minor, int* cloc
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// impl: 0 = auto (tiled kernel, FMA-filter arithmetic, when the shape allows, else generic),
-//       1 = generic kernel only, 2 = tiled kernel with the reference's exact arithmetic in the hot loop,
-//       3 = tiled kernel with FMA-filter arithmetic.  2 and 3 fail on shapes the tiled kernel rejects.
+// impl: 0 = auto (tiled kernel with the centred-expansion filter when the shape allows, else generic),
+//       1 = generic kernel only,
+//       2 / 3 / 4 = tiled kernel with exact / FMA-difference / centred-expansion hot-loop arithmetic
+//       (these fail on shapes the tiled kernel rejects).  Results are bit-identical for every impl.
 extern "C" int vpn_chamfer_workspace_bytes(int B, int P, int M, int impl, size_t* bytes) {
   if (B < 0 || P <= 0 || M <= 0 || !bytes) { vpn_set_error("chamfer workspace: bad arguments"); return VPN_ERR_ARG; }
   size_t simple = align256((size_t)B * P * 8) + align256((size_t)B * M * 8);
@@ -72,25 +73,58 @@ extern "C" int vpn_chamfer_workspace_bytes(int B, int P, int M, int impl, size_t
   return VPN_OK;
 }
 
-extern "C" int vpn_chamfer_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
-                               int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, void* stream) {
+static int chamfer_fwd_impl(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
+                            int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, cudaStream_t s,
+                            cudaEvent_t* ev) {
   if (B < 0 || P <= 0 || M <= 0) { vpn_set_error("chamfer fwd: bad shape B=%d P=%d M=%d", B, P, M); return VPN_ERR_SHAPE; }
   if (B == 0) return VPN_OK;
   if (B > 65535) { vpn_set_error("chamfer fwd: batch > 65535 unsupported"); return VPN_ERR_SHAPE; }
   if (!p1 || !p2 || !min1 || !idx1 || !min2 || !idx2 || !workspace) { vpn_set_error("chamfer fwd: null pointer"); return VPN_ERR_ARG; }
-  cudaStream_t s = (cudaStream_t)stream;
   bool tiled_ok = vpn::chamfer_tiled_supported(B, P, M) != 0;
-  if (impl < 0 || impl > 3) { vpn_set_error("chamfer fwd: bad impl %d", impl); return VPN_ERR_ARG; }
+  if (impl < 0 || impl > 4) { vpn_set_error("chamfer fwd: bad impl %d", impl); return VPN_ERR_ARG; }
   if (impl >= 2 && !tiled_ok) { vpn_set_error("chamfer fwd: tiled kernel does not support this shape"); return VPN_ERR_SHAPE; }
   if (impl != 1 && tiled_ok) {
-    int mode = impl == 2 ? 0 : (impl == 3 ? 1 : -1);
-    return vpn::chamfer_tiled_fwd(p1, p2, min1, idx1, min2, idx2, B, P, M, workspace, workspace_bytes, sm_count(), mode, s);
+    int mode = impl == 0 ? -1 : impl - 2;
+    return vpn::chamfer_tiled_fwd(p1, p2, min1, idx1, min2, idx2, B, P, M, workspace, workspace_bytes, mode, s, ev);
   }
   size_t need = align256((size_t)B * P * 8) + align256((size_t)B * M * 8);
   if (workspace_bytes < need) { vpn_set_error("chamfer fwd: workspace too small (%zu < %zu)", workspace_bytes, need); return VPN_ERR_WORKSPACE; }
   vpn::u64* key1 = reinterpret_cast<vpn::u64*>(workspace);
   vpn::u64* key2 = reinterpret_cast<vpn::u64*>(reinterpret_cast<char*>(workspace) + align256((size_t)B * P * 8));
+  if (ev) { cudaEventRecord(ev[0], s); }
   int rc = vpn::chamfer_simple_direction(p1, p2, min1, idx1, key1, B, P, M, sm_count(), s);
   if (rc) return rc;
-  return vpn::chamfer_simple_direction(p2, p1, min2, idx2, key2, B, M, P, sm_count(), s);
+  if (ev) { cudaEventRecord(ev[1], s); cudaEventRecord(ev[2], s); cudaEventRecord(ev[3], s); }
+  rc = vpn::chamfer_simple_direction(p2, p1, min2, idx2, key2, B, M, P, sm_count(), s);
+  if (ev) { cudaEventRecord(ev[4], s); }
+  return rc;
+}
+
+extern "C" int vpn_chamfer_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
+                               int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  return chamfer_fwd_impl(p1, p2, min1, idx1, min2, idx2, B, P, M, workspace, workspace_bytes, impl, (cudaStream_t)stream, nullptr);
+}
+
+// Measurement variant: runs the forward `reps` times with CUDA events between its stages on `stream`
+// and returns the mean device time of each stage in stage_ms[4] (HOST pointer):
+//   tiled  : [0] main kernel, [1] MODE_DIFF fall-back launch, [2] row recovery, [3] column recovery
+//   generic: [0] direction 1, [1] 0, [2] 0, [3] direction 2.        Synchronises the stream.
+extern "C" int vpn_chamfer_fwd_timed(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
+                                     int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, int reps,
+                                     float* stage_ms, void* stream) {
+  if (reps < 1 || !stage_ms) { vpn_set_error("chamfer timed: bad arguments"); return VPN_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaEvent_t ev[5];
+  for (int i = 0; i < 5; ++i) if (cudaEventCreate(&ev[i]) != cudaSuccess) { vpn_set_error("chamfer timed: event create failed"); return VPN_ERR_CUDA; }
+  double acc[4] = {0, 0, 0, 0};
+  int rc = VPN_OK;
+  for (int r = 0; r < reps && rc == VPN_OK; ++r) {
+    rc = chamfer_fwd_impl(p1, p2, min1, idx1, min2, idx2, B, P, M, workspace, workspace_bytes, impl, s, ev);
+    if (rc) break;
+    if (cudaEventSynchronize(ev[4]) != cudaSuccess) { vpn_set_error("chamfer timed: %s", cudaGetErrorString(cudaGetLastError())); rc = VPN_ERR_CUDA; break; }
+    for (int i = 0; i < 4; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms; }
+  }
+  for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
+  if (rc == VPN_OK) for (int i = 0; i < 4; ++i) stage_ms[i] = (float)(acc[i] / reps);
+  return rc;
 }

@@ -6,67 +6,64 @@
 //
 // Structure
 //   main kernel   : CTA = 256 threads; each thread owns R rows of cloud 1 held as packed f32x2
-//                   register pairs (FADD2/FMUL2/FFMA2, two pairs per issue slot); columns of cloud 2
+//                   register pairs (FADD2/FMUL2/FFMA2: two pairs per issue slot); the columns of cloud 2
 //                   are staged through shared memory in chunks of kCW and broadcast to all lanes.
-//                   The hot loop is branch free: it only tracks VALUES - per-row running minima
+//                   The hot loop is branch free and only tracks VALUES: per-row running minima
 //                   (FMNMX3) and per-column warp minima (FMNMX3 + CREDUX.MIN.F32).  At the end of each
-//                   chunk it folds them into a tiny candidate record: best value + bit mask of the
+//                   chunk they are folded into a tiny candidate record: best value + bit mask of the
 //                   chunks (rows) / warps (columns) that can still hold the arg-min.
-//   recovery      : one thread per row / per column re-evaluates only the candidate chunks with the
-//                   reference's exact arithmetic and picks (min sqrt(d), first index) - torch.min's
-//                   tie rule - so the arg-min is bit-exact whatever arithmetic the hot loop used.
+//   recovery      : warp-cooperative kernels re-evaluate only the candidate chunks with the
+//                   reference's exact arithmetic and pick (min sqrt(d), first index) - torch.min's
+//                   tie rule - so min and arg-min are bit-exact whatever arithmetic the hot loop used.
 //
 // Arithmetic modes of the hot loop (recovery is always exact):
-//   MODE_EXACT : d = fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)), the reference's own rounding sequence
-//                (8 flop per pair on the FP32 pipe, no fusion) - candidate slack covers only the
-//                sqrt rounding classes.
-//   MODE_DIFF  : same differences, FMA-accumulated squares (6 pipe ops per pair).  Relative error
-//                vs the reference <= ~6 ulp, absorbed by a 2^-18 relative candidate slack.
+//   MODE_EXACT  : d = fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)), the reference's own rounding sequence
+//                 (8 pipe ops per pair).  Candidate slack: the sqrt rounding class only (2^-20 relative).
+//   MODE_DIFF   : same differences, FMA-accumulated squares (6 pipe ops per pair).  Differs from the
+//                 reference by <= ~7 ulp; slack 2^-18 relative.
+//   MODE_EXPAND : |p-t|^2 = |p|^2 + |t|^2 - 2 p.t on coordinates centred on the tile's centroid
+//                 (4 pipe ops per pair: 3 FFMA2 + 1 FADD2 per two pairs).  With rho = tile radius the
+//                 error vs the reference is <= max(384 u rho^2, 96 u d) (u = 2^-24; derivation in
+//                 DESIGN.md), absorbed by the slack 2.5 * 2^-15 rho^2 + 2^-15 |x|.  Inputs whose centred
+//                 magnitudes overflow the analysis raise a per-sample flag and that sample is redone
+//                 by a MODE_DIFF launch (all other CTAs of that launch exit immediately).
 //
 // NOTE on ptxas: mul.rn.f32x2 followed by add.rn.f32x2 IS contracted into FFMA2 by ptxas 12.9 even
 // with --fmad=false (the scalar .rn forms are not).  The exact mode therefore performs its two
 // additions as fma(x, 1.0, y) with the 1.0 passed as a kernel argument, which rounds exactly like
 // an add and cannot be contracted.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace vpn {
 
-enum { MODE_EXACT = 0, MODE_DIFF = 1 };
+enum { MODE_EXACT = 0, MODE_DIFF = 1, MODE_EXPAND = 2 };
 
 constexpr int kTThreads = 256;
 constexpr int kTWarps = kTThreads / 32;
 constexpr int kCW = 128;                  // columns per chunk (candidate granularity for rows)
 constexpr int kMaxChunksPerSplit = 64;    // bits in the row candidate mask
+constexpr float kBig = 1.0e30f;           // centred magnitudes^2 above this fall back to MODE_DIFF
 
 __device__ __forceinline__ u64 pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void upk(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ float min3f(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float warp_min_f32(float a) { float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(a)); return r; }
-
 __device__ __forceinline__ float inf_f() { return __int_as_float(0x7f800000); }
 
-// Upper bound of the set of hot-loop values that may still belong to the arg-min when the smallest
-// hot-loop value seen is x (sqrt rounding class of the reference + hot-loop arithmetic error).
-template <int MODE>
-__device__ __forceinline__ float thr_of(float x) {
-  const float rel = (MODE == MODE_EXACT) ? 9.5367431640625e-07f /* 2^-20 */ : 3.814697265625e-06f /* 2^-18 */;
-  return __fadd_ru(__fmaf_ru(x, rel, x), 1e-36f);
+// Upper bound of the hot-loop values that may still belong to the arg-min when the smallest hot-loop
+// value seen is x: x + rel |x| + abs, rounded up.
+__device__ __forceinline__ float thr_of(float x, float rel, float abs_) {
+  return __fadd_ru(__fmaf_ru(fabsf(x), rel, x), abs_);
 }
-
-// Squared distances of one packed row pair against one broadcast column.
-template <int MODE>
-__device__ __forceinline__ u64 pair_d2(u64 px, u64 py, u64 pz, float cx, float cy, float cz, float one) {
-  u64 dx = sub2(px, pk(cx, cx)), dy = sub2(py, pk(cy, cy)), dz = sub2(pz, pk(cz, cz));
-  if (MODE == MODE_EXACT) {
-    u64 xx = mul2(dx, dx), yy = mul2(dy, dy), zz = mul2(dz, dz);
-    u64 o2 = pk(one, one);
-    return fma2(fma2(xx, o2, yy), o2, zz);          // fl(fl(xx + yy) + zz), never contracted
-  } else {
-    return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-  }
+__device__ __forceinline__ float mode_rel(int mode) {
+  return mode == MODE_EXACT ? 9.5367431640625e-07f /* 2^-20 */
+       : mode == MODE_DIFF ? 3.814697265625e-06f   /* 2^-18 */
+                           : 3.0517578125e-05f;     /* 2^-15 */
 }
 
 __device__ __forceinline__ float exact_d2s(float ax, float ay, float az, float bx, float by, float bz) {
@@ -81,7 +78,29 @@ struct TiledSmem {
   float rs_best[R][kTThreads];
   float rs_thr[R][kTThreads];
   u64 rs_mask[R][kTThreads];
+  float red[kTWarps][4];
+  float ctr[4];
 };
+
+// Row constants held per packed row pair.
+//   EXACT / DIFF : c0,c1,c2 = (px,py,pz)
+//   EXPAND       : c0,c1,c2 = -2 (px,py,pz) centred, c3 = |p|^2 centred
+template <int MODE>
+__device__ __forceinline__ u64 pair_val(u64 c0, u64 c1, u64 c2, u64 c3, const float4& col, float one) {
+  if (MODE == MODE_EXPAND) {
+    u64 e = fma2(c0, pk(col.x, col.x), c3);
+    e = fma2(c1, pk(col.y, col.y), e);
+    e = fma2(c2, pk(col.z, col.z), e);
+    return add2(e, pk(col.w, col.w));
+  }
+  u64 dx = sub2(c0, pk(col.x, col.x)), dy = sub2(c1, pk(col.y, col.y)), dz = sub2(c2, pk(col.z, col.z));
+  if (MODE == MODE_EXACT) {
+    u64 xx = mul2(dx, dx), yy = mul2(dy, dy), zz = mul2(dz, dz);
+    u64 o2 = pk(one, one);
+    return fma2(fma2(xx, o2, yy), o2, zz);          // fl(fl(xx + yy) + zz), never contracted
+  }
+  return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+}
 
 // grid: x = row tile, y = column split, z = sample
 template <int R, int MODE>
@@ -89,26 +108,74 @@ __global__ void __launch_bounds__(kTThreads, (R <= 8 ? 2 : 1))
 chamfer_tiled_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                      float* __restrict__ rbest, u64* __restrict__ rmask,
                      float* __restrict__ cbest, unsigned* __restrict__ cmask,
-                     int P, int M, int nchunks, int cps, float one) {
+                     float2* __restrict__ tslack, int* __restrict__ fallback,
+                     int P, int M, int nchunks, int cps, float one, int only_flagged) {
   constexpr int TM = kTThreads * R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TiledSmem<R>& sm = *reinterpret_cast<TiledSmem<R>*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_i = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
   const int ntiles = gridDim.x, nsplit = gridDim.y;
+  if (only_flagged && fallback[b] == 0) return;
   const float* A = p1 + (size_t)b * P * 3;
   const float* T = p2 + (size_t)b * M * 3;
 
-  u64 px[R / 2], py[R / 2], pz[R / 2];
+  u64 c0[R / 2], c1[R / 2], c2[R / 2], c3[R / 2];
   float rm[R];
+  float cx = 0.f, cy = 0.f, cz = 0.f;
+  float slack_rel = mode_rel(MODE), slack_abs = 1e-36f;
+  {
+    float x[R], y[R], z[R];
 #pragma unroll
-  for (int rp = 0; rp < R / 2; ++rp) {
-    int i0 = min(tile_i * TM + (2 * rp) * kTThreads + tid, P - 1);
-    int i1 = min(tile_i * TM + (2 * rp + 1) * kTThreads + tid, P - 1);
-    px[rp] = pk(A[3 * (size_t)i0], A[3 * (size_t)i1]);
-    py[rp] = pk(A[3 * (size_t)i0 + 1], A[3 * (size_t)i1 + 1]);
-    pz[rp] = pk(A[3 * (size_t)i0 + 2], A[3 * (size_t)i1 + 2]);
+    for (int r = 0; r < R; ++r) {
+      int i = min(tile_i * TM + r * kTThreads + tid, P - 1);
+      x[r] = A[3 * (size_t)i]; y[r] = A[3 * (size_t)i + 1]; z[r] = A[3 * (size_t)i + 2];
+    }
+    if (MODE == MODE_EXPAND) {
+      // tile centroid (any centre is valid; the centroid keeps the radius, hence the slack, small)
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) { sx += x[r]; sy += y[r]; sz += z[r]; }
+      sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+      if (lane == 0) { sm.red[warp][0] = sx; sm.red[warp][1] = sy; sm.red[warp][2] = sz; }
+      __syncthreads();
+      if (tid < 3) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kTWarps; ++w) s += sm.red[w][tid];
+        sm.ctr[tid] = s / (float)TM;
+      }
+      __syncthreads();
+      cx = sm.ctr[0]; cy = sm.ctr[1]; cz = sm.ctr[2];
+      float rho2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        x[r] = __fsub_rn(x[r], cx); y[r] = __fsub_rn(y[r], cy); z[r] = __fsub_rn(z[r], cz);
+        rho2 = fmaxf(rho2, fmaf(z[r], z[r], fmaf(y[r], y[r], x[r] * x[r])));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) rho2 = fmaxf(rho2, __shfl_xor_sync(0xffffffffu, rho2, o));
+      __syncthreads();
+      if (lane == 0) sm.red[warp][3] = rho2;
+      __syncthreads();
+      rho2 = sm.red[0][3];
+#pragma unroll
+      for (int w = 1; w < kTWarps; ++w) rho2 = fmaxf(rho2, sm.red[w][3]);
+      if (!(rho2 < kBig)) { if (tid == 0) atomicOr(&fallback[b], 1); rho2 = 0.f; }
+      slack_abs = __fmaf_ru(8.0e-5f, rho2, 1e-36f);          // 2.5 * 2^-15 rho^2 (+ margin), see header
+    }
+#pragma unroll
+    for (int rp = 0; rp < R / 2; ++rp) {
+      const int r0 = 2 * rp, r1 = 2 * rp + 1;
+      if (MODE == MODE_EXPAND) {
+        c0[rp] = pk(-2.f * x[r0], -2.f * x[r1]); c1[rp] = pk(-2.f * y[r0], -2.f * y[r1]); c2[rp] = pk(-2.f * z[r0], -2.f * z[r1]);
+        c3[rp] = pk(fmaf(z[r0], z[r0], fmaf(y[r0], y[r0], x[r0] * x[r0])), fmaf(z[r1], z[r1], fmaf(y[r1], y[r1], x[r1] * x[r1])));
+      } else {
+        c0[rp] = pk(x[r0], x[r1]); c1[rp] = pk(y[r0], y[r1]); c2[rp] = pk(z[r0], z[r1]); c3[rp] = 0ull;
+      }
+    }
   }
+  if (tid == 0 && split == 0) tslack[(size_t)b * ntiles + tile_i] = make_float2(slack_rel, slack_abs);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     rm[r] = inf_f();
@@ -116,9 +183,20 @@ chamfer_tiled_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   }
   const int c_first = split * cps;
   const int c_last = min(nchunks, c_first + cps);
+
+  auto make_col = [&](float tx, float ty, float tz) -> float4 {
+    if (MODE == MODE_EXPAND) {
+      float x = __fsub_rn(tx, cx), y = __fsub_rn(ty, cy), z = __fsub_rn(tz, cz);
+      float c = fmaf(z, z, fmaf(y, y, x * x));
+      if (!(c < kBig)) atomicOr(&fallback[b], 1);
+      return make_float4(x, y, z, c);
+    }
+    return make_float4(tx, ty, tz, 0.f);
+  };
+
   if (tid < kCW) {
     int col = min(c_first * kCW + tid, M - 1);
-    sm.tile[0][tid] = make_float4(T[3 * (size_t)col], T[3 * (size_t)col + 1], T[3 * (size_t)col + 2], 0.f);
+    sm.tile[0][tid] = make_col(T[3 * (size_t)col], T[3 * (size_t)col + 1], T[3 * (size_t)col + 2]);
   }
   __syncthreads();
 
@@ -135,12 +213,12 @@ chamfer_tiled_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     float* cw = sm.colw[buf][warp];
 #pragma unroll 2
     for (int k = 0; k < kCW; k += 2) {
-      const float4 c0 = tl[k], c1 = tl[k + 1];
+      const float4 q0 = tl[k], q1 = tl[k + 1];
       float cm0 = inf_f(), cm1 = inf_f();
 #pragma unroll
       for (int rp = 0; rp < R / 2; ++rp) {
-        u64 d0 = pair_d2<MODE>(px[rp], py[rp], pz[rp], c0.x, c0.y, c0.z, one);
-        u64 d1 = pair_d2<MODE>(px[rp], py[rp], pz[rp], c1.x, c1.y, c1.z, one);
+        u64 d0 = pair_val<MODE>(c0[rp], c1[rp], c2[rp], c3[rp], q0, one);
+        u64 d1 = pair_val<MODE>(c0[rp], c1[rp], c2[rp], c3[rp], q1, one);
         float a0, b0, a1, b1;
         upk(d0, a0, b0); upk(d1, a1, b1);
         rm[2 * rp] = min3f(rm[2 * rp], a0, a1);
@@ -159,13 +237,13 @@ chamfer_tiled_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       rm[r] = inf_f();
       if (m <= sm.rs_thr[r][tid]) {
         const float best = sm.rs_best[r][tid];
-        const float tm = thr_of<MODE>(m);
+        const float tm = thr_of(m, slack_rel, slack_abs);
         u64 mask = (tm < best) ? 0ull : sm.rs_mask[r][tid];
         sm.rs_mask[r][tid] = mask | bit;
         if (m < best) { sm.rs_best[r][tid] = m; sm.rs_thr[r][tid] = tm; }
       }
     }
-    if (has_next) sm.tile[buf ^ 1][tid] = make_float4(nx, ny, nz, 0.f);
+    if (has_next) sm.tile[buf ^ 1][tid] = make_col(nx, ny, nz);
     __syncthreads();
     // per-column candidate record of this tile: best warp minimum + mask of warps within slack
     if (tid < kCW) {
@@ -175,7 +253,7 @@ chamfer_tiled_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         float best = inf_f();
 #pragma unroll
         for (int i = 0; i < kTWarps; ++i) { w[i] = sm.colw[buf][i][tid]; best = fminf(best, w[i]); }
-        const float t = thr_of<MODE>(best);
+        const float t = thr_of(best, slack_rel, slack_abs);
         unsigned mask = 0;
 #pragma unroll
         for (int i = 0; i < kTWarps; ++i) mask |= (w[i] <= t) ? (1u << i) : 0u;
@@ -194,92 +272,158 @@ chamfer_tiled_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   }
 }
 
-// Exact (min sqrt(d), first index) update shared by both recovery kernels.
-struct ExactBest {
-  float d, hi, v; int i;
-  __device__ __forceinline__ void init() { d = inf_f(); hi = inf_f(); v = inf_f(); i = 0x7fffffff; }
-  __device__ __forceinline__ void offer(float dd, int idx) {
-    if (dd <= hi) {
-      float vv = sqrtf(dd);
-      if (vv < v || (vv == v && idx < i)) { v = vv; i = idx; }
-      if (dd < d) { d = dd; hi = thr_of<MODE_EXACT>(dd); }
-    }
-  }
-};
+// ---------------------------------------------------------------------------------------------
+// recovery: exact (min sqrt(d), first index) over the candidate chunks, one warp per 32 rows / columns
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned warp_min_u32(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
 
-template <int MODE>
-__global__ void __launch_bounds__(128)
-chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
-                            const float* __restrict__ rbest, const u64* __restrict__ rmask,
-                            float* __restrict__ min1, int* __restrict__ idx1,
-                            int P, int M, int nsplit, int cps) {
-  const int b = blockIdx.y;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= P) return;
-  const float* T = p2 + (size_t)b * M * 3;
-  const float* a = p1 + 3 * ((size_t)b * P + row);
-  const float ax = a[0], ay = a[1], az = a[2];
-  float g = inf_f();
-  for (int s = 0; s < nsplit; ++s) g = fminf(g, rbest[((size_t)b * nsplit + s) * P + row]);
-  const float gthr = thr_of<MODE>(g);
-  ExactBest eb; eb.init();
-  for (int s = 0; s < nsplit; ++s) {
-    size_t o = ((size_t)b * nsplit + s) * P + row;
-    if (!(rbest[o] <= gthr)) continue;
-    u64 mask = rmask[o];
-    while (mask) {
-      int cb = __ffsll((long long)mask) - 1;
-      mask &= mask - 1;
-      int c0 = (s * cps + cb) * kCW;
-      int c1 = min(M, c0 + kCW);
-      for (int col = c0; col < c1; ++col) {
-        const float* t = T + 3 * (size_t)col;
-        eb.offer(exact_d2s(ax, ay, az, __ldg(t), __ldg(t + 1), __ldg(t + 2)), col);
-      }
-    }
-  }
-  min1[(size_t)b * P + row] = eb.v;
-  idx1[(size_t)b * P + row] = eb.i;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(128)
-chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
-                            const float* __restrict__ cbest, const unsigned* __restrict__ cmask,
-                            float* __restrict__ min2, int* __restrict__ idx2,
-                            int P, int M, int ntiles, int R) {
-  const int b = blockIdx.y;
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= M) return;
-  const float* A = p1 + (size_t)b * P * 3;
-  const float* t = p2 + 3 * ((size_t)b * M + col);
-  const float tx = t[0], ty = t[1], tz = t[2];
-  const int TM = kTThreads * R;
-  float g = inf_f();
-  for (int ti = 0; ti < ntiles; ++ti) g = fminf(g, cbest[((size_t)b * ntiles + ti) * M + col]);
-  const float gthr = thr_of<MODE>(g);
-  ExactBest eb; eb.init();
-  for (int ti = 0; ti < ntiles; ++ti) {
-    size_t o = ((size_t)b * ntiles + ti) * M + col;
-    if (!(cbest[o] <= gthr)) continue;
-    unsigned mask = cmask[o];
-    while (mask) {
-      int w = __ffs((int)mask) - 1;
-      mask &= mask - 1;
-      for (int r = 0; r < R; ++r) {
-        int r0 = ti * TM + r * kTThreads + w * 32;
-        int r1 = min(P, r0 + 32);
-        for (int row = r0; row < r1; ++row) {
-          const float* a = A + 3 * (size_t)row;
-          eb.offer(exact_d2s(__ldg(a), __ldg(a + 1), __ldg(a + 2), tx, ty, tz), row);
+// Lexicographic (value, index) minimum of per-lane exact squared distances d[0..N) with indices idx0+k*stride... the
+// caller passes, per lane, its local best over ascending indices as (dmin, and recomputes candidates below).
+struct WarpBest {
+  // Given this lane's exact squared distances d[k] (k < n, +inf where invalid) and their indices, returns the
+  // warp-wide (min sqrt(d), lowest index at that value) in (v, i); every lane gets the result.
+  template <int N>
+  static __device__ __forceinline__ void reduce(const float (&d)[N], const int (&idx)[N], float& v_out, int& i_out) {
+    float dm = d[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) dm = fminf(dm, d[k]);
+    const float wmin = __uint_as_float(warp_min_u32(__float_as_uint(dm)));     // d >= +0: uint order == float order
+    const float hi = thr_of(wmin, 9.5367431640625e-07f, 1e-36f);              // covers wmin's sqrt rounding class
+    float vl = inf_f(); int il = 0x7fffffff;
+    if (dm <= hi) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        if (d[k] <= hi) {
+          float v = sqrtf(d[k]);
+          if (v < vl || (v == vl && idx[k] < il)) { vl = v; il = idx[k]; }
         }
       }
     }
+    const unsigned vmin = warp_min_u32(__float_as_uint(vl));
+    const unsigned imin = warp_min_u32(__float_as_uint(vl) == vmin ? (unsigned)il : 0xffffffffu);
+    v_out = __uint_as_float(vmin); i_out = (int)imin;
   }
-  min2[(size_t)b * M + col] = eb.v;
-  idx2[(size_t)b * M + col] = eb.i;
+};
+
+__global__ void __launch_bounds__(128)
+chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                            const float* __restrict__ rbest, const u64* __restrict__ rmask,
+                            const float2* __restrict__ tslack, float* __restrict__ min1, int* __restrict__ idx1,
+                            int P, int M, int nsplit, int cps, int TM, int ntiles) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (row0 >= P) return;
+  const int row = min(row0 + lane, P - 1);
+  const bool valid = row0 + lane < P;
+  const float* T = p2 + (size_t)b * M * 3;
+  const float* a = p1 + 3 * ((size_t)b * P + row);
+  const float ax = a[0], ay = a[1], az = a[2];
+  const float2 sl = tslack[(size_t)b * ntiles + row / TM];
+  float g = inf_f();
+  for (int s = 0; s < nsplit; ++s) g = fminf(g, rbest[((size_t)b * nsplit + s) * P + row]);
+  const float gthr = thr_of(g, sl.x, sl.y);
+  float best_v = inf_f(); int best_i = 0x7fffffff;
+  for (int s = 0; s < nsplit; ++s) {
+    const size_t o = ((size_t)b * nsplit + s) * P + row;
+    u64 mk = (valid && rbest[o] <= gthr) ? rmask[o] : 0ull;
+    // NaN rows (g = NaN) keep no candidates and report (inf, INT_MAX)
+    for (int r = 0; r < 32; ++r) {
+      unsigned mlo = __shfl_sync(0xffffffffu, (unsigned)mk, r), mhi = __shfl_sync(0xffffffffu, (unsigned)(mk >> 32), r);
+      u64 m = ((u64)mhi << 32) | mlo;
+      if (m == 0ull) continue;
+      const float rx = __shfl_sync(0xffffffffu, ax, r), ry = __shfl_sync(0xffffffffu, ay, r), rz = __shfl_sync(0xffffffffu, az, r);
+      while (m) {
+        const int cb = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int col0 = (s * cps + cb) * kCW + 4 * lane;
+        float d[4]; int id[4];
+        if (col0 + 4 <= M) {
+          const float4* src = reinterpret_cast<const float4*>(T + 3 * (size_t)col0);
+          // 4 consecutive points = 12 floats = 3 x 16 B; (b*M + col0)*12 B is 16 B aligned when M*12 % 16 == 0
+          float f[12];
+          if ((((size_t)b * M * 3 + 3 * (size_t)col0) & 3) == 0 && ((reinterpret_cast<uintptr_t>(p2) & 15) == 0)) {
+            float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2);
+            f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
+            f[8] = v2.x; f[9] = v2.y; f[10] = v2.z; f[11] = v2.w;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) f[k] = __ldg(T + 3 * (size_t)col0 + k);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { d[k] = exact_d2s(rx, ry, rz, f[3 * k], f[3 * k + 1], f[3 * k + 2]); id[k] = col0 + k; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            int col = col0 + k;
+            id[k] = col;
+            if (col < M) { const float* t = T + 3 * (size_t)col; d[k] = exact_d2s(rx, ry, rz, __ldg(t), __ldg(t + 1), __ldg(t + 2)); }
+            else d[k] = inf_f();
+          }
+        }
+        float v; int i;
+        WarpBest::reduce<4>(d, id, v, i);
+        if (lane == r && (v < best_v || (v == best_v && i < best_i))) { best_v = v; best_i = i; }
+      }
+    }
+  }
+  if (valid) { min1[(size_t)b * P + row] = best_v; idx1[(size_t)b * P + row] = best_i; }
 }
 
+template <int R>
+__global__ void __launch_bounds__(128)
+chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                            const float* __restrict__ cbest, const unsigned* __restrict__ cmask,
+                            const float2* __restrict__ tslack, float* __restrict__ min2, int* __restrict__ idx2,
+                            int P, int M, int ntiles) {
+  constexpr int TM = kTThreads * R;
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int col0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (col0 >= M) return;
+  const int col = min(col0 + lane, M - 1);
+  const bool valid = col0 + lane < M;
+  const float* A = p1 + (size_t)b * P * 3;
+  const float* t = p2 + 3 * ((size_t)b * M + col);
+  const float tx = t[0], ty = t[1], tz = t[2];
+  float g = inf_f(), rel = 0.f, ab = 0.f;
+  for (int ti = 0; ti < ntiles; ++ti) {
+    g = fminf(g, cbest[((size_t)b * ntiles + ti) * M + col]);
+    float2 sl = tslack[(size_t)b * ntiles + ti];
+    rel = fmaxf(rel, sl.x); ab = fmaxf(ab, sl.y);
+  }
+  const float gthr = thr_of(g, rel, ab);
+  float best_v = inf_f(); int best_i = 0x7fffffff;
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const size_t o = ((size_t)b * ntiles + ti) * M + col;
+    unsigned mk = (valid && cbest[o] <= gthr) ? cmask[o] : 0u;
+    for (int r = 0; r < 32; ++r) {
+      unsigned m = __shfl_sync(0xffffffffu, mk, r);
+      if (m == 0u) continue;
+      const float qx = __shfl_sync(0xffffffffu, tx, r), qy = __shfl_sync(0xffffffffu, ty, r), qz = __shfl_sync(0xffffffffu, tz, r);
+      while (m) {
+        const int w = __ffs((int)m) - 1;
+        m &= m - 1;
+        float d[R]; int id[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+          const int rowi = ti * TM + rr * kTThreads + w * 32 + lane;
+          id[rr] = rowi;
+          if (rowi < P) { const float* a = A + 3 * (size_t)rowi; d[rr] = exact_d2s(__ldg(a), __ldg(a + 1), __ldg(a + 2), qx, qy, qz); }
+          else d[rr] = inf_f();
+        }
+        float v; int i;
+        WarpBest::reduce<R>(d, id, v, i);
+        if (lane == r && (v < best_v || (v == best_v && i < best_i))) { best_v = v; best_i = i; }
+      }
+    }
+  }
+  if (valid) { min2[(size_t)b * M + col] = best_v; idx2[(size_t)b * M + col] = best_i; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
 struct TiledPlan { int R, ntiles, nchunks, nsplit, cps; };
 
 static bool make_plan(int B, int P, int M, int sm_count, TiledPlan& pl) {
@@ -294,6 +438,7 @@ static bool make_plan(int B, int P, int M, int sm_count, TiledPlan& pl) {
     long long slots = (long long)sm_count * (R <= 8 ? 2 : 1);
     if (waste <= 1.26 && nt * B * pl.nchunks >= 2 * slots) { pick = R; break; }
   }
+  if (const char* e = getenv("VPN_TILED_R")) { int r = atoi(e); if (r == 4 || r == 8 || r == 16) pick = r; }   // tuning override
   pl.R = pick;
   int tm = kTThreads * pl.R;
   pl.ntiles = (P + tm - 1) / tm;
@@ -311,33 +456,35 @@ static bool make_plan(int B, int P, int M, int sm_count, TiledPlan& pl) {
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct TiledWs { size_t rbest, rmask, cbest, cmask, total; };
+struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, total; };
 static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   TiledWs w; size_t o = 0;
   w.rbest = o; o += al256((size_t)B * pl.nsplit * P * 4);
   w.rmask = o; o += al256((size_t)B * pl.nsplit * P * 8);
   w.cbest = o; o += al256((size_t)B * pl.ntiles * M * 4);
   w.cmask = o; o += al256((size_t)B * pl.ntiles * M * 4);
+  w.tslack = o; o += al256((size_t)B * pl.ntiles * 8);
+  w.fallback = o; o += al256((size_t)B * 4);
   w.total = o;
   return w;
 }
 
-static int g_plan_sms = 148;
+static const int kPlanSms = 148;   // B200; a fixed value keeps workspace queries and launches consistent
 
 int chamfer_tiled_supported(int B, int P, int M) {
   TiledPlan pl;
-  return make_plan(B, P, M, g_plan_sms, pl) ? 1 : 0;
+  return make_plan(B, P, M, kPlanSms, pl) ? 1 : 0;
 }
 
 size_t chamfer_tiled_workspace_bytes(int B, int P, int M) {
   TiledPlan pl;
-  if (!make_plan(B, P, M, g_plan_sms, pl)) return 0;
+  if (!make_plan(B, P, M, kPlanSms, pl)) return 0;
   return ws_layout(B, P, M, pl).total;
 }
 
 template <int R, int MODE>
 static int launch_main(const float* p1, const float* p2, char* ws, const TiledWs& wl, const TiledPlan& pl,
-                       int B, int P, int M, cudaStream_t s) {
+                       int B, int P, int M, int only_flagged, cudaStream_t s) {
   static bool attr_set = false;
   size_t smem = sizeof(TiledSmem<R>);
   if (!attr_set) {
@@ -349,43 +496,68 @@ static int launch_main(const float* p1, const float* p2, char* ws, const TiledWs
   chamfer_tiled_kernel<R, MODE><<<grid, kTThreads, smem, s>>>(
       p1, p2, reinterpret_cast<float*>(ws + wl.rbest), reinterpret_cast<u64*>(ws + wl.rmask),
       reinterpret_cast<float*>(ws + wl.cbest), reinterpret_cast<unsigned*>(ws + wl.cmask),
-      P, M, pl.nchunks, pl.cps, 1.0f);
+      reinterpret_cast<float2*>(ws + wl.tslack), reinterpret_cast<int*>(ws + wl.fallback),
+      P, M, pl.nchunks, pl.cps, 1.0f, only_flagged);
   return vpn_check_launch("chamfer_tiled_kernel");
 }
 
-template <int MODE>
-static int run_mode(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
-                    int B, int P, int M, char* ws, const TiledWs& wl, const TiledPlan& pl, cudaStream_t s) {
-  int rc;
-  switch (pl.R) {
-    case 16: rc = launch_main<16, MODE>(p1, p2, ws, wl, pl, B, P, M, s); break;
-    case 8:  rc = launch_main<8, MODE>(p1, p2, ws, wl, pl, B, P, M, s); break;
-    default: rc = launch_main<4, MODE>(p1, p2, ws, wl, pl, B, P, M, s); break;
+template <int R>
+static int launch_main_mode(int mode, const float* p1, const float* p2, char* ws, const TiledWs& wl, const TiledPlan& pl,
+                            int B, int P, int M, int only_flagged, cudaStream_t s) {
+  switch (mode) {
+    case MODE_EXACT: return launch_main<R, MODE_EXACT>(p1, p2, ws, wl, pl, B, P, M, only_flagged, s);
+    case MODE_DIFF:  return launch_main<R, MODE_DIFF>(p1, p2, ws, wl, pl, B, P, M, only_flagged, s);
+    default:         return launch_main<R, MODE_EXPAND>(p1, p2, ws, wl, pl, B, P, M, only_flagged, s);
   }
-  if (rc) return rc;
-  chamfer_recover_rows_kernel<MODE><<<dim3((P + 127) / 128, B), 128, 0, s>>>(
-      p1, p2, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
-      min1, idx1, P, M, pl.nsplit, pl.cps);
-  rc = vpn_check_launch("chamfer_recover_rows_kernel");
-  if (rc) return rc;
-  chamfer_recover_cols_kernel<MODE><<<dim3((M + 127) / 128, B), 128, 0, s>>>(
-      p1, p2, reinterpret_cast<const float*>(ws + wl.cbest), reinterpret_cast<const unsigned*>(ws + wl.cmask),
-      min2, idx2, P, M, pl.ntiles, pl.R);
-  return vpn_check_launch("chamfer_recover_cols_kernel");
 }
 
-// mode: -1 auto, 0 exact, 1 diff
+static int launch_any(int mode, const float* p1, const float* p2, char* ws, const TiledWs& wl, const TiledPlan& pl,
+                      int B, int P, int M, int only_flagged, cudaStream_t s) {
+  switch (pl.R) {
+    case 16: return launch_main_mode<16>(mode, p1, p2, ws, wl, pl, B, P, M, only_flagged, s);
+    case 8:  return launch_main_mode<8>(mode, p1, p2, ws, wl, pl, B, P, M, only_flagged, s);
+    default: return launch_main_mode<4>(mode, p1, p2, ws, wl, pl, B, P, M, only_flagged, s);
+  }
+}
+
+// mode: -1 auto, 0 exact, 1 diff, 2 expand.  events (optional, 5 entries) bracket the stages for profiling.
 int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
-                      int B, int P, int M, void* ws, size_t ws_bytes, int sm_count, int mode, cudaStream_t s) {
-  (void)sm_count;
+                      int B, int P, int M, void* ws_, size_t ws_bytes, int mode, cudaStream_t s, cudaEvent_t* ev) {
   TiledPlan pl;
-  if (!make_plan(B, P, M, g_plan_sms, pl)) { vpn_set_error("chamfer tiled: unsupported shape"); return VPN_ERR_SHAPE; }
+  if (!make_plan(B, P, M, kPlanSms, pl)) { vpn_set_error("chamfer tiled: unsupported shape"); return VPN_ERR_SHAPE; }
   TiledWs wl = ws_layout(B, P, M, pl);
   if (ws_bytes < wl.total) { vpn_set_error("chamfer tiled: workspace too small (%zu < %zu)", ws_bytes, wl.total); return VPN_ERR_WORKSPACE; }
-  if (mode < 0) mode = MODE_DIFF;
-  char* w = reinterpret_cast<char*>(ws);
-  if (mode == MODE_EXACT) return run_mode<MODE_EXACT>(p1, p2, min1, idx1, min2, idx2, B, P, M, w, wl, pl, s);
-  return run_mode<MODE_DIFF>(p1, p2, min1, idx1, min2, idx2, B, P, M, w, wl, pl, s);
+  if (mode < 0) mode = MODE_EXPAND;
+  char* ws = reinterpret_cast<char*>(ws_);
+  int rc;
+  if (ev) cudaEventRecord(ev[0], s);
+  if (mode == MODE_EXPAND) {
+    if (cudaMemsetAsync(ws + wl.fallback, 0, (size_t)B * 4, s) != cudaSuccess) { vpn_set_error("chamfer tiled: memset failed"); return VPN_ERR_CUDA; }
+  }
+  if ((rc = launch_any(mode, p1, p2, ws, wl, pl, B, P, M, 0, s))) return rc;
+  if (ev) cudaEventRecord(ev[1], s);
+  if (mode == MODE_EXPAND) {
+    if ((rc = launch_any(MODE_DIFF, p1, p2, ws, wl, pl, B, P, M, 1, s))) return rc;
+  }
+  if (ev) cudaEventRecord(ev[2], s);
+  const int TM = kTThreads * pl.R;
+  chamfer_recover_rows_kernel<<<dim3((P + 127) / 128, B), 128, 0, s>>>(
+      p1, p2, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
+      reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nsplit, pl.cps, TM, pl.ntiles);
+  if ((rc = vpn_check_launch("chamfer_recover_rows_kernel"))) return rc;
+  if (ev) cudaEventRecord(ev[3], s);
+  dim3 cg((M + 127) / 128, B);
+  const float* cb = reinterpret_cast<const float*>(ws + wl.cbest);
+  const unsigned* cmk = reinterpret_cast<const unsigned*>(ws + wl.cmask);
+  const float2* tsl = reinterpret_cast<const float2*>(ws + wl.tslack);
+  switch (pl.R) {
+    case 16: chamfer_recover_cols_kernel<16><<<cg, 128, 0, s>>>(p1, p2, cb, cmk, tsl, min2, idx2, P, M, pl.ntiles); break;
+    case 8:  chamfer_recover_cols_kernel<8><<<cg, 128, 0, s>>>(p1, p2, cb, cmk, tsl, min2, idx2, P, M, pl.ntiles); break;
+    default: chamfer_recover_cols_kernel<4><<<cg, 128, 0, s>>>(p1, p2, cb, cmk, tsl, min2, idx2, P, M, pl.ntiles); break;
+  }
+  rc = vpn_check_launch("chamfer_recover_cols_kernel");
+  if (ev) cudaEventRecord(ev[4], s);
+  return rc;
 }
 
 }  // namespace vpn

@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import VpnError, check, ptr, require, stream_ptr
 
 KIND_SPHERE, KIND_CUBOID, KIND_TEMPLATE, KIND_POINTS = 0, 1, 2, 3
-CHAMFER_AUTO, CHAMFER_GENERIC, CHAMFER_TILED_EXACT, CHAMFER_TILED_FMA = 0, 1, 2, 3
+CHAMFER_AUTO, CHAMFER_GENERIC, CHAMFER_TILED_EXACT, CHAMFER_TILED_FMA, CHAMFER_TILED_EXPAND = 0, 1, 2, 3, 4
 
 f32 = torch.float32
 
@@ -220,6 +220,27 @@ def chamfer_nn(points1: torch.Tensor, points2: torch.Tensor, impl: int = CHAMFER
     assert points2.dim() == 3 and points2.size(-1) == 3
     assert points1.size(0) == points2.size(0)
     return _ChamferNN.apply(points1, points2, impl)
+
+
+def chamfer_nn_stage_ms(points1: torch.Tensor, points2: torch.Tensor, impl: int = CHAMFER_AUTO, reps: int = 5):
+    """Device time (ms, mean of `reps`) of the forward's stages, measured with CUDA events on the launch stream:
+    {'main', 'fallback', 'rows', 'cols', 'total'}.  Measurement helper for bench.py."""
+    lib = _lib.load()
+    p1 = require(points1.contiguous(), f32, "points1"); p2 = require(points2.contiguous(), f32, "points2")
+    b, p, _ = p1.shape
+    m = p2.shape[1]
+    dev = p1.device
+    min1 = torch.empty((b, p), dtype=f32, device=dev); idx1 = torch.empty((b, p), dtype=torch.int32, device=dev)
+    min2 = torch.empty((b, m), dtype=f32, device=dev); idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+    nb = ctypes.c_size_t(0)
+    check(lib.vpn_chamfer_workspace_bytes(b, p, m, impl, ctypes.byref(nb)), "vpn_chamfer_workspace_bytes")
+    ws = _scratch_bytes(nb.value, dev)
+    ms = (ctypes.c_float * 4)()
+    check(lib.vpn_chamfer_fwd_timed(ptr(p1), ptr(p2), ptr(min1), ptr(idx1), ptr(min2), ptr(idx2), b, p, m, ptr(ws),
+                                    nb.value, impl, reps, ms, stream_ptr(dev)), "vpn_chamfer_fwd_timed")
+    out = dict(zip(("main", "fallback", "rows", "cols"), [float(x) for x in ms]))
+    out["total"] = sum(out.values())
+    return out
 
 
 def chamfer_distance(points1, points2, each_batch=False, w1=1.0, w2=1.0, impl: int = CHAMFER_AUTO):
