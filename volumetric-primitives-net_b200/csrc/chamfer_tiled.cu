@@ -273,152 +273,254 @@ chamfer_tiled_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
 }
 
 // ---------------------------------------------------------------------------------------------
-// recovery: exact (min sqrt(d), first index) over the candidate chunks, one warp per 32 rows / columns
+// recovery: exact (min sqrt(d), first index) over the candidate chunks only.
+// Work items (row, column chunk) / (column, warp block) are compacted per CTA and split into sub-units so
+// that all threads stay busy; the scanned cloud (the sample's targets, or the tile's rows) sits in shared
+// memory and every lane walks it with a lane-rotated start, which makes the float4 reads conflict free.
+// Results are merged with a 64-bit atomicMin on (float_bits(v) << 32 | index): value, then lowest index.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned warp_min_u32(unsigned v) { return __reduce_min_sync(0xffffffffu, v); }
+constexpr int kRecThreads = 1024;
+constexpr int kSegChunks = 64;                       // column chunks resident in shared memory per segment
+constexpr int kItemCap = 4096;
 
-// Lexicographic (value, index) minimum of per-lane exact squared distances d[0..N) with indices idx0+k*stride... the
-// caller passes, per lane, its local best over ascending indices as (dmin, and recomputes candidates below).
-struct WarpBest {
-  // Given this lane's exact squared distances d[k] (k < n, +inf where invalid) and their indices, returns the
-  // warp-wide (min sqrt(d), lowest index at that value) in (v, i); every lane gets the result.
-  template <int N>
-  static __device__ __forceinline__ void reduce(const float (&d)[N], const int (&idx)[N], float& v_out, int& i_out) {
-    float dm = d[0];
-#pragma unroll
-    for (int k = 1; k < N; ++k) dm = fminf(dm, d[k]);
-    const float wmin = __uint_as_float(warp_min_u32(__float_as_uint(dm)));     // d >= +0: uint order == float order
-    const float hi = thr_of(wmin, 9.5367431640625e-07f, 1e-36f);              // covers wmin's sqrt rounding class
-    float vl = inf_f(); int il = 0x7fffffff;
-    if (dm <= hi) {
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        if (d[k] <= hi) {
-          float v = sqrtf(d[k]);
-          if (v < vl || (v == vl && idx[k] < il)) { vl = v; il = idx[k]; }
-        }
-      }
+struct ExactBest {
+  float d, hi, v; int i;
+  __device__ __forceinline__ void init() { d = inf_f(); hi = inf_f(); v = inf_f(); i = 0x7fffffff; }
+  // dd = exact squared distance (NaN for padding: never accepted).  Any visiting order is allowed.
+  __device__ __forceinline__ void offer(float dd, int idx) {
+    if (dd <= hi) {
+      float vv = sqrtf(dd);
+      if (vv < v || (vv == v && idx < i)) { v = vv; i = idx; }
+      if (dd < d) { d = dd; hi = thr_of(dd, 9.5367431640625e-07f, 1e-36f); }   // covers dd's sqrt rounding class
     }
-    const unsigned vmin = warp_min_u32(__float_as_uint(vl));
-    const unsigned imin = warp_min_u32(__float_as_uint(vl) == vmin ? (unsigned)il : 0xffffffffu);
-    v_out = __uint_as_float(vmin); i_out = (int)imin;
   }
+  __device__ __forceinline__ u64 key() const { return ((u64)__float_as_uint(v) << 32) | (unsigned)i; }
 };
 
-__global__ void __launch_bounds__(128)
+// Branch-free scan of 32 squared distances held in registers (d[kk] belongs to index idx0 + ((kk + rot) & 31)).
+// Phase 1 found dm = min d.  If every d within dm's sqrt rounding class equals dm, the winner is the lowest
+// index with d == dm and v = sqrt(dm) - decided without divergence; otherwise (rare: near ties) fall back
+// to the order-independent ExactBest walk.  Returns false when the unit holds no valid point.
+__device__ __forceinline__ bool unit_best(const float (&d)[32], float dm, int idx0, int rot, u64& key) {
+  if (!(dm < inf_f())) {                       // all padding, or genuinely infinite distances
+    bool any = false;
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) any |= (d[kk] == inf_f());
+    if (!any) return false;
+  }
+  const float hi = thr_of(dm, 9.5367431640625e-07f, 1e-36f);
+  int first = 64; bool amb = false;
+#pragma unroll
+  for (int kk = 0; kk < 32; ++kk) {
+    const int k = (kk + rot) & 31;
+    const bool eq = d[kk] == dm;
+    amb |= (d[kk] <= hi) && !eq;
+    first = eq ? min(first, k) : first;
+  }
+  if (!amb) { key = ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)(idx0 + first); return true; }
+  ExactBest eb; eb.init();
+#pragma unroll
+  for (int kk = 0; kk < 32; ++kk) eb.offer(d[kk], idx0 + ((kk + rot) & 31));
+  key = eb.key();
+  return eb.i != 0x7fffffff;
+}
+
+// exclusive prefix sum of `cnt` over the CTA (kRecThreads threads); returns the offset, *total gets the sum
+__device__ __forceinline__ int block_exclusive_scan(int cnt, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];                                    // kRecThreads / 32 == 32 warps
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+    warp_sums[lane] = winc - w;
+    if (lane == 31) warp_sums[32] = winc;
+  }
+  __syncthreads();
+  int off = warp_sums[warp] + inc - cnt;
+  *total = warp_sums[32];
+  __syncthreads();
+  return off;
+}
+
+// grid: x = block of kRecThreads rows, y = sample.  dynamic smem: float4 cols[min(nchunks,64)*128]
+__global__ void __launch_bounds__(kRecThreads, 1)
 chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                             const float* __restrict__ rbest, const u64* __restrict__ rmask,
                             const float2* __restrict__ tslack, float* __restrict__ min1, int* __restrict__ idx1,
-                            int P, int M, int nsplit, int cps, int TM, int ntiles) {
-  const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
-  if (row0 >= P) return;
-  const int row = min(row0 + lane, P - 1);
-  const bool valid = row0 + lane < P;
+                            int P, int M, int nchunks, int nsplit, int cps, int TM, int ntiles) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* cols = reinterpret_cast<float4*>(smem_raw);
+  __shared__ float4 rowc[kRecThreads];
+  __shared__ u64 key[kRecThreads];
+  __shared__ unsigned items[kItemCap];
+  __shared__ int warp_sums[33];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int row = blockIdx.x * kRecThreads + tid;
+  const bool valid = row < P;
   const float* T = p2 + (size_t)b * M * 3;
-  const float* a = p1 + 3 * ((size_t)b * P + row);
-  const float ax = a[0], ay = a[1], az = a[2];
-  const float2 sl = tslack[(size_t)b * ntiles + row / TM];
-  float g = inf_f();
-  for (int s = 0; s < nsplit; ++s) g = fminf(g, rbest[((size_t)b * nsplit + s) * P + row]);
-  const float gthr = thr_of(g, sl.x, sl.y);
-  float best_v = inf_f(); int best_i = 0x7fffffff;
-  for (int s = 0; s < nsplit; ++s) {
-    const size_t o = ((size_t)b * nsplit + s) * P + row;
-    u64 mk = (valid && rbest[o] <= gthr) ? rmask[o] : 0ull;
-    // NaN rows (g = NaN) keep no candidates and report (inf, INT_MAX)
-    for (int r = 0; r < 32; ++r) {
-      unsigned mlo = __shfl_sync(0xffffffffu, (unsigned)mk, r), mhi = __shfl_sync(0xffffffffu, (unsigned)(mk >> 32), r);
-      u64 m = ((u64)mhi << 32) | mlo;
-      if (m == 0ull) continue;
-      const float rx = __shfl_sync(0xffffffffu, ax, r), ry = __shfl_sync(0xffffffffu, ay, r), rz = __shfl_sync(0xffffffffu, az, r);
-      while (m) {
-        const int cb = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const int col0 = (s * cps + cb) * kCW + 4 * lane;
-        float d[4]; int id[4];
-        if (col0 + 4 <= M) {
-          const float4* src = reinterpret_cast<const float4*>(T + 3 * (size_t)col0);
-          // 4 consecutive points = 12 floats = 3 x 16 B; (b*M + col0)*12 B is 16 B aligned when M*12 % 16 == 0
-          float f[12];
-          if ((((size_t)b * M * 3 + 3 * (size_t)col0) & 3) == 0 && ((reinterpret_cast<uintptr_t>(p2) & 15) == 0)) {
-            float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2);
-            f[0] = v0.x; f[1] = v0.y; f[2] = v0.z; f[3] = v0.w; f[4] = v1.x; f[5] = v1.y; f[6] = v1.z; f[7] = v1.w;
-            f[8] = v2.x; f[9] = v2.y; f[10] = v2.z; f[11] = v2.w;
-          } else {
-#pragma unroll
-            for (int k = 0; k < 12; ++k) f[k] = __ldg(T + 3 * (size_t)col0 + k);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { d[k] = exact_d2s(rx, ry, rz, f[3 * k], f[3 * k + 1], f[3 * k + 2]); id[k] = col0 + k; }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            int col = col0 + k;
-            id[k] = col;
-            if (col < M) { const float* t = T + 3 * (size_t)col; d[k] = exact_d2s(rx, ry, rz, __ldg(t), __ldg(t + 1), __ldg(t + 2)); }
-            else d[k] = inf_f();
-          }
-        }
-        float v; int i;
-        WarpBest::reduce<4>(d, id, v, i);
-        if (lane == r && (v < best_v || (v == best_v && i < best_i))) { best_v = v; best_i = i; }
+  float g = inf_f(), gthr = inf_f();
+  if (valid) {
+    const float* a = p1 + 3 * ((size_t)b * P + row);
+    rowc[tid] = make_float4(a[0], a[1], a[2], 0.f);
+    for (int s = 0; s < nsplit; ++s) g = fminf(g, rbest[((size_t)b * nsplit + s) * P + row]);
+    const float2 sl = tslack[(size_t)b * ntiles + row / TM];
+    gthr = thr_of(g, sl.x, sl.y);
+  }
+  key[tid] = ~0ull;
+  const int nseg = (nchunks + kSegChunks - 1) / kSegChunks;
+  const float qnan = __int_as_float(0x7fc00000);
+  for (int seg = 0; seg < nseg; ++seg) {
+    __syncthreads();
+    const int seg_chunks = min(kSegChunks, nchunks - seg * kSegChunks);
+    for (int i = tid; i < seg_chunks * kCW; i += kRecThreads) {
+      int col = seg * kSegChunks * kCW + i;
+      cols[i] = col < M ? make_float4(T[3 * (size_t)col], T[3 * (size_t)col + 1], T[3 * (size_t)col + 2], 0.f)
+                        : make_float4(qnan, qnan, qnan, 0.f);
+    }
+    u64 segmask = 0ull;
+    if (valid) {
+      for (int s = 0; s < nsplit; ++s) {
+        const size_t o = ((size_t)b * nsplit + s) * P + row;
+        if (!(rbest[o] <= gthr)) continue;
+        const u64 m = rmask[o];
+        const int rel = s * cps - seg * kSegChunks;
+        if (rel >= 0) { if (rel < 64) segmask |= m << rel; }
+        else if (-rel < 64) segmask |= m >> (-rel);
       }
+      if (seg_chunks < 64) segmask &= (1ull << seg_chunks) - 1ull;
+    }
+    int total;
+    const int off = block_exclusive_scan(__popcll(segmask), warp_sums, &total);   // syncs: cols[] is loaded too
+    for (int base = 0; base < total; base += kItemCap) {
+      int j = off;
+      for (u64 mm = segmask; mm; mm &= mm - 1, ++j)
+        if (j >= base && j < base + kItemCap) items[j - base] = ((unsigned)tid << 6) | (unsigned)(__ffsll((long long)mm) - 1);
+      __syncthreads();
+      const int units = min(kItemCap, total - base) * 4;           // 4 sub-units of 32 columns per item
+      for (int it = tid; it < units; it += kRecThreads) {
+        const unsigned item = items[it >> 2];
+        const int r = item >> 6, c = item & 63, quarter = it & 3;
+        const float4 rc = rowc[r];
+        const float4* src = cols + c * kCW + quarter * 32;
+        const int gcol = (seg * kSegChunks + c) * kCW + quarter * 32;
+        float d[32], dm = inf_f();
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+          const float4 q = src[(kk + lane) & 31];
+          d[kk] = exact_d2s(rc.x, rc.y, rc.z, q.x, q.y, q.z);
+          dm = fminf(dm, d[kk]);
+        }
+        u64 kv;
+        if (unit_best(d, dm, gcol, lane, kv)) atomicMin(&key[r], kv);
+      }
+      __syncthreads();
     }
   }
-  if (valid) { min1[(size_t)b * P + row] = best_v; idx1[(size_t)b * P + row] = best_i; }
+  __syncthreads();
+  if (valid) {
+    const u64 kv = key[tid];
+    min1[(size_t)b * P + row] = __uint_as_float((unsigned)(kv >> 32));
+    idx1[(size_t)b * P + row] = (int)(unsigned)(kv & 0xffffffffu);
+  }
 }
 
-template <int R>
-__global__ void __launch_bounds__(128)
-chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
-                            const float* __restrict__ cbest, const unsigned* __restrict__ cmask,
-                            const float2* __restrict__ tslack, float* __restrict__ min2, int* __restrict__ idx2,
-                            int P, int M, int ntiles) {
-  constexpr int TM = kTThreads * R;
+// per column: threshold over all tiles' records
+__global__ void chamfer_col_thr_kernel(const float* __restrict__ cbest, const float2* __restrict__ tslack,
+                                       float* __restrict__ cthr, int M, int ntiles) {
   const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int col0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
-  if (col0 >= M) return;
-  const int col = min(col0 + lane, M - 1);
-  const bool valid = col0 + lane < M;
-  const float* A = p1 + (size_t)b * P * 3;
-  const float* t = p2 + 3 * ((size_t)b * M + col);
-  const float tx = t[0], ty = t[1], tz = t[2];
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= M) return;
   float g = inf_f(), rel = 0.f, ab = 0.f;
   for (int ti = 0; ti < ntiles; ++ti) {
     g = fminf(g, cbest[((size_t)b * ntiles + ti) * M + col]);
-    float2 sl = tslack[(size_t)b * ntiles + ti];
+    const float2 sl = tslack[(size_t)b * ntiles + ti];
     rel = fmaxf(rel, sl.x); ab = fmaxf(ab, sl.y);
   }
-  const float gthr = thr_of(g, rel, ab);
-  float best_v = inf_f(); int best_i = 0x7fffffff;
-  for (int ti = 0; ti < ntiles; ++ti) {
-    const size_t o = ((size_t)b * ntiles + ti) * M + col;
-    unsigned mk = (valid && cbest[o] <= gthr) ? cmask[o] : 0u;
-    for (int r = 0; r < 32; ++r) {
-      unsigned m = __shfl_sync(0xffffffffu, mk, r);
-      if (m == 0u) continue;
-      const float qx = __shfl_sync(0xffffffffu, tx, r), qy = __shfl_sync(0xffffffffu, ty, r), qz = __shfl_sync(0xffffffffu, tz, r);
-      while (m) {
-        const int w = __ffs((int)m) - 1;
-        m &= m - 1;
-        float d[R]; int id[R];
+  cthr[(size_t)b * M + col] = thr_of(g, rel, ab);
+}
+
+// grid: x = row tile, y = sample.  dynamic smem: float4 rows[256*R].  key2 (B,M) u64 pre-filled with 0xFF.
+template <int R>
+__global__ void __launch_bounds__(kRecThreads, 1)
+chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                            const float* __restrict__ cbest, const unsigned* __restrict__ cmask,
+                            const float* __restrict__ cthr, u64* __restrict__ key2, int P, int M, int ntiles) {
+  constexpr int TM = kTThreads * R;
+  constexpr int kSub = (R >= 4) ? 4 : R;                 // sub-units per (column, warp block) item
+  constexpr int kRunsPerSub = R / kSub;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* rows = reinterpret_cast<float4*>(smem_raw);
+  __shared__ unsigned items[kItemCap];
+  __shared__ int warp_sums[33];
+  const int b = blockIdx.y, ti = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const float* A = p1 + (size_t)b * P * 3;
+  const float qnan = __int_as_float(0x7fc00000);
+  for (int i = tid; i < TM; i += kRecThreads) {
+    int rowi = ti * TM + i;
+    rows[i] = rowi < P ? make_float4(A[3 * (size_t)rowi], A[3 * (size_t)rowi + 1], A[3 * (size_t)rowi + 2], 0.f)
+                       : make_float4(qnan, qnan, qnan, 0.f);
+  }
+  const size_t rec0 = ((size_t)b * ntiles + ti) * M;
+  // columns are visited in slabs of kRecThreads * 8 so that one slab's items normally fit the list
+  for (int slab = 0; slab < M; slab += kRecThreads * 8) {
+    unsigned mk[8];
+    int cnt = 0;
 #pragma unroll
-        for (int rr = 0; rr < R; ++rr) {
-          const int rowi = ti * TM + rr * kTThreads + w * 32 + lane;
-          id[rr] = rowi;
-          if (rowi < P) { const float* a = A + 3 * (size_t)rowi; d[rr] = exact_d2s(__ldg(a), __ldg(a + 1), __ldg(a + 2), qx, qy, qz); }
-          else d[rr] = inf_f();
+    for (int u = 0; u < 8; ++u) {
+      const int col = slab + u * kRecThreads + tid;
+      mk[u] = 0u;
+      if (col < M && cbest[rec0 + col] <= cthr[(size_t)b * M + col]) mk[u] = cmask[rec0 + col] & 0xffu;
+      cnt += __popc(mk[u]);
+    }
+    int total;
+    const int off = block_exclusive_scan(cnt, warp_sums, &total);
+    for (int base = 0; base < total; base += kItemCap) {
+      int j = off;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        for (unsigned mm = mk[u]; mm; mm &= mm - 1, ++j)
+          if (j >= base && j < base + kItemCap)
+            items[j - base] = ((unsigned)(u * kRecThreads + tid) << 3) | (unsigned)(__ffs((int)mm) - 1);
+      __syncthreads();
+      const int units = min(kItemCap, total - base) * kSub;
+      for (int it = tid; it < units; it += kRecThreads) {
+        const unsigned item = items[it / kSub];
+        const int col = slab + (int)(item >> 3), w = item & 7, sub = it % kSub;
+        const float* t = p2 + 3 * ((size_t)b * M + col);
+        const float tx = __ldg(t), ty = __ldg(t + 1), tz = __ldg(t + 2);
+        u64 best = ~0ull;
+#pragma unroll 1
+        for (int rr = sub * kRunsPerSub; rr < (sub + 1) * kRunsPerSub; ++rr) {
+          const int base_row = rr * kTThreads + w * 32;
+          float d[32], dm = inf_f();
+#pragma unroll
+          for (int kk = 0; kk < 32; ++kk) {
+            const float4 a = rows[base_row + ((kk + lane) & 31)];
+            d[kk] = exact_d2s(a.x, a.y, a.z, tx, ty, tz);
+            dm = fminf(dm, d[kk]);
+          }
+          u64 kv;
+          if (unit_best(d, dm, ti * TM + base_row, lane, kv)) best = kv < best ? kv : best;
         }
-        float v; int i;
-        WarpBest::reduce<R>(d, id, v, i);
-        if (lane == r && (v < best_v || (v == best_v && i < best_i))) { best_v = v; best_i = i; }
+        if (best != ~0ull) atomicMin(&key2[(size_t)b * M + col], best);
       }
+      __syncthreads();
     }
   }
-  if (valid) { min2[(size_t)b * M + col] = best_v; idx2[(size_t)b * M + col] = best_i; }
+}
+
+__global__ void chamfer_unpack_key_kernel(const u64* __restrict__ key, float* __restrict__ mn, int* __restrict__ idx, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u64 k = key[i];
+  mn[i] = __uint_as_float((unsigned)(k >> 32));
+  idx[i] = (int)(unsigned)(k & 0xffffffffu);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -456,7 +558,7 @@ static bool make_plan(int B, int P, int M, int sm_count, TiledPlan& pl) {
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, total; };
+struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, cthr, key2, total; };
 static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   TiledWs w; size_t o = 0;
   w.rbest = o; o += al256((size_t)B * pl.nsplit * P * 4);
@@ -465,6 +567,8 @@ static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   w.cmask = o; o += al256((size_t)B * pl.ntiles * M * 4);
   w.tslack = o; o += al256((size_t)B * pl.ntiles * 8);
   w.fallback = o; o += al256((size_t)B * 4);
+  w.cthr = o; o += al256((size_t)B * M * 4);
+  w.key2 = o; o += al256((size_t)B * M * 8);
   w.total = o;
   return w;
 }
@@ -541,21 +645,56 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   }
   if (ev) cudaEventRecord(ev[2], s);
   const int TM = kTThreads * pl.R;
-  chamfer_recover_rows_kernel<<<dim3((P + 127) / 128, B), 128, 0, s>>>(
-      p1, p2, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
-      reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nsplit, pl.cps, TM, pl.ntiles);
-  if ((rc = vpn_check_launch("chamfer_recover_rows_kernel"))) return rc;
+  {
+    static bool attr_rows = false;
+    const size_t smem_rows = (size_t)(pl.nchunks < kSegChunks ? pl.nchunks : kSegChunks) * kCW * sizeof(float4);
+    if (!attr_rows) {
+      if (cudaFuncSetAttribute(chamfer_recover_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(kSegChunks * kCW * sizeof(float4))) != cudaSuccess) {
+        vpn_set_error("chamfer tiled: smem attribute (rows recovery)"); return VPN_ERR_CUDA;
+      }
+      attr_rows = true;
+    }
+    chamfer_recover_rows_kernel<<<dim3((P + kRecThreads - 1) / kRecThreads, B), kRecThreads, smem_rows, s>>>(
+        p1, p2, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
+        reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nchunks, pl.nsplit, pl.cps, TM, pl.ntiles);
+    if ((rc = vpn_check_launch("chamfer_recover_rows_kernel"))) return rc;
+  }
   if (ev) cudaEventRecord(ev[3], s);
-  dim3 cg((M + 127) / 128, B);
   const float* cb = reinterpret_cast<const float*>(ws + wl.cbest);
   const unsigned* cmk = reinterpret_cast<const unsigned*>(ws + wl.cmask);
   const float2* tsl = reinterpret_cast<const float2*>(ws + wl.tslack);
-  switch (pl.R) {
-    case 16: chamfer_recover_cols_kernel<16><<<cg, 128, 0, s>>>(p1, p2, cb, cmk, tsl, min2, idx2, P, M, pl.ntiles); break;
-    case 8:  chamfer_recover_cols_kernel<8><<<cg, 128, 0, s>>>(p1, p2, cb, cmk, tsl, min2, idx2, P, M, pl.ntiles); break;
-    default: chamfer_recover_cols_kernel<4><<<cg, 128, 0, s>>>(p1, p2, cb, cmk, tsl, min2, idx2, P, M, pl.ntiles); break;
+  float* cthr = reinterpret_cast<float*>(ws + wl.cthr);
+  u64* key2 = reinterpret_cast<u64*>(ws + wl.key2);
+  if (cudaMemsetAsync(key2, 0xFF, (size_t)B * M * 8, s) != cudaSuccess) { vpn_set_error("chamfer tiled: memset failed"); return VPN_ERR_CUDA; }
+  chamfer_col_thr_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(cb, tsl, cthr, M, pl.ntiles);
+  if ((rc = vpn_check_launch("chamfer_col_thr_kernel"))) return rc;
+  {
+    static bool attr_cols[3] = {false, false, false};
+    const int ai = pl.R == 16 ? 0 : (pl.R == 8 ? 1 : 2);
+    const size_t smem_cols = (size_t)TM * sizeof(float4);
+    dim3 cg(pl.ntiles, B);
+    cudaError_t e = cudaSuccess;
+    switch (pl.R) {
+      case 16:
+        if (!attr_cols[ai]) e = cudaFuncSetAttribute(chamfer_recover_cols_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols);
+        chamfer_recover_cols_kernel<16><<<cg, kRecThreads, smem_cols, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, pl.ntiles); break;
+      case 8:
+        if (!attr_cols[ai]) e = cudaFuncSetAttribute(chamfer_recover_cols_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols);
+        chamfer_recover_cols_kernel<8><<<cg, kRecThreads, smem_cols, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, pl.ntiles); break;
+      default:
+        if (!attr_cols[ai]) e = cudaFuncSetAttribute(chamfer_recover_cols_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols);
+        chamfer_recover_cols_kernel<4><<<cg, kRecThreads, smem_cols, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, pl.ntiles); break;
+    }
+    if (e != cudaSuccess) { vpn_set_error("chamfer tiled: smem attribute (cols recovery)"); return VPN_ERR_CUDA; }
+    attr_cols[ai] = true;
   }
-  rc = vpn_check_launch("chamfer_recover_cols_kernel");
+  if ((rc = vpn_check_launch("chamfer_recover_cols_kernel"))) return rc;
+  {
+    size_t n = (size_t)B * M;
+    chamfer_unpack_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(key2, min2, idx2, n);
+  }
+  rc = vpn_check_launch("chamfer_unpack_key_kernel");
   if (ev) cudaEventRecord(ev[4], s);
   return rc;
 }
