@@ -83,6 +83,14 @@ int vpn_chamfer_bwd(const float* p1, const float* p2, const float* min1, const i
                     const float* min2, const int* idx2, const float* g1, const float* g2,
                     float* grad_p1, float* grad_p2, int B, int P, int M, void* stream);
 
+/* Fused loss head/tail of ChamferDistanceLoss (chamfer_distance.py:25-28): loss[b] = w1*mean(min1[b]) + w2*mean(min2[b]);
+ * the backward takes the per-sample upstream gradient grad_loss (B) instead of full (B,P)/(B,M) tensors. */
+int vpn_chamfer_loss_fwd(const float* min1, const float* min2, float w1, float w2, float* loss,
+                         float* scratch /* >= 64*B floats */, int B, int P, int M, void* stream);
+int vpn_chamfer_loss_bwd(const float* p1, const float* p2, const float* min1, const int* idx1,
+                         const float* min2, const int* idx2, const float* grad_loss, float w1, float w2,
+                         float* grad_p1, float* grad_p2, int B, int P, int M, void* stream);
+
 /* ---- soft silhouette (modules/loss/silhouette.py:13-23 -> render/vertex_renderer.py:15-26 -> kaolin DIB-R)
  * verts (B,V,3), faces (F,3) int32 shared topology, cam_rot (B,3,3), cam_pos (B,3), proj = (px,py,pz).
  * alpha (B,H,W); covered (B,H,W) uint8; normals (B,F,3) or NULL.  bwd needs the workspace as fwd left it. */

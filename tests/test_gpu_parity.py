@@ -265,6 +265,39 @@ def test_chamfer_backward_vs_oracle(vpn, O):
         close(a.grad, gp1, atol=1e-6); close(c.grad, gp2, atol=1e-6)
 
 
+@pytest.mark.parametrize("case", ["uniform", "lattice", "duplicates", "identical"])
+def test_chamfer_small_first_cloud_bit_exact(vpn, c_oracle, case):
+    """VP-diverse shapes (vp_diverse.py:12-18: K centres vs M targets) take the one-launch small-P kernel."""
+    gen = torch.Generator().manual_seed(41 + len(case))
+    for (b, p, m) in ((2, 16, 8192), (3, 1, 1), (1, 64, 257), (2, 5, 3), (1, 33, 1000), (32, 32, 2048)):
+        p1, p2 = adversarial_clouds(case, b, p, m, gen)
+        ref = c_oracle(p1.numpy(), p2.numpy())
+        got = run_nn(vpn, p1, p2, IMPLS["auto"])
+        for name, r_, g_ in zip(("min1", "idx1", "min2", "idx2"), ref, got):
+            same(g_, r_, f"smallp/{case}/{(b, p, m)}/{name}")
+
+
+@pytest.mark.parametrize("shape", [(2, 300, 200), (1, 2048, 1024), (3, 16, 500), (2, 4096, 512)])
+def test_chamfer_loss_fused_vs_oracle(vpn, O, shape):
+    """ChamferDistanceLoss.forward (chamfer_distance.py:10-30) through the fused loss head/tail kernels:
+    per-sample values, weights, and gradients to both clouds against autograd through the dense oracle."""
+    b, p, m = shape
+    gen = torch.Generator().manual_seed(p + m)
+    p1, p2 = torch.rand(b, p, 3, generator=gen), torch.rand(b, m, 3, generator=gen)
+    wb = torch.rand(b, generator=gen) + 0.5
+    for (w1, w2) in ((1.0, 1.0), (0.5, 1.0)):
+        ao, co = p1.clone().requires_grad_(), p2.clone().requires_grad_()
+        ref = O.chamfer_dense(ao, co, each_batch=True, w1=w1, w2=w2)
+        (ref * wb).sum().backward()
+        a, c = p1.cuda().requires_grad_(), p2.cuda().requires_grad_()
+        got = vpn.chamfer_distance(a, c, each_batch=True, w1=w1, w2=w2)
+        close(got, ref, atol=0)
+        (got * wb.cuda()).sum().backward()
+        close(a.grad, ao.grad, atol=1e-4 * float(ao.grad.abs().max()))
+        close(c.grad, co.grad, atol=1e-4 * float(co.grad.abs().max()))
+        close(vpn.chamfer_distance(a.detach(), c.detach(), w1=w1, w2=w2), ref.mean(), atol=0)
+
+
 def test_chamfer_zero_distance_gives_nan_like_reference(vpn):
     p = torch.rand(1, 8, 3).cuda().requires_grad_()
     vpn.chamfer_distance(p, p.detach().clone()).backward()

@@ -1,0 +1,20 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, smoke, bench lines, then the two ncu captures (launch list + full set of the
+# dominant kernel).  Usage: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh TAG'
+TAG=${1:-r01x}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/smi_$TAG.txt 2>&1
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_$TAG.log
+python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke_$TAG.log
+python bench.py > gpurun_out/bench_c2_$TAG.log 2>&1; echo "bench c2 rc=$?"
+python bench.py --workload c3 --no-cpu-baseline > gpurun_out/bench_c3_$TAG.log 2>&1; echo "bench c3 rc=$?"
+python bench.py --workload c1 --no-cpu-baseline > gpurun_out/bench_c1_$TAG.log 2>&1; echo "bench c1 rc=$?"
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain_$TAG.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_$TAG.log 2>&1
+echo "ncu launches rc=$?"
+python tools/ncu_chamfer.py 4 32 > gpurun_out/plain_ncu_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:chamfer_tiled_kernel<.int.16, .int.2>' -s 1 -c 1 -f -o gpurun_out/prof_tiled_$TAG \
+    python tools/ncu_chamfer.py 4 32 > gpurun_out/ncu_full_$TAG.log 2>&1
+echo "ncu full rc=$?"
+tail -c 600 gpurun_out/pytest_$TAG.log

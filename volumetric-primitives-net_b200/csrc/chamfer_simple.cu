@@ -89,10 +89,12 @@ __global__ void chamfer_unpack_kernel(const u64* __restrict__ key, float* __rest
 //   row term : dL/dp1[i] = (g1[i] / (2 v1[i])) * 2 (p1[i] - p2[idx1[i]])          -> plain store
 //   col term : dL/dp1[idx2[j]] += (g2[j] / (2 v2[j])) * 2 (p1[idx2[j]] - p2[j])    -> atomic scatter
 // and the negatives into dL/dp2 when requested.  v == 0 gives inf * 0 = NaN, as in the reference.
+// Upstream gradient of min1/min2: either a full tensor g (B,n), or a per-sample gradient gl (B) of the fused
+// loss w1*mean(min1) + w2*mean(min2) times the scalar `scale` (= w1/P or w2/M).
 __global__ void chamfer_bwd_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                                         const float* __restrict__ min1, const int* __restrict__ idx1,
-                                        const float* __restrict__ g1, float* __restrict__ gp1,
-                                        float* __restrict__ gp2, int P, int M) {
+                                        const float* __restrict__ g1, const float* __restrict__ gl, float scale,
+                                        float* __restrict__ gp1, float* __restrict__ gp2, int P, int M) {
   const int b = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
@@ -100,7 +102,8 @@ __global__ void chamfer_bwd_rows_kernel(const float* __restrict__ p1, const floa
   int j = idx1[ri];
   const float* a = p1 + 3 * ri;
   const float* t = p2 + 3 * ((size_t)b * M + j);
-  float coef = g1[ri] / (2.0f * min1[ri]);
+  float up = g1 ? g1[ri] : gl[b] * scale;
+  float coef = up / (2.0f * min1[ri]);
   float cx = coef * (2.0f * (a[0] - t[0])), cy = coef * (2.0f * (a[1] - t[1])), cz = coef * (2.0f * (a[2] - t[2]));
   gp1[3 * ri] = cx; gp1[3 * ri + 1] = cy; gp1[3 * ri + 2] = cz;
   if (gp2) {
@@ -109,25 +112,101 @@ __global__ void chamfer_bwd_rows_kernel(const float* __restrict__ p1, const floa
   }
 }
 
+constexpr int kSmallP = 64;      // clouds this small are accumulated in shared memory before the global scatter
+
 __global__ void chamfer_bwd_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                                         const float* __restrict__ min2, const int* __restrict__ idx2,
-                                        const float* __restrict__ g2, float* __restrict__ gp1,
-                                        float* __restrict__ gp2, int P, int M) {
+                                        const float* __restrict__ g2, const float* __restrict__ gl, float scale,
+                                        float* __restrict__ gp1, float* __restrict__ gp2, int P, int M) {
+  __shared__ float acc[kSmallP * 3];
   const int b = blockIdx.y;
+  const bool small = P <= kSmallP;          // e.g. VP-diverse: 8192 targets scatter into 16 centres
+  if (small) { for (int k = threadIdx.x; k < P * 3; k += blockDim.x) acc[k] = 0.f; __syncthreads(); }
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= M) return;
+  if (j < M) {
   size_t cj = (size_t)b * M + j;
   int i = idx2[cj];
   const float* a = p1 + 3 * ((size_t)b * P + i);
   const float* t = p2 + 3 * cj;
-  float coef = g2[cj] / (2.0f * min2[cj]);
+  float up = g2 ? g2[cj] : gl[b] * scale;
+  float coef = up / (2.0f * min2[cj]);
   float cx = coef * (2.0f * (a[0] - t[0])), cy = coef * (2.0f * (a[1] - t[1])), cz = coef * (2.0f * (a[2] - t[2]));
-  float* o = gp1 + 3 * ((size_t)b * P + i);
+  float* o = small ? acc + 3 * i : gp1 + 3 * ((size_t)b * P + i);
   atomicAdd(o, cx); atomicAdd(o + 1, cy); atomicAdd(o + 2, cz);
   if (gp2) {
     float* o2 = gp2 + 3 * cj;
     atomicAdd(o2, -cx); atomicAdd(o2 + 1, -cy); atomicAdd(o2 + 2, -cz);
   }
+  }
+  if (small) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < P * 3; k += blockDim.x) if (acc[k] != 0.f) atomicAdd(gp1 + (size_t)b * P * 3 + k, acc[k]);
+  }
+}
+
+// Small first cloud (P <= kSmallP, e.g. the K primitive centres of VP-diverse, vp_diverse.py:12-18): one launch
+// for both directions.  One thread per target evaluates all P centres (exact arithmetic, IEEE sqrt); the
+// column minimum is thread local, the row minima are reduced warp -> block (shared 64-bit keys) -> global.
+__global__ void __launch_bounds__(256)
+chamfer_smallp_kernel(const float* __restrict__ p1, const float* __restrict__ p2, u64* __restrict__ key1,
+                      float* __restrict__ min2, int* __restrict__ idx2, int P, int M) {
+  __shared__ float4 cen[kSmallP];
+  __shared__ u64 bkey[kSmallP];
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  if (threadIdx.x < P) {
+    const float* a = p1 + 3 * ((size_t)b * P + threadIdx.x);
+    cen[threadIdx.x] = make_float4(a[0], a[1], a[2], 0.f);
+    bkey[threadIdx.x] = ~0ull;
+  }
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = j < M;
+  const float* t = p2 + 3 * ((size_t)b * M + min(j, M - 1));
+  const float tx = t[0], ty = t[1], tz = t[2];
+  float best_v = __int_as_float(0x7f800000); int best_i = 0;
+  for (int k = 0; k < P; ++k) {
+    const float4 c = cen[k];
+    const float v = sqrtf(exact_d2(c.x, c.y, c.z, tx, ty, tz));
+    if (v < best_v) { best_v = v; best_i = k; }                      // ascending k: first index on ties
+    const unsigned vb = valid ? __float_as_uint(v) : 0xffffffffu;
+    const unsigned vmin = __reduce_min_sync(0xffffffffu, vb);
+    const unsigned jmin = __reduce_min_sync(0xffffffffu, vb == vmin ? (unsigned)j : 0xffffffffu);
+    if (lane == 0 && vmin != 0xffffffffu) atomicMin(&bkey[k], ((u64)vmin << 32) | jmin);
+  }
+  if (valid) { min2[(size_t)b * M + j] = best_v; idx2[(size_t)b * M + j] = best_i; }
+  __syncthreads();
+  if (threadIdx.x < P && bkey[threadIdx.x] != ~0ull) atomicMin(&key1[(size_t)b * P + threadIdx.x], bkey[threadIdx.x]);
+}
+
+// per sample: loss[b] = w1 * mean(min1[b]) + w2 * mean(min2[b])      (chamfer_distance.py:25-28)
+// stage 1: kLossSlices blocks per sample write partial sums; stage 2 adds them in a fixed order (deterministic).
+constexpr int kLossSlices = 32;
+
+__global__ void __launch_bounds__(256)
+chamfer_loss_partial_kernel(const float* __restrict__ min1, const float* __restrict__ min2,
+                            float2* __restrict__ partial, int P, int M) {
+  __shared__ float red[2][8];
+  const int b = blockIdx.y, sl = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = sl * blockDim.x + threadIdx.x; i < P; i += blockDim.x * kLossSlices) s1 += min1[(size_t)b * P + i];
+  for (int i = sl * blockDim.x + threadIdx.x; i < M; i += blockDim.x * kLossSlices) s2 += min2[(size_t)b * M + i];
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; c += red[1][w]; }
+    partial[(size_t)b * kLossSlices + sl] = make_float2(a, c);
+  }
+}
+
+__global__ void chamfer_loss_final_kernel(const float2* __restrict__ partial, float w1, float w2,
+                                          float* __restrict__ loss, int B, int P, int M) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float a = 0.f, c = 0.f;
+  for (int k = 0; k < kLossSlices; ++k) { float2 v = partial[(size_t)b * kLossSlices + k]; a += v.x; c += v.y; }
+  loss[b] = w1 * (a / (float)P) + w2 * (c / (float)M);
 }
 
 // one direction: for every row of A the nearest column of Bp
@@ -136,7 +215,7 @@ int chamfer_simple_direction(const float* A, const float* Bp, float* mn, int* id
   cudaError_t e = cudaMemsetAsync(key, 0xFF, (size_t)B * nA * sizeof(u64), s);
   if (e != cudaSuccess) { vpn_set_error("chamfer: memset failed: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
   int row_blocks = (nA + kSimpleThreads * kSimpleRows - 1) / (kSimpleThreads * kSimpleRows);
-  // split the columns so that small row counts (VP-diverse: 16 rows) still fill the SMs
+  // split the columns so that small row counts still fill the SMs
   long long want = 4LL * sm_count;
   int segs = (int)((want + (long long)row_blocks * B - 1) / ((long long)row_blocks * B));
   int max_segs = (nB + kSimpleTile - 1) / kSimpleTile;
@@ -153,6 +232,19 @@ int chamfer_simple_direction(const float* A, const float* Bp, float* mn, int* id
   chamfer_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(key, mn, idx, n);
   return vpn_check_launch("chamfer_unpack_kernel");
 }
+
+// both directions in one launch for a small first cloud; key1 (B,P) u64 scratch
+int chamfer_smallp(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2, u64* key1,
+                   int B, int P, int M, cudaStream_t s) {
+  if (cudaMemsetAsync(key1, 0xFF, (size_t)B * P * sizeof(u64), s) != cudaSuccess) { vpn_set_error("chamfer: memset failed"); return VPN_ERR_CUDA; }
+  chamfer_smallp_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(p1, p2, key1, min2, idx2, P, M);
+  int rc = vpn_check_launch("chamfer_smallp_kernel");
+  if (rc) return rc;
+  size_t n = (size_t)B * P;
+  chamfer_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(key1, min1, idx1, n);
+  return vpn_check_launch("chamfer_unpack_kernel");
+}
+int chamfer_smallp_limit() { return kSmallP; }
 
 }  // namespace vpn
 
@@ -172,9 +264,47 @@ extern "C" int vpn_chamfer_bwd(const float* p1, const float* p2, const float* mi
     cudaError_t e = cudaMemsetAsync(grad_p2, 0, (size_t)B * M * 3 * sizeof(float), s);
     if (e != cudaSuccess) { vpn_set_error("chamfer bwd: memset failed: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
   }
-  chamfer_bwd_rows_kernel<<<dim3((P + 255) / 256, B), 256, 0, s>>>(p1, p2, min1, idx1, g1, grad_p1, grad_p2, P, M);
+  chamfer_bwd_rows_kernel<<<dim3((P + 255) / 256, B), 256, 0, s>>>(p1, p2, min1, idx1, g1, nullptr, 0.f, grad_p1, grad_p2, P, M);
   int rc = vpn_check_launch("chamfer_bwd_rows_kernel");
   if (rc) return rc;
-  chamfer_bwd_cols_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(p1, p2, min2, idx2, g2, grad_p1, grad_p2, P, M);
+  chamfer_bwd_cols_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(p1, p2, min2, idx2, g2, nullptr, 0.f, grad_p1, grad_p2, P, M);
+  return vpn_check_launch("chamfer_bwd_cols_kernel");
+}
+
+// scratch: >= 64 * B floats of device memory (partial sums)
+extern "C" int vpn_chamfer_loss_fwd(const float* min1, const float* min2, float w1, float w2, float* loss,
+                                    float* scratch, int B, int P, int M, void* stream) {
+  if (B < 0 || P <= 0 || M <= 0) { vpn_set_error("chamfer loss: bad shape"); return VPN_ERR_SHAPE; }
+  if (B == 0) return VPN_OK;
+  if (B > 65535) { vpn_set_error("chamfer loss: batch > 65535 unsupported"); return VPN_ERR_SHAPE; }
+  if (!min1 || !min2 || !loss || !scratch) { vpn_set_error("chamfer loss: null pointer"); return VPN_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  float2* partial = reinterpret_cast<float2*>(scratch);
+  chamfer_loss_partial_kernel<<<dim3(kLossSlices, B), 256, 0, s>>>(min1, min2, partial, P, M);
+  int rc = vpn_check_launch("chamfer_loss_partial_kernel");
+  if (rc) return rc;
+  chamfer_loss_final_kernel<<<(B + 127) / 128, 128, 0, s>>>(partial, w1, w2, loss, B, P, M);
+  return vpn_check_launch("chamfer_loss_final_kernel");
+}
+
+extern "C" int vpn_chamfer_loss_bwd(const float* p1, const float* p2, const float* min1, const int* idx1,
+                                    const float* min2, const int* idx2, const float* grad_loss, float w1, float w2,
+                                    float* grad_p1, float* grad_p2, int B, int P, int M, void* stream) {
+  if (B < 0 || P <= 0 || M <= 0) { vpn_set_error("chamfer loss bwd: bad shape"); return VPN_ERR_SHAPE; }
+  if (B == 0) return VPN_OK;
+  if (B > 65535) { vpn_set_error("chamfer loss bwd: batch > 65535 unsupported"); return VPN_ERR_SHAPE; }
+  if (!p1 || !p2 || !min1 || !idx1 || !min2 || !idx2 || !grad_loss || !grad_p1) {
+    vpn_set_error("chamfer loss bwd: null pointer"); return VPN_ERR_ARG;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (grad_p2 && cudaMemsetAsync(grad_p2, 0, (size_t)B * M * 3 * sizeof(float), s) != cudaSuccess) {
+    vpn_set_error("chamfer loss bwd: memset failed"); return VPN_ERR_CUDA;
+  }
+  chamfer_bwd_rows_kernel<<<dim3((P + 255) / 256, B), 256, 0, s>>>(p1, p2, min1, idx1, nullptr, grad_loss, w1 / (float)P,
+                                                                    grad_p1, grad_p2, P, M);
+  int rc = vpn_check_launch("chamfer_bwd_rows_kernel");
+  if (rc) return rc;
+  chamfer_bwd_cols_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(p1, p2, min2, idx2, nullptr, grad_loss, w2 / (float)M,
+                                                                    grad_p1, grad_p2, P, M);
   return vpn_check_launch("chamfer_bwd_cols_kernel");
 }

@@ -243,10 +243,56 @@ def chamfer_nn_stage_ms(points1: torch.Tensor, points2: torch.Tensor, impl: int 
     return out
 
 
+class _ChamferLoss(torch.autograd.Function):
+    """Per-sample loss w1*mean(min1) + w2*mean(min2) with the nearest-neighbour search, the two means and the
+    whole backward as vpn_b200 kernels (no (B,P)/(B,M) gradient tensors, no elementwise torch launches)."""
+
+    @staticmethod
+    def forward(ctx, p1, p2, w1, w2, impl):
+        lib = _lib.load()
+        p1 = require(p1.contiguous(), f32, "points1")
+        p2 = require(p2.contiguous(), f32, "points2")
+        b, p, _ = p1.shape
+        m = p2.shape[1]
+        dev = p1.device
+        min1 = torch.empty((b, p), dtype=f32, device=dev); idx1 = torch.empty((b, p), dtype=torch.int32, device=dev)
+        min2 = torch.empty((b, m), dtype=f32, device=dev); idx2 = torch.empty((b, m), dtype=torch.int32, device=dev)
+        nb = ctypes.c_size_t(0)
+        check(lib.vpn_chamfer_workspace_bytes(b, p, m, impl, ctypes.byref(nb)), "vpn_chamfer_workspace_bytes")
+        ws = _scratch_bytes(nb.value, dev)
+        st = stream_ptr(dev)
+        check(lib.vpn_chamfer_fwd(ptr(p1), ptr(p2), ptr(min1), ptr(idx1), ptr(min2), ptr(idx2), b, p, m,
+                                  ptr(ws), nb.value, impl, st), "vpn_chamfer_fwd")
+        loss = torch.empty((b,), dtype=f32, device=dev)
+        part = torch.empty((b * 64,), dtype=f32, device=dev)
+        check(lib.vpn_chamfer_loss_fwd(ptr(min1), ptr(min2), float(w1), float(w2), ptr(loss), ptr(part), b, p, m, st),
+              "vpn_chamfer_loss_fwd")
+        ctx.save_for_backward(p1, p2, min1, idx1, min2, idx2)
+        ctx.w = (float(w1), float(w2))
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        lib = _lib.load()
+        p1, p2, min1, idx1, min2, idx2 = ctx.saved_tensors
+        b, p, _ = p1.shape
+        m = p2.shape[1]
+        dev = p1.device
+        gloss = gloss.contiguous()
+        gp1 = torch.empty_like(p1)
+        gp2 = torch.empty_like(p2) if ctx.needs_input_grad[1] else None
+        check(lib.vpn_chamfer_loss_bwd(ptr(p1), ptr(p2), ptr(min1), ptr(idx1), ptr(min2), ptr(idx2), ptr(gloss),
+                                       ctx.w[0], ctx.w[1], ptr(gp1), ptr(gp2), b, p, m, stream_ptr(dev)),
+              "vpn_chamfer_loss_bwd")
+        return (gp1 if ctx.needs_input_grad[0] else None), gp2, None, None, None
+
+
 def chamfer_distance(points1, points2, each_batch=False, w1=1.0, w2=1.0, impl: int = CHAMFER_AUTO):
     """ChamferDistanceLoss.forward (chamfer_distance.py:10-30)."""
-    min1, _, min2, _ = chamfer_nn(points1, points2, impl)
-    loss = w1 * min1.mean(1) + w2 * min2.mean(1)
+    assert points1.dim() == 3 and points1.size(-1) == 3          # chamfer_distance.py:33-35
+    assert points2.dim() == 3 and points2.size(-1) == 3
+    assert points1.size(0) == points2.size(0)
+    loss = _ChamferLoss.apply(points1, points2, w1, w2, impl)
     return loss if each_batch else loss.mean()
 
 
