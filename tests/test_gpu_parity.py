@@ -150,7 +150,7 @@ def test_mesh_vertices_golden(vpn, golden, golden_templates):
 # ------------------------------------------------------------------------------------------------
 # Chamfer
 # ------------------------------------------------------------------------------------------------
-IMPLS = {"generic": 1, "tiled_exact": 2, "tiled_fma": 3, "tiled_expand": 4, "auto": 0}
+IMPLS = {"generic": 1, "tiled_exact": 2, "tiled_fma": 3, "tiled_expand": 4, "tiled_tc": 5, "auto": 0}
 
 
 def run_nn(vpn, p1, p2, impl):
@@ -196,7 +196,7 @@ def adversarial_clouds(name, b, p, m, gen):
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("impl", ["generic", "tiled_exact", "tiled_fma", "tiled_expand"])
+@pytest.mark.parametrize("impl", ["generic", "tiled_exact", "tiled_fma", "tiled_expand", "tiled_tc"])
 @pytest.mark.parametrize("case", ["uniform", "lattice", "duplicates", "offset", "identical", "surface"])
 def test_chamfer_nn_bit_exact(vpn, c_oracle, impl, case):
     gen = torch.Generator().manual_seed(sum(map(ord, case)))
@@ -216,7 +216,7 @@ def test_chamfer_full_size_slice(vpn, c_oracle):
     gen = torch.Generator().manual_seed(1234)
     p1, p2 = torch.rand(2, 65536, 3, generator=gen) - 0.5, torch.rand(2, 8192, 3, generator=gen) - 0.5
     ref = c_oracle(p1.numpy(), p2.numpy())
-    for impl in ("auto", "tiled_exact", "tiled_fma", "tiled_expand", "generic"):
+    for impl in ("auto", "tiled_tc", "tiled_exact", "tiled_fma", "tiled_expand", "generic"):
         got = run_nn(vpn, p1, p2, IMPLS[impl])
         for name, r_, g_ in zip(("min1", "idx1", "min2", "idx2"), ref, got):
             same(g_, r_, f"{impl}/{name}")
@@ -296,6 +296,32 @@ def test_chamfer_loss_fused_vs_oracle(vpn, O, shape):
         close(a.grad, ao.grad, atol=1e-4 * float(ao.grad.abs().max()))
         close(c.grad, co.grad, atol=1e-4 * float(co.grad.abs().max()))
         close(vpn.chamfer_distance(a.detach(), c.detach(), w1=w1, w2=w2), ref.mean(), atol=0)
+
+
+@pytest.mark.parametrize("impl", ["tiled_tc", "tiled_expand"])
+def test_chamfer_out_of_range_sample_falls_back(vpn, c_oracle, impl):
+    """Coordinates too large for the centred-expansion filters flag the sample; it is redone exactly and the
+    other samples of the batch are unaffected."""
+    gen = torch.Generator().manual_seed(77)
+    p1, p2 = torch.rand(3, 2048, 3, generator=gen), torch.rand(3, 640, 3, generator=gen)
+    p1[1, 100] = torch.tensor([3e18, -2e18, 1e18])
+    p2[2, 7] = torch.tensor([-3e18, 0.0, 1e17])
+    ref = c_oracle(p1.numpy(), p2.numpy())
+    got = run_nn(vpn, p1, p2, IMPLS[impl])
+    for name, r_, g_ in zip(("min1", "idx1", "min2", "idx2"), ref, got):
+        same(g_, r_, f"{impl}/fallback/{name}")
+
+
+@pytest.mark.parametrize("shape", [(1, 512, 128), (2, 640, 129), (1, 16384, 2048), (2, 5000, 8192), (1, 2048 * 3 + 1, 1000)])
+def test_chamfer_tc_shapes(vpn, c_oracle, shape):
+    """Ragged tiles, column splits and every tile height of the tensor-core filter."""
+    b, p, m = shape
+    gen = torch.Generator().manual_seed(p * 3 + m)
+    p1, p2 = adversarial_clouds("surface", b, p, m, gen)
+    ref = c_oracle(p1.numpy(), p2.numpy())
+    got = run_nn(vpn, p1, p2, IMPLS["tiled_tc"])
+    for name, r_, g_ in zip(("min1", "idx1", "min2", "idx2"), ref, got):
+        same(g_, r_, f"tc/{shape}/{name}")
 
 
 def test_chamfer_zero_distance_gives_nan_like_reference(vpn):

@@ -4,7 +4,7 @@
 TAG=${1:-r01x}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/smi_$TAG.txt 2>&1
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_$TAG.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_$TAG.log
 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke_$TAG.log
 python bench.py > gpurun_out/bench_c2_$TAG.log 2>&1; echo "bench c2 rc=$?"
 python bench.py --workload c3 --no-cpu-baseline > gpurun_out/bench_c3_$TAG.log 2>&1; echo "bench c3 rc=$?"

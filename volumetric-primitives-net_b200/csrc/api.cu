@@ -27,8 +27,8 @@ int chamfer_simple_direction(const float* A, const float* Bp, float* mn, int* id
 int chamfer_smallp(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2, u64* key1,
                    int B, int P, int M, cudaStream_t s);
 int chamfer_smallp_limit();
-int chamfer_tiled_supported(int B, int P, int M);
-size_t chamfer_tiled_workspace_bytes(int B, int P, int M);
+int chamfer_tiled_supported(int B, int P, int M, int mode);
+size_t chamfer_tiled_workspace_bytes(int B, int P, int M, int mode);
 int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                       int B, int P, int M, void* ws, size_t ws_bytes, int mode, cudaStream_t s, cudaEvent_t* ev);
 }
@@ -64,14 +64,17 @@ extern "C" int vpn_device_info(int* sms, int* cc_major, int* cc_minor, int* cloc
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// impl: 0 = auto (tiled kernel with the centred-expansion filter when the shape allows, else generic),
+// impl: 0 = auto (tensor-core filter when the shape allows, else the CUDA-core tiled kernel, else generic),
 //       1 = generic kernel only,
-//       2 / 3 / 4 = tiled kernel with exact / FMA-difference / centred-expansion hot-loop arithmetic
-//       (these fail on shapes the tiled kernel rejects).  Results are bit-identical for every impl.
+//       2 / 3 / 4 = CUDA-core tiled kernel with exact / FMA-difference / centred-expansion hot-loop arithmetic,
+//       5 = tcgen05 tensor-core filter (chamfer_tc.cu)
+//       (2-5 fail on shapes the kernel rejects).  Results are bit-identical for every impl.
+static int impl_mode(int impl) { return impl == 0 ? -1 : impl - 2; }
 extern "C" int vpn_chamfer_workspace_bytes(int B, int P, int M, int impl, size_t* bytes) {
   if (B < 0 || P <= 0 || M <= 0 || !bytes) { vpn_set_error("chamfer workspace: bad arguments"); return VPN_ERR_ARG; }
   size_t simple = align256((size_t)B * P * 8) + align256((size_t)B * M * 8);
-  size_t tiled = (impl != 1 && vpn::chamfer_tiled_supported(B, P, M)) ? vpn::chamfer_tiled_workspace_bytes(B, P, M) : 0;
+  if (impl < 0 || impl > 5) { vpn_set_error("chamfer workspace: bad impl %d", impl); return VPN_ERR_ARG; }
+  size_t tiled = (impl != 1 && vpn::chamfer_tiled_supported(B, P, M, impl_mode(impl))) ? vpn::chamfer_tiled_workspace_bytes(B, P, M, impl_mode(impl)) : 0;
   *bytes = simple > tiled ? simple : tiled;
   return VPN_OK;
 }
@@ -83,11 +86,11 @@ static int chamfer_fwd_impl(const float* p1, const float* p2, float* min1, int* 
   if (B == 0) return VPN_OK;
   if (B > 65535) { vpn_set_error("chamfer fwd: batch > 65535 unsupported"); return VPN_ERR_SHAPE; }
   if (!p1 || !p2 || !min1 || !idx1 || !min2 || !idx2 || !workspace) { vpn_set_error("chamfer fwd: null pointer"); return VPN_ERR_ARG; }
-  bool tiled_ok = vpn::chamfer_tiled_supported(B, P, M) != 0;
-  if (impl < 0 || impl > 4) { vpn_set_error("chamfer fwd: bad impl %d", impl); return VPN_ERR_ARG; }
+  if (impl < 0 || impl > 5) { vpn_set_error("chamfer fwd: bad impl %d", impl); return VPN_ERR_ARG; }
+  bool tiled_ok = impl != 1 && vpn::chamfer_tiled_supported(B, P, M, impl_mode(impl)) != 0;
   if (impl >= 2 && !tiled_ok) { vpn_set_error("chamfer fwd: tiled kernel does not support this shape"); return VPN_ERR_SHAPE; }
   if (impl != 1 && tiled_ok) {
-    int mode = impl == 0 ? -1 : impl - 2;
+    int mode = impl_mode(impl);
     return vpn::chamfer_tiled_fwd(p1, p2, min1, idx1, min2, idx2, B, P, M, workspace, workspace_bytes, mode, s, ev);
   }
   size_t need = align256((size_t)B * P * 8) + align256((size_t)B * M * 8);

@@ -37,7 +37,7 @@
 
 namespace vpn {
 
-enum { MODE_EXACT = 0, MODE_DIFF = 1, MODE_EXPAND = 2 };
+enum { MODE_EXACT = 0, MODE_DIFF = 1, MODE_EXPAND = 2, MODE_TC = 3 };
 
 constexpr int kTThreads = 256;
 constexpr int kTWarps = kTThreads / 32;
@@ -353,8 +353,10 @@ __global__ void __launch_bounds__(kRecThreads, 1)
 chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                             const float* __restrict__ rbest, const u64* __restrict__ rmask,
                             const float2* __restrict__ tslack, float* __restrict__ min1, int* __restrict__ idx1,
-                            int P, int M, int nchunks, int nsplit, int cps, int TM, int ntiles) {
+                            int P, int M, int nchunks, int nsplit, int cps, int TM, int ntiles,
+                            const int* __restrict__ skip) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (skip && skip[blockIdx.y]) return;                  // sample redone by chamfer_flagged_kernel
   float4* cols = reinterpret_cast<float4*>(smem_raw);
   __shared__ float4 rowc[kRecThreads];
   __shared__ u64 key[kRecThreads];
@@ -445,15 +447,21 @@ __global__ void chamfer_col_thr_kernel(const float* __restrict__ cbest, const fl
   cthr[(size_t)b * M + col] = thr_of(g, rel, ab);
 }
 
-// grid: x = row tile, y = sample.  dynamic smem: float4 rows[256*R].  key2 (B,M) u64 pre-filled with 0xFF.
-template <int R>
+// grid: x = row tile, y = sample.  dynamic smem: float4 rows[TM].  key2 (B,M) u64 pre-filled with 0xFF.
+// Candidate bit k of a (tile, column) record names the rows
+//   TC == false : rows rr * 256 + k * 32 + [0,32), rr = 0..R-1   (warp k of chamfer_tiled_kernel<R>, TM = 256 R)
+//   TC == true  : rows k * 128 + [0,128)                          (row block k of chamfer_tc_kernel, TM = 128 R)
+template <int R, bool TC>
 __global__ void __launch_bounds__(kRecThreads, 1)
 chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                             const float* __restrict__ cbest, const unsigned* __restrict__ cmask,
-                            const float* __restrict__ cthr, u64* __restrict__ key2, int P, int M, int ntiles) {
-  constexpr int TM = kTThreads * R;
-  constexpr int kSub = (R >= 4) ? 4 : R;                 // sub-units per (column, warp block) item
-  constexpr int kRunsPerSub = R / kSub;
+                            const float* __restrict__ cthr, u64* __restrict__ key2, int P, int M, int ntiles,
+                            const int* __restrict__ skip) {
+  constexpr int TM = TC ? 128 * R : kTThreads * R;
+  constexpr int kSub = TC ? 4 : ((R >= 4) ? 4 : R);      // sub-units per (column, bit) item
+  constexpr int kRunsPerSub = TC ? 1 : R / kSub;
+  constexpr unsigned kBitMask = TC ? ((1u << R) - 1u) : 0xffu;
+  if (skip && skip[blockIdx.y]) return;                  // sample redone by chamfer_flagged_kernel
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* rows = reinterpret_cast<float4*>(smem_raw);
   __shared__ unsigned items[kItemCap];
@@ -475,7 +483,7 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
     for (int u = 0; u < 8; ++u) {
       const int col = slab + u * kRecThreads + tid;
       mk[u] = 0u;
-      if (col < M && cbest[rec0 + col] <= cthr[(size_t)b * M + col]) mk[u] = cmask[rec0 + col] & 0xffu;
+      if (col < M && cbest[rec0 + col] <= cthr[(size_t)b * M + col]) mk[u] = cmask[rec0 + col] & kBitMask;
       cnt += __popc(mk[u]);
     }
     int total;
@@ -486,18 +494,18 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
       for (int u = 0; u < 8; ++u)
         for (unsigned mm = mk[u]; mm; mm &= mm - 1, ++j)
           if (j >= base && j < base + kItemCap)
-            items[j - base] = ((unsigned)(u * kRecThreads + tid) << 3) | (unsigned)(__ffs((int)mm) - 1);
+            items[j - base] = ((unsigned)(u * kRecThreads + tid) << 4) | (unsigned)(__ffs((int)mm) - 1);
       __syncthreads();
       const int units = min(kItemCap, total - base) * kSub;
       for (int it = tid; it < units; it += kRecThreads) {
         const unsigned item = items[it / kSub];
-        const int col = slab + (int)(item >> 3), w = item & 7, sub = it % kSub;
+        const int col = slab + (int)(item >> 4), w = item & 15, sub = it % kSub;
         const float* t = p2 + 3 * ((size_t)b * M + col);
         const float tx = __ldg(t), ty = __ldg(t + 1), tz = __ldg(t + 2);
         u64 best = ~0ull;
 #pragma unroll 1
         for (int rr = sub * kRunsPerSub; rr < (sub + 1) * kRunsPerSub; ++rr) {
-          const int base_row = rr * kTThreads + w * 32;
+          const int base_row = TC ? (w * 128 + rr * 32) : (rr * kTThreads + w * 32);
           float d[32], dm = inf_f();
 #pragma unroll
           for (int kk = 0; kk < 32; ++kk) {
@@ -515,9 +523,11 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
   }
 }
 
-__global__ void chamfer_unpack_key_kernel(const u64* __restrict__ key, float* __restrict__ mn, int* __restrict__ idx, size_t n) {
+__global__ void chamfer_unpack_key_kernel(const u64* __restrict__ key, float* __restrict__ mn, int* __restrict__ idx, size_t n,
+                                          const int* __restrict__ skip, int per_sample) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (skip && skip[i / (size_t)per_sample]) return;
   u64 k = key[i];
   mn[i] = __uint_as_float((unsigned)(k >> 32));
   idx[i] = (int)(unsigned)(k & 0xffffffffu);
@@ -526,10 +536,33 @@ __global__ void chamfer_unpack_key_kernel(const u64* __restrict__ key, float* __
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-struct TiledPlan { int R, ntiles, nchunks, nsplit, cps; };
+struct TiledPlan { int R, ntiles, nchunks, nsplit, cps, tc, TM; };
 
+// chamfer_tc.cu
+size_t chamfer_tc_smem_bytes(int NB);
+int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
+                      float2* tslack, int* fallback, int B, int P, int M, int NB, int ntiles, int nsplit,
+                      int nchunks, int cps, cudaStream_t s);
+int chamfer_flagged_launch(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
+                           const int* fallback, int B, int P, int M, cudaStream_t s);
+
+static void finish_plan(TiledPlan& pl, int B, long long slots, int min_cps) {
+  long long base = (long long)pl.ntiles * B;
+  long long s = (4 * slots + base - 1) / base;
+  long long smin = (pl.nchunks + kMaxChunksPerSplit - 1) / kMaxChunksPerSplit;
+  long long smax = pl.nchunks / min_cps;
+  if (s > smax) s = smax;
+  if (s < smin) s = smin;
+  if (s > pl.nchunks) s = pl.nchunks;
+  if (s < 1) s = 1;
+  pl.cps = (int)((pl.nchunks + s - 1) / s);
+  pl.nsplit = (pl.nchunks + pl.cps - 1) / pl.cps;
+}
+
+// CUDA-core kernel: tile = 256 R rows (R rows per thread)
 static bool make_plan(int B, int P, int M, int sm_count, TiledPlan& pl) {
   if (P < 1024 || M < kCW || B < 1) return false;
+  pl.tc = 0;
   pl.nchunks = (M + kCW - 1) / kCW;
   const int rs[3] = {16, 8, 4};
   int pick = 4;
@@ -542,17 +575,31 @@ static bool make_plan(int B, int P, int M, int sm_count, TiledPlan& pl) {
   }
   if (const char* e = getenv("VPN_TILED_R")) { int r = atoi(e); if (r == 4 || r == 8 || r == 16) pick = r; }   // tuning override
   pl.R = pick;
-  int tm = kTThreads * pl.R;
-  pl.ntiles = (P + tm - 1) / tm;
-  long long base = (long long)pl.ntiles * B;
-  long long slots = (long long)sm_count * (pl.R <= 8 ? 2 : 1);
-  long long s = (4 * slots + base - 1) / base;
-  long long smin = (pl.nchunks + kMaxChunksPerSplit - 1) / kMaxChunksPerSplit;
-  if (s < smin) s = smin;
-  if (s > pl.nchunks) s = pl.nchunks;
-  if (s < 1) s = 1;
-  pl.cps = (int)((pl.nchunks + s - 1) / s);
-  pl.nsplit = (pl.nchunks + pl.cps - 1) / pl.cps;
+  pl.TM = kTThreads * pl.R;
+  pl.ntiles = (P + pl.TM - 1) / pl.TM;
+  finish_plan(pl, B, (long long)sm_count * (pl.R <= 8 ? 2 : 1), 1);
+  return pl.nsplit <= 65535;
+}
+
+// tensor-core kernel: tile = 128 NB rows (NB row blocks), one CTA per SM; R holds NB
+static bool make_plan_tc(int B, int P, int M, int sm_count, TiledPlan& pl) {
+  if (P < 512 || M < kCW || B < 1) return false;
+  pl.tc = 1;
+  pl.nchunks = (M + kCW - 1) / kCW;
+  const int nbs[3] = {16, 8, 4};
+  int pick = 4;
+  for (int k = 0; k < 3; ++k) {
+    int nb = nbs[k], tm = 128 * nb;
+    long long nt = (P + tm - 1) / tm;
+    double waste = (double)(nt * tm) / P;
+    if (waste <= 1.26 && nt * B * pl.nchunks >= 2LL * sm_count * 8) { pick = nb; break; }
+  }
+  if (const char* e = getenv("VPN_TC_NB")) { int r = atoi(e); if (r == 4 || r == 8 || r == 16) pick = r; }      // tuning override
+  pl.R = pick;
+  pl.TM = 128 * pl.R;
+  pl.ntiles = (P + pl.TM - 1) / pl.TM;
+  // every CTA first builds its row operands: keep >= 4 column chunks per CTA so that this is amortised
+  finish_plan(pl, B, sm_count, 4);
   return pl.nsplit <= 65535;
 }
 
@@ -575,14 +622,21 @@ static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
 
 static const int kPlanSms = 148;   // B200; a fixed value keeps workspace queries and launches consistent
 
-int chamfer_tiled_supported(int B, int P, int M) {
-  TiledPlan pl;
-  return make_plan(B, P, M, kPlanSms, pl) ? 1 : 0;
+// mode: -1 auto, MODE_*.  Auto prefers the tensor-core filter.
+static bool plan_for(int mode, int B, int P, int M, TiledPlan& pl) {
+  if (mode == MODE_TC) return make_plan_tc(B, P, M, kPlanSms, pl);
+  if (mode >= 0) return make_plan(B, P, M, kPlanSms, pl);
+  return make_plan_tc(B, P, M, kPlanSms, pl) || make_plan(B, P, M, kPlanSms, pl);
 }
 
-size_t chamfer_tiled_workspace_bytes(int B, int P, int M) {
+int chamfer_tiled_supported(int B, int P, int M, int mode) {
   TiledPlan pl;
-  if (!make_plan(B, P, M, kPlanSms, pl)) return 0;
+  return plan_for(mode, B, P, M, pl) ? 1 : 0;
+}
+
+size_t chamfer_tiled_workspace_bytes(int B, int P, int M, int mode) {
+  TiledPlan pl;
+  if (!plan_for(mode, B, P, M, pl)) return 0;
   return ws_layout(B, P, M, pl).total;
 }
 
@@ -624,27 +678,55 @@ static int launch_any(int mode, const float* p1, const float* p2, char* ws, cons
   }
 }
 
-// mode: -1 auto, 0 exact, 1 diff, 2 expand.  events (optional, 5 entries) bracket the stages for profiling.
+template <int R, bool TC>
+static int launch_recover_cols(const float* p1, const float* p2, const float* cb, const unsigned* cmk, const float* cthr,
+                               u64* key2, int B, int P, int M, int ntiles, const int* skip, cudaStream_t s) {
+  static bool attr = false;
+  const size_t smem = (size_t)(TC ? 128 * R : kTThreads * R) * sizeof(float4);
+  if (!attr) {
+    if (cudaFuncSetAttribute(chamfer_recover_cols_kernel<R, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      vpn_set_error("chamfer tiled: smem attribute (cols recovery)"); return VPN_ERR_CUDA;
+    }
+    attr = true;
+  }
+  chamfer_recover_cols_kernel<R, TC><<<dim3(ntiles, B), kRecThreads, smem, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, ntiles, skip);
+  return vpn_check_launch("chamfer_recover_cols_kernel");
+}
+
+// mode: -1 auto, 0 exact, 1 diff, 2 expand, 3 tensor-core filter.  events (optional, 5 entries) bracket the stages.
 int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                       int B, int P, int M, void* ws_, size_t ws_bytes, int mode, cudaStream_t s, cudaEvent_t* ev) {
   TiledPlan pl;
-  if (!make_plan(B, P, M, kPlanSms, pl)) { vpn_set_error("chamfer tiled: unsupported shape"); return VPN_ERR_SHAPE; }
+  if (!plan_for(mode, B, P, M, pl)) { vpn_set_error("chamfer tiled: unsupported shape"); return VPN_ERR_SHAPE; }
+  if (mode < 0) mode = pl.tc ? MODE_TC : MODE_EXPAND;
   TiledWs wl = ws_layout(B, P, M, pl);
   if (ws_bytes < wl.total) { vpn_set_error("chamfer tiled: workspace too small (%zu < %zu)", ws_bytes, wl.total); return VPN_ERR_WORKSPACE; }
-  if (mode < 0) mode = MODE_EXPAND;
   char* ws = reinterpret_cast<char*>(ws_);
+  int* fallback = reinterpret_cast<int*>(ws + wl.fallback);
+  const int* skip = nullptr;
   int rc;
   if (ev) cudaEventRecord(ev[0], s);
-  if (mode == MODE_EXPAND) {
-    if (cudaMemsetAsync(ws + wl.fallback, 0, (size_t)B * 4, s) != cudaSuccess) { vpn_set_error("chamfer tiled: memset failed"); return VPN_ERR_CUDA; }
+  if (mode == MODE_EXPAND || mode == MODE_TC) {
+    if (cudaMemsetAsync(fallback, 0, (size_t)B * 4, s) != cudaSuccess) { vpn_set_error("chamfer tiled: memset failed"); return VPN_ERR_CUDA; }
   }
-  if ((rc = launch_any(mode, p1, p2, ws, wl, pl, B, P, M, 0, s))) return rc;
-  if (ev) cudaEventRecord(ev[1], s);
-  if (mode == MODE_EXPAND) {
-    if ((rc = launch_any(MODE_DIFF, p1, p2, ws, wl, pl, B, P, M, 1, s))) return rc;
+  if (mode == MODE_TC) {
+    rc = chamfer_tc_launch(p1, p2, reinterpret_cast<float*>(ws + wl.rbest), reinterpret_cast<u64*>(ws + wl.rmask),
+                           reinterpret_cast<float*>(ws + wl.cbest), reinterpret_cast<unsigned*>(ws + wl.cmask),
+                           reinterpret_cast<float2*>(ws + wl.tslack), fallback, B, P, M, pl.R, pl.ntiles, pl.nsplit,
+                           pl.nchunks, pl.cps, s);
+    if (rc) return rc;
+    if (ev) cudaEventRecord(ev[1], s);
+    // samples outside the filter's validity range (non-finite / huge coordinates): exact brute force, recovery skips them
+    if ((rc = chamfer_flagged_launch(p1, p2, min1, idx1, min2, idx2, fallback, B, P, M, s))) return rc;
+    skip = fallback;
+  } else {
+    if ((rc = launch_any(mode, p1, p2, ws, wl, pl, B, P, M, 0, s))) return rc;
+    if (ev) cudaEventRecord(ev[1], s);
+    if (mode == MODE_EXPAND) {
+      if ((rc = launch_any(MODE_DIFF, p1, p2, ws, wl, pl, B, P, M, 1, s))) return rc;
+    }
   }
   if (ev) cudaEventRecord(ev[2], s);
-  const int TM = kTThreads * pl.R;
   {
     static bool attr_rows = false;
     const size_t smem_rows = (size_t)(pl.nchunks < kSegChunks ? pl.nchunks : kSegChunks) * kCW * sizeof(float4);
@@ -657,7 +739,7 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
     }
     chamfer_recover_rows_kernel<<<dim3((P + kRecThreads - 1) / kRecThreads, B), kRecThreads, smem_rows, s>>>(
         p1, p2, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
-        reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nchunks, pl.nsplit, pl.cps, TM, pl.ntiles);
+        reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nchunks, pl.nsplit, pl.cps, pl.TM, pl.ntiles, skip);
     if ((rc = vpn_check_launch("chamfer_recover_rows_kernel"))) return rc;
   }
   if (ev) cudaEventRecord(ev[3], s);
@@ -669,30 +751,23 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   if (cudaMemsetAsync(key2, 0xFF, (size_t)B * M * 8, s) != cudaSuccess) { vpn_set_error("chamfer tiled: memset failed"); return VPN_ERR_CUDA; }
   chamfer_col_thr_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(cb, tsl, cthr, M, pl.ntiles);
   if ((rc = vpn_check_launch("chamfer_col_thr_kernel"))) return rc;
-  {
-    static bool attr_cols[3] = {false, false, false};
-    const int ai = pl.R == 16 ? 0 : (pl.R == 8 ? 1 : 2);
-    const size_t smem_cols = (size_t)TM * sizeof(float4);
-    dim3 cg(pl.ntiles, B);
-    cudaError_t e = cudaSuccess;
+  if (pl.tc) {
     switch (pl.R) {
-      case 16:
-        if (!attr_cols[ai]) e = cudaFuncSetAttribute(chamfer_recover_cols_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols);
-        chamfer_recover_cols_kernel<16><<<cg, kRecThreads, smem_cols, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, pl.ntiles); break;
-      case 8:
-        if (!attr_cols[ai]) e = cudaFuncSetAttribute(chamfer_recover_cols_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols);
-        chamfer_recover_cols_kernel<8><<<cg, kRecThreads, smem_cols, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, pl.ntiles); break;
-      default:
-        if (!attr_cols[ai]) e = cudaFuncSetAttribute(chamfer_recover_cols_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols);
-        chamfer_recover_cols_kernel<4><<<cg, kRecThreads, smem_cols, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, pl.ntiles); break;
+      case 16: rc = launch_recover_cols<16, true>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
+      case 8:  rc = launch_recover_cols<8, true>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
+      default: rc = launch_recover_cols<4, true>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
     }
-    if (e != cudaSuccess) { vpn_set_error("chamfer tiled: smem attribute (cols recovery)"); return VPN_ERR_CUDA; }
-    attr_cols[ai] = true;
+  } else {
+    switch (pl.R) {
+      case 16: rc = launch_recover_cols<16, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
+      case 8:  rc = launch_recover_cols<8, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
+      default: rc = launch_recover_cols<4, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
+    }
   }
-  if ((rc = vpn_check_launch("chamfer_recover_cols_kernel"))) return rc;
+  if (rc) return rc;
   {
     size_t n = (size_t)B * M;
-    chamfer_unpack_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(key2, min2, idx2, n);
+    chamfer_unpack_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(key2, min2, idx2, n, skip, M);
   }
   rc = vpn_check_launch("chamfer_unpack_key_kernel");
   if (ev) cudaEventRecord(ev[4], s);

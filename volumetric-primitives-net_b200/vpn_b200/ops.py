@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import VpnError, check, ptr, require, stream_ptr
 
 KIND_SPHERE, KIND_CUBOID, KIND_TEMPLATE, KIND_POINTS = 0, 1, 2, 3
-CHAMFER_AUTO, CHAMFER_GENERIC, CHAMFER_TILED_EXACT, CHAMFER_TILED_FMA, CHAMFER_TILED_EXPAND = 0, 1, 2, 3, 4
+CHAMFER_AUTO, CHAMFER_GENERIC, CHAMFER_TILED_EXACT, CHAMFER_TILED_FMA, CHAMFER_TILED_EXPAND, CHAMFER_TILED_TC = 0, 1, 2, 3, 4, 5
 
 f32 = torch.float32
 
