@@ -1,6 +1,6 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, smoke, bench lines, then the two ncu captures (launch list + full set of the
-# dominant kernel).  Usage: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh TAG'
+# One GPU-box pass: parity tests, smoke, bench lines, then the ncu captures (launch list + full set of the
+# dominant kernels).  Usage: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh TAG'
 TAG=${1:-r01x}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/smi_$TAG.txt 2>&1
@@ -13,8 +13,11 @@ python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain_$TAG.l
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "ncu launches rc=$?"
-python tools/ncu_chamfer.py 4 32 > gpurun_out/plain_ncu_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:chamfer_tiled_kernel<.int.16, .int.2>' -s 1 -c 1 -f -o gpurun_out/prof_tiled_$TAG \
-    python tools/ncu_chamfer.py 4 32 > gpurun_out/ncu_full_$TAG.log 2>&1
-echo "ncu full rc=$?"
+python tools/ncu_chamfer.py 0 32 > gpurun_out/plain_ncu_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:chamfer_tc_kernel|chamfer_recover' -s 3 -c 3 -f -o gpurun_out/prof_chamfer_$TAG \
+    python tools/ncu_chamfer.py 0 32 > gpurun_out/ncu_full_$TAG.log 2>&1
+echo "ncu full chamfer rc=$?"
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:pose_fwd_kernel|pose_bwd_partial|sil_raster|chamfer_bwd|chamfer_loss_bwd' -s 12 -c 8 -f -o gpurun_out/prof_step_$TAG \
+    python bench.py --workload c3 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_step_$TAG.log 2>&1
+echo "ncu full step rc=$?"
 tail -c 600 gpurun_out/pytest_$TAG.log

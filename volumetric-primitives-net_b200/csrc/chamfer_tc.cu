@@ -5,28 +5,32 @@
 // the smallest hot value and a bit mask of the places that can still hold the arg-min; the exact recovery
 // kernels then redo only those places with the reference's own arithmetic, so min and arg-min stay bit-exact.
 //
-// What moves to the tensor core: the distance itself.  With coordinates centred on the row tile's centroid,
-//     |p - t|^2 = |p|^2 + |t|^2 - 2 p.t = R_i . C_j,     a 16-term dot product of
-//     R_i = [ahx ahx alx  ahy ahy aly  ahz ahz alz  sh sl 1 1  alx aly alz]      a = -2p = ah + al (tf32 split),
-//     C_j = [thx tlx thx  thy tly thy  thz tlz thz  1  1  ch cl tlx tly tlz]     s = |p|^2 = sh + sl, c = |t|^2 = ch + cl
-// (every product of two tf32 numbers is exact in the fp32 accumulator; the split keeps 22 bits per operand).
-// A block is 128 rows x 128 columns: tcgen05.mma kind::tf32 M=128 N=128 K=8, two K steps, issued twice -
-// D1 = R C^T (TMEM lane = row) and D2 = C R^T (TMEM lane = column) - so that BOTH minima are per-thread
-// reductions after a tcgen05.ld.32x32b: no shuffles, no shared-memory exchange.  Per pair the CUDA cores
-// spend one TMEM read + one FMNMX per direction (measured 375 clk per block per SM for the epilogue,
-// tools/tc_probe.cu) instead of 4 packed FMA-pipe ops + 2 FMNMX in the CUDA-core kernel.
+// What moves to the tensor core: the distance itself.  With coordinates centred on the row tile's centroid and
+// scaled by a power of two S (so that every magnitude fits fp16: S * max(|p|, |t|) < 128),
+//     S^2 |p - t|^2 = |P|^2 + |T|^2 - 2 P.T = R_i . C_j,     a 16-term dot product of fp16 numbers
+//     R_i = [ahx ahx alx alx  ahy ahy aly aly  ahz ahz alz alz  sh sl 1  1 ]      a = -2P = ah + al (fp16 split),
+//     C_j = [thx tlx thx tlx  thy tly thy tly  thz tlz thz tlz  1  1  ch cl]      s = |P|^2 = sh + sl, c = |T|^2 = ch + cl
+// (every product of two fp16 numbers is exact in the fp32 accumulator; the split keeps 22 bits per operand).
+// One tcgen05.mma kind::f16 M=128 N=256 K=16 fills one 128 x 256 accumulator ("stage"); it is issued in both
+// orientations - D1 = R C^T (TMEM lane = row) and D2 = C R^T (TMEM lane = column) - so that BOTH minima are
+// per-thread reductions after a tcgen05.ld.32x32b: no shuffles, no shared-memory exchange.  Per pair the CUDA
+// cores spend one TMEM read + half an FMNMX3 per direction instead of 4 packed FMA-pipe ops + 2 FMNMX in the
+// CUDA-core kernel.  (A tf32 version with K = 8 x 2 was measured first: each K step re-reads and re-writes the
+// whole accumulator, 373 clk per stage on the tensor side alone; kind::f16 needs one K step.)
 //
-// Error of the hot value against the reference's d: the omitted split terms are <= 2 * 2^-22 |a||t| per
-// coordinate, s and c carry <= 3u each, the accumulator adds <= 16 roundings; measured over random tiles
-// 2^-21.9 (|p|+|t|)^2 (tools/tc_probe.cu test 4); the filter assumes E = 2^-19 (|p|+|t|)^2, which by the
-// argument in DESIGN.md section 4.1 gives err <= max(16 E rho^2, 4 E d), covered twice by the slack
-// 1e-4 rho^2 + 2^-15 |x|.
+// Error of the hot value against the reference's d (scaled units): the split keeps a and t to 2^-22 relative,
+// s and c carry <= 3u each, the accumulator adds <= 16 roundings: <= 2^-19.4 (|P|+|T|)^2; fp16 subnormal low
+// parts add <= 2^-21 (|P|+|T|), which is below 2^-19 (|P|+|T|)^2 once |P|+|T| >= 1/4 and below 2^-23 otherwise.
+// With E = 2^-19 (|P|+|T|)^2 the argument in DESIGN.md section 4.1 gives err <= max(16 E rho^2, 4 E d) for each of
+// the two values compared, i.e. a threshold of 32 E rho^2 + 8 E |x|; the kernel uses four times that,
+// 2.5e-4 rho^2 + 2^-20 + 2^-14 |x| (scaled units).  Measured error over random tiles (tools/tc_err.cu): 2^-19.85
+// relative, 2^-23.7 absolute for |P|+|T| < 1/4.
 //
-// CTA = 10 warps over one tile of NB x 128 rows, swept twice (D1 blocks, then D2 blocks): warps 0-7 read the
-// accumulators (lane quarter q = warp % 4, every second block) and keep the per-row candidate records in shared
-// memory / emit the per-column records, warp 8 builds the C_j operands of the next column chunk, warp 9 (one
-// elected lane) issues the MMAs.  TMEM holds a ring of four 128-column accumulators; accumulators and column
-// buffers are handed over with mbarriers (tcgen05.commit on the MMA side).
+// CTA = 10 warps over one tile of NB x 128 rows, swept twice (D1 stages, then D2 stages): warps 0-7 read the
+// accumulators and keep the per-row candidate records in shared memory / emit the per-column records, warp 8
+// builds the C_j operands of the next 256 columns, warp 9 (one elected lane) issues the MMAs.  TMEM holds two
+// stages; accumulators and column buffers are handed over with mbarriers (tcgen05.commit on the MMA side).
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace vpn {
@@ -34,23 +38,26 @@ namespace vpn {
 constexpr int kTcBlk = 128;                    // rows per block = columns per chunk = MMA M = MMA N
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
-constexpr int kTcBlkBytes = kTcBlk * 64;       // 128 points x 16 tf32
+constexpr int kTcBlkBytes = kTcBlk * 32;       // 128 points x 16 fp16
 constexpr float kTcBig = 1.0e30f;
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float tc_inf() { return __int_as_float(0x7f800000); }
 
-// shared-memory matrix descriptor, K-major, no swizzle: 8-row groups SBO bytes apart, the two 16-byte K halves
-// of one MMA LBO bytes apart (cute::UMMA::SmemDescriptor, version 1)
+// shared-memory matrix descriptor, K-major, no swizzle: 8-row groups SBO = 256 bytes apart, the two 16-byte K
+// halves (8 fp16 each) of a row LBO = 128 bytes apart (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D f32, A/B tf32, both K-major, N=128, M=128
-constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcBlk >> 3) << 17) | ((uint32_t)(kTcBlk >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D f32, A/B f16, both K-major, N=256, M=128
+constexpr uint32_t kTcIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(2 * kTcBlk >> 3) << 17) | ((uint32_t)(kTcBlk >> 4) << 24);
 
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t accumulate) {
+#if defined(VPN_TC_VARIANT) && VPN_TC_VARIANT == 3       // probe: epilogue alone
+  return;
+#endif
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                :: "r"(d_tmem), "l"(a), "l"(b), "r"(kTcIdesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ bool tc_elect() {
@@ -87,74 +94,108 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ float tc_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r); }
 __device__ __forceinline__ float tc_min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float tc_thr(float x, float rel, float abs_) { return __fadd_ru(__fmaf_ru(fabsf(x), rel, x), abs_); }
 
-// one operand row (16 tf32) of point `idx` inside a 128-point tile: 8-row groups of 512 B, four 128-B core
-// matrices (8 rows x 16 B) per group, one per 4 consecutive k
-__device__ __forceinline__ void tc_store_operand(unsigned char* tile, int idx, float4 k0, float4 k1, float4 k2, float4 k3) {
-  unsigned char* base = tile + (idx >> 3) * 512 + (idx & 7) * 16;
-  *reinterpret_cast<float4*>(base) = k0;
-  *reinterpret_cast<float4*>(base + 128) = k1;
-  *reinterpret_cast<float4*>(base + 256) = k2;
-  *reinterpret_cast<float4*>(base + 384) = k3;
+// x = hi + lo with hi, lo fp16 (lo may be subnormal); returned packed as (first, second) halves of a 32-bit word
+__device__ __forceinline__ void tc_split(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
 }
-// x, y, z centred.  Row operand R_i (is_row) or column operand C_j; returns |.|^2
+__device__ __forceinline__ uint32_t tc_pack(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// X, Y, Z centred and scaled.  Writes the row operand R_i (is_row) or column operand C_j of point `idx` of a
+// 128-point tile: 8-row groups of 256 B, two 128-B core matrices (8 rows x 16 B) per group, k 0-7 and k 8-15.
+// Returns |.|^2 (scaled).
 __device__ __forceinline__ float tc_make_operand(unsigned char* tile, int idx, float x, float y, float z, bool is_row) {
   const float n2 = fmaf(z, z, fmaf(y, y, x * x));
-  const float nh = tc_tf32(n2), nl = tc_tf32(n2 - nh);
+  __half nh, nl, xh, xl, yh, yl, zh, zl;
+  tc_split(n2, nh, nl);
   if (is_row) { x *= -2.f; y *= -2.f; z *= -2.f; }
-  const float xh = tc_tf32(x), yh = tc_tf32(y), zh = tc_tf32(z);
-  const float xl = tc_tf32(x - xh), yl = tc_tf32(y - yh), zl = tc_tf32(z - zh);
-  if (is_row)
-    tc_store_operand(tile, idx, make_float4(xh, xh, xl, yh), make_float4(yh, yl, zh, zh), make_float4(zl, nh, nl, 1.f),
-                     make_float4(1.f, xl, yl, zl));
-  else
-    tc_store_operand(tile, idx, make_float4(xh, xl, xh, yh), make_float4(yl, yh, zh, zl), make_float4(zh, 1.f, 1.f, nh),
-                     make_float4(nl, xl, yl, zl));
+  tc_split(x, xh, xl); tc_split(y, yh, yl); tc_split(z, zh, zl);
+  const __half one = __float2half_rn(1.0f);
+  uint4 k0, k1;
+  if (is_row) {
+    k0 = make_uint4(tc_pack(xh, xh), tc_pack(xl, xl), tc_pack(yh, yh), tc_pack(yl, yl));
+    k1 = make_uint4(tc_pack(zh, zh), tc_pack(zl, zl), tc_pack(nh, nl), tc_pack(one, one));
+  } else {
+    k0 = make_uint4(tc_pack(xh, xl), tc_pack(xh, xl), tc_pack(yh, yl), tc_pack(yh, yl));
+    k1 = make_uint4(tc_pack(zh, zl), tc_pack(zh, zl), tc_pack(one, one), tc_pack(nh, nl));
+  }
+  unsigned char* base = tile + (idx >> 3) * 256 + (idx & 7) * 16;
+  *reinterpret_cast<uint4*>(base) = k0;
+  *reinterpret_cast<uint4*>(base + 128) = k1;
   return n2;
 }
 
-#ifdef VPN_TC_PROF
-// cycle accounting of CTA (0,0,0): [0] mma wait colfull [1] mma wait empty [2] mma issue [3] epi(row) wait full
-// [4] epi(row) ld [5] epi(row) min+fold [6] epi(col) wait full [7] epi(col) ld [8] epi(col) min+fold [9] setup [10] total
-__device__ long long g_tc_prof[16];
-#define TC_PROF_DECL long long pt_ = clock64(); const bool pon_ = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0
-#define TC_PROF(slot) do { if (pon_) { long long n_ = clock64(); atomicAdd((unsigned long long*)&g_tc_prof[slot], (unsigned long long)(n_ - pt_)); pt_ = n_; } } while (0)
-#else
-#define TC_PROF_DECL
-#define TC_PROF(slot)
-#endif
-
 // dynamic shared memory carve-up (NB = row blocks per tile)
 struct TcSmem {
-  unsigned char* rows; unsigned char* cols; float* rs_best; float* rs_thr; u64* rs_mask; float* colw;
+  unsigned char* rows; unsigned char* cols; float* rs_best; uint32_t* rs_mask; float* colw;
   u64* bars; float* red; uint32_t* tmem_slot;
 };
 __host__ __device__ inline size_t tc_smem_bytes(int NB) {
-  return (size_t)NB * kTcBlkBytes + 2 * kTcBlkBytes + (size_t)NB * kTcBlk * 16 + 2 * (size_t)NB * kTcBlk * 4 + 16 * 8 + 64 * 4 + 16;
+  return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 8 + 2 * (size_t)NB * kTcBlk * 4 + 16 * 8 + 64 * 4 + 16;
 }
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
   TcSmem s;
   s.rows = p; p += (size_t)NB * kTcBlkBytes;
-  s.cols = p; p += 2 * kTcBlkBytes;
-  s.rs_mask = reinterpret_cast<u64*>(p); p += (size_t)NB * kTcBlk * 8;
-  s.rs_best = reinterpret_cast<float*>(p); p += (size_t)NB * kTcBlk * 4;
-  s.rs_thr = reinterpret_cast<float*>(p); p += (size_t)NB * kTcBlk * 4;
-  s.colw = reinterpret_cast<float*>(p); p += 2 * (size_t)NB * kTcBlk * 4;
+  s.cols = p; p += 4 * kTcBlkBytes;                                   // two buffers of 256 columns
+  s.rs_best = reinterpret_cast<float*>(p); p += 2 * (size_t)NB * kTcBlk * 4;      // [column half][row]
+  s.rs_mask = reinterpret_cast<uint32_t*>(p); p += 2 * (size_t)NB * kTcBlk * 4;
+  s.colw = reinterpret_cast<float*>(p); p += 2 * (size_t)NB * kTcBlk * 4;         // [chunk parity][row block][column]
   s.bars = reinterpret_cast<u64*>(p); p += 16 * 8;
   s.red = reinterpret_cast<float*>(p); p += 64 * 4;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p);
   return s;
 }
 
+// Minimum of this thread's TMEM lane over 128 accumulator columns starting at taddr.  The loads of the second
+// half are in flight while the first half is reduced; the stage is handed back to the MMA warp (mbarrier
+// `empty_bar`) as soon as all 128 values are in registers.  (Carrying a prefetched first half of the next stage
+// across loop iterations, and 16 warps x 64 columns, both measured slower: 765 and 631 clk per stage against 580.)
+__device__ __forceinline__ float tc_lane_min128(uint32_t taddr, uint32_t empty_bar, int lane) {
+  float v0[32], v1[32], v2[32], v3[32];
+  tc_ld32(taddr, v0); tc_ld32(taddr + 32, v1);
+  tc_wait_ld();
+  tc_ld32(taddr + 64, v2); tc_ld32(taddr + 96, v3);
+  float m0 = tc_inf(), m1 = tc_inf();
+#if !defined(VPN_TC_VARIANT) || VPN_TC_VARIANT != 1      // probe 1: TMEM reads, no reduction
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) { m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]); }
+#endif
+  tc_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) tc_mbar_arrive(empty_bar);
+#if !defined(VPN_TC_VARIANT) || VPN_TC_VARIANT != 1
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) { m0 = tc_min3(m0, v2[k], v2[k + 1]); m1 = tc_min3(m1, v3[k], v3[k + 1]); }
+#else
+  m0 = v0[1] + v1[2]; m1 = v2[3] + v3[7];
+#endif
+  return fminf(m0, m1);
+}
+
 // grid: x = row tile (NB * 128 rows), y = column split, z = sample
+//
+// Work unit ("stage") = one 128-lane x 256-column accumulator: tcgen05.mma kind::f16 M=128 N=256 K=16, one commit.
+// TMEM (512 columns) holds two stages.  The column chunks of the split are taken in pairs (j, hc + j), hc = half
+// the chunks of the split: the 256-column operand buffer holds chunk j in its first half and chunk hc + j in its
+// second.
+//   phase 0 (row minima)   : stage (j, r) = R_r (128 rows) x [C_j C_{hc+j}]^T; TMEM lane = row, the thread of column
+//                            half h reduces the 128 values of chunk (h ? hc + j : j);
+//   phase 1 (column minima): stage (chunk, rp) = C_chunk (128 columns) x [R_2rp R_2rp+1]^T; TMEM lane = column, the
+//                            thread of half h reduces over the 128 rows of block 2 rp + h.
+// Roles: warps 0-7 epilogue (warp = 4 h + q: TMEM lane quarter q, column half h), warp 8 builds the column operands,
+// warp 9 issues the MMAs (one elected lane).
+// Measured (tools/tc_var.cu, clk per stage per SM): tensor side alone 324, epilogue alone 558 (TMEM reads 136 and
+// 128 FMNMX3 = 256 do not overlap: they share the register-file write port), together 580.
 __global__ void __launch_bounds__(kTcThreads, 1)
 chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                   float* __restrict__ rbest, u64* __restrict__ rmask,
                   float* __restrict__ cbest, unsigned* __restrict__ cmask,
-                  float2* __restrict__ tslack, int* __restrict__ fallback,
+                  float2* __restrict__ tslack, int* __restrict__ fallback, const float* __restrict__ tmax,
                   int P, int M, int NB, int nchunks, int cps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const TcSmem sm = tc_carve(smem_raw, NB);
@@ -162,21 +203,20 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   const int tile_i = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
   const int ntiles = gridDim.x, nsplit = gridDim.y;
   const int TM = NB * kTcBlk;
-  TC_PROF_DECL;
-#ifdef VPN_TC_PROF
-  const long long pstart_ = pt_;
-#endif
   const float* A = p1 + (size_t)b * P * 3;
   const float* T = p2 + (size_t)b * M * 3;
   const int c_first = split * cps;
   const int c_last = min(nchunks, c_first + cps);
-  // barriers (8 bytes each): +0..+24 accumulator stage full, +32..+56 stage empty, +64/+72 column buffer full,
-  // +80/+88 column buffer empty
+  // barriers (8 bytes each): +0/+8 stage full, +16/+24 stage empty, +32/+40 column buffer full, +48/+56 column buffer empty
   const uint32_t bar0 = tc_smem_u32(sm.bars);
+  const uint32_t bar_full = bar0, bar_empty = bar0 + 16, bar_cfull = bar0 + 32, bar_cempty = bar0 + 48;
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) tc_mbar_init(bar0 + 8 * i, 1);
-    for (int i = 4; i < 8; ++i) tc_mbar_init(bar0 + 8 * i, 4);          // the four warps (one per TMEM lane quarter) that read the stage
-    for (int i = 8; i < 12; ++i) tc_mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc_mbar_init(bar_full + 8 * i, 1);
+      tc_mbar_init(bar_empty + 8 * i, kTcEpiWarps);                    // every epilogue warp reads every stage
+      tc_mbar_init(bar_cfull + 8 * i, 1);
+      tc_mbar_init(bar_cempty + 8 * i, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -184,11 +224,20 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
-  // ---- tile centroid and radius (any centre is valid; the centroid keeps the radius, hence the slack, small)
+  // ---- tile centroid, radius and scale (any centre is valid; the centroid keeps the radius, hence the slack, small).
+  // Each thread keeps its rows (<= 7 of the 2048) in registers across the three steps.
+  constexpr int kRowsPerThread = (16 * kTcBlk + kTcThreads - 1) / kTcThreads;      // 7
+  float rx[kRowsPerThread], ry[kRowsPerThread], rz[kRowsPerThread];
   float sx = 0.f, sy = 0.f, sz = 0.f;
-  for (int i = tid; i < TM; i += kTcThreads) {
-    const int row = min(tile_i * TM + i, P - 1);
-    sx += A[3 * (size_t)row]; sy += A[3 * (size_t)row + 1]; sz += A[3 * (size_t)row + 2];
+#pragma unroll
+  for (int k = 0; k < kRowsPerThread; ++k) {
+    const int i = tid + k * kTcThreads;
+    rx[k] = ry[k] = rz[k] = 0.f;
+    if (i < TM) {
+      const int row = min(tile_i * TM + i, P - 1);
+      rx[k] = A[3 * (size_t)row]; ry[k] = A[3 * (size_t)row + 1]; rz[k] = A[3 * (size_t)row + 2];
+      sx += rx[k]; sy += ry[k]; sz += rz[k];
+    }
   }
   sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
   if (lane == 0) { sm.red[warp * 4] = sx; sm.red[warp * 4 + 1] = sy; sm.red[warp * 4 + 2] = sz; }
@@ -201,171 +250,185 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   __syncthreads();
   const float cx = sm.red[48], cy = sm.red[49], cz = sm.red[50];
   float rho2 = 0.f;
-  for (int i = tid; i < TM; i += kTcThreads) {
-    const int row = min(tile_i * TM + i, P - 1);
-    const float x = __fsub_rn(A[3 * (size_t)row], cx), y = __fsub_rn(A[3 * (size_t)row + 1], cy), z = __fsub_rn(A[3 * (size_t)row + 2], cz);
-    const float n2 = tc_make_operand(sm.rows + (size_t)(i >> 7) * kTcBlkBytes, i & 127, x, y, z, true);
-    rho2 = fmaxf(rho2, n2);
-    if (!(n2 < kTcBig)) rho2 = tc_inf();
-    sm.rs_best[i] = tc_inf(); sm.rs_thr[i] = tc_inf(); sm.rs_mask[i] = 0ull;
+#pragma unroll
+  for (int k = 0; k < kRowsPerThread; ++k) {
+    if (tid + k * kTcThreads < TM) {
+      rx[k] = __fsub_rn(rx[k], cx); ry[k] = __fsub_rn(ry[k], cy); rz[k] = __fsub_rn(rz[k], cz);
+      const float n2 = fmaf(rz[k], rz[k], fmaf(ry[k], ry[k], rx[k] * rx[k]));
+      rho2 = (n2 < kTcBig) ? fmaxf(rho2, n2) : tc_inf();
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) rho2 = fmaxf(rho2, __shfl_xor_sync(0xffffffffu, rho2, o));
   if (lane == 0) sm.red[warp * 4 + 3] = rho2;
+  __syncthreads();
+  rho2 = sm.red[3];
+  for (int w = 1; w < kTcThreads / 32; ++w) rho2 = fmaxf(rho2, sm.red[w * 4 + 3]);
+  // scale: |P|, |T| < 128 in scaled units.  |t - c| <= sqrt(3) (max|t_k| + max|c_k|) for every target of the sample.
+  float reach = fmaxf(sqrtf(rho2), 1.7320509f * (tmax[b] + fmaxf(fabsf(cx), fmaxf(fabsf(cy), fabsf(cz))))) * 1.001f;
+  if (!(reach < 1.0e15f)) { if (tid == 0) atomicOr(&fallback[b], 1); reach = 1.f; rho2 = 0.f; }
+  int ex = 0;
+  frexpf(reach, &ex);                                               // reach < 2^ex
+  ex = max(-40, min(50, ex));
+  const float S = scalbnf(1.f, 7 - ex), invS2 = scalbnf(1.f, 2 * ex - 14);
+#pragma unroll
+  for (int k = 0; k < kRowsPerThread; ++k) {
+    const int i = tid + k * kTcThreads;
+    if (i < TM) {
+      tc_make_operand(sm.rows + (size_t)(i >> 7) * kTcBlkBytes, i & 127, rx[k] * S, ry[k] * S, rz[k] * S, true);
+      sm.rs_best[i] = tc_inf(); sm.rs_best[TM + i] = tc_inf();
+      sm.rs_mask[i] = 0u; sm.rs_mask[TM + i] = 0u;
+    }
+  }
   tc_fence_async_smem();                      // operand rows were written with generic stores; the MMA reads them through the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  rho2 = sm.red[3];
-  for (int w = 1; w < kTcThreads / 32; ++w) rho2 = fmaxf(rho2, sm.red[w * 4 + 3]);
-  if (!(rho2 < kTcBig)) { if (tid == 0) atomicOr(&fallback[b], 1); rho2 = 0.f; }
-  const float slack_rel = 3.0517578125e-05f;                      // 2^-15
-  const float slack_abs = __fmaf_ru(1.0e-4f, rho2, 1e-36f);
-  if (tid == 0 && split == 0) tslack[(size_t)b * ntiles + tile_i] = make_float2(slack_rel, slack_abs);
+  // all hot values and thresholds below are in scaled units (x S^2); records are stored unscaled
+  // the true arg-min and the best hot value each err by <= max(16 E rho^2, 4 E d): the threshold needs 32 E rho^2 + 8 E |x|
+  // = 6.1e-5 rho^2 + 2^-16 |x| at E = 2^-19; both are taken 4 x larger (measured E over random tiles: 2^-19.85)
+  const float slack_rel = 6.103515625e-05f;                       // 2^-14
+  const float slack_abs = __fmaf_ru(2.5e-4f, rho2 * (S * S), 9.5367431640625e-07f);      // + 2^-20: fp16 subnormal low parts
+  if (tid == 0 && split == 0) tslack[(size_t)b * ntiles + tile_i] = make_float2(slack_rel, slack_abs * invS2);
   const uint32_t tbase = *sm.tmem_slot;
-  if (warp == 0) TC_PROF(9);
 
-  // The tile is swept twice: phase 0 accumulates D1 = R C^T blocks (TMEM lane = row -> row minima), phase 1
-  // D2 = C R^T blocks (TMEM lane = column -> column minima).  One direction at a time leaves all four 128-column
-  // accumulators of TMEM to one ring, deep enough to cover the MMA round trip.
-  const int nc = c_last - c_first;
-  const int per_phase = nc * NB;
+  const int nc = c_last - c_first;             // chunks of this split (<= 64)
+  const int hc = (nc + 1) >> 1;                // chunk pairs (<= 32)
+  const int NP = NB >> 1;                      // row-block pairs
   if (warp == kTcEpiWarps) {
-    // ===== column-operand builder (both phases) =====
-    for (int cc = 0; cc < 2 * nc; ++cc) {
-      const int c = c_first + (cc < nc ? cc : cc - nc);
+    // ===== column-operand builder (one pass per phase) =====
+    for (int cc = 0; cc < 2 * hc; ++cc) {
+      const int j = cc < hc ? cc : cc - hc;
       const int cb = cc & 1, use = cc >> 1;
-      tc_mbar_wait(bar0 + 80 + 8 * cb, (use & 1) ^ 1);
-      unsigned char* dst = sm.cols + cb * kTcBlkBytes;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int j = k * 32 + lane;
-        const int col = min(c * kTcBlk + j, M - 1);
+      tc_mbar_wait(bar_cempty + 8 * cb, (use & 1) ^ 1);
+      unsigned char* dst = sm.cols + cb * 2 * kTcBlkBytes;
+#pragma unroll 2
+      for (int k = 0; k < 8; ++k) {
+        const int jj = k * 32 + lane;                               // 0..255: half = jj >> 7
+        int chunk = c_first + ((jj >> 7) ? hc + j : j);
+        if (chunk >= c_last) chunk = c_first + j;                   // unpaired last chunk: duplicate, never recorded
+        const int col = min(chunk * kTcBlk + (jj & 127), M - 1);
         const float x = __fsub_rn(T[3 * (size_t)col], cx), y = __fsub_rn(T[3 * (size_t)col + 1], cy), z = __fsub_rn(T[3 * (size_t)col + 2], cz);
-        const float n2 = tc_make_operand(dst, j, x, y, z, false);
-        if (!(n2 < kTcBig)) atomicOr(&fallback[b], 1);
+        const float n2 = tc_make_operand(dst + (jj >> 7) * kTcBlkBytes, jj & 127, x * S, y * S, z * S, false);
+        if (!(n2 < 20000.f)) atomicOr(&fallback[b], 1);             // cannot happen for finite targets (|T| < 128)
       }
       tc_fence_async_smem();
       __syncwarp();
-      if (lane == 0) tc_mbar_arrive(bar0 + 64 + 8 * cb);
+      if (lane == 0) tc_mbar_arrive(bar_cfull + 8 * cb);
     }
   } else if (warp == kTcEpiWarps + 1) {
     // ===== MMA issuer: the whole warp walks the loop (warp-uniform operands), one elected lane issues =====
-    {
-      const uint32_t rows_a = tc_smem_u32(sm.rows), cols_a = tc_smem_u32(sm.cols);
-      const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
-      const uint64_t drows = tc_desc(rows_a);
-      uint32_t it = 0;
-      for (int cc = 0; cc < 2 * nc; ++cc) {
-        const int cb = cc & 1, cuse = cc >> 1;
-        const bool phase1 = cc >= nc;
-        tc_mbar_wait(bar0 + 64 + 8 * cb, cuse & 1);
-        tc_fence_after();
-        TC_PROF(0);
-        const uint64_t dc0 = tc_desc(cols_a + cb * kTcBlkBytes), dc1 = dc0 + (256 >> 4);
+    const uint32_t rows_a = tc_smem_u32(sm.rows), cols_a = tc_smem_u32(sm.cols);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    const uint64_t drows = tc_desc(rows_a);
+    uint32_t it = 0;
+    for (int cc = 0; cc < 2 * hc; ++cc) {
+      const int j = cc < hc ? cc : cc - hc;
+      const int cb = cc & 1, cuse = cc >> 1;
+      tc_mbar_wait(bar_cfull + 8 * cb, cuse & 1);
+      tc_fence_after();
+      const uint64_t dcols = tc_desc(cols_a + cb * 2 * kTcBlkBytes);
+      if (cc < hc) {
         for (int r = 0; r < NB; ++r, ++it) {
-          const uint32_t st = it & 3;
-          const uint64_t dr0 = drows + (uint64_t)(r * (kTcBlkBytes >> 4)), dr1 = dr0 + (256 >> 4);
-          tc_mbar_wait(bar0 + 32 + 8 * st, ((it >> 2) & 1) ^ 1);
+          const uint32_t st = it & 1;
+          tc_mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
           tc_fence_after();
-          TC_PROF(1);
-          const uint32_t d = tb + st * 128;
           if (tc_elect()) {
-            if (!phase1) { tc_mma(d, dr0, dc0, 0); tc_mma(d, dr1, dc1, 1); }      // D1[row][col]
-            else         { tc_mma(d, dc0, dr0, 0); tc_mma(d, dc1, dr1, 1); }      // D2[col][row]
-            tc_commit(bar0 + 8 * st);
+            const uint64_t dr = drows + (uint64_t)(r * (kTcBlkBytes >> 4));
+            const uint32_t d = tb + st * 256;
+            tc_mma(d, dr, dcols, 0);                                        // D[row][2 chunks]
+            tc_commit(bar_full + 8 * st);
           }
           __syncwarp();
-          TC_PROF(2);
-        }
-        if (tc_elect()) tc_commit(bar0 + 80 + 8 * cb);               // column buffer free once these MMAs retire
-        __syncwarp();
-      }
-    }
-  } else {
-    // ===== epilogue: 8 warps; warp = 4 g + q reads TMEM lanes [32 q, 32 q + 32) of the blocks with it % 2 == g =====
-    // Each thread owns one TMEM lane and reads its 128 accumulator columns as two halves; the loads of the next
-    // half (or of this warp's next block) are in flight while the current half is reduced.
-    const int q = warp & 3, g = warp >> 2;
-    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-    const int li = q * 32 + lane;                                    // row in block (phase 0) / column in chunk (phase 1)
-    const int total = 2 * per_phase;
-    float v0[32], v1[32];
-    if (g < total) {
-      tc_mbar_wait(bar0 + 8 * g, 0);
-      tc_fence_after();
-      tc_ld32(tlane + g * 128, v0); tc_ld32(tlane + g * 128 + 32, v1);
-    }
-    for (int it = g; it < total; it += 2) {
-      const uint32_t st = it & 3;
-      float v2[32], v3[32];
-      tc_wait_ld();
-      if (q == 0 && g == 0) TC_PROF(3);
-      tc_ld32(tlane + st * 128 + 64, v2); tc_ld32(tlane + st * 128 + 96, v3);
-      float m0 = tc_inf(), m1 = tc_inf();
-#pragma unroll
-      for (int k = 0; k < 32; k += 2) { m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]); }
-      tc_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc_mbar_arrive(bar0 + 32 + 8 * st);             // all 128 columns are in registers: the accumulator can be overwritten
-      if (q == 0 && g == 0) TC_PROF(4);
-      if (it + 2 < total) {
-        const uint32_t nst = (it + 2) & 3;
-        tc_mbar_wait(bar0 + 8 * nst, ((it + 2) >> 2) & 1);
-        tc_fence_after();
-        tc_ld32(tlane + nst * 128, v0); tc_ld32(tlane + nst * 128 + 32, v1);
-      }
-#pragma unroll
-      for (int k = 0; k < 32; k += 2) { m0 = tc_min3(m0, v2[k], v2[k + 1]); m1 = tc_min3(m1, v3[k], v3[k + 1]); }
-      const float m = fminf(m0, m1);
-      const bool phase1 = it >= per_phase;
-      const int itp = phase1 ? it - per_phase : it;
-      const int cl = itp / NB, r = itp - cl * NB;                    // chunk (relative to c_first), row block
-      if (!phase1) {
-        const int ri = r * kTcBlk + li;
-        if (m <= sm.rs_thr[ri]) {
-          const u64 bit = 1ull << cl;
-          const float best = sm.rs_best[ri];
-          const float tm = tc_thr(m, slack_rel, slack_abs);
-          const u64 mask = (tm < best) ? 0ull : sm.rs_mask[ri];
-          sm.rs_mask[ri] = mask | bit;
-          if (m < best) { sm.rs_best[ri] = m; sm.rs_thr[ri] = tm; }
         }
       } else {
-        float* cw = sm.colw + (size_t)(cl & 1) * NB * kTcBlk;
-        cw[r * kTcBlk + li] = m;
-        if (r >= NB - 2) {
-          // the two warps of this lane quarter meet once per chunk; warp g = 1 (it holds r = NB - 1) merges
-          asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
-          if (r == NB - 1) {
-            const int col = (c_first + cl) * kTcBlk + li;
-            if (col < M) {
-              float best = tc_inf();
-              for (int i = 0; i < NB; ++i) best = fminf(best, cw[i * kTcBlk + li]);
-              const float t = tc_thr(best, slack_rel, slack_abs);
-              unsigned mask = 0;
-              for (int i = 0; i < NB; ++i) mask |= (cw[i * kTcBlk + li] <= t) ? (1u << i) : 0u;
-              const size_t o = ((size_t)b * ntiles + tile_i) * M + col;
-              cbest[o] = best; cmask[o] = mask;
+        const int nh = (c_first + hc + j < c_last) ? 2 : 1;
+        for (int h = 0; h < nh; ++h) {
+          const uint64_t dc = dcols + (uint64_t)(h * (kTcBlkBytes >> 4));
+          for (int rp = 0; rp < NP; ++rp, ++it) {
+            const uint32_t st = it & 1;
+            tc_mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            if (tc_elect()) {
+              const uint64_t dr = drows + (uint64_t)(rp * (2 * kTcBlkBytes >> 4));
+              const uint32_t d = tb + st * 256;
+              tc_mma(d, dc, dr, 0);                                         // D[col][2 row blocks]
+              tc_commit(bar_full + 8 * st);
             }
+            __syncwarp();
           }
         }
       }
-      if (q == 0 && g == 0) TC_PROF(5);
+      if (tc_elect()) tc_commit(bar_cempty + 8 * cb);               // column buffer free once these MMAs retire
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: warp = 4 h + q reads TMEM lanes [32 q, 32 q + 32), accumulator columns [128 h, 128 h + 128) =====
+    const int q = warp & 3, h = warp >> 2;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + h * 128;
+    const int li = q * 32 + lane;                                    // row in block (phase 0) / column in chunk (phase 1)
+    uint32_t it = 0;
+    // ---- phase 0: row minima; record (h, row): best value and the mask of chunk pairs j whose chunk may hold the arg-min
+    float* my_best = sm.rs_best + (size_t)h * TM;
+    uint32_t* my_mask = sm.rs_mask + (size_t)h * TM;
+    for (int j = 0; j < hc; ++j) {
+      const bool valid = c_first + (h ? hc + j : j) < c_last;
+      for (int r = 0; r < NB; ++r, ++it) {
+        const uint32_t st = it & 1;
+        tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
+        tc_fence_after();
+        const float m = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
+        const int ri = r * kTcBlk + li;
+        const float best = my_best[ri];
+        if (valid && m <= tc_thr(best, slack_rel, slack_abs)) {
+          const float tm = tc_thr(m, slack_rel, slack_abs);
+          const uint32_t mask = (tm < best) ? 0u : my_mask[ri];
+          my_mask[ri] = mask | (1u << j);
+          if (m < best) my_best[ri] = m;
+        }
+      }
+    }
+    // ---- phase 1: column minima per 128-row block, merged per chunk into (best, mask of row blocks)
+    int cseq = 0;
+    for (int j = 0; j < hc; ++j) {
+      const int nh = (c_first + hc + j < c_last) ? 2 : 1;
+      for (int hh = 0; hh < nh; ++hh, ++cseq) {
+        float* cw = sm.colw + (size_t)(cseq & 1) * NB * kTcBlk;
+        for (int rp = 0; rp < NP; ++rp, ++it) {
+          const uint32_t st = it & 1;
+          tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
+          tc_fence_after();
+          cw[(2 * rp + h) * kTcBlk + li] = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
+        }
+        // the two warps of this lane quarter meet once per chunk; they take turns merging
+        asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
+        if ((cseq & 1) == h) {
+          const int col = (c_first + (hh ? hc + j : j)) * kTcBlk + li;
+          if (col < M) {
+            float best = tc_inf();
+            for (int i = 0; i < NB; ++i) best = fminf(best, cw[i * kTcBlk + li]);
+            const float t = tc_thr(best, slack_rel, slack_abs);
+            unsigned mask = 0;
+            for (int i = 0; i < NB; ++i) mask |= (cw[i * kTcBlk + li] <= t) ? (1u << i) : 0u;
+            const size_t o = ((size_t)b * ntiles + tile_i) * M + col;
+            cbest[o] = best * invS2; cmask[o] = mask;
+          }
+        }
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-#ifdef VPN_TC_PROF
-  if (pon_ && warp == 0) atomicAdd((unsigned long long*)&g_tc_prof[10], (unsigned long long)(clock64() - pstart_));
-#endif
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
   for (int i = tid; i < TM; i += kTcThreads) {
     const int row = tile_i * TM + i;
     if (row < P) {
+      const float b0 = sm.rs_best[i], b1 = sm.rs_best[TM + i];
+      const float best = fminf(b0, b1);
+      const float t = tc_thr(best, slack_rel, slack_abs);
+      const u64 mask = ((b0 <= t) ? (u64)sm.rs_mask[i] : 0ull) | ((b1 <= t) ? ((u64)sm.rs_mask[TM + i] << hc) : 0ull);
       const size_t o = ((size_t)b * nsplit + split) * P + row;
-      rbest[o] = sm.rs_best[i]; rmask[o] = sm.rs_mask[i];
+      rbest[o] = best * invS2; rmask[o] = mask;
     }
   }
 }
@@ -405,11 +468,30 @@ chamfer_flagged_kernel(const float* __restrict__ p1, const float* __restrict__ p
   }
 }
 
-int chamfer_tc_max_blocks() { return 16; }
+// largest |coordinate| of every sample's targets (the tensor-core kernel scales by it).  grid: x = sample
+__global__ void __launch_bounds__(256)
+chamfer_tc_bounds_kernel(const float* __restrict__ p2, float* __restrict__ tmax, int M) {
+  __shared__ float red[8];
+  const float* T = p2 + (size_t)blockIdx.x * M * 3;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < 3 * M; i += 256) {
+    const float v = fabsf(T[i]);
+    m = (v <= m) ? m : v;                                           // NaN sticks
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const float x = __shfl_xor_sync(0xffffffffu, m, o); m = (x <= m) ? m : x; }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = (red[w] <= m) ? m : red[w];
+    tmax[blockIdx.x] = m;
+  }
+}
+
 size_t chamfer_tc_smem_bytes(int NB) { return tc_smem_bytes(NB); }
 
 int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
-                      float2* tslack, int* fallback, int B, int P, int M, int NB, int ntiles, int nsplit,
+                      float2* tslack, int* fallback, float* tmax, int B, int P, int M, int NB, int ntiles, int nsplit,
                       int nchunks, int cps, cudaStream_t s) {
   static int attr_for = 0;
   const size_t smem = tc_smem_bytes(NB);
@@ -418,7 +500,10 @@ int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask
     if (e != cudaSuccess) { vpn_set_error("chamfer tc: smem attribute: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
     attr_for = (int)tc_smem_bytes(16);
   }
-  chamfer_tc_kernel<<<dim3(ntiles, nsplit, B), kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback,
+  chamfer_tc_bounds_kernel<<<B, 256, 0, s>>>(p2, tmax, M);
+  int rc = vpn_check_launch("chamfer_tc_bounds_kernel");
+  if (rc) return rc;
+  chamfer_tc_kernel<<<dim3(ntiles, nsplit, B), kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax,
                                                                       P, M, NB, nchunks, cps);
   return vpn_check_launch("chamfer_tc_kernel");
 }

@@ -541,7 +541,7 @@ struct TiledPlan { int R, ntiles, nchunks, nsplit, cps, tc, TM; };
 // chamfer_tc.cu
 size_t chamfer_tc_smem_bytes(int NB);
 int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
-                      float2* tslack, int* fallback, int B, int P, int M, int NB, int ntiles, int nsplit,
+                      float2* tslack, int* fallback, float* tmax, int B, int P, int M, int NB, int ntiles, int nsplit,
                       int nchunks, int cps, cudaStream_t s);
 int chamfer_flagged_launch(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                            const int* fallback, int B, int P, int M, cudaStream_t s);
@@ -605,7 +605,7 @@ static bool make_plan_tc(int B, int P, int M, int sm_count, TiledPlan& pl) {
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, cthr, key2, total; };
+struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, tmax, cthr, key2, total; };
 static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   TiledWs w; size_t o = 0;
   w.rbest = o; o += al256((size_t)B * pl.nsplit * P * 4);
@@ -614,6 +614,7 @@ static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   w.cmask = o; o += al256((size_t)B * pl.ntiles * M * 4);
   w.tslack = o; o += al256((size_t)B * pl.ntiles * 8);
   w.fallback = o; o += al256((size_t)B * 4);
+  w.tmax = o; o += al256((size_t)B * 4);
   w.cthr = o; o += al256((size_t)B * M * 4);
   w.key2 = o; o += al256((size_t)B * M * 8);
   w.total = o;
@@ -712,7 +713,7 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   if (mode == MODE_TC) {
     rc = chamfer_tc_launch(p1, p2, reinterpret_cast<float*>(ws + wl.rbest), reinterpret_cast<u64*>(ws + wl.rmask),
                            reinterpret_cast<float*>(ws + wl.cbest), reinterpret_cast<unsigned*>(ws + wl.cmask),
-                           reinterpret_cast<float2*>(ws + wl.tslack), fallback, B, P, M, pl.R, pl.ntiles, pl.nsplit,
+                           reinterpret_cast<float2*>(ws + wl.tslack), fallback, reinterpret_cast<float*>(ws + wl.tmax), B, P, M, pl.R, pl.ntiles, pl.nsplit,
                            pl.nchunks, pl.cps, s);
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[1], s);
