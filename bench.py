@@ -102,24 +102,28 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def cpu_reference_step(workload, rows_per_sample, threads):
+def cpu_reference_step(workload, rows_per_sample, threads, rows_per_slice=8192):
     """The reference's own formulation on the host (oracle port, op for op: dense (B,P,M,3) broadcast,
-    modules/loss/chamfer_distance.py:14-23), fwd + bwd to (v,q,t), on a bounded slice of the workload:
-    one sample, `rows_per_sample` of its K*N predicted points (whole primitives)."""
+    modules/loss/chamfer_distance.py:14-23), fwd + bwd to (v,q,t), on a bounded sample of the workload:
+    one sample, `rows_per_sample` of its K*N predicted points, taken as slices of whole primitives (the dense
+    temporaries of one slice are ~1 GB each; a whole C2 sample at once needs 15 GB)."""
     from oracle import vpn_oracle as O
     kind, b, k, n, m, res = WORKLOADS[workload]
-    kk = max(1, rows_per_sample // n)
+    per = max(1, rows_per_slice // n)                    # primitives per slice
+    kk = min(k, max(per, (rows_per_sample // n) // per * per))
     torch.set_num_threads(threads)
     data = synthetic(workload, "cpu")[0]
-    v, q, t = (data[x][:1, :kk].clone().requires_grad_() for x in ("v", "q", "t"))
     tgt = data["target"][:1]
     g = torch.Generator().manual_seed(1)
-    u = torch.rand(1, kk, n, 2 if kind == "sphere" else 3, generator=g)
-    t0 = time.perf_counter()
-    pts = O.sample_predict_points(kind, v, q, t, u)
-    loss = O.chamfer_dense(pts, tgt) + 0.1 * O.chamfer_dense(t, tgt, w1=0.5, w2=1.0)
-    loss.backward()
-    dt = time.perf_counter() - t0
+    dt = 0.0
+    for k0 in range(0, kk, per):
+        v, q, t = (data[x][:1, k0:k0 + per].clone().requires_grad_() for x in ("v", "q", "t"))
+        u = torch.rand(1, v.shape[1], n, 2 if kind == "sphere" else 3, generator=g)
+        t0 = time.perf_counter()
+        pts = O.sample_predict_points(kind, v, q, t, u)
+        loss = O.chamfer_dense(pts, tgt) + 0.1 * O.chamfer_dense(t, tgt, w1=0.5, w2=1.0)
+        loss.backward()
+        dt += time.perf_counter() - t0
     frac = (kk * n) / float(k * n)          # share of one sample's pair work that was timed
     return dt, frac, kk * n
 
@@ -131,9 +135,9 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     kind, b, k, n, m, res = WORKLOADS[args.workload]
-    rows = min(k * n, 8192)
+    rows = min(k * n, 32768)
     for _ in range(args.warmup):
-        cpu_reference_step(args.workload, rows, threads)
+        cpu_reference_step(args.workload, min(rows, 8192), threads)
     times = []
     for _ in range(args.steps):
         dt, frac, used = cpu_reference_step(args.workload, rows, threads)
@@ -294,12 +298,23 @@ def main():
         sm_mhz_max = sampler.summary()["sm_max_mhz"] or 1965
         nominal = 148 * 128 * 2 * sm_mhz_max * 1e6 / 1e12
         peak_tf = max(peak["ffma2"], peak["ffma"])
-        roofline = {"kernel": "chamfer_tiled_kernel (main kernel of vpn_chamfer_fwd; both Chamfer directions in one pass)",
+        main_kernel = vpn_b200.chamfer_main_kernel_name(b, k * n, m, args.chamfer_impl)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))[args.workload][main_kernel]
+        except Exception:
+            pass
+        roofline = {"kernel": main_kernel + " (main kernel of vpn_chamfer_fwd; both Chamfer directions in one launch)",
                     "bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "peak_source": "live FFMA2 stream probe (vpn_fp32_peak_probe), burst; MEASURED_PEAKS.json has no FP32 "
                                    "entry; nominal 148 SM x 128 lanes x 2 x max clock given beside it",
                     "peak_nominal": nominal, "frac_of_nominal": achieved / nominal, "ms": main_ms,
-                    "algorithmic_flops": flops, "traffic": None,
+                    "algorithmic_flops": flops, "traffic": traffic,
+                    "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                                      "capture of this launch)" if traffic else None,
+                    "note": "achieved = 8 flop per (predicted, target) pair / kernel time, against the FP32 FMA peak the "
+                            "north star names; chamfer_tc_kernel evaluates the pairs on the tensor cores (fp16-split "
+                            "operands, fp32 accumulate) and is bounded by TMEM reads + FMNMX on the ALU pipe, see DESIGN.md 4.1",
                     "forward_total": {"ms": cham_ms, "stages_ms": stage, "achieved": flops / (cham_ms * 1e-3) / 1e12,
                                       "frac": flops / (cham_ms * 1e-3) / 1e12 / peak_tf,
                                       "note": "main kernel + exact recovery kernels: the time to the final min / arg-min"}}
@@ -314,10 +329,35 @@ def main():
                   "achieved": sbytes / (samp_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                   "frac": sbytes / (samp_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms": samp_ms,
                   "algorithmic_bytes": sbytes, "traffic": None}
+        roof_r = None
+        if res:
+            from vpn_b200 import templates
+            with torch.no_grad():
+                tv, tf = templates.template(kind, dev)
+                verts = vpn_b200.mesh_vertices(tv, s["v"], s["q"], s["t"])
+                faces = step_fn.composed_faces(k, dev)
+                rot, pos = vpn_b200.look_at_cameras(torch.zeros(b, device=dev), torch.zeros(b, device=dev), torch.ones(b, device=dev))
+                for _ in range(2):
+                    vpn_b200.soft_silhouette(verts, faces, rot, pos, res, res)
+                re_ = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+                for i in range(reps):
+                    flush.zero_()
+                    re_[i][0].record()
+                    vpn_b200.soft_silhouette(verts, faces, rot, pos, res, res)
+                    re_[i][1].record()
+                torch.cuda.synchronize()
+                r_ms = sum(a.elapsed_time(bb) for a, bb in re_) / reps
+            rbytes = 12 * b * verts.shape[1] + 12 * faces.shape[0] + 4 * b * res * res
+            roof_r = {"kernel": "sil_project_kernel + sil_faces_kernel + sil_raster_fwd_kernel (vpn_silhouette_fwd, whole batch)",
+                      "bound": "hbm", "achieved": rbytes / (r_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": rbytes / (r_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms": r_ms,
+                      "algorithmic_bytes": rbytes, "traffic": None, "faces": int(faces.shape[0]),
+                      "pixel_face_tests_per_s": b * res * res * float(faces.shape[0]) / (r_ms * 1e-3),
+                      "note": "algorithmic bytes are ~1 us of HBM time: the rasteriser is latency / ALU bound (DESIGN.md 4.4)"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            rows = min(k * n, 8192)
+            rows = min(k * n, 65536)
             cpu_reference_step(args.workload, min(rows, n), threads)      # warm-up on one primitive
             dt, frac, used = cpu_reference_step(args.workload, rows, threads)
             cpu = {"value": 1.0 / (dt / frac), "unit": "samples/s", "cores": threads, "kind": "port",
@@ -334,7 +374,7 @@ def main():
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps},
-                "roofline": roofline, "roofline_sampling": roof_s, "cpu_baseline": cpu,
+                "roofline": roofline, "roofline_sampling": roof_s, "roofline_raster": roof_r, "cpu_baseline": cpu,
                 "fp32_peak_probe_tflops": peak}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -67,11 +67,15 @@ int vpn_view_points(int mode, int transpose, const float* in, const float* dists
 /* ---- Chamfer nearest neighbours, both directions (modules/loss/chamfer_distance.py:14-23) ------------
  * p1 (B,P,3), p2 (B,M,3) -> min1 (B,P) = min_j sqrt(d_ij), idx1 (B,P) int32 = first arg-min, min2 (B,M),
  * idx2 (B,M).  Arg-mins are bit-exact to torch.min over the reference's dense distance tensor.
- * impl: 0 auto, 1 generic kernel, 2/3/4 tiled kernel with exact / FMA-difference / centred-expansion
- * hot-loop arithmetic (identical results; the hot loop only selects candidates, the recovery is exact). */
+ * impl: 0 auto (tensor-core filter when the shape allows, else the CUDA-core tiled kernel, else generic),
+ * 1 generic kernel, 2/3/4 CUDA-core tiled kernel with exact / FMA-difference / centred-expansion hot-loop
+ * arithmetic, 5 tcgen05 tensor-core filter (fp16-split operands, fp32 accumulate).  Results are identical for
+ * every impl: the hot loop only selects candidates, the recovery kernels redo them with the reference's arithmetic. */
 int vpn_chamfer_workspace_bytes(int B, int P, int M, int impl, size_t* bytes);
 int vpn_chamfer_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                     int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, void* stream);
+/* Name of the kernel the forward spends its time in for this shape and impl (static string; measurement label). */
+const char* vpn_chamfer_main_kernel(int B, int P, int M, int impl);
 /* Measurement variant: `reps` forwards with CUDA events between the stages; stage_ms is a HOST float[4]
  * (main kernel, fall-back launch, row recovery, column recovery), mean ms per stage.  Synchronises. */
 int vpn_chamfer_fwd_timed(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
@@ -103,6 +107,15 @@ int vpn_silhouette_bwd(const int* faces, const float* cam_rot, float proj_x, flo
                        float expand, int knum, float multiplier, float delta, const float* grad_alpha,
                        const unsigned char* covered, float* grad_verts, void* workspace, size_t workspace_bytes,
                        int B, int V, int F, int H, int W, void* stream);
+
+/* ---- area-weighted mesh surface sampling: kaolin TriangleMesh.sample at train_sphere.py:71-80, dataset/dataset.py:162-165
+ * verts (B,V,3), faces (F,3) int32 shared topology, u (B,n,3) uniforms in [0,1): [face draw, u1, u2].
+ * points (B,n,3) = (1-sqrt(u1)) v0 + sqrt(u1)(1-u2) v1 + sqrt(u1) u2 v2 of face_idx (B,n) int32 = first face whose
+ * cumulative area share exceeds the face draw.  cdf: scratch (B,F) floats.  bwd overwrites grad_verts (B,V,3). */
+int vpn_mesh_sample_fwd(const float* verts, const int* faces, const float* u, float* points, int* face_idx,
+                        float* cdf, int B, int V, int F, int n, void* stream);
+int vpn_mesh_sample_bwd(const int* faces, const float* u, const int* face_idx, const float* grad_points,
+                        float* grad_verts, int B, int V, int F, int n, void* stream);
 
 /* ---- measurement helper: achieved FP32 FMA throughput (the Chamfer roofline denominator) ----------------
  * scratch: >= 64 device floats, the first 16 finite and near 1.0.  Synchronises the stream. */

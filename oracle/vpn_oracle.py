@@ -20,6 +20,12 @@ Parity status
   functions in the "render" section restate the published DIB-R algorithm (Chen et al.,
   NeurIPS 2019) with kaolin v0.1's default constants as recalled in SURVEY.md section 8(a-R).
 
+* mesh surface sampling (kaolin v0.1 TriangleMesh.sample, call sites train_sphere.py:71-80 and
+  dataset/dataset.py:162-165; same absent dependency): PARITY UNPINNED.  `mesh_sample` restates
+  kaolin v0.1's published formula (area-weighted face choice, sqrt-u barycentric point) with the
+  three random draws made explicit inputs; kaolin's own RNG stream (Categorical.sample + two
+  Uniform.sample) cannot be replayed, so parity beyond "same distribution" is not claimed.
+
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 """
 from __future__ import annotations
@@ -324,6 +330,57 @@ def compose_meshes(vertices: List[torch.Tensor], faces: List[torch.Tensor]):
         fo.append(f + off)
         off += vtx.size(0)
     return torch.cat(vertices), torch.cat(fo)
+
+
+def mesh_face_cdf(verts: np.ndarray, faces: np.ndarray, lanes: int = 256, eps: float = 1e-10) -> np.ndarray:
+    """Cumulative area shares of the faces, fp32, as kaolin v0.1 TriangleMesh.sample computes the areas
+    (call site train_sphere.py:76): edge vectors x = v0 - v1, y = v1 - v2, area = sqrt(a + b + c) / 2 with
+    a, b, c the squared cross-product components, shares = area / (sum(area) + eps).  Every operation is
+    rounded to fp32 separately (a chain of torch ops).  The summation order is fixed: `lanes` consecutive
+    chunks of ceil(F / lanes) faces, running sum inside a chunk, chunk totals added in order (kaolin's
+    torch.sum / Categorical normalisation order is unspecified)."""
+    f32 = np.float32
+    v = verts.astype(f32)
+    x = v[faces[:, 0]] - v[faces[:, 1]]
+    y = v[faces[:, 1]] - v[faces[:, 2]]
+    a = x[:, 1] * y[:, 2] - x[:, 2] * y[:, 1]
+    b = x[:, 2] * y[:, 0] - x[:, 0] * y[:, 2]
+    c = x[:, 0] * y[:, 1] - x[:, 1] * y[:, 0]
+    area = np.sqrt((a * a + b * b) + c * c) / f32(2.0)
+    nf = faces.shape[0]
+    per = (nf + lanes - 1) // lanes
+    local = np.zeros(nf, dtype=f32)
+    totals = np.zeros(lanes, dtype=f32)
+    for lane in range(lanes):
+        run = f32(0.0)
+        for f in range(lane * per, min(nf, (lane + 1) * per)):
+            run = f32(run + area[f])
+            local[f] = run
+        totals[lane] = run
+    base = np.zeros(lanes, dtype=f32)
+    acc = f32(0.0)
+    for lane in range(lanes):
+        base[lane] = acc
+        acc = f32(acc + totals[lane])
+    denom = f32(acc + f32(eps))
+    lane_of = np.minimum(np.arange(nf) // per, lanes - 1)
+    return ((local + base[lane_of]).astype(f32) / denom).astype(f32)
+
+
+def mesh_sample(verts: torch.Tensor, faces: torch.Tensor, u: torch.Tensor):
+    """kaolin v0.1 TriangleMesh.sample(n) (train_sphere.py:71-80) with explicit draws u (n,3) in [0,1):
+    face = first face whose cumulative area share exceeds u[:,0] (inverse CDF in place of Categorical.sample),
+    su = sqrt(u[:,1]), p = (1 - su) v0 + su (1 - u2) v1 + su u2 v2.  Differentiable w.r.t. verts through the
+    barycentric weights, as kaolin's index_select chain is.  Returns (points (n,3), face_idx (n,) int64)."""
+    cdf = torch.from_numpy(mesh_face_cdf(verts.detach().numpy(), faces.numpy()))
+    nf = faces.shape[0]
+    face = torch.searchsorted(cdf, u[:, 0].contiguous(), right=True).clamp(max=nf - 1)
+    sel = faces[face]
+    v0, v1, v2 = verts[sel[:, 0]], verts[sel[:, 1]], verts[sel[:, 2]]
+    su = torch.sqrt(u[:, 1:2])
+    vv = u[:, 2:3]
+    pts = ((1.0 - su) * v0 + (su * (1.0 - vv)) * v1) + (su * vv) * v2
+    return pts, face
 
 
 def compose_primitive_meshes(template, faces, volumes, rotates, translates):

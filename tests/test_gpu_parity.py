@@ -424,3 +424,65 @@ def test_sampling_dropin_consumes_reference_rng_stream(vpn, O):
     assert ms.Sampling.cone_sampling(v, q, t, 10) is None
     with pytest.raises(AssertionError):
         ms.Sampling.sphere_sampling(v, q[:, :3], t, 10)
+
+
+# ------------------------------------------------------------------------------------------------
+# mesh surface sampling (TriangleMesh.sample, train_sphere.py:71-80)
+# ------------------------------------------------------------------------------------------------
+def _mesh386(golden_templates, b, seed):
+    g = torch.Generator().manual_seed(seed)
+    verts = torch.from_numpy(golden_templates["sphere386_vertices"]).float()
+    faces = torch.from_numpy(golden_templates["sphere386_faces"]).long()
+    offs = torch.tanh(torch.randn(b, verts.shape[0], 3, generator=g)) * 0.05        # SDNet-shaped vertex offsets
+    return verts[None] + offs, faces, g
+
+
+@pytest.mark.parametrize("b,n", [(1, 16384), (3, 1000), (2, 1)])
+def test_mesh_sample_matches_oracle(vpn, O, golden_templates, b, n):
+    verts, faces, g = _mesh386(golden_templates, b, 3)
+    u = torch.rand(b, n, 3, generator=g)
+    u[:, 0, 0] = 0.0                                   # first face
+    if n > 2:
+        u[:, 1, 0] = 0.99999994                        # largest draw below 1: last face with a non-zero share
+        u[:, 2, 1] = 0.0                               # sqrt(0): the point is vertex 0 of its face
+    vd = C(verts).requires_grad_()
+    pts, fidx = vpn.sample_mesh_surface(vd, C(faces).int(), C(u))
+    up = torch.rand(b, n, 3, generator=g)
+    (pts * C(up)).sum().backward()
+    for i in range(b):
+        vo = verts[i].clone().requires_grad_()
+        po, fo = O.mesh_sample(vo, faces, u[i])
+        same(fidx[i].long(), fo, "face choice")                       # integer output: bit-exact
+        same(pts[i], po.detach(), "points")                           # same fp32 operation order: bit-exact
+        (po * up[i]).sum().backward()
+        close(vd.grad[i], vo.grad, rtol=RTOL, atol=1e-5 * float(vo.grad.abs().max()), what="grad verts")
+
+
+def test_mesh_sample_is_area_weighted(vpn, O, golden_templates):
+    verts, faces, g = _mesh386(golden_templates, 1, 5)
+    n = 400000
+    u = torch.rand(1, n, 3, generator=g)
+    pts, fidx = vpn.sample_mesh_surface(C(verts), C(faces).int(), C(u))
+    share = np.diff(np.concatenate([[0.0], O.mesh_face_cdf(verts[0].numpy(), faces.numpy())]))
+    freq = np.bincount(fidx[0].cpu().numpy(), minlength=faces.shape[0]) / n
+    assert np.abs(freq - share).max() < 4 * np.sqrt(share.max() / n)       # 4 sigma of a binomial share
+    # every point lies in the plane of, and inside, its triangle
+    v = verts[0].numpy(); f = faces.numpy()[fidx[0].cpu().numpy()]
+    p = pts[0].cpu().numpy()
+    a, b_, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    nrm = np.cross(b_ - a, c - a); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    assert np.abs(((p - a) * nrm).sum(1)).max() < 1e-6
+
+
+def test_dropin_triangle_mesh_sample(vpn, golden_templates):
+    import modules.meshing as mm
+    verts, faces, _ = _mesh386(golden_templates, 2, 9)
+    meshes = [mm.TriangleMesh(C(verts[i]).requires_grad_(), C(faces)) for i in range(2)]
+    pts, fidx = meshes[0].sample(4096)
+    assert pts.shape == (4096, 3) and fidx.shape == (4096,) and fidx.dtype == torch.int64
+    pts.sum().backward()
+    close(meshes[0].vertices.grad.sum(), 3 * 4096.0, rtol=1e-5)
+    batch = mm.TriangleMesh.sample_batch(meshes, 1024)
+    assert batch.shape == (2, 1024, 3)
+    r = batch.norm(dim=2)
+    assert float(r.min()) > 0.3 and float(r.max()) < 0.6           # 386.obj radius 0.45-0.47 + offsets <= 0.05*sqrt(3)

@@ -144,3 +144,29 @@ def test_silhouette_oracle_sanity(golden_templates):
     assert torch.isfinite(verts.grad).all() and verts.grad.abs().sum() > 0
     # camera sits at (1,0,0) for dist=1, elev=azim=0
     np.testing.assert_allclose(pos.numpy(), [1, 0, 0], atol=1e-7)
+
+
+def test_mesh_sample_oracle_properties(golden_templates):
+    """kaolin's TriangleMesh.sample is absent (parity unpinned): pin the restatement's own invariants."""
+    from oracle import vpn_oracle as O
+    verts = torch.from_numpy(golden_templates["sphere386_vertices"]).float()
+    faces = torch.from_numpy(golden_templates["sphere386_faces"]).long()
+    cdf = O.mesh_face_cdf(verts.numpy(), faces.numpy())
+    assert cdf.dtype == np.float32 and np.all(np.diff(cdf) >= 0) and abs(float(cdf[-1]) - 1.0) < 1e-6
+    # triangle areas against a float64 cross product
+    v = verts.double().numpy(); f = faces.numpy()
+    area = 0.5 * np.linalg.norm(np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]]), axis=1)
+    np.testing.assert_allclose(np.diff(np.concatenate([[0.0], cdf.astype(np.float64)])), area / area.sum(), rtol=2e-4, atol=1e-7)
+    g = torch.Generator().manual_seed(0)
+    u = torch.rand(50000, 3, generator=g)
+    vt = verts.clone().requires_grad_()
+    pts, face = O.mesh_sample(vt, faces, u)
+    assert pts.shape == (50000, 3) and face.dtype == torch.int64 and int(face.min()) >= 0 and int(face.max()) < faces.shape[0]
+    # u0 = 0 -> face 0; sqrt(u1) = 0 -> vertex 0 of the face
+    p0, f0 = O.mesh_sample(verts, faces, torch.tensor([[0.0, 0.0, 0.3]]))
+    assert int(f0[0]) == 0 and torch.equal(p0[0], verts[faces[0, 0]])
+    pts.sum().backward()
+    np.testing.assert_allclose(float(vt.grad.sum()), 3 * 50000.0, rtol=1e-5)       # barycentric weights sum to 1
+    freq = np.bincount(face.numpy(), minlength=faces.shape[0]) / 50000.0
+    share = area / area.sum()
+    assert np.abs(freq - share).max() < 5 * np.sqrt(share.max() / 50000.0)

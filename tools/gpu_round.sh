@@ -7,6 +7,7 @@ nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_rea
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_$TAG.log
 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke_$TAG.log
 python bench.py > gpurun_out/bench_c2_$TAG.log 2>&1; echo "bench c2 rc=$?"
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1; echo "bench reference rc=$?"
 python bench.py --workload c3 --no-cpu-baseline > gpurun_out/bench_c3_$TAG.log 2>&1; echo "bench c3 rc=$?"
 python bench.py --workload c1 --no-cpu-baseline > gpurun_out/bench_c1_$TAG.log 2>&1; echo "bench c1 rc=$?"
 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain_$TAG.log 2>&1 &&

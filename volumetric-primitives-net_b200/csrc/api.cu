@@ -107,6 +107,15 @@ static int chamfer_fwd_impl(const float* p1, const float* p2, float* min1, int* 
   return rc;
 }
 
+namespace vpn { int chamfer_tiled_uses_tc(int B, int P, int M, int mode); }
+extern "C" const char* vpn_chamfer_main_kernel(int B, int P, int M, int impl) {
+  if (impl < 0 || impl > 5 || B <= 0 || P <= 0 || M <= 0) return "invalid";
+  if (impl != 1 && vpn::chamfer_tiled_supported(B, P, M, impl_mode(impl)))
+    return vpn::chamfer_tiled_uses_tc(B, P, M, impl_mode(impl)) ? "chamfer_tc_kernel" : "chamfer_tiled_kernel";
+  if (impl == 0 && P <= vpn::chamfer_smallp_limit()) return "chamfer_smallp_kernel";
+  return "chamfer_simple_kernel";
+}
+
 extern "C" int vpn_chamfer_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                                int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, void* stream) {
   return chamfer_fwd_impl(p1, p2, min1, idx1, min2, idx2, B, P, M, workspace, workspace_bytes, impl, (cudaStream_t)stream, nullptr);

@@ -635,6 +635,11 @@ int chamfer_tiled_supported(int B, int P, int M, int mode) {
   return plan_for(mode, B, P, M, pl) ? 1 : 0;
 }
 
+int chamfer_tiled_uses_tc(int B, int P, int M, int mode) {
+  TiledPlan pl;
+  return (plan_for(mode, B, P, M, pl) && pl.tc) ? 1 : 0;
+}
+
 size_t chamfer_tiled_workspace_bytes(int B, int P, int M, int mode) {
   TiledPlan pl;
   if (!plan_for(mode, B, P, M, pl)) return 0;

@@ -29,6 +29,9 @@ struct RasterParams {
 
 struct __align__(16) FaceRec { float ax, ay, bx, by, cx, cy, front, pad; };
 
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
 // cam = rot (v - pos);  xy = (cam.xy * proj.xy) / (cam.z * proj.z)
 __global__ void sil_project_kernel(const float* __restrict__ verts, const float* __restrict__ rot,
                                    const float* __restrict__ pos, float px, float py, float pz,
@@ -52,12 +55,18 @@ __global__ void sil_project_kernel(const float* __restrict__ verts, const float*
   o[1] = __fdiv_rn(__fmul_rn(c[1], py), zz);
 }
 
-__global__ void sil_faces_kernel(const float* __restrict__ cam, const float* __restrict__ xy,
-                                 const int* __restrict__ faces, FaceRec* __restrict__ rec,
-                                 float* __restrict__ normals, int V, int F, float mult) {
+// Also writes, per batch of kRThreads consecutive faces (= one block here, one binning step of the rasteriser), the
+// union of the expanded bounding boxes of its front faces: (min xmin, max xmax, min ymin, max ymax).
+__global__ void __launch_bounds__(256)
+sil_faces_kernel(const float* __restrict__ cam, const float* __restrict__ xy,
+                 const int* __restrict__ faces, FaceRec* __restrict__ rec,
+                 float* __restrict__ normals, float4* __restrict__ batch_box, int V, int F, float mult, float em) {
+  __shared__ float4 s_box[8];
   const int b = blockIdx.y;
   int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
+  const float inf = __int_as_float(0x7f800000);
+  float4 box = make_float4(inf, -inf, inf, -inf);
+  if (f < F) {
   int i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
   const float* c0 = cam + 3 * ((size_t)b * V + i0);
   const float* c1 = cam + 3 * ((size_t)b * V + i1);
@@ -82,10 +91,27 @@ __global__ void sil_faces_kernel(const float* __restrict__ cam, const float* __r
     float* n = normals + 3 * ((size_t)b * F + f);
     n[0] = nx / len; n[1] = ny / len; n[2] = nz / len;
   }
+  if (r.front > 0.5f)
+    box = make_float4(__fsub_rn(min3(r.ax, r.bx, r.cx), em), __fadd_rn(max3(r.ax, r.bx, r.cx), em),
+                      __fsub_rn(min3(r.ay, r.by, r.cy), em), __fadd_rn(max3(r.ay, r.by, r.cy), em));
+  }
+  // NaN coordinates must not hide a batch: fminf / fmaxf drop NaN operands, so a NaN box is widened to everything
+  if (!(box.x == box.x) || !(box.y == box.y) || !(box.z == box.z) || !(box.w == box.w)) box = make_float4(-inf, inf, -inf, inf);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    box.x = fminf(box.x, __shfl_xor_sync(0xffffffffu, box.x, o)); box.y = fmaxf(box.y, __shfl_xor_sync(0xffffffffu, box.y, o));
+    box.z = fminf(box.z, __shfl_xor_sync(0xffffffffu, box.z, o)); box.w = fmaxf(box.w, __shfl_xor_sync(0xffffffffu, box.w, o));
+  }
+  if ((threadIdx.x & 31) == 0) s_box[threadIdx.x >> 5] = box;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      box.x = fminf(box.x, s_box[w].x); box.y = fmaxf(box.y, s_box[w].y);
+      box.z = fminf(box.z, s_box[w].z); box.w = fmaxf(box.w, s_box[w].w);
+    }
+    batch_box[(size_t)b * gridDim.x + blockIdx.x] = box;
+  }
 }
-
-__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
-__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 // Squared distance pixel -> triangle, DIB-R's 6 cases; returns d2 and the winning case (first minimum).
 __device__ __forceinline__ float tri_dist2(const FaceRec& r, float X, float Y, float mult, float eps, int& which) {
@@ -126,23 +152,29 @@ __device__ __forceinline__ bool inside_tri(const FaceRec& r, float X, float Y, f
   return w0 >= 0.f && w1 >= 0.f && w2 >= 0.f;
 }
 
-// Shared tile walker: calls fn(face_index, record) for every face binned to this tile, in index order.
-// All threads of the CTA must call it; fn is invoked per thread (pixel).
+// Shared tile walker: calls fn(face_index, record, tight bbox) for every face binned to this tile, in index order.
+// All threads of the CTA must call it; fn is invoked per thread (pixel).  Batches of kRThreads faces whose union
+// box (sil_faces_kernel) misses the tile are skipped without touching their records.
 template <typename Fn>
-__device__ __forceinline__ void walk_tile_faces(const FaceRec* __restrict__ rec, int F, float xL, float xR,
-                                                float yB, float yT, float em, Fn fn) {
+__device__ __forceinline__ void walk_tile_faces(const FaceRec* __restrict__ rec, const float4* __restrict__ batch_box,
+                                                int F, float xL, float xR, float yB, float yT, float em, Fn fn) {
   __shared__ FaceRec s_rec[kRThreads];
+  __shared__ float4 s_box[kRThreads];                  // tight bbox: xmin, xmax, ymin, ymax
   __shared__ int s_idx[kRThreads];
   __shared__ int s_wcount[kRThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int f0 = 0; f0 < F; f0 += kRThreads) {
+    const float4 bb = batch_box[f0 / kRThreads];
+    if (!(bb.x <= xR && bb.y > xL && bb.z <= yT && bb.w > yB)) continue;          // uniform over the CTA
     const int f = f0 + tid;
     bool hit = false;
     FaceRec r;
+    float4 tb;
     if (f < F) {
       r = rec[f];
-      float xmin = __fsub_rn(min3(r.ax, r.bx, r.cx), em), xmax = __fadd_rn(max3(r.ax, r.bx, r.cx), em);
-      float ymin = __fsub_rn(min3(r.ay, r.by, r.cy), em), ymax = __fadd_rn(max3(r.ay, r.by, r.cy), em);
+      tb = make_float4(min3(r.ax, r.bx, r.cx), max3(r.ax, r.bx, r.cx), min3(r.ay, r.by, r.cy), max3(r.ay, r.by, r.cy));
+      float xmin = __fsub_rn(tb.x, em), xmax = __fadd_rn(tb.y, em);
+      float ymin = __fsub_rn(tb.z, em), ymax = __fadd_rn(tb.w, em);
       hit = (r.front > 0.5f) && xmin <= xR && xmax > xL && ymin <= yT && ymax > yB;
     }
     unsigned bal = __ballot_sync(0xffffffffu, hit);
@@ -153,10 +185,10 @@ __device__ __forceinline__ void walk_tile_faces(const FaceRec* __restrict__ rec,
     for (int w = 0; w < kRThreads / 32; ++w) { int c = s_wcount[w]; if (w < warp) base += c; total += c; }
     if (hit) {
       int slot = base + __popc(bal & ((1u << lane) - 1u));
-      s_rec[slot] = r; s_idx[slot] = f;
+      s_rec[slot] = r; s_box[slot] = tb; s_idx[slot] = f;
     }
     __syncthreads();
-    for (int k = 0; k < total; ++k) fn(s_idx[k], s_rec[k]);
+    for (int k = 0; k < total; ++k) fn(s_idx[k], s_rec[k], s_box[k]);
     __syncthreads();
   }
 }
@@ -168,7 +200,7 @@ __device__ __forceinline__ void pixel_coords(const RasterParams& rp, int w, int 
 
 // grid: x = tile x, y = tile y, z = sample
 __global__ void __launch_bounds__(kRThreads)
-sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, float* __restrict__ alpha,
+sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restrict__ box_all, float* __restrict__ alpha,
                       unsigned char* __restrict__ covered_out, RasterParams rp) {
   const int b = blockIdx.z;
   const int w = blockIdx.x * kTile + (threadIdx.x % kTile), h = blockIdx.y * kTile + (threadIdx.x / kTile);
@@ -181,11 +213,12 @@ sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, float* __restrict__ a
   (void)dummy;
   const float em = __fmul_rn(rp.expand, rp.mult);
   bool covered = false; int kid = 0; float prod = 1.0f;
-  walk_tile_faces(rec, rp.F, xL, xR, yB, yT, em, [&](int, const FaceRec& r) {
-    float txmin = min3(r.ax, r.bx, r.cx), txmax = max3(r.ax, r.bx, r.cx);
-    float tymin = min3(r.ay, r.by, r.cy), tymax = max3(r.ay, r.by, r.cy);
+  const float4* boxes = box_all + (size_t)b * ((rp.F + kRThreads - 1) / kRThreads);
+  walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, em, [&](int, const FaceRec& r, const float4& tb) {
+    if (covered) return;                                // alpha is 1 whatever follows
+    const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
     if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
-    if (X >= txmin && X < txmax && Y >= tymin && Y < tymax && inside_tri(r, X, Y, rp.eps)) covered = true;
+    if (X >= txmin && X < txmax && Y >= tymin && Y < tymax && inside_tri(r, X, Y, rp.eps)) { covered = true; return; }
     if (kid < rp.knum) {
       int which;
       float d2 = tri_dist2(r, X, Y, rp.mult, rp.eps, which);
@@ -203,7 +236,7 @@ sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, float* __restrict__ a
 
 // Backward of the soft term: d alpha / d (scaled screen coords of the recorded faces).
 __global__ void __launch_bounds__(kRThreads)
-sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float* __restrict__ galpha,
+sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restrict__ box_all, const float* __restrict__ galpha,
                       const unsigned char* __restrict__ covered_in, float* __restrict__ gface, RasterParams rp) {
   const int b = blockIdx.z;
   const int w = blockIdx.x * kTile + (threadIdx.x % kTile), h = blockIdx.y * kTile + (threadIdx.x / kTile);
@@ -222,10 +255,10 @@ sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float* __restri
   }
   int kid = 0;
   int fid[kKnumMax]; float prob[kKnumMax];
-  walk_tile_faces(rec, rp.F, xL, xR, yB, yT, em, [&](int f, const FaceRec& r) {
+  const float4* boxes = box_all + (size_t)b * ((rp.F + kRThreads - 1) / kRThreads);
+  walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, em, [&](int f, const FaceRec& r, const float4& tb) {
     if (!active || kid >= rp.knum) return;
-    float txmin = min3(r.ax, r.bx, r.cx), txmax = max3(r.ax, r.bx, r.cx);
-    float tymin = min3(r.ay, r.by, r.cy), tymax = max3(r.ay, r.by, r.cy);
+    const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
     if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
     int which;
     float d2 = tri_dist2(r, X, Y, rp.mult, rp.eps, which);
@@ -298,13 +331,14 @@ __global__ void sil_face_to_vertex_kernel(const float* __restrict__ gface, const
 }
 
 static size_t al256s(size_t x) { return (x + 255) & ~(size_t)255; }
-struct SilWs { size_t cam, xy, rec, gface, total; };
+struct SilWs { size_t cam, xy, rec, gface, box, total; };
 static SilWs sil_layout(int B, int V, int F) {
   SilWs w; size_t o = 0;
   w.cam = o; o += al256s((size_t)B * V * 3 * 4);
   w.xy = o; o += al256s((size_t)B * V * 2 * 4);
   w.rec = o; o += al256s((size_t)B * F * sizeof(FaceRec));
   w.gface = o; o += al256s((size_t)B * F * 6 * 4);
+  w.box = o; o += al256s((size_t)B * ((F + kRThreads - 1) / kRThreads) * sizeof(float4));
   w.total = o;
   return w;
 }
@@ -346,11 +380,13 @@ extern "C" int vpn_silhouette_fwd(const float* verts, const int* faces, const fl
   cudaStream_t s = (cudaStream_t)stream;
   sil_project_kernel<<<dim3((V + 255) / 256, B), 256, 0, s>>>(verts, cam_rot, cam_pos, proj_x, proj_y, proj_z, cam, xy, V);
   if ((rc = vpn_check_launch("sil_project_kernel"))) return rc;
-  sil_faces_kernel<<<dim3((F + 255) / 256, B), 256, 0, s>>>(cam, xy, faces, rec, normals, V, F, multiplier);
+  float4* boxes = reinterpret_cast<float4*>(ws + wl.box);
+  sil_faces_kernel<<<dim3((F + kRThreads - 1) / kRThreads, B), kRThreads, 0, s>>>(cam, xy, faces, rec, normals, boxes, V, F, multiplier,
+                                                                                  expand * multiplier);
   if ((rc = vpn_check_launch("sil_faces_kernel"))) return rc;
   RasterParams rp{H, W, F, knum, expand, multiplier, delta, 1e-15f};
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
-  sil_raster_fwd_kernel<<<grid, kRThreads, 0, s>>>(rec, alpha, covered, rp);
+  sil_raster_fwd_kernel<<<grid, kRThreads, 0, s>>>(rec, boxes, alpha, covered, rp);
   return vpn_check_launch("sil_raster_fwd_kernel");
 }
 
@@ -376,7 +412,7 @@ extern "C" int vpn_silhouette_bwd(const int* faces, const float* cam_rot, float 
   }
   RasterParams rp{H, W, F, knum, expand, multiplier, delta, 1e-15f};
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
-  sil_raster_bwd_kernel<<<grid, kRThreads, 0, s>>>(rec, grad_alpha, covered, gface, rp);
+  sil_raster_bwd_kernel<<<grid, kRThreads, 0, s>>>(rec, reinterpret_cast<const float4*>(ws + wl.box), grad_alpha, covered, gface, rp);
   if ((rc = vpn_check_launch("sil_raster_bwd_kernel"))) return rc;
   sil_face_to_vertex_kernel<<<dim3((F + 255) / 256, B), 256, 0, s>>>(gface, faces, cam, cam_rot, proj_x, proj_y, proj_z,
                                                                       multiplier, grad_verts, V, F);

@@ -25,6 +25,20 @@ class TriangleMesh:
         v, f = templates.parse_obj(path)
         return cls(torch.from_numpy(v), torch.from_numpy(f).long(), topology_key=('obj', path))
 
+    def sample(self, num_samples: int):
+        """kaolin TriangleMesh.sample (train_sphere.py:76, dataset.py:165): (points (n,3), face_idx (n,) int64),
+        area-weighted, drawn on the device; differentiable w.r.t. the vertices."""
+        u = torch.rand((1, num_samples, 3), device=self.vertices.device)
+        points, face_idx = ops.sample_mesh_surface(self.vertices[None], self.faces.to(torch.int32), u)
+        return points[0], face_idx[0].long()
+
+    @staticmethod
+    def sample_batch(meshes: list, num_samples: int):
+        """All meshes of a batch (shared topology) in two launches: what train_sphere.py:71-80 loops over."""
+        verts = torch.stack([m.vertices for m in meshes])
+        u = torch.rand((len(meshes), num_samples, 3), device=verts.device)
+        return ops.sample_mesh_surface(verts, meshes[0].faces.to(torch.int32), u)[0]
+
     def to(self, device):
         self.vertices = self.vertices.to(device)
         self.faces = self.faces.to(device)

@@ -374,6 +374,55 @@ def soft_silhouette(verts, faces, rot, pos, height: int, width: int, want_normal
     return _SoftSilhouette.apply(verts, faces, rot, pos, int(height), int(width), bool(want_normals))
 
 
+# --------------------------------------------------------------------------------------
+# mesh surface sampling
+# --------------------------------------------------------------------------------------
+class _MeshSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, faces, u):
+        lib = _lib.load()
+        verts = require(verts.contiguous(), f32, "verts")
+        faces = require(faces.contiguous(), torch.int32, "faces")
+        u = require(u.contiguous(), f32, "uniforms")
+        b, v, _ = verts.shape
+        f, n, dev = faces.shape[0], u.shape[1], verts.device
+        points = torch.empty((b, n, 3), dtype=f32, device=dev)
+        face_idx = torch.empty((b, n), dtype=torch.int32, device=dev)
+        cdf = torch.empty((b, f), dtype=f32, device=dev)
+        check(lib.vpn_mesh_sample_fwd(ptr(verts), ptr(faces), ptr(u), ptr(points), ptr(face_idx), ptr(cdf), b, v, f, n,
+                                      stream_ptr(dev)), "vpn_mesh_sample_fwd")
+        ctx.save_for_backward(faces, u, face_idx)
+        ctx.dims = (b, v, f, n)
+        ctx.mark_non_differentiable(face_idx)
+        return points, face_idx
+
+    @staticmethod
+    def backward(ctx, gpoints, _gidx):
+        lib = _lib.load()
+        faces, u, face_idx = ctx.saved_tensors
+        b, v, f, n = ctx.dims
+        dev = u.device
+        gverts = torch.empty((b, v, 3), dtype=f32, device=dev)
+        check(lib.vpn_mesh_sample_bwd(ptr(faces), ptr(u), ptr(face_idx), ptr(gpoints.contiguous()), ptr(gverts), b, v, f, n,
+                                      stream_ptr(dev)), "vpn_mesh_sample_bwd")
+        return gverts, None, None
+
+
+def sample_mesh_surface(verts, faces, uniforms):
+    """Batched TriangleMesh.sample (train_sphere.py:71-80): verts (B,V,3), faces (F,3) int32 shared topology,
+    uniforms (B,n,3) in [0,1) = [face draw, u1, u2].  Returns (points (B,n,3), face_idx (B,n) int32); the gradient
+    flows to the vertices through the barycentric weights."""
+    assert verts.dim() == 3 and verts.size(-1) == 3 and faces.dim() == 2 and faces.size(-1) == 3
+    assert uniforms.dim() == 3 and uniforms.size(-1) == 3 and uniforms.size(0) == verts.size(0)
+    return _MeshSample.apply(verts, faces, uniforms)
+
+
+def chamfer_main_kernel_name(b: int, p: int, m: int, impl: int = CHAMFER_AUTO) -> str:
+    """Name of the kernel vpn_chamfer_fwd spends its time in for this shape / impl (bench.py's roofline label)."""
+    lib = _lib.load()
+    return lib.vpn_chamfer_main_kernel(b, p, m, impl).decode()
+
+
 def fp32_peak_tflops(device=None, reps: int = 3):
     """Achieved FP32 FMA throughput (TFLOP/s) of scalar FFMA and packed FFMA2 streams on this GPU."""
     lib = _lib.load()
