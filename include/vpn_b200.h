@@ -48,6 +48,10 @@ unsigned long long vpn_launch_count(void);
  * v (nprim,3), q (nprim,4) = (axis, turn fraction), t (nprim,3) or NULL (rotate only), out (nprim,N,3). */
 int vpn_pose_points_fwd(int kind, const float* v, const float* q, const float* t, const float* src,
                         float* out, int nprim, int N, void* stream);
+/* Measurement variant: `reps` launches back to back, launch i reading srcs[i % nsrc] (HOST array of device pointers),
+ * one CUDA-event pair around the stream of launches; *ms_per_launch is a HOST float.  Synchronises. */
+int vpn_pose_points_fwd_timed(int kind, const float* v, const float* q, const float* t, const float* const* srcs,
+                              int nsrc, float* out, int nprim, int N, int reps, float* ms_per_launch, void* stream);
 int vpn_pose_bwd_workspace_floats(int nprim, int N, size_t* floats);
 /* grad_out (nprim,N,3) -> grad_v (nprim,3), grad_q (nprim,4), grad_t (nprim,3); any may be NULL.
  * grad_points (nprim,N,3) is written for VPN_KIND_POINTS only (may be NULL). */

@@ -377,7 +377,7 @@ def mesh_sample(verts: torch.Tensor, faces: torch.Tensor, u: torch.Tensor):
     face = torch.searchsorted(cdf, u[:, 0].contiguous(), right=True).clamp(max=nf - 1)
     sel = faces[face]
     v0, v1, v2 = verts[sel[:, 0]], verts[sel[:, 1]], verts[sel[:, 2]]
-    su = torch.sqrt(u[:, 1:2])
+    su = _ieee_sqrt(u[:, 1:2])          # torch-CPU sqrt (MKL VML) is 1 ulp off for some inputs; the reference's device is IEEE
     vv = u[:, 2:3]
     pts = ((1.0 - su) * v0 + (su * (1.0 - vv)) * v1) + (su * vv) * v2
     return pts, face

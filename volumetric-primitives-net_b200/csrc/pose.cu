@@ -55,22 +55,43 @@ __device__ __forceinline__ void load_prim(int KIND, PrimShared& ps, const float*
   }
 }
 
-// Unit "direction" d of point n such that canonical = d (.) v   (for KIND_POINTS: canonical = d).
+// Source words per point: 2 uniforms (sphere) or 3 floats (cuboid uniforms, template vertex, caller point).
+template <int KIND> struct SrcWidth { static constexpr int value = (KIND == KIND_SPHERE) ? 2 : 3; };
+
+constexpr int kPoseThreads = 256;
+constexpr int kPosePointsPerThread = 4;      // consecutive points per thread and step: 48-byte (3 x float4) accesses
+constexpr int kPoseSteps = 2;                // steps per CTA: a CTA covers 2048 points of one primitive
+
+// The source words of 4 consecutive points starting at n0, 16-byte loads when the layout allows.
 template <int KIND>
-__device__ __forceinline__ void canonical_dir(const PrimShared& ps, const float* __restrict__ src,
-                                              size_t prim, int n, int N, float* d) {
+__device__ __forceinline__ void load_src4(const float* __restrict__ src, size_t prim, int n0, int N, int vec_ok,
+                                          float (&u)[4 * SrcWidth<KIND>::value]) {
+  constexpr int W = SrcWidth<KIND>::value;
+  const float* base = (KIND == KIND_TEMPLATE) ? src + (size_t)W * n0 : src + (size_t)W * (prim * (size_t)N + n0);
+  if (vec_ok && n0 + 4 <= N) {
+    const float4* b4 = reinterpret_cast<const float4*>(base);
+#pragma unroll
+    for (int i = 0; i < W; ++i) { float4 x = b4[i]; u[4 * i] = x.x; u[4 * i + 1] = x.y; u[4 * i + 2] = x.z; u[4 * i + 3] = x.w; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4 * W; ++i) u[i] = (n0 + i / W < N) ? base[i] : 0.f;
+  }
+}
+
+// Unit "direction" d of point n such that canonical = d (.) v   (for KIND_POINTS: canonical = d); u = the point's
+// source words.
+template <int KIND>
+__device__ __forceinline__ void canonical_dir(const PrimShared& ps, const float* u, int n, float* d) {
   if (KIND == KIND_SPHERE) {
-    // sphere.py:26-27,37-43.  src = uniforms (.., N, 2): [elev draw, azim draw]
-    float2 u = *reinterpret_cast<const float2*>(src + 2 * (prim * (size_t)N + n));
-    float elev = __fadd_rn(-acosf(__fsub_rn(1.0f, __fmul_rn(2.0f, u.x))), 1.5707963705062866f);
-    float azim = __fmul_rn(__fmul_rn(u.y, 2.0f), VPN_PI);
+    // sphere.py:26-27,37-43.  u = [elev draw, azim draw]
+    float elev = __fadd_rn(-acosf(__fsub_rn(1.0f, __fmul_rn(2.0f, u[0]))), 1.5707963705062866f);
+    float azim = __fmul_rn(__fmul_rn(u[1], 2.0f), VPN_PI);
     float ce = cosf(elev), se = sinf(elev);
     d[0] = __fmul_rn(ce, sinf(azim));
     d[1] = se;
     d[2] = __fmul_rn(ce, cosf(azim));
   } else if (KIND == KIND_CUBOID) {
-    // cuboid.py:56-101.  src = uniforms (.., N, 3)
-    const float* u = src + 3 * (prim * (size_t)N + n);
+    // cuboid.py:56-101.  u = three uniforms; the face of point n pins one coordinate to +-1
     d[0] = fmaf(2.0f, u[0], -1.0f);
     d[1] = fmaf(2.0f, u[1], -1.0f);
     d[2] = fmaf(2.0f, u[2], -1.0f);
@@ -79,12 +100,9 @@ __device__ __forceinline__ void canonical_dir(const PrimShared& ps, const float*
     for (int f = 4; f >= 0; --f) if (n < ps.cum[f]) face = f;
     float pin = (face & 1) ? -1.0f : 1.0f;
     if ((face >> 1) == 0) d[0] = pin; else if ((face >> 1) == 1) d[1] = pin; else d[2] = pin;
-  } else if (KIND == KIND_TEMPLATE) {
-    // meshing/sphere.py:17, cuboid.py:17.  src = template vertices (N, 3), shared by all primitives
-    d[0] = src[3 * n + 0]; d[1] = src[3 * n + 1]; d[2] = src[3 * n + 2];
   } else {
-    const float* p = src + 3 * (prim * (size_t)N + n);
-    d[0] = p[0]; d[1] = p[1]; d[2] = p[2];
+    // template vertex (meshing/sphere.py:17, cuboid.py:17) or caller point
+    d[0] = u[0]; d[1] = u[1]; d[2] = u[2];
   }
 }
 
@@ -95,39 +113,48 @@ __device__ __forceinline__ void rotate_add(const PrimShared& ps, const float* c,
   o[2] = __fadd_rn(fmaf(r[8], c[2], fmaf(r[7], c[1], r[6] * c[0])), ps.t[2]);
 }
 
-constexpr int kPoseThreads = 256;
-constexpr int kPosePointsPerThread = 4;
-
-// grid: x = primitive (b*K + k), y = slice of kPoseThreads*kPosePointsPerThread points.
+// grid: x = primitive (b*K + k), y = slice of kPoseThreads * kPosePointsPerThread * kPoseSteps points.
+// All source loads of the CTA are issued before the pose (sin, cos, sqrt, divisions by one thread) is waited for.
 template <int KIND>
 __global__ void __launch_bounds__(kPoseThreads)
 pose_fwd_kernel(const float* __restrict__ v, const float* __restrict__ q, const float* __restrict__ t,
                 const float* __restrict__ src, float* __restrict__ out, int N, int vec_ok) {
+  constexpr int W = SrcWidth<KIND>::value;
   __shared__ PrimShared ps;
   const size_t prim = blockIdx.x;
+  const int base_n = blockIdx.y * (kPoseThreads * kPosePointsPerThread * kPoseSteps) + threadIdx.x * kPosePointsPerThread;
+  float u[kPoseSteps][4 * W];
+#pragma unroll
+  for (int s = 0; s < kPoseSteps; ++s) {
+    const int n0 = base_n + s * kPoseThreads * kPosePointsPerThread;
+    if (n0 < N) load_src4<KIND>(src, prim, n0, N, vec_ok, u[s]);
+  }
   if (threadIdx.x == 0) load_prim(KIND, ps, v, q, t, (int)prim, N);
   __syncthreads();
-  const int n0 = (blockIdx.y * kPoseThreads + threadIdx.x) * kPosePointsPerThread;
-  if (n0 >= N) return;
-  float o[kPosePointsPerThread][3];
-  const int cnt = min(kPosePointsPerThread, N - n0);
 #pragma unroll
-  for (int i = 0; i < kPosePointsPerThread; ++i) {
-    if (i < cnt) {
-      float d[3], c[3];
-      canonical_dir<KIND>(ps, src, prim, n0 + i, N, d);
-      c[0] = __fmul_rn(d[0], ps.v[0]); c[1] = __fmul_rn(d[1], ps.v[1]); c[2] = __fmul_rn(d[2], ps.v[2]);
-      rotate_add(ps, c, o[i]);
+  for (int s = 0; s < kPoseSteps; ++s) {
+    const int n0 = base_n + s * kPoseThreads * kPosePointsPerThread;
+    if (n0 >= N) break;
+    float o[kPosePointsPerThread][3];
+    const int cnt = min(kPosePointsPerThread, N - n0);
+#pragma unroll
+    for (int i = 0; i < kPosePointsPerThread; ++i) {
+      if (i < cnt) {
+        float d[3], c[3];
+        canonical_dir<KIND>(ps, &u[s][W * i], n0 + i, d);
+        c[0] = __fmul_rn(d[0], ps.v[0]); c[1] = __fmul_rn(d[1], ps.v[1]); c[2] = __fmul_rn(d[2], ps.v[2]);
+        rotate_add(ps, c, o[i]);
+      }
     }
-  }
-  float* dst = out + 3 * (prim * (size_t)N + n0);
-  if (vec_ok && cnt == kPosePointsPerThread) {
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    d4[0] = make_float4(o[0][0], o[0][1], o[0][2], o[1][0]);
-    d4[1] = make_float4(o[1][1], o[1][2], o[2][0], o[2][1]);
-    d4[2] = make_float4(o[2][2], o[3][0], o[3][1], o[3][2]);
-  } else {
-    for (int i = 0; i < cnt; ++i) { dst[3 * i] = o[i][0]; dst[3 * i + 1] = o[i][1]; dst[3 * i + 2] = o[i][2]; }
+    float* dst = out + 3 * (prim * (size_t)N + n0);
+    if (vec_ok && cnt == kPosePointsPerThread) {
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      d4[0] = make_float4(o[0][0], o[0][1], o[0][2], o[1][0]);
+      d4[1] = make_float4(o[1][1], o[1][2], o[2][0], o[2][1]);
+      d4[2] = make_float4(o[2][2], o[3][0], o[3][1], o[3][2]);
+    } else {
+      for (int i = 0; i < cnt; ++i) { dst[3 * i] = o[i][0]; dst[3 * i + 1] = o[i][1]; dst[3 * i + 2] = o[i][2]; }
+    }
   }
 }
 
@@ -140,41 +167,58 @@ template <int KIND>
 __global__ void __launch_bounds__(kPoseThreads)
 pose_bwd_partial_kernel(const float* __restrict__ v, const float* __restrict__ q,
                         const float* __restrict__ src, const float* __restrict__ gout,
-                        float* __restrict__ partial, float* __restrict__ gpts, int N) {
+                        float* __restrict__ partial, float* __restrict__ gpts, int N, int vec_ok) {
+  constexpr int W = SrcWidth<KIND>::value;
   __shared__ PrimShared ps;
   __shared__ float red[kPoseThreads / 32][16];
   const size_t prim = blockIdx.x;
-  if (threadIdx.x == 0) load_prim(KIND, ps, v, q, nullptr, (int)prim, N);
-  __syncthreads();
+  const int base_n = blockIdx.y * (kPoseThreads * kPosePointsPerThread * kPoseSteps) + threadIdx.x * kPosePointsPerThread;
   float acc[15];
 #pragma unroll
   for (int i = 0; i < 15; ++i) acc[i] = 0.f;
-  const int n0 = (blockIdx.y * kPoseThreads + threadIdx.x) * kPosePointsPerThread;
+  // two steps' worth of loads in flight at a time (source words + upstream gradient: 6 x float4 per step)
+  float u[2][4 * W], gg[2][12];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int n0 = base_n + s * kPoseThreads * kPosePointsPerThread;
+    if (n0 < N) { load_src4<KIND>(src, prim, n0, N, vec_ok, u[s]); load_src4<KIND_POINTS>(gout, prim, n0, N, vec_ok, gg[s]); }
+  }
+  if (threadIdx.x == 0) load_prim(KIND, ps, v, q, nullptr, (int)prim, N);
+  __syncthreads();
   const float* r = ps.pose.r;
 #pragma unroll
-  for (int i = 0; i < kPosePointsPerThread; ++i) {
-    int n = n0 + i;
-    if (n < N) {
-      float d[3], c[3], g[3], rg[3];
-      canonical_dir<KIND>(ps, src, prim, n, N, d);
-      const float* gp = gout + 3 * (prim * (size_t)N + n);
-      g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
+  for (int s = 0; s < kPoseSteps; ++s) {
+    const int n0 = base_n + s * kPoseThreads * kPosePointsPerThread;
+    if (n0 < N) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a) c[a] = d[a] * ps.v[a];
+      for (int i = 0; i < kPosePointsPerThread; ++i) {
+        const int n = n0 + i;
+        if (n < N) {
+          float d[3], c[3], rg[3];
+          canonical_dir<KIND>(ps, &u[s & 1][W * i], n, d);
+          const float* g = &gg[s & 1][3 * i];
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
+          for (int a = 0; a < 3; ++a) c[a] = d[a] * ps.v[a];
 #pragma unroll
-        for (int b = 0; b < 3; ++b) acc[3 * a + b] += g[a] * c[b];
+          for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int a = 0; a < 3; ++a) acc[9 + a] += g[a];
+            for (int b = 0; b < 3; ++b) acc[3 * a + b] += g[a] * c[b];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) rg[a] = r[a] * g[0] + r[3 + a] * g[1] + r[6 + a] * g[2];
+          for (int a = 0; a < 3; ++a) acc[9 + a] += g[a];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) acc[12 + a] += rg[a] * d[a];
-      if (KIND == KIND_POINTS && gpts) {
-        float* o = gpts + 3 * (prim * (size_t)N + n);
-        o[0] = rg[0]; o[1] = rg[1]; o[2] = rg[2];
+          for (int a = 0; a < 3; ++a) rg[a] = r[a] * g[0] + r[3 + a] * g[1] + r[6 + a] * g[2];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) acc[12 + a] += rg[a] * d[a];
+          if (KIND == KIND_POINTS && gpts) {
+            float* o = gpts + 3 * (prim * (size_t)N + n);
+            o[0] = rg[0]; o[1] = rg[1]; o[2] = rg[2];
+          }
+        }
       }
+    }
+    if (s + 2 < kPoseSteps) {
+      const int n2 = base_n + (s + 2) * kPoseThreads * kPosePointsPerThread;
+      if (n2 < N) { load_src4<KIND>(src, prim, n2, N, vec_ok, u[s & 1]); load_src4<KIND_POINTS>(gout, prim, n2, N, vec_ok, gg[s & 1]); }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -227,7 +271,7 @@ __global__ void cuboid_counts_kernel(const float* __restrict__ v, int* __restric
 }
 
 static inline int slices_for(int N) {
-  int per = kPoseThreads * kPosePointsPerThread;
+  int per = kPoseThreads * kPosePointsPerThread * kPoseSteps;
   return (N + per - 1) / per;
 }
 
@@ -250,7 +294,7 @@ extern "C" int vpn_pose_points_fwd(int kind, const float* v, const float* q, con
   if (!q || !src || !out || (kind != KIND_POINTS && !v)) { vpn_set_error("pose fwd: null pointer"); return VPN_ERR_ARG; }
   dim3 grid(nprim, slices_for(N)), block(kPoseThreads);
   cudaStream_t s = (cudaStream_t)stream;
-  int vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  int vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   switch (kind) {
     case KIND_SPHERE:   pose_fwd_kernel<KIND_SPHERE><<<grid, block, 0, s>>>(v, q, t, src, out, N, vec_ok); break;
     case KIND_CUBOID:   pose_fwd_kernel<KIND_CUBOID><<<grid, block, 0, s>>>(v, q, t, src, out, N, vec_ok); break;
@@ -258,6 +302,26 @@ extern "C" int vpn_pose_points_fwd(int kind, const float* v, const float* q, con
     default:            pose_fwd_kernel<KIND_POINTS><<<grid, block, 0, s>>>(v, q, t, src, out, N, vec_ok); break;
   }
   return vpn_check_launch("pose_fwd_kernel");
+}
+
+// Measurement variant: `reps` forward launches back to back on `stream`, launch i reading srcs[i % nsrc] (HOST array
+// of device pointers: rotate more bytes than L2 holds and every launch reads cold inputs), one CUDA-event pair around
+// the whole stream of launches; *ms_per_launch (HOST) = elapsed / reps.  Synchronises.
+extern "C" int vpn_pose_points_fwd_timed(int kind, const float* v, const float* q, const float* t, const float* const* srcs,
+                                         int nsrc, float* out, int nprim, int N, int reps, float* ms_per_launch, void* stream) {
+  if (!srcs || nsrc < 1 || reps < 1 || !ms_per_launch) { vpn_set_error("pose timed: bad arguments"); return VPN_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { vpn_set_error("pose timed: event create failed"); return VPN_ERR_CUDA; }
+  int rc = VPN_OK;
+  for (int i = 0; i < nsrc && rc == VPN_OK; ++i) rc = vpn_pose_points_fwd(kind, v, q, t, srcs[i], out, nprim, N, stream);   // warm-up
+  cudaEventRecord(e0, s);
+  for (int i = 0; i < reps && rc == VPN_OK; ++i) rc = vpn_pose_points_fwd(kind, v, q, t, srcs[i % nsrc], out, nprim, N, stream);
+  cudaEventRecord(e1, s);
+  if (rc == VPN_OK && cudaEventSynchronize(e1) != cudaSuccess) { vpn_set_error("pose timed: %s", cudaGetErrorString(cudaGetLastError())); rc = VPN_ERR_CUDA; }
+  if (rc == VPN_OK) { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *ms_per_launch = ms / reps; }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return rc;
 }
 
 extern "C" int vpn_pose_points_bwd(int kind, const float* v, const float* q, const float* src, const float* grad_out,
@@ -270,11 +334,12 @@ extern "C" int vpn_pose_points_bwd(int kind, const float* v, const float* q, con
   if (workspace_floats < (size_t)nprim * ns * 16) { vpn_set_error("pose bwd: workspace too small"); return VPN_ERR_WORKSPACE; }
   dim3 grid(nprim, ns), block(kPoseThreads);
   cudaStream_t s = (cudaStream_t)stream;
+  int vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(grad_out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   switch (kind) {
-    case KIND_SPHERE:   pose_bwd_partial_kernel<KIND_SPHERE><<<grid, block, 0, s>>>(v, q, src, grad_out, workspace, nullptr, N); break;
-    case KIND_CUBOID:   pose_bwd_partial_kernel<KIND_CUBOID><<<grid, block, 0, s>>>(v, q, src, grad_out, workspace, nullptr, N); break;
-    case KIND_TEMPLATE: pose_bwd_partial_kernel<KIND_TEMPLATE><<<grid, block, 0, s>>>(v, q, src, grad_out, workspace, nullptr, N); break;
-    default:            pose_bwd_partial_kernel<KIND_POINTS><<<grid, block, 0, s>>>(v, q, src, grad_out, workspace, grad_points, N); break;
+    case KIND_SPHERE:   pose_bwd_partial_kernel<KIND_SPHERE><<<grid, block, 0, s>>>(v, q, src, grad_out, workspace, nullptr, N, vec_ok); break;
+    case KIND_CUBOID:   pose_bwd_partial_kernel<KIND_CUBOID><<<grid, block, 0, s>>>(v, q, src, grad_out, workspace, nullptr, N, vec_ok); break;
+    case KIND_TEMPLATE: pose_bwd_partial_kernel<KIND_TEMPLATE><<<grid, block, 0, s>>>(v, q, src, grad_out, workspace, nullptr, N, vec_ok); break;
+    default:            pose_bwd_partial_kernel<KIND_POINTS><<<grid, block, 0, s>>>(v, q, src, grad_out, workspace, grad_points, N, vec_ok); break;
   }
   int rc = vpn_check_launch("pose_bwd_partial_kernel");
   if (rc) return rc;

@@ -22,6 +22,8 @@ _SIGNATURES = {
     "vpn_launch_count": (ctypes.c_ulonglong, []),
     "vpn_device_info": (c_int, [POINTER(c_int)] * 4),
     "vpn_pose_points_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "vpn_pose_points_fwd_timed": (c_int, [c_int, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_void_p, c_int, c_int,
+                                          c_int, POINTER(c_float), c_void_p]),
     "vpn_pose_bwd_workspace_floats": (c_int, [c_int, c_int, POINTER(c_size_t)]),
     "vpn_pose_points_bwd": (c_int, [c_int] + [c_void_p] * 9 + [c_size_t, c_int, c_int, c_void_p]),
     "vpn_cuboid_face_counts": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -417,6 +417,23 @@ def sample_mesh_surface(verts, faces, uniforms):
     return _MeshSample.apply(verts, faces, uniforms)
 
 
+def sample_primitives_ms(kind: str, v, q, t, uniform_sets, reps: int = 32) -> float:
+    """Mean device time (ms) of one fused sample+pose launch over a stream of `reps` launches that rotate through
+    `uniform_sets` (list of (B,K,N,2|3) tensors; make their total size exceed L2 for cold reads).  Measurement helper."""
+    lib = _lib.load()
+    kid = {"sphere": KIND_SPHERE, "cuboid": KIND_CUBOID}[kind]
+    b, k, vf, qf, tf = _flat_prims(v.detach(), q.detach(), t.detach())
+    n = uniform_sets[0].shape[2]
+    dev = qf.device
+    srcs = [require(u.contiguous(), f32, "uniforms") for u in uniform_sets]
+    arr = (ctypes.c_void_p * len(srcs))(*[u.data_ptr() for u in srcs])
+    out = torch.empty((b * k, n, 3), dtype=f32, device=dev)
+    ms = ctypes.c_float(0)
+    check(lib.vpn_pose_points_fwd_timed(kid, ptr(vf), ptr(qf), ptr(tf), arr, len(srcs), ptr(out), b * k, n, reps,
+                                        ctypes.byref(ms), stream_ptr(dev)), "vpn_pose_points_fwd_timed")
+    return float(ms.value)
+
+
 def chamfer_main_kernel_name(b: int, p: int, m: int, impl: int = CHAMFER_AUTO) -> str:
     """Name of the kernel vpn_chamfer_fwd spends its time in for this shape / impl (bench.py's roofline label)."""
     lib = _lib.load()
