@@ -29,18 +29,29 @@ for p in (REPO, PKG):
 import torch  # noqa: E402
 
 WORKLOADS = {
-    # name: (kind, B per GPU, K, N, M, render resolution or 0)
+    # name: (kind, B per GPU, K, N, M, render resolution or 0)          BASELINE.json configs[0..4]
     "c1": ("sphere", 1, 16, 1024, 2048, 64),
     "c2": ("cuboid", 32, 16, 4096, 8192, 0),
     "c3": ("cuboid", 32, 32, 4096, 8192, 128),
+    "c4": ("cuboid", 256, 32, 4096, 8192, 128),       # B = 256 in TOTAL, split over the ranks (strong scaling)
+    "c5": ("sphere", 8, 128, 128, 16384, 256),        # train_gcn.py shape: the K*128 mesh vertices are the predicted points
 }
+STRONG = {"c4"}            # workloads whose B is the global batch
+VERTEX_MODE = {"c5"}       # Chamfer on the composed mesh vertices (train_gcn.py:127-130) instead of surface samples
+
+
+def per_gpu_batch(workload, world):
+    b = WORKLOADS[workload][1]
+    return max(1, b // world) if workload in STRONG else b
+
 GRAD_NUMEL = 22_875_848          # VPNetOneRes parameters at K = 16
 METRIC = "primitive-loss fwd+bwd samples/sec"
 
 
-def synthetic(workload, device, seed=1234, sets=1):
+def synthetic(workload, device, seed=1234, sets=1, batch=None):
     """Network-output-shaped primitives + ShapeNet-shaped targets, fp32."""
     kind, b, k, n, m, res = WORKLOADS[workload]
+    b = batch or b
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(sets):
@@ -156,9 +167,11 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def describe(workload):
+def describe(workload, world=1):
     kind, b, k, n, m, res = WORKLOADS[workload]
-    s = f"{workload}: B={b}/GPU, {k} {kind} primitives x {n} samples (P={k * n}), Chamfer vs M={m} targets + VP-diverse"
+    b = per_gpu_batch(workload, world)
+    what = "template vertices" if workload in VERTEX_MODE else "samples"
+    s = f"{workload}: B={b}/GPU, {k} {kind} primitives x {n} {what} (P={k * n}), Chamfer vs M={m} targets + VP-diverse"
     if res:
         s += f" + {res}x{res} soft-silhouette L1"
     return s + ", fwd+bwd to (v,q,t)"
@@ -191,19 +204,22 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     kind, b, k, n, m, res = WORKLOADS[args.workload]
+    b = per_gpu_batch(args.workload, world)
+    vertex_mode = args.workload in VERTEX_MODE
     width = 2 if kind == "sphere" else 3
     nsets = 4
-    host = synthetic(args.workload, "cpu", seed=1234 + rank, sets=nsets)
+    host = synthetic(args.workload, "cpu", seed=1234 + rank, sets=nsets, batch=b)
     devsets = [{kk: (vv.to(dev) if vv is not None else None) for kk, vv in s.items()} for s in host]
     pinned = [{kk: (vv.pin_memory() if vv is not None else None) for kk, vv in s.items()} for s in host]
-    cfg = vpn_b200.PrimitiveLossConfig(kind=kind, l_sil=(1.0 if res else 0.0), chamfer_impl=args.chamfer_impl)
+    cfg = vpn_b200.PrimitiveLossConfig(kind=kind, l_sil=(1.0 if res else 0.0), chamfer_impl=args.chamfer_impl,
+                                       vertex_chamfer=vertex_mode)
     step_fn = vpn_b200.PrimitiveLoss(cfg)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
     sync = vdist.GradientAllReduce(GRAD_NUMEL, dev) if world > 1 else None
 
     def one_step(s, grads_out=None):
         v, q, t = (s[x].detach().requires_grad_() for x in ("v", "q", "t"))
-        u = torch.rand((b, k, n, width), device=dev)               # drawn on device, like the reference
+        u = None if vertex_mode else torch.rand((b, k, n, width), device=dev)      # drawn on device, like the reference
         out = step_fn(v, q, t, u, s["target"], silhouettes=s["sil"])
         out["total"].backward()
         if sync is not None:
@@ -277,8 +293,11 @@ def main():
         # ---- roofline of the dominant kernel group: Chamfer forward (FP32 pipe) ----------------------
         s = devsets[0]
         with torch.no_grad():
-            u = torch.rand((b, k, n, width), device=dev)
-            pts = vpn_b200.sample_primitives(kind, s["v"], s["q"], s["t"], u)
+            if vertex_mode:
+                from vpn_b200 import templates as _tpl
+                pts = vpn_b200.mesh_vertices(_tpl.template(kind, dev)[0], s["v"], s["q"], s["t"])
+            else:
+                pts = vpn_b200.sample_primitives(kind, s["v"], s["q"], s["t"], torch.rand((b, k, n, width), device=dev))
             reps = 10
             vpn_b200.chamfer_nn_stage_ms(pts, s["target"], args.chamfer_impl, reps=3)
             stage = vpn_b200.chamfer_nn_stage_ms(pts, s["target"], args.chamfer_impl, reps=reps)
@@ -286,9 +305,9 @@ def main():
             # sampling kernel: a stream of launches over rotating uniform buffers larger than L2 in total (every
             # launch reads cold inputs; no write-flush, whose dirty lines would be written back during the launch)
             sbytes = b * k * n * (12 + 4 * width)
-            nrot = max(2, -(-300_000_000 // sbytes))
-            us = [torch.rand((b, k, n, width), device=dev) for _ in range(nrot)]
+            nrot = min(64, max(2, -(-300_000_000 // sbytes)))
             nl = 4 * nrot
+            us = [torch.rand((b, k, n, width), device=dev) for _ in range(nrot)]
             samp_ms = vpn_b200.sample_primitives_ms(kind, s["v"], s["q"], s["t"], us, reps=nl)
             del us
         peak = vpn_b200.fp32_peak_tflops(dev)
@@ -365,9 +384,10 @@ def main():
                    "sample": f"1 sample, {used} of {k * n} predicted points x {m} targets, dense torch-CPU formulation "
                              f"of the reference (fwd+bwd, no render term), {dt:.1f} s, scaled linearly to a full sample"}
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "strong" if args.workload in STRONG else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": describe(args.workload), "global_batch": world * b,
+                "config": {"workload": describe(args.workload, world), "global_batch": world * b,
                            "parallelism": f"dp{world}", "l2": "256 MB L2 flush between timed iterations, outside the "
                            "per-step CUDA-event pairs; 4 rotating input sets",
                            "allreduce_numel": GRAD_NUMEL if world > 1 else 0,

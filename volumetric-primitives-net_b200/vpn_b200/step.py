@@ -30,6 +30,7 @@ class PrimitiveLossConfig:
     silhouette_loss: str = "L1"       # config.py:27
     img_size: int = 128               # config.py:46
     chamfer_impl: int = ops.CHAMFER_AUTO
+    vertex_chamfer: bool = False      # train_gcn.py:127-130: the Chamfer term scores the composed mesh vertices, not samples
 
 
 class PrimitiveLoss:
@@ -54,7 +55,12 @@ class PrimitiveLoss:
         cfg = self.cfg
         out: Dict[str, torch.Tensor] = {}
         b, k = q.shape[:2]
-        points = ops.sample_primitives(cfg.kind, v, q, t, uniforms)
+        verts = None
+        if cfg.vertex_chamfer:
+            tv, _ = templates.template(cfg.kind, v.device)
+            points = verts = ops.mesh_vertices(tv, v, q, t)
+        else:
+            points = ops.sample_primitives(cfg.kind, v, q, t, uniforms)
         out["points"] = points
         total = None
 
@@ -74,8 +80,9 @@ class PrimitiveLoss:
             add("vp_div", ops.chamfer_distance(t.contiguous(), view_center_points, w1=0.5, w2=1.0,
                                                impl=cfg.chamfer_impl) * cfg.l_vp_div)
         if cfg.l_sil:
-            tv, _ = templates.template(cfg.kind, v.device)
-            verts = ops.mesh_vertices(tv, v, q, t)
+            if verts is None:
+                tv, _ = templates.template(cfg.kind, v.device)
+                verts = ops.mesh_vertices(tv, v, q, t)
             faces = self.composed_faces(k, v.device)
             h, w = silhouettes.shape[-2:]
             # IS_VIEW_CENTER: dist = 1, elev = azim = 0 for every sample (train.py:172-174)
