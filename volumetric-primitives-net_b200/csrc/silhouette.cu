@@ -198,48 +198,114 @@ __device__ __forceinline__ void pixel_coords(const RasterParams& rp, int w, int 
   Y = __fmul_rn(__fdiv_rn(rp.mult, (float)rp.H), (float)(rp.H - 2 * h - 1));
 }
 
+// Per-tile candidate lists in dynamic shared memory, [k][pixel] so that a pixel's thread writes conflict free:
+//   cand  u16 [kKnumMax][256]  face index of the pixel's k-th soft candidate (F <= 65535)
+//   fac   f32 [kKnumMax][256]  forward: 1 - prob; backward: prob
+//   which u8  [kKnumMax][256]  backward: winning distance case
+struct TileLists { unsigned short* cand; float* fac; unsigned char* which; };
+__device__ __forceinline__ TileLists tile_lists(unsigned char* p) {
+  TileLists t;
+  t.fac = reinterpret_cast<float*>(p); p += kKnumMax * kRThreads * sizeof(float);
+  t.cand = reinterpret_cast<unsigned short*>(p); p += kKnumMax * kRThreads * sizeof(unsigned short);
+  t.which = p;
+  return t;
+}
+constexpr size_t kTileListBytesFwd = kKnumMax * kRThreads * (sizeof(float) + sizeof(unsigned short));
+constexpr size_t kTileListBytesBwd = kTileListBytesFwd + kKnumMax * kRThreads;
+
+// Exclusive prefix sum of cnt over the CTA's 256 threads into s_off[0..256] (s_off[256] = total).
+__device__ __forceinline__ void tile_offsets(int cnt, int* s_off, int* s_wsum) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  int base = 0;
+#pragma unroll
+  for (int w = 0; w < kRThreads / 32; ++w) if (w < warp) base += s_wsum[w];
+  s_off[tid] = base + inc - cnt;
+  if (tid == kRThreads - 1) s_off[kRThreads] = base + inc;
+  __syncthreads();
+}
+// pixel p of the tile that owns work item `it`: largest p with s_off[p] <= it
+__device__ __forceinline__ int item_pixel(const int* s_off, int it) {
+  int lo = 0, hi = kRThreads - 1;
+#pragma unroll
+  for (int step = 0; step < 8; ++step) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (s_off[mid] <= it) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// The soft term costs ~200 instructions per (pixel, face) pair and only a few pixels of a warp lie inside a face's
+// expanded box, so the tile is done in three passes:
+//   A  pixel-parallel, cheap: walk the binned faces in index order; coverage test; remember the first knum candidates
+//   B  work-parallel, dense : one (pixel, candidate) item per thread - distance, prob          (all lanes busy)
+//   C  pixel-parallel       : product of the pixel's factors in candidate order (the order DIB-R multiplies in)
 // grid: x = tile x, y = tile y, z = sample
 __global__ void __launch_bounds__(kRThreads)
 sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restrict__ box_all, float* __restrict__ alpha,
                       unsigned char* __restrict__ covered_out, RasterParams rp) {
-  const int b = blockIdx.z;
-  const int w = blockIdx.x * kTile + (threadIdx.x % kTile), h = blockIdx.y * kTile + (threadIdx.x / kTile);
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ int s_off[kRThreads + 1];
+  __shared__ int s_wsum[kRThreads / 32];
+  const TileLists tl = tile_lists(s_dyn);
+  const int b = blockIdx.z, tid = threadIdx.x;
+  const int w = blockIdx.x * kTile + (tid % kTile), h = blockIdx.y * kTile + (tid / kTile);
+  const bool in_img = (w < rp.W && h < rp.H);
   const FaceRec* rec = rec_all + (size_t)b * rp.F;
   float X, Y; pixel_coords(rp, min(w, rp.W - 1), min(h, rp.H - 1), X, Y);
   // pixel-centre extent of the tile (x grows with w, y shrinks with h)
-  float xL, xR, yT, yB, dummy;
+  float xL, xR, yT, yB;
   pixel_coords(rp, blockIdx.x * kTile, blockIdx.y * kTile, xL, yT);
   pixel_coords(rp, min(blockIdx.x * kTile + kTile - 1, rp.W - 1), min(blockIdx.y * kTile + kTile - 1, rp.H - 1), xR, yB);
-  (void)dummy;
   const float em = __fmul_rn(rp.expand, rp.mult);
-  bool covered = false; int kid = 0; float prod = 1.0f;
+  bool covered = false; int cnt = 0;
   const float4* boxes = box_all + (size_t)b * ((rp.F + kRThreads - 1) / kRThreads);
-  walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, em, [&](int, const FaceRec& r, const float4& tb) {
+  walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, em, [&](int f, const FaceRec& r, const float4& tb) {
     if (covered) return;                                // alpha is 1 whatever follows
     const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
     if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
     if (X >= txmin && X < txmax && Y >= tymin && Y < tymax && inside_tri(r, X, Y, rp.eps)) { covered = true; return; }
-    if (kid < rp.knum) {
-      int which;
-      float d2 = tri_dist2(r, X, Y, rp.mult, rp.eps, which);
-      float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
-      prod = __fmul_rn(prod, __fsub_rn(1.0f, expf(-z)));
-      ++kid;
-    }
+    if (cnt < rp.knum) { tl.cand[cnt * kRThreads + tid] = (unsigned short)f; ++cnt; }
   });
-  if (w < rp.W && h < rp.H) {
-    size_t o = ((size_t)b * rp.H + h) * rp.W + w;
+  const int mine = (in_img && !covered) ? cnt : 0;
+  tile_offsets(mine, s_off, s_wsum);
+  const int total = s_off[kRThreads];
+  for (int it = tid; it < total; it += kRThreads) {
+    const int p = item_pixel(s_off, it), k = it - s_off[p];
+    const FaceRec r = rec[tl.cand[k * kRThreads + p]];
+    float PX, PY;
+    pixel_coords(rp, min((int)(blockIdx.x * kTile + (p % kTile)), rp.W - 1), min((int)(blockIdx.y * kTile + (p / kTile)), rp.H - 1), PX, PY);
+    int which;
+    const float d2 = tri_dist2(r, PX, PY, rp.mult, rp.eps, which);
+    const float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
+    tl.fac[k * kRThreads + p] = __fsub_rn(1.0f, expf(-z));
+  }
+  __syncthreads();
+  if (in_img) {
+    float prod = 1.0f;
+    for (int k = 0; k < mine; ++k) prod = __fmul_rn(prod, tl.fac[k * kRThreads + tid]);
+    const size_t o = ((size_t)b * rp.H + h) * rp.W + w;
     alpha[o] = covered ? 1.0f : __fsub_rn(1.0f, prod);
     covered_out[o] = covered ? 1 : 0;
   }
 }
 
-// Backward of the soft term: d alpha / d (scaled screen coords of the recorded faces).
+// Backward of the soft term: d alpha / d (scaled screen coords of the recorded faces).  Same three passes; pass C is
+// work-parallel too: one (pixel, candidate) item per thread, scattered into the per-face buffer with atomics.
 __global__ void __launch_bounds__(kRThreads)
 sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restrict__ box_all, const float* __restrict__ galpha,
                       const unsigned char* __restrict__ covered_in, float* __restrict__ gface, RasterParams rp) {
-  const int b = blockIdx.z;
-  const int w = blockIdx.x * kTile + (threadIdx.x % kTile), h = blockIdx.y * kTile + (threadIdx.x / kTile);
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ int s_off[kRThreads + 1];
+  __shared__ int s_wsum[kRThreads / 32];
+  __shared__ float s_g[kRThreads];
+  const TileLists tl = tile_lists(s_dyn);
+  const int b = blockIdx.z, tid = threadIdx.x;
+  const int w = blockIdx.x * kTile + (tid % kTile), h = blockIdx.y * kTile + (tid / kTile);
   const bool in_img = (w < rp.W && h < rp.H);
   const FaceRec* rec = rec_all + (size_t)b * rp.F;
   float X, Y; pixel_coords(rp, min(w, rp.W - 1), min(h, rp.H - 1), X, Y);
@@ -253,50 +319,64 @@ sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
     g = galpha[o];
     active = (covered_in[o] == 0) && (g != 0.f);
   }
-  int kid = 0;
-  int fid[kKnumMax]; float prob[kKnumMax];
+  s_g[tid] = g;
+  int cnt = 0;
   const float4* boxes = box_all + (size_t)b * ((rp.F + kRThreads - 1) / kRThreads);
-  walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, em, [&](int f, const FaceRec& r, const float4& tb) {
-    if (!active || kid >= rp.knum) return;
-    const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
-    if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
+  if (__syncthreads_or(active)) {                       // tiles without an uncovered pixel that has a gradient do nothing
+    walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, em, [&](int f, const FaceRec& r, const float4& tb) {
+      if (!active || cnt >= rp.knum) return;
+      const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
+      if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
+      tl.cand[cnt * kRThreads + tid] = (unsigned short)f; ++cnt;
+    });
+  }
+  tile_offsets(cnt, s_off, s_wsum);
+  const int total = s_off[kRThreads];
+  if (total == 0) return;
+  for (int it = tid; it < total; it += kRThreads) {
+    const int p = item_pixel(s_off, it), k = it - s_off[p];
+    const FaceRec r = rec[tl.cand[k * kRThreads + p]];
+    float PX, PY;
+    pixel_coords(rp, min((int)(blockIdx.x * kTile + (p % kTile)), rp.W - 1), min((int)(blockIdx.y * kTile + (p / kTile)), rp.H - 1), PX, PY);
     int which;
-    float d2 = tri_dist2(r, X, Y, rp.mult, rp.eps, which);
-    float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
-    fid[kid] = f; prob[kid] = expf(-z);
-    ++kid;
-  });
-  if (!active || kid == 0) return;
-  // alpha = 1 - prod_k (1 - p_k);  d alpha / d p_k = prod_{j != k} (1 - p_j)
-  float suffix[kKnumMax + 1];
-  suffix[kid] = 1.0f;
-  for (int k = kid - 1; k >= 0; --k) suffix[k] = suffix[k + 1] * (1.0f - prob[k]);
-  float prefix = 1.0f;
-  for (int k = 0; k < kid; ++k) {
-    const float dadp = prefix * suffix[k + 1];
-    prefix *= (1.0f - prob[k]);
-    const FaceRec r = rec[fid[k]];
-    int which;
-    (void)tri_dist2(r, X, Y, rp.mult, rp.eps, which);
+    const float d2 = tri_dist2(r, PX, PY, rp.mult, rp.eps, which);
+    const float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
+    tl.fac[k * kRThreads + p] = expf(-z);
+    tl.which[k * kRThreads + p] = (unsigned char)which;
+  }
+  __syncthreads();
+  for (int it = tid; it < total; it += kRThreads) {
+    const int p = item_pixel(s_off, it), k = it - s_off[p], n = s_off[p + 1] - s_off[p];
+    // alpha = 1 - prod_j (1 - p_j);  d alpha / d p_k = prod_{j != k} (1 - p_j), multiplied in the order prefix * suffix
+    float prefix = 1.0f, suffix = 1.0f;
+    for (int j = 0; j < k; ++j) prefix *= (1.0f - tl.fac[j * kRThreads + p]);
+    for (int j = n - 1; j > k; --j) suffix *= (1.0f - tl.fac[j * kRThreads + p]);
+    const float dadp = prefix * suffix;
+    const float prob = tl.fac[k * kRThreads + p];
+    const int which = tl.which[k * kRThreads + p];
+    const int f = tl.cand[k * kRThreads + p];
+    const FaceRec r = rec[f];
+    float PX, PY;
+    pixel_coords(rp, min((int)(blockIdx.x * kTile + (p % kTile)), rp.W - 1), min((int)(blockIdx.y * kTile + (p / kTile)), rp.H - 1), PX, PY);
     // p = exp(-delta d2 / mult^2)  ->  dp/dd2 = -p delta / mult^2
-    const float gd2 = g * dadp * (-prob[k]) * rp.delta / (rp.mult * rp.mult);
+    const float gd2 = s_g[p] * dadp * (-prob) * rp.delta / (rp.mult * rp.mult);
     float gr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float vx[3] = {r.ax, r.bx, r.cx}, vy[3] = {r.ay, r.by, r.cy};
     if (which < 3) {
       const int i1 = which, i2 = (which + 1) % 3;
       const float x1 = vx[i1], y1 = vy[i1], x2 = vx[i2], y2 = vy[i2];
       const float A = y2 - y1, Bc = x1 - x2, C = x2 * y1 - x1 * y2;
-      const float up = A * X + Bc * Y + C, de = A * A + Bc * Bc + rp.eps;
+      const float up = A * PX + Bc * PY + C, de = A * A + Bc * Bc + rp.eps;
       const float gU = gd2 * 2.0f * up / de, gD = -gd2 * up * up / (de * de);
-      const float gA = gU * X + gD * 2.0f * A, gB = gU * Y + gD * 2.0f * Bc, gC = gU;
+      const float gA = gU * PX + gD * 2.0f * A, gB = gU * PY + gD * 2.0f * Bc, gC = gU;
       gr[2 * i1] += gB - gC * y2;  gr[2 * i1 + 1] += -gA + gC * x2;
       gr[2 * i2] += -gB + gC * y1; gr[2 * i2 + 1] += gA - gC * x1;
     } else {
       const int i = which - 3;
-      gr[2 * i] = gd2 * 2.0f * (vx[i] - X);
-      gr[2 * i + 1] = gd2 * 2.0f * (vy[i] - Y);
+      gr[2 * i] = gd2 * 2.0f * (vx[i] - PX);
+      gr[2 * i + 1] = gd2 * 2.0f * (vy[i] - PY);
     }
-    float* o = gface + 6 * ((size_t)b * rp.F + fid[k]);
+    float* o = gface + 6 * ((size_t)b * rp.F + f);
 #pragma unroll
     for (int c = 0; c < 6; ++c) if (gr[c] != 0.f) atomicAdd(o + c, gr[c]);
   }
@@ -357,6 +437,7 @@ static int sil_check(int B, int V, int F, int H, int W, int knum) {
   if (B < 0 || V <= 0 || F <= 0 || H <= 0 || W <= 0) { vpn_set_error("silhouette: bad shape"); return VPN_ERR_SHAPE; }
   if (B > 65535) { vpn_set_error("silhouette: batch > 65535 unsupported"); return VPN_ERR_SHAPE; }
   if (knum < 1 || knum > kKnumMax) { vpn_set_error("silhouette: knum must be in [1, %d]", kKnumMax); return VPN_ERR_ARG; }
+  if (F > 65535) { vpn_set_error("silhouette: more than 65535 faces per mesh unsupported (16-bit candidate lists)"); return VPN_ERR_SHAPE; }
   return VPN_OK;
 }
 
@@ -386,7 +467,14 @@ extern "C" int vpn_silhouette_fwd(const float* verts, const int* faces, const fl
   if ((rc = vpn_check_launch("sil_faces_kernel"))) return rc;
   RasterParams rp{H, W, F, knum, expand, multiplier, delta, 1e-15f};
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
-  sil_raster_fwd_kernel<<<grid, kRThreads, 0, s>>>(rec, boxes, alpha, covered, rp);
+  static bool attr_fwd = false;
+  if (!attr_fwd) {
+    if (cudaFuncSetAttribute(sil_raster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileListBytesFwd) != cudaSuccess) {
+      vpn_set_error("silhouette fwd: smem attribute"); return VPN_ERR_CUDA;
+    }
+    attr_fwd = true;
+  }
+  sil_raster_fwd_kernel<<<grid, kRThreads, kTileListBytesFwd, s>>>(rec, boxes, alpha, covered, rp);
   return vpn_check_launch("sil_raster_fwd_kernel");
 }
 
@@ -412,7 +500,14 @@ extern "C" int vpn_silhouette_bwd(const int* faces, const float* cam_rot, float 
   }
   RasterParams rp{H, W, F, knum, expand, multiplier, delta, 1e-15f};
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
-  sil_raster_bwd_kernel<<<grid, kRThreads, 0, s>>>(rec, reinterpret_cast<const float4*>(ws + wl.box), grad_alpha, covered, gface, rp);
+  static bool attr_bwd = false;
+  if (!attr_bwd) {
+    if (cudaFuncSetAttribute(sil_raster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileListBytesBwd) != cudaSuccess) {
+      vpn_set_error("silhouette bwd: smem attribute"); return VPN_ERR_CUDA;
+    }
+    attr_bwd = true;
+  }
+  sil_raster_bwd_kernel<<<grid, kRThreads, kTileListBytesBwd, s>>>(rec, reinterpret_cast<const float4*>(ws + wl.box), grad_alpha, covered, gface, rp);
   if ((rc = vpn_check_launch("sil_raster_bwd_kernel"))) return rc;
   sil_face_to_vertex_kernel<<<dim3((F + 255) / 256, B), 256, 0, s>>>(gface, faces, cam, cam_rot, proj_x, proj_y, proj_z,
                                                                       multiplier, grad_verts, V, F);
