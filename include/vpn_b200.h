@@ -121,6 +121,17 @@ int vpn_mesh_sample_fwd(const float* verts, const int* faces, const float* u, fl
 int vpn_mesh_sample_bwd(const int* faces, const float* u, const int* face_idx, const float* grad_points,
                         float* grad_verts, int B, int V, int F, int n, void* stream);
 
+/* ---- EMD approximation by auction: modules/loss/emd (emd_module.py:29-79, emd_cuda.cu:227-316)
+ * xyz1 (B,n,3) predicted (bidders), xyz2 (B,n,3) ground truth (objects), coordinates normalised to [0,1].
+ * dist (B,n) = squared distance to the assigned object, assignment (B,n) int32 (not necessarily a bijection).
+ * One launch; ties resolved deterministically (lowest index).  Workspace only for n > 4096 (state in HBM). */
+int vpn_emd_workspace_bytes(int B, int n, size_t* bytes);
+int vpn_emd_fwd(const float* xyz1, const float* xyz2, float* dist, int* assignment, void* workspace,
+                size_t workspace_bytes, int B, int n, float eps, int iters, void* stream);
+/* grad_xyz1 (B,n,3) = 2 grad_dist (xyz1 - xyz2[assignment]); xyz2 receives no gradient (emd_module.py:66-67). */
+int vpn_emd_bwd(const float* xyz1, const float* xyz2, const int* assignment, const float* grad_dist,
+                float* grad_xyz1, int B, int n, void* stream);
+
 /* ---- measurement helper: achieved FP32 FMA throughput (the Chamfer roofline denominator) ----------------
  * scratch: >= 64 device floats, the first 16 finite and near 1.0.  Synchronises the stream. */
 int vpn_fp32_peak_probe(float* scratch, int reps, double* tflops_ffma, double* tflops_ffma2, void* stream);

@@ -26,6 +26,14 @@ Parity status
   three random draws made explicit inputs; kaolin's own RNG stream (Categorical.sample + two
   Uniform.sample) cannot be replayed, so parity beyond "same distribution" is not claimed.
 
+* EMD auction loss (modules/loss/emd, SURVEY.md section 8f "next" #1): the reference implementation is
+  non-deterministic by construction (racing writes decide which of several equal bidders wins,
+  emd_cuda.cu:181-194, and its value arithmetic mixes double and contracted fp32, :141,219) and cannot be
+  run here (no GPU in the build container; the extension does not compile against current ATen).
+  `emd_auction` restates its algorithm with the races resolved deterministically (lowest index wins) and
+  plain separately-rounded fp32 arithmetic: PARITY IS STATISTICAL - same auction, same eps / iteration
+  schedule; tests check validity and near-optimality of the assignment against scipy's exact solver.
+
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 """
 from __future__ import annotations
@@ -289,6 +297,78 @@ def vp_diverse(translates: Sequence[torch.Tensor], gt_points: torch.Tensor) -> t
     assert isinstance(translates, list)
     centres = torch.cat([t[:, None, :] for t in translates], dim=1)
     return chamfer_dense(centres, gt_points, w1=0.5, w2=1.0)
+
+
+# --------------------------------------------------------------------------------------
+# EMD auction  (modules/loss/emd/emd_cuda.cu, emd_module.py)
+# --------------------------------------------------------------------------------------
+def emd_auction(xyz1: np.ndarray, xyz2: np.ndarray, eps: float, iters: int, row_block: int = 512):
+    """emd_cuda_forward (emd_cuda.cu:227-281) for one sample: xyz1 (n,3) bidders, xyz2 (n,3) objects, fp32.
+    Returns (dist (n,) fp32 squared distance to the assigned object, assignment (n,) int32).
+
+    Per iteration (emd_cuda.cu:257-269): the unassigned bidders each find the object maximising
+    value = 3 - |x2 - x1| - price (Bid, :95-179; best = first maximum, better = second largest value),
+    bid increment = best - better + eps, per-object maximum increment; the bidder whose increment is within
+    1e-6 of the object's maximum wins it (GetMax, :181-194; here the LOWEST such bidder - the reference lets
+    racing writes decide), evicts the previous owner, and the price rises by its increment (Assign, :196-216).
+    In the last iteration every still unassigned bidder takes its preferred object unconditionally, so the
+    result need not be a bijection.  dist = |x1 - x2[assignment]|^2 (CalcDist, :218-226).
+    Arithmetic: fp32, every operation rounded separately ((dx^2 + dy^2) + dz^2, IEEE sqrt, (3 - s) - price)."""
+    f32 = np.float32
+    x1 = np.ascontiguousarray(xyz1, dtype=f32)
+    x2 = np.ascontiguousarray(xyz2, dtype=f32)
+    n = x1.shape[0]
+    assert x2.shape[0] == n and iters >= 1
+    assignment = np.full(n, -1, dtype=np.int32)
+    assignment_inv = np.full(n, -1, dtype=np.int32)
+    price = np.zeros(n, dtype=f32)
+    max_inc = np.full(n, f32(-1e9), dtype=f32)
+    epsf = f32(eps)
+    for it in range(iters):
+        last = it == iters - 1
+        un = np.nonzero(assignment == -1)[0]
+        if un.size == 0:
+            continue
+        best = np.empty(un.size, dtype=f32); better = np.empty(un.size, dtype=f32)
+        best_i = np.empty(un.size, dtype=np.int64)
+        for r0 in range(0, un.size, row_block):
+            rows = un[r0:r0 + row_block]
+            d = x2[None, :, :] - x1[rows, None, :]
+            d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+            val = (f32(3.0) - np.sqrt(d2)) - price[None, :]
+            bi = np.argmax(val, axis=1)                                 # first maximum
+            ar = np.arange(rows.size)
+            bv = val[ar, bi]
+            val[ar, bi] = -np.inf
+            sv = np.maximum(val.max(axis=1), f32(-1e9)) if n > 1 else np.full(rows.size, f32(-1e9), dtype=f32)
+            best[r0:r0 + rows.size] = bv; better[r0:r0 + rows.size] = sv; best_i[r0:r0 + rows.size] = bi
+        inc = ((best - better).astype(f32) + epsf).astype(f32)
+        np.maximum.at(max_inc, best_i, inc)
+        # winner of an object: lowest bidder whose increment is within 1e-6 (compared in double) of the maximum
+        mx = max_inc[best_i].astype(np.float64)
+        ok = (inc.astype(np.float64) - 1e-6 <= mx) & (mx <= inc.astype(np.float64) + 1e-6)
+        winner = np.full(n, np.iinfo(np.int32).max, dtype=np.int64)
+        np.minimum.at(winner, best_i[ok], un[ok])
+        for u, j in enumerate(un):                                       # ascending bidder order
+            t = best_i[u]
+            if last or winner[t] == j:
+                old = assignment_inv[t]
+                if not last and old != -1:
+                    assignment[old] = -1
+                assignment_inv[t] = j
+                assignment[j] = t
+                price[t] = f32(price[t] + inc[u])
+                max_inc[t] = f32(-1e9)
+    d = x1 - x2[assignment]
+    dist = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    return dist.astype(f32), assignment
+
+
+def emd_backward(xyz1: np.ndarray, xyz2: np.ndarray, assignment: np.ndarray, grad_dist: np.ndarray) -> np.ndarray:
+    """NmDistanceGradKernel (emd_cuda.cu:283-300): d dist / d xyz1 = 2 g (x1 - x2[assignment]); xyz2 gets no
+    gradient (emd_module.py:66-67 returns zeros)."""
+    g = (grad_dist.astype(np.float32) * np.float32(2.0))[:, None]
+    return (g * (xyz1.astype(np.float32) - xyz2.astype(np.float32)[assignment])).astype(np.float32)
 
 
 # --------------------------------------------------------------------------------------

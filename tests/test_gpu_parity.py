@@ -269,7 +269,7 @@ def test_chamfer_backward_vs_oracle(vpn, O):
 def test_chamfer_small_first_cloud_bit_exact(vpn, c_oracle, case):
     """VP-diverse shapes (vp_diverse.py:12-18: K centres vs M targets) take the one-launch small-P kernel."""
     gen = torch.Generator().manual_seed(41 + len(case))
-    for (b, p, m) in ((2, 16, 8192), (3, 1, 1), (1, 64, 257), (2, 5, 3), (1, 33, 1000), (32, 32, 2048)):
+    for (b, p, m) in ((2, 16, 8192), (3, 1, 1), (1, 64, 257), (2, 5, 3), (1, 33, 1000), (32, 32, 2048), (2, 128, 4096), (1, 256, 300)):
         p1, p2 = adversarial_clouds(case, b, p, m, gen)
         ref = c_oracle(p1.numpy(), p2.numpy())
         got = run_nn(vpn, p1, p2, IMPLS["auto"])
@@ -527,3 +527,42 @@ def test_step_config_shapes(vpn, O, name, kind, b, k, n, m, res, vertex):
     same(gi[1].long(), ri[1], f"{name} idx1"); same(gi[3].long(), ri[3], f"{name} idx2")
     for got, want, nm in ((vc.grad, vo.grad, "v"), (qc.grad, qo.grad, "q"), (tc.grad, to.grad, "t")):
         close(got, want, rtol=1e-3, atol=2e-4 * float(want.abs().max()), what=f"{name} grad {nm}")
+
+
+# ------------------------------------------------------------------------------------------------
+# EMD auction (modules/loss/emd): one launch per forward, deterministic; bit-exact against the restatement
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("b,n,eps,iters", [(3, 2048, 0.005, 50), (2, 1024, 0.002, 10), (2, 37, 0.005, 50), (1, 1, 0.005, 3),
+                                            (2, 4096, 0.005, 20), (1, 5000, 0.01, 8)])
+def test_emd_auction_matches_oracle(vpn, O, b, n, eps, iters):
+    g = torch.Generator().manual_seed(100 + n)
+    x1 = torch.rand(b, n, 3, generator=g)
+    x2 = torch.rand(b, n, 3, generator=g)
+    if n >= 64:
+        x2[:, :8] = x2[:, 8:16]                    # duplicate objects: exact ties between best and second best
+        x1[0, :4] = x1[0, 4:8]                     # duplicate bidders: equal increments on the same object
+    xc = C(x1).requires_grad_()
+    dist, ass = vpn.emd_auction(xc, C(x2), eps, iters)
+    up = torch.rand(b, n, generator=g)
+    (dist * C(up)).sum().backward()
+    for i in range(b):
+        d_ref, a_ref = O.emd_auction(x1[i].numpy(), x2[i].numpy(), eps, iters)
+        same(ass[i], a_ref, f"assignment sample {i}")                  # integer output: bit-exact
+        same(dist[i], d_ref, f"dist sample {i}")
+        close(xc.grad[i], O.emd_backward(x1[i].numpy(), x2[i].numpy(), a_ref, up[i].numpy()), rtol=1e-6, atol=1e-7)
+
+
+def test_emd_dropin_matches_reference_call(vpn):
+    """train.py:188-195: dist, assignment = EarthMoverDistanceLoss()(predict_points, gt_points, 0.005, 50); sqrt(dist).mean()."""
+    import modules.loss as ml
+    g = torch.Generator().manual_seed(8)
+    p = C(torch.rand(2, 2048, 3, generator=g)).requires_grad_()
+    q = C(torch.rand(2, 2048, 3, generator=g))
+    dist, ass = ml.EarthMoverDistanceLoss()(p, q, 0.005, 50)
+    assert dist.shape == (2, 2048) and ass.shape == (2, 2048) and ass.dtype == torch.int32
+    assert int(ass.min()) >= 0 and int(ass.max()) < 2048
+    loss = torch.sqrt(dist).mean()
+    loss.backward()
+    assert torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0
+    with pytest.raises(AssertionError):
+        ml.EarthMoverDistanceLoss()(p[:, :1000], q[:, :1000], 0.005, 50)      # n % 1024 != 0 (emd_module.py:39)

@@ -112,7 +112,7 @@ __global__ void chamfer_bwd_rows_kernel(const float* __restrict__ p1, const floa
   }
 }
 
-constexpr int kSmallP = 64;      // clouds this small are accumulated in shared memory before the global scatter
+constexpr int kSmallP = 256;      // clouds this small are accumulated in shared memory before the global scatter
 
 __global__ void chamfer_bwd_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                                         const float* __restrict__ min2, const int* __restrict__ idx2,

@@ -1,13 +1,13 @@
 """Drop-in for the hot-path part of the reference's `modules` package (modules/__init__.py:1-8).
 
 Same names, call signatures and AssertionError behaviour as the reference for transform, sampling,
-loss (Chamfer / VP-diverse / silhouette), render (VertexRenderer) and meshing; everything underneath
-runs as vpn_b200 CUDA kernels.  Networks, datasets, augmentation, visualisation and the EMD extension
-are out of scope and stay with the reference.
+loss (Chamfer / VP-diverse / silhouette / EMD auction), render (VertexRenderer) and meshing; everything
+underneath runs as vpn_b200 CUDA kernels.  Networks, datasets, augmentation and visualisation are out of
+scope and stay with the reference.
 """
 from .meshing import Meshing
 from .sampling import Sampling
-from .loss import ChamferDistanceLoss, SilhouetteLoss, VPDiverseLoss
+from .loss import ChamferDistanceLoss, EarthMoverDistanceLoss, SilhouetteLoss, VPDiverseLoss
 from .render import VertexRenderer
 from .transform import (transform_points, view_to_obj_points, obj_to_view_points, rotate_points,
                         rotate_points_forward_x_axis, translate_points)

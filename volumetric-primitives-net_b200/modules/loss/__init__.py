@@ -1,5 +1,4 @@
-"""Drop-in for modules/loss (reference: loss/chamfer_distance.py, vp_diverse.py, silhouette.py).
-EarthMoverDistanceLoss (loss/emd) is out of scope and stays with the reference."""
+"""Drop-in for modules/loss (reference: loss/chamfer_distance.py, vp_diverse.py, silhouette.py, emd/emd_module.py)."""
 import torch
 import torch.nn as nn
 
@@ -56,3 +55,20 @@ class SilhouetteLoss(nn.Module):
         h, w = gt_silhouettes.shape[-2:]
         predict_silhouettes = render_alpha_batch(predict_meshes, dists, elevs, azims, h, w)   # (B,1,H,W)
         return self.loss_func(predict_silhouettes, gt_silhouettes)
+
+
+class EarthMoverDistanceLoss(nn.Module):
+    """emd/emd_module.py:72-79: forward(input1, input2, eps, iters) -> (dist (B,n), assignment (B,n) int32).
+    Same preconditions as the reference (emd_module.py:37-40)."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, input1, input2, eps, iters):
+        batchsize, n, _ = input1.size()
+        _, m, _ = input2.size()
+        assert n == m
+        assert input1.size()[0] == input2.size()[0]
+        assert n % 1024 == 0
+        assert batchsize <= 512
+        return ops.emd_auction(input1.contiguous().float(), input2.contiguous().float(), eps, iters)

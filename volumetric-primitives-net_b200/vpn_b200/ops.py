@@ -417,6 +417,45 @@ def sample_mesh_surface(verts, faces, uniforms):
     return _MeshSample.apply(verts, faces, uniforms)
 
 
+# --------------------------------------------------------------------------------------
+# EMD auction
+# --------------------------------------------------------------------------------------
+class _EmdAuction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, eps, iters):
+        lib = _lib.load()
+        xyz1 = require(xyz1.contiguous(), f32, "xyz1"); xyz2 = require(xyz2.contiguous(), f32, "xyz2")
+        b, n, _ = xyz1.shape
+        dev = xyz1.device
+        dist = torch.empty((b, n), dtype=f32, device=dev)
+        assignment = torch.empty((b, n), dtype=torch.int32, device=dev)
+        nb = ctypes.c_size_t(0)
+        check(lib.vpn_emd_workspace_bytes(b, n, ctypes.byref(nb)), "vpn_emd_workspace_bytes")
+        ws = _scratch_bytes(nb.value, dev)
+        check(lib.vpn_emd_fwd(ptr(xyz1), ptr(xyz2), ptr(dist), ptr(assignment), ptr(ws), nb.value, b, n, float(eps), int(iters),
+                              stream_ptr(dev)), "vpn_emd_fwd")
+        ctx.save_for_backward(xyz1, xyz2, assignment)
+        ctx.mark_non_differentiable(assignment)
+        return dist, assignment
+
+    @staticmethod
+    def backward(ctx, gdist, _gidx):
+        lib = _lib.load()
+        xyz1, xyz2, assignment = ctx.saved_tensors
+        b, n, _ = xyz1.shape
+        g1 = torch.empty_like(xyz1)
+        check(lib.vpn_emd_bwd(ptr(xyz1), ptr(xyz2), ptr(assignment), ptr(gdist.contiguous()), ptr(g1), b, n,
+                              stream_ptr(xyz1.device)), "vpn_emd_bwd")
+        g2 = torch.zeros_like(xyz2) if ctx.needs_input_grad[1] else None      # emd_module.py:66-67: zeros for xyz2
+        return g1, g2, None, None
+
+
+def emd_auction(xyz1, xyz2, eps: float, iters: int):
+    """emdFunction.apply (emd_module.py:29-79): (dist (B,n) squared distance to the assigned point, assignment (B,n) int32)."""
+    assert xyz1.dim() == 3 and xyz1.size(-1) == 3 and xyz2.shape == xyz1.shape        # emd_module.py:37-38: n == m, same batch
+    return _EmdAuction.apply(xyz1, xyz2, eps, iters)
+
+
 def sample_primitives_ms(kind: str, v, q, t, uniform_sets, reps: int = 32) -> float:
     """Mean device time (ms) of one fused sample+pose launch over a stream of `reps` launches that rotate through
     `uniform_sets` (list of (B,K,N,2|3) tensors; make their total size exceed L2 for cold reads).  Measurement helper."""
