@@ -124,7 +124,7 @@ int vpn_mesh_sample_bwd(const int* faces, const float* u, const int* face_idx, c
 /* ---- EMD approximation by auction: modules/loss/emd (emd_module.py:29-79, emd_cuda.cu:227-316)
  * xyz1 (B,n,3) predicted (bidders), xyz2 (B,n,3) ground truth (objects), coordinates normalised to [0,1].
  * dist (B,n) = squared distance to the assigned object, assignment (B,n) int32 (not necessarily a bijection).
- * One launch; ties resolved deterministically (lowest index).  Workspace only for n > 4096 (state in HBM). */
+ * One launch (thread-block cluster per sample); ties resolved deterministically (lowest index). */
 int vpn_emd_workspace_bytes(int B, int n, size_t* bytes);
 int vpn_emd_fwd(const float* xyz1, const float* xyz2, float* dist, int* assignment, void* workspace,
                 size_t workspace_bytes, int B, int n, float eps, int iters, void* stream);
