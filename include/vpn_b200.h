@@ -132,6 +132,11 @@ int vpn_emd_fwd(const float* xyz1, const float* xyz2, float* dist, int* assignme
 int vpn_emd_bwd(const float* xyz1, const float* xyz2, const int* assignment, const float* grad_dist,
                 float* grad_xyz1, int B, int n, void* stream);
 
+/* ---- gradient all-reduce over NVSwitch multicast (NVLS): in-place SUM of a symmetric fp32 buffer
+ * multicast_ptr: multicast virtual address of the buffer (numel % 4 == 0, 16-byte aligned).  The caller brackets the
+ * call with cross-rank barriers on the stream.  The reference is single process: no counterpart. */
+int vpn_allreduce_nvls(void* multicast_ptr, size_t numel, int rank, int world, void* stream);
+
 /* ---- measurement helper: achieved FP32 FMA throughput (the Chamfer roofline denominator) ----------------
  * scratch: >= 64 device floats, the first 16 finite and near 1.0.  Synchronises the stream. */
 int vpn_fp32_peak_probe(float* scratch, int reps, double* tflops_ffma, double* tflops_ffma2, void* stream);

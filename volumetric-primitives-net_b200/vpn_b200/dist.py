@@ -8,6 +8,7 @@ process); it is issued on a side stream so it overlaps whatever the caller runs 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -29,13 +30,62 @@ def local_loss_scale(global_batch: int, rank: int, world: int) -> float:
 
 
 class GradientAllReduce:
-    """Sum all-reduce of one flat gradient buffer on a dedicated stream (NCCL), joined on demand."""
+    """Sum all-reduce of one flat gradient buffer on a dedicated stream, joined on demand.
 
-    def __init__(self, numel: int, device, dtype=torch.float32):
-        self.buf = torch.zeros(numel, dtype=dtype, device=device)
+    mode "nvls": the buffer is symmetric memory with a multicast mapping and the reduction is ONE launch of
+    vpn_allreduce_nvls (csrc/allreduce.cu: multimem.ld_reduce + multimem.st through the NVSwitch), bracketed by the
+    symmetric-memory barriers.  Every rank must take the same path, so the ranks agree on it with a MIN all-reduce
+    after a trial run and otherwise use NCCL's all-reduce (mode "nccl").  VPN_ALLREDUCE=nccl|nvls|auto overrides."""
+
+    def __init__(self, numel: int, device, dtype=torch.float32, prefer: Optional[str] = None):
+        prefer = prefer or os.environ.get("VPN_ALLREDUCE", "auto")
         self.cuda = torch.device(device).type == "cuda"
         self.stream = torch.cuda.Stream(device=device) if self.cuda else None
         self.done: Optional[torch.cuda.Event] = None
+        self.mode, self.nvls_error, self._full, self._handle = "none", None, None, None
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.buf = None
+        if distributed and self.cuda and dtype == torch.float32 and prefer in ("auto", "nvls"):
+            self._try_nvls(numel, device)
+        if self.buf is None:
+            self.buf = torch.zeros(numel, dtype=dtype, device=device)
+            self.mode = "nccl all_reduce" if distributed and self.cuda else ("gloo all_reduce" if distributed else "none")
+
+    def _nvls_launch(self):
+        from . import _lib
+        h = self._handle
+        h.barrier(channel=0)
+        _lib.check(_lib.load().vpn_allreduce_nvls(h.multicast_ptr, self._full.numel(), h.rank, h.world_size,
+                                                  _lib.stream_ptr(self._full.device)), "vpn_allreduce_nvls")
+        h.barrier(channel=1)
+
+    def _try_nvls(self, numel, device):
+        ok = 0
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            padded = -(-numel // 4096) * 4096                 # 16-byte aligned per-rank slices for any world size
+            self._full = symm_mem.empty(padded, dtype=torch.float32, device=device)
+            self._handle = symm_mem.rendezvous(self._full, dist.group.WORLD.group_name)
+            if not getattr(self._handle, "multicast_ptr", 0):
+                raise RuntimeError("no multicast (NVLS) mapping")
+            # trial: sum of (rank + 1) over the ranks
+            self._full.fill_(float(self._handle.rank + 1))
+            self._nvls_launch()
+            torch.cuda.synchronize(device)
+            w = self._handle.world_size
+            if not bool((self._full == float(w * (w + 1) // 2)).all()):
+                raise RuntimeError("NVLS trial all-reduce gave a wrong sum")
+            ok = 1
+        except Exception as e:                                # noqa: BLE001 - any failure means "use NCCL"
+            self.nvls_error = repr(e)[:300]
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            self._full.zero_()
+            self.buf = self._full[:numel]
+            self.mode = "nvls multimem kernel (vpn_allreduce_nvls)"
+        else:
+            self._full, self._handle = None, None
 
     def launch(self):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -45,7 +95,10 @@ class GradientAllReduce:
             return
         self.stream.wait_stream(torch.cuda.current_stream(self.buf.device))
         with torch.cuda.stream(self.stream):
-            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
+            if self._handle is not None:
+                self._nvls_launch()
+            else:
+                dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
             self.done = torch.cuda.Event()
             self.done.record(self.stream)
 
