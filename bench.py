@@ -392,6 +392,7 @@ def main():
                            "per-step CUDA-event pairs; 4 rotating input sets",
                            "allreduce_numel": GRAD_NUMEL if world > 1 else 0,
                            "allreduce": (sync.mode if sync is not None else None),
+                           "allreduce_trial_ms": (sync.trial_ms if sync is not None else None),
                            "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps},
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -48,6 +48,15 @@ class PrimitiveLoss:
             cache[key] = torch.cat([tf + i * nv for i in range(k)], dim=0).contiguous()
         return cache[key]
 
+    def default_cameras(self, b: int, device):
+        """IS_VIEW_CENTER cameras: dist = 1, elev = azim = 0 for every sample (train.py:172-174); built once per batch size."""
+        key = ("cam", b, str(device))
+        cache = self.__dict__.setdefault("_cams", {})
+        if key not in cache:
+            cache[key] = ops.look_at_cameras(torch.zeros(b, device=device), torch.zeros(b, device=device),
+                                             torch.ones(b, device=device))
+        return cache[key]
+
     def __call__(self, v: torch.Tensor, q: torch.Tensor, t: torch.Tensor, uniforms: torch.Tensor,
                  view_center_points: torch.Tensor, silhouettes: Optional[torch.Tensor] = None,
                  canonical_points: Optional[torch.Tensor] = None, dists=None, elevs=None, azims=None,
@@ -85,11 +94,13 @@ class PrimitiveLoss:
                 verts = ops.mesh_vertices(tv, v, q, t)
             faces = self.composed_faces(k, v.device)
             h, w = silhouettes.shape[-2:]
-            # IS_VIEW_CENTER: dist = 1, elev = azim = 0 for every sample (train.py:172-174)
-            one = torch.ones(b, device=v.device)
-            zero = torch.zeros(b, device=v.device)
-            rot, pos = ops.look_at_cameras(zero if azims is None else azims, zero if elevs is None else elevs,
-                                           one if dists is None else dists)
+            if azims is None and elevs is None and dists is None:
+                rot, pos = self.default_cameras(b, v.device)
+            else:
+                one = torch.ones(b, device=v.device)
+                zero = torch.zeros(b, device=v.device)
+                rot, pos = ops.look_at_cameras(zero if azims is None else azims, zero if elevs is None else elevs,
+                                               one if dists is None else dists)
             alpha, _, _ = ops.soft_silhouette(verts, faces, rot, pos, h, w)
             diff = alpha[:, None] - silhouettes
             sil = diff.abs().mean() if cfg.silhouette_loss == "L1" else (diff * diff).mean()
