@@ -297,10 +297,11 @@ struct ExactBest {
   __device__ __forceinline__ u64 key() const { return ((u64)__float_as_uint(v) << 32) | (unsigned)i; }
 };
 
-// Branch-free scan of 32 squared distances held in registers (d[kk] belongs to index idx0 + ((kk + rot) & 31)).
-// Phase 1 found dm = min d.  If every d within dm's sqrt rounding class equals dm, the winner is the lowest
-// index with d == dm and v = sqrt(dm) - decided without divergence; otherwise (rare: near ties) fall back
-// to the order-independent ExactBest walk.  Returns false when the unit holds no valid point.
+// Scan of 32 squared distances held in registers (d[kk] belongs to index idx0 + ((kk + rot) & 31)).
+// Phase 1 found dm = min d.  One more pass counts the values within dm's sqrt rounding class and sums their
+// positions (two predicated integer adds per value).  If the count is 1 the winner is that position and
+// v = sqrt(dm) - no index bookkeeping per value; otherwise (ties / near ties, rare) fall back to the
+// order-independent ExactBest walk.  Returns false when the unit holds no valid point.
 __device__ __forceinline__ bool unit_best(const float (&d)[32], float dm, int idx0, int rot, u64& key) {
   if (!(dm < inf_f())) {                       // all padding, or genuinely infinite distances
     bool any = false;
@@ -309,15 +310,14 @@ __device__ __forceinline__ bool unit_best(const float (&d)[32], float dm, int id
     if (!any) return false;
   }
   const float hi = thr_of(dm, 9.5367431640625e-07f, 1e-36f);
-  int first = 64; bool amb = false;
+  int cnt = 0, pos = 0;
 #pragma unroll
   for (int kk = 0; kk < 32; ++kk) {
-    const int k = (kk + rot) & 31;
-    const bool eq = d[kk] == dm;
-    amb |= (d[kk] <= hi) && !eq;
-    first = eq ? min(first, k) : first;
+    const bool in = d[kk] <= hi;               // NaN padding compares false
+    cnt += in ? 1 : 0;
+    pos += in ? kk : 0;
   }
-  if (!amb) { key = ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)(idx0 + first); return true; }
+  if (cnt == 1) { key = ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)(idx0 + ((pos + rot) & 31)); return true; }
   ExactBest eb; eb.init();
 #pragma unroll
   for (int kk = 0; kk < 32; ++kk) eb.offer(d[kk], idx0 + ((kk + rot) & 31));
