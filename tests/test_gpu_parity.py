@@ -579,3 +579,27 @@ def test_emd_auction_cluster_sizes_agree(vpn, O, cluster, monkeypatch):
         d_ref, a_ref = O.emd_auction(x1[1].numpy(), x2[1].numpy(), 0.005, iters)
         same(ass[1], a_ref, f"assignment n={n} cluster={cluster}")
         same(dist[1], d_ref, f"dist n={n} cluster={cluster}")
+
+
+# ------------------------------------------------------------------------------------------------
+# empty batches: every entry point returns empty outputs of the right shape and launches nothing harmful
+# ------------------------------------------------------------------------------------------------
+def test_empty_batch(vpn, golden_templates):
+    dev = "cuda"
+    z = lambda *s: torch.zeros(*s, device=dev)
+    pts = vpn.sample_primitives("cuboid", z(0, 4, 3), z(0, 4, 4), z(0, 4, 3), z(0, 4, 16, 3))
+    assert pts.shape == (0, 64, 3)
+    m1, i1, m2, i2 = vpn.chamfer_nn(z(0, 2048, 3), z(0, 256, 3))
+    assert m1.shape == (0, 2048) and i2.shape == (0, 256) and i1.dtype == torch.int32
+    assert vpn.chamfer_distance(z(0, 2048, 3), z(0, 256, 3), each_batch=True).shape == (0,)
+    tv = torch.from_numpy(golden_templates["sphere_vertices"]).float().to(dev)
+    tf = torch.from_numpy(golden_templates["sphere_faces"]).int().to(dev)
+    verts = vpn.mesh_vertices(tv, z(0, 2, 3), z(0, 2, 4), z(0, 2, 3))
+    assert verts.shape == (0, 2 * tv.shape[0], 3)
+    alpha, covered, _ = vpn.soft_silhouette(verts, torch.cat([tf, tf + tv.shape[0]]), z(0, 3, 3), z(0, 3), 32, 32)
+    assert alpha.shape == (0, 32, 32) and covered.shape == (0, 32, 32)
+    p, f = vpn.sample_mesh_surface(z(0, tv.shape[0], 3), tf, z(0, 100, 3))
+    assert p.shape == (0, 100, 3) and f.shape == (0, 100)
+    d, a = vpn.emd_auction(z(0, 1024, 3), z(0, 1024, 3), 0.005, 10)
+    assert d.shape == (0, 1024) and a.shape == (0, 1024)
+    torch.cuda.synchronize()
