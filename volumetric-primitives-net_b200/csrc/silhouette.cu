@@ -152,12 +152,15 @@ __device__ __forceinline__ bool inside_tri(const FaceRec& r, float X, float Y, f
   return w0 >= 0.f && w1 >= 0.f && w2 >= 0.f;
 }
 
-// Shared tile walker: calls fn(face_index, record, tight bbox) for every face binned to this tile, in index order.
-// All threads of the CTA must call it; fn is invoked per thread (pixel).  Batches of kRThreads faces whose union
-// box (sil_faces_kernel) misses the tile are skipped without touching their records.
+// Shared tile walker: calls fn(face_index, record, tight bbox) for the faces binned to this tile that can touch the
+// calling WARP's pixels, in index order.  All threads of the CTA must call it; fn is invoked per thread (pixel).
+// Two culls before any per-pixel work: batches of kRThreads faces whose union box (sil_faces_kernel) misses the tile
+// are skipped without touching their records; of the binned faces, 32 at a time are tested by the lanes against the
+// warp's own pixel block (wxL..wyT: pixel-centre extent of the warp's 8 x 4 pixels) and only the hits are walked.
 template <typename Fn>
 __device__ __forceinline__ void walk_tile_faces(const FaceRec* __restrict__ rec, const float4* __restrict__ batch_box,
-                                                int F, float xL, float xR, float yB, float yT, float em, Fn fn) {
+                                                int F, float xL, float xR, float yB, float yT,
+                                                float wxL, float wxR, float wyB, float wyT, float em, Fn fn) {
   __shared__ FaceRec s_rec[kRThreads];
   __shared__ float4 s_box[kRThreads];                  // tight bbox: xmin, xmax, ymin, ymax
   __shared__ int s_idx[kRThreads];
@@ -188,9 +191,27 @@ __device__ __forceinline__ void walk_tile_faces(const FaceRec* __restrict__ rec,
       s_rec[slot] = r; s_box[slot] = tb; s_idx[slot] = f;
     }
     __syncthreads();
-    for (int k = 0; k < total; ++k) fn(s_idx[k], s_rec[k], s_box[k]);
+    for (int k0 = 0; k0 < total; k0 += 32) {
+      bool mine = false;
+      if (k0 + lane < total) {
+        const float4 b4 = s_box[k0 + lane];
+        mine = __fsub_rn(b4.x, em) <= wxR && __fadd_rn(b4.y, em) > wxL && __fsub_rn(b4.z, em) <= wyT && __fadd_rn(b4.w, em) > wyB;
+      }
+      for (unsigned bits = __ballot_sync(0xffffffffu, mine); bits; bits &= bits - 1) {
+        const int k = k0 + __ffs((int)bits) - 1;
+        fn(s_idx[k], s_rec[k], s_box[k]);
+      }
+    }
     __syncthreads();
   }
+}
+
+// Thread / list slot p of a tile -> pixel inside the tile: a warp covers an 8 x 4 block (not a 16 x 2 strip), which
+// makes its footprint small in both directions for the warp-level face cull of walk_tile_faces.
+__device__ __forceinline__ void tile_px(int p, int& px, int& py) {
+  const int warp = p >> 5, lane = p & 31;
+  px = ((warp & 1) << 3) + (lane & 7);
+  py = ((warp >> 1) << 2) + (lane >> 3);
 }
 
 __device__ __forceinline__ void pixel_coords(const RasterParams& rp, int w, int h, float& X, float& Y) {
@@ -253,18 +274,21 @@ sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
   __shared__ int s_wsum[kRThreads / 32];
   const TileLists tl = tile_lists(s_dyn);
   const int b = blockIdx.z, tid = threadIdx.x;
-  const int w = blockIdx.x * kTile + (tid % kTile), h = blockIdx.y * kTile + (tid / kTile);
+  int px, py; tile_px(tid, px, py);
+  const int w = blockIdx.x * kTile + px, h = blockIdx.y * kTile + py;
   const bool in_img = (w < rp.W && h < rp.H);
   const FaceRec* rec = rec_all + (size_t)b * rp.F;
   float X, Y; pixel_coords(rp, min(w, rp.W - 1), min(h, rp.H - 1), X, Y);
-  // pixel-centre extent of the tile (x grows with w, y shrinks with h)
-  float xL, xR, yT, yB;
+  // pixel-centre extent of the tile and of this warp's 8 x 4 block (x grows with w, y shrinks with h)
+  float xL, xR, yT, yB, wxL, wxR, wyT, wyB;
   pixel_coords(rp, blockIdx.x * kTile, blockIdx.y * kTile, xL, yT);
   pixel_coords(rp, min(blockIdx.x * kTile + kTile - 1, rp.W - 1), min(blockIdx.y * kTile + kTile - 1, rp.H - 1), xR, yB);
+  pixel_coords(rp, min(w - (px & 7), rp.W - 1), min(h - (py & 3), rp.H - 1), wxL, wyT);
+  pixel_coords(rp, min(w - (px & 7) + 7, rp.W - 1), min(h - (py & 3) + 3, rp.H - 1), wxR, wyB);
   const float em = __fmul_rn(rp.expand, rp.mult);
   bool covered = false; int cnt = 0;
   const float4* boxes = box_all + (size_t)b * ((rp.F + kRThreads - 1) / kRThreads);
-  walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, em, [&](int f, const FaceRec& r, const float4& tb) {
+  walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, wxL, wxR, wyB, wyT, em, [&](int f, const FaceRec& r, const float4& tb) {
     if (covered) return;                                // alpha is 1 whatever follows
     const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
     if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
@@ -278,7 +302,8 @@ sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
     const int p = item_pixel(s_off, it), k = it - s_off[p];
     const FaceRec r = rec[tl.cand[k * kRThreads + p]];
     float PX, PY;
-    pixel_coords(rp, min((int)(blockIdx.x * kTile + (p % kTile)), rp.W - 1), min((int)(blockIdx.y * kTile + (p / kTile)), rp.H - 1), PX, PY);
+    int qx, qy; tile_px(p, qx, qy);
+    pixel_coords(rp, min((int)(blockIdx.x * kTile) + qx, rp.W - 1), min((int)(blockIdx.y * kTile) + qy, rp.H - 1), PX, PY);
     int which;
     const float d2 = tri_dist2(r, PX, PY, rp.mult, rp.eps, which);
     const float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
@@ -305,13 +330,16 @@ sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
   __shared__ float s_g[kRThreads];
   const TileLists tl = tile_lists(s_dyn);
   const int b = blockIdx.z, tid = threadIdx.x;
-  const int w = blockIdx.x * kTile + (tid % kTile), h = blockIdx.y * kTile + (tid / kTile);
+  int px, py; tile_px(tid, px, py);
+  const int w = blockIdx.x * kTile + px, h = blockIdx.y * kTile + py;
   const bool in_img = (w < rp.W && h < rp.H);
   const FaceRec* rec = rec_all + (size_t)b * rp.F;
   float X, Y; pixel_coords(rp, min(w, rp.W - 1), min(h, rp.H - 1), X, Y);
-  float xL, xR, yT, yB;
+  float xL, xR, yT, yB, wxL, wxR, wyT, wyB;
   pixel_coords(rp, blockIdx.x * kTile, blockIdx.y * kTile, xL, yT);
   pixel_coords(rp, min(blockIdx.x * kTile + kTile - 1, rp.W - 1), min(blockIdx.y * kTile + kTile - 1, rp.H - 1), xR, yB);
+  pixel_coords(rp, min(w - (px & 7), rp.W - 1), min(h - (py & 3), rp.H - 1), wxL, wyT);
+  pixel_coords(rp, min(w - (px & 7) + 7, rp.W - 1), min(h - (py & 3) + 3, rp.H - 1), wxR, wyB);
   const float em = __fmul_rn(rp.expand, rp.mult);
   float g = 0.f; bool active = false;
   if (in_img) {
@@ -323,7 +351,7 @@ sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
   int cnt = 0;
   const float4* boxes = box_all + (size_t)b * ((rp.F + kRThreads - 1) / kRThreads);
   if (__syncthreads_or(active)) {                       // tiles without an uncovered pixel that has a gradient do nothing
-    walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, em, [&](int f, const FaceRec& r, const float4& tb) {
+    walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, wxL, wxR, wyB, wyT, em, [&](int f, const FaceRec& r, const float4& tb) {
       if (!active || cnt >= rp.knum) return;
       const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
       if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
@@ -337,7 +365,8 @@ sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
     const int p = item_pixel(s_off, it), k = it - s_off[p];
     const FaceRec r = rec[tl.cand[k * kRThreads + p]];
     float PX, PY;
-    pixel_coords(rp, min((int)(blockIdx.x * kTile + (p % kTile)), rp.W - 1), min((int)(blockIdx.y * kTile + (p / kTile)), rp.H - 1), PX, PY);
+    int qx, qy; tile_px(p, qx, qy);
+    pixel_coords(rp, min((int)(blockIdx.x * kTile) + qx, rp.W - 1), min((int)(blockIdx.y * kTile) + qy, rp.H - 1), PX, PY);
     int which;
     const float d2 = tri_dist2(r, PX, PY, rp.mult, rp.eps, which);
     const float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
@@ -357,7 +386,8 @@ sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
     const int f = tl.cand[k * kRThreads + p];
     const FaceRec r = rec[f];
     float PX, PY;
-    pixel_coords(rp, min((int)(blockIdx.x * kTile + (p % kTile)), rp.W - 1), min((int)(blockIdx.y * kTile + (p / kTile)), rp.H - 1), PX, PY);
+    int qx, qy; tile_px(p, qx, qy);
+    pixel_coords(rp, min((int)(blockIdx.x * kTile) + qx, rp.W - 1), min((int)(blockIdx.y * kTile) + qy, rp.H - 1), PX, PY);
     // p = exp(-delta d2 / mult^2)  ->  dp/dd2 = -p delta / mult^2
     const float gd2 = s_g[p] * dadp * (-prob) * rp.delta / (rp.mult * rp.mult);
     float gr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
