@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chamfer-impl", type=int, default=0)
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from a CUDA graph (vpn_b200.GraphedPrimitiveLoss); auto falls back to eager launches")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -217,7 +219,22 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
     sync = vdist.GradientAllReduce(GRAD_NUMEL, dev) if world > 1 else None
 
+    graphed, graph_error = None, None
+    if args.graph != "off":
+        try:
+            d0 = devsets[0]
+            graphed = vpn_b200.GraphedPrimitiveLoss(cfg, d0["v"], d0["q"], d0["t"], d0["target"], d0["sil"], n_samples=n)
+        except Exception as e:                               # noqa: BLE001 - eager launches are always available
+            graph_error = repr(e)[:200]
+            if args.graph == "on":
+                raise
+
     def one_step(s, grads_out=None):
+        if graphed is not None:
+            loss, gv, gq, gt = graphed(s["v"], s["q"], s["t"], s["target"], s["sil"])
+            if sync is not None:
+                sync.launch()
+            return loss, gv, gq, gt
         v, q, t = (s[x].detach().requires_grad_() for x in ("v", "q", "t"))
         u = None if vertex_mode else torch.rand((b, k, n, width), device=dev)      # drawn on device, like the reference
         out = step_fn(v, q, t, u, s["target"], silhouettes=s["sil"])
@@ -249,7 +266,7 @@ def main():
         evs[i][1].record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
-    launches = (lib.vpn_launch_count() - launches0) // args.steps
+    launches = graphed.launches_per_step if graphed is not None else (lib.vpn_launch_count() - launches0) // args.steps
     sampler.stop_flag = True
     step_ms = [a.elapsed_time(bb) for a, bb in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -390,6 +407,7 @@ def main():
                 "config": {"workload": describe(args.workload, world), "global_batch": world * b,
                            "parallelism": f"dp{world}", "l2": "256 MB L2 flush between timed iterations, outside the "
                            "per-step CUDA-event pairs; 4 rotating input sets",
+                           "cuda_graph": graphed is not None, "cuda_graph_error": graph_error,
                            "allreduce_numel": GRAD_NUMEL if world > 1 else 0,
                            "allreduce": (sync.mode if sync is not None else None),
                            "allreduce_trial_ms": (sync.trial_ms if sync is not None else None),

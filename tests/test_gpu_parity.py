@@ -603,3 +603,28 @@ def test_empty_batch(vpn, golden_templates):
     d, a = vpn.emd_auction(z(0, 1024, 3), z(0, 1024, 3), 0.005, 10)
     assert d.shape == (0, 1024) and a.shape == (0, 1024)
     torch.cuda.synchronize()
+
+
+def test_graphed_step_matches_eager(vpn, O):
+    """GraphedPrimitiveLoss replays the captured step: same loss / gradients as the eager step on the same uniforms is not
+    testable (the graph draws its own), so compare a vertex-Chamfer step (no random draw) and check the sampled one runs."""
+    g = torch.Generator().manual_seed(3)
+    b, k, m, res = 2, 8, 1024, 32
+    v, q, t = O.synthetic_primitives(b, k); t = t * 0.3
+    tgt = (torch.rand(b, m, 3, generator=g) - 0.5) * 0.8
+    gt = (torch.rand(b, 1, res, res, generator=g) > 0.5).float()
+    cfg = vpn.PrimitiveLossConfig(kind="sphere", l_sil=1.0, vertex_chamfer=True)
+    gr = vpn.GraphedPrimitiveLoss(cfg, C(v), C(q), C(t), C(tgt), C(gt))
+    for scale in (1.0, 0.7):                                   # second call: new inputs through the static buffers
+        vc, qc, tc = (C(x * scale if i == 0 else x).requires_grad_() for i, x in enumerate((v, q, t)))
+        loss, gv, gq, gtt = gr(vc.detach(), qc.detach(), tc.detach(), C(tgt), C(gt))
+        out = vpn.PrimitiveLoss(cfg)(vc, qc, tc, None, C(tgt), silhouettes=C(gt))
+        out["total"].backward()
+        close(loss, out["total"], rtol=1e-6)
+        close(gv, vc.grad, rtol=1e-5, atol=1e-7); close(gq, qc.grad, rtol=1e-5, atol=1e-7); close(gtt, tc.grad, rtol=1e-5, atol=1e-7)
+    assert gr.launches_per_step > 5
+    cfg2 = vpn.PrimitiveLossConfig(kind="cuboid")
+    gs = vpn.GraphedPrimitiveLoss(cfg2, C(v), C(q), C(t), C(tgt), None, n_samples=256)
+    l1 = gs(C(v), C(q), C(t), C(tgt))[0].item()
+    l2 = gs(C(v), C(q), C(t), C(tgt))[0].item()
+    assert l1 > 0 and l2 > 0 and l1 != l2                      # a fresh uniform draw every replay

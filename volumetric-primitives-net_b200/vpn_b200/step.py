@@ -108,3 +108,60 @@ class PrimitiveLoss:
             add("sil", sil * cfg.l_sil)
         out["total"] = total
         return out
+
+
+class GraphedPrimitiveLoss:
+    """The same step - draw uniforms, forward, backward to (v, q, t) - captured once into a CUDA graph and replayed.
+
+    The step is ~20 of our launches plus torch's bookkeeping kernels; at small batch sizes (BASELINE config 1: B = 1) and
+    in the end-to-end loop, where a device-to-host read forces a synchronisation every step, the host's launch latency is
+    what is being timed.  Replaying removes it.  Shapes are fixed at construction; inputs are copied into static buffers
+    (device-to-device or pinned-host-to-device, stream ordered), results are read from static buffers.
+
+        g = GraphedPrimitiveLoss(cfg, v, q, t, targets, silhouettes)      # example tensors give the shapes
+        loss, gv, gq, gt = g(v, q, t, targets, silhouettes)               # static output buffers, overwritten by the next call
+    """
+
+    def __init__(self, config: PrimitiveLossConfig, v, q, t, targets, silhouettes=None, n_samples: int = 0, warmup: int = 3):
+        from . import _lib
+        self.cfg = config
+        self.step = PrimitiveLoss(config)
+        dev = v.device
+        self.v = v.detach().clone().requires_grad_()
+        self.q = q.detach().clone().requires_grad_()
+        self.t = t.detach().clone().requires_grad_()
+        self.targets = targets.detach().clone()
+        self.sil = None if silhouettes is None else silhouettes.detach().clone()
+        b, k = q.shape[:2]
+        self.ushape = None if config.vertex_chamfer else (b, k, n_samples, 2 if config.kind == "sphere" else 3)
+        assert config.vertex_chamfer or n_samples > 0, "n_samples (points per primitive) is required unless vertex_chamfer"
+
+        def run():
+            u = None if self.ushape is None else torch.rand(self.ushape, device=dev)      # drawn on the device, as the reference does
+            out = self.step(self.v, self.q, self.t, u, self.targets, silhouettes=self.sil)
+            gv, gq, gt = torch.autograd.grad(out["total"], (self.v, self.q, self.t))
+            return out["total"], gv, gq, gt
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up off the capture: caches, function attributes, allocator
+            for _ in range(warmup):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        lib = _lib.load()
+        n0 = lib.vpn_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.gv, self.gq, self.gt = run()
+        self.launches_per_step = int(lib.vpn_launch_count() - n0)      # our kernels inside one replay
+
+    def __call__(self, v, q, t, targets, silhouettes=None):
+        self.v.data.copy_(v, non_blocking=True)
+        self.q.data.copy_(q, non_blocking=True)
+        self.t.data.copy_(t, non_blocking=True)
+        self.targets.copy_(targets, non_blocking=True)
+        if self.sil is not None and silhouettes is not None:
+            self.sil.copy_(silhouettes, non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.gv, self.gq, self.gt
