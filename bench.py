@@ -277,12 +277,22 @@ def main():
     value = world * b * args.steps / (total_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers ("e2e") ------------------------------
+    # results land in pinned host buffers with asynchronous copies and ONE synchronisation per step
+    host_out = [torch.empty((), pin_memory=True), torch.empty((b, k, 3), pin_memory=True),
+                torch.empty((b, k, 4), pin_memory=True), torch.empty((b, k, 3), pin_memory=True)]
+    done = torch.cuda.Event()
+
     def e2e_step(ps):
-        s = {kk: (vv.to(dev, non_blocking=True) if vv is not None else None) for kk, vv in ps.items()}
-        loss, gv, gq, gt = one_step(s)
+        # with the graph the pinned inputs are copied straight into its static buffers; eager: fresh device tensors
+        s = ps if graphed is not None else {kk: (vv.to(dev, non_blocking=True) if vv is not None else None) for kk, vv in ps.items()}
+        res = one_step(s)
         if sync is not None:
             sync.join()
-        return loss.cpu(), gv.cpu(), gq.cpu(), gt.cpu()
+        for h, d in zip(host_out, res):
+            h.copy_(d.detach(), non_blocking=True)
+        done.record()
+        done.synchronize()
+        return host_out
 
     for i in range(2):
         e2e_step(pinned[i % nsets])

@@ -71,6 +71,26 @@ __device__ __forceinline__ void pose_backward(const float* __restrict__ q, const
   gq[3] = gth * VPN_PI;      // d(half angle)/dw = PI (the modulo has unit slope)
 }
 
+// Programmatic dependent launch (PDL).  A kernel launched through launch_pdl() may be scheduled while its predecessor in
+// the stream is still running; pdl_enter() first lets ITS successor do the same, then blocks until the predecessor has
+// completed and its writes are visible.  It must come before the kernel's first global-memory access.  In a kernel
+// launched the ordinary way both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -115,6 +115,7 @@ __device__ __forceinline__ void rotate_add(const PrimShared& ps, const float* c,
 
 // grid: x = primitive (b*K + k), y = slice of kPoseThreads * kPosePointsPerThread * kPoseSteps points.
 // All source loads of the CTA are issued before the pose (sin, cos, sqrt, divisions by one thread) is waited for.
+// Launched as a programmatic dependent launch: the launch latency overlaps the tail of the previous kernel.
 template <int KIND>
 __global__ void __launch_bounds__(kPoseThreads)
 pose_fwd_kernel(const float* __restrict__ v, const float* __restrict__ q, const float* __restrict__ t,
@@ -123,6 +124,7 @@ pose_fwd_kernel(const float* __restrict__ v, const float* __restrict__ q, const 
   __shared__ PrimShared ps;
   const size_t prim = blockIdx.x;
   const int base_n = blockIdx.y * (kPoseThreads * kPosePointsPerThread * kPoseSteps) + threadIdx.x * kPosePointsPerThread;
+  pdl_enter();      // launched with launch_pdl: this CTA may already be resident while the previous kernel drains
   float u[kPoseSteps][4 * W];
 #pragma unroll
   for (int s = 0; s < kPoseSteps; ++s) {
@@ -296,10 +298,10 @@ extern "C" int vpn_pose_points_fwd(int kind, const float* v, const float* q, con
   cudaStream_t s = (cudaStream_t)stream;
   int vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   switch (kind) {
-    case KIND_SPHERE:   pose_fwd_kernel<KIND_SPHERE><<<grid, block, 0, s>>>(v, q, t, src, out, N, vec_ok); break;
-    case KIND_CUBOID:   pose_fwd_kernel<KIND_CUBOID><<<grid, block, 0, s>>>(v, q, t, src, out, N, vec_ok); break;
-    case KIND_TEMPLATE: pose_fwd_kernel<KIND_TEMPLATE><<<grid, block, 0, s>>>(v, q, t, src, out, N, vec_ok); break;
-    default:            pose_fwd_kernel<KIND_POINTS><<<grid, block, 0, s>>>(v, q, t, src, out, N, vec_ok); break;
+    case KIND_SPHERE:   launch_pdl(pose_fwd_kernel<KIND_SPHERE>, grid, block, 0, s, v, q, t, src, out, N, vec_ok); break;
+    case KIND_CUBOID:   launch_pdl(pose_fwd_kernel<KIND_CUBOID>, grid, block, 0, s, v, q, t, src, out, N, vec_ok); break;
+    case KIND_TEMPLATE: launch_pdl(pose_fwd_kernel<KIND_TEMPLATE>, grid, block, 0, s, v, q, t, src, out, N, vec_ok); break;
+    default:            launch_pdl(pose_fwd_kernel<KIND_POINTS>, grid, block, 0, s, v, q, t, src, out, N, vec_ok); break;
   }
   return vpn_check_launch("pose_fwd_kernel");
 }
