@@ -74,11 +74,19 @@ def synthetic(workload, device, seed=1234, sets=1, batch=None):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi-equivalent clock / throttle sampling (NVML) during the timed region."""
+    """nvidia-smi-equivalent clock / throttle sampling (NVML) during the timed region: rank 0 only, first sample as soon
+    as the host has enqueued the timed steps (arm()), then one every 30 ms while the GPU executes them.
+    Every NVML query stalls the sampled GPU's work for about a millisecond (2 GPUs, r01y logs: with four samples in
+    a 60 ms region rank 0 reached every all-reduce 0.21 ms late and rank 1 waited for it, 3.15 vs 2.94 ms per step;
+    with eight ranks polling every 10 ms the 8-GPU step went from 3.2 to 3.7 ms), so the rate is kept low."""
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True, period_s=0.03):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.period_s, self.nv = period_s, None
+        self.armed = threading.Event()
+        if not enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -96,7 +104,8 @@ class ClockSampler(threading.Thread):
                  nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
-        while not self.stop_flag:
+        self.armed.wait()
+        while True:                                  # at least one sample, taken right after arm()
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -105,7 +114,16 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            if self.stop_flag:
+                break
+            time.sleep(self.period_s)
+
+    def arm(self):
+        self.armed.set()
+
+    def stop(self):
+        self.stop_flag = True
+        self.armed.set()
 
     def summary(self):
         s = sorted(self.samples)
@@ -251,28 +269,42 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=(rank == 0 and os.environ.get("VPN_BENCH_NO_CLOCKS", "0") != "1"))
     sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]      # end of the rank's own compute, before the join
+    do_flush = os.environ.get("VPN_BENCH_FLUSH", "1") != "0"
     launches0 = lib.vpn_launch_count()
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
     for i in range(args.steps):
-        flush.zero_()                                               # L2 flush between timed iterations
+        if do_flush:
+            flush.zero_()                                           # L2 flush between timed iterations
         evs[i][0].record()
         one_step(devsets[i % nsets])
+        mids[i].record()
         if sync is not None:
             sync.join()
         evs[i][1].record()
+    sampler.arm()                       # all timed steps are enqueued; sample clocks while the GPU runs them
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
     launches = graphed.launches_per_step if graphed is not None else (lib.vpn_launch_count() - launches0) // args.steps
-    sampler.stop_flag = True
+    sampler.stop()
+    sampler.join(timeout=5.0)
     step_ms = [a.elapsed_time(bb) for a, bb in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    # per rank: mean step time and the part of it spent in the rank's own kernels (the rest is the all-reduce + waiting
+    # for the slowest rank)
+    own_ms = sum(a.elapsed_time(m_) for (a, _), m_ in zip(evs, mids)) / args.steps
+    rank_ms = torch.tensor([sum(step_ms) / args.steps, own_ms], dtype=torch.float64, device=dev)
+    rank_all = [rank_ms]
     if world > 1:
         dist.barrier()
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        rank_all = [torch.zeros_like(rank_ms) for _ in range(world)]
+        dist.all_gather(rank_all, rank_ms)
+    rank_all = [[round(float(x), 4) for x in r_.tolist()] for r_ in rank_all]
     total_ms = float(total_ms.item())
     value = world * b * args.steps / (total_ms * 1e-3)
 
@@ -428,7 +460,8 @@ def main():
                            "allreduce_numel": GRAD_NUMEL if world > 1 else 0,
                            "allreduce": (sync.mode if sync is not None else None),
                            "allreduce_trial_ms": (sync.trial_ms if sync is not None else None),
-                           "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps},
+                           "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
+                           "rank_ms_step_and_own_kernels": rank_all, "l2_flush": do_flush},
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps},
