@@ -35,9 +35,13 @@ WORKLOADS = {
     "c3": ("cuboid", 32, 32, 4096, 8192, 128),
     "c4": ("cuboid", 256, 32, 4096, 8192, 128),       # B = 256 in TOTAL, split over the ranks (strong scaling)
     "c5": ("sphere", 8, 128, 128, 16384, 256),        # train_gcn.py shape: the K*128 mesh vertices are the predicted points
+    # c2 as train.py:152-163 runs it: BOTH big Chamfers (view frame + canonical frame through view_to_obj_points; the
+    # reference computes the second even at its default weight L_CAN_CD = 0) + VP-diverse
+    "c2f": ("cuboid", 32, 16, 4096, 8192, 0),
 }
 STRONG = {"c4"}            # workloads whose B is the global batch
 VERTEX_MODE = {"c5"}       # Chamfer on the composed mesh vertices (train_gcn.py:127-130) instead of surface samples
+FAITHFUL = {"c2f"}         # canonical-frame Chamfer included (l_can_cd = 1 so that it is computed AND differentiated)
 
 
 def per_gpu_batch(workload, world):
@@ -69,7 +73,15 @@ def synthetic(workload, device, seed=1234, sets=1, batch=None):
         bi = torch.arange(b)[:, None]
         tgt = centre[bi, which] + p * half[bi, which]
         sil = (torch.rand(b, 1, res, res, generator=g) > 0.5).float() if res else None
-        out.append(dict(v=v, q=q, t=t, target=tgt.contiguous(), sil=sil))
+        d = dict(v=v, q=q, t=t, target=tgt.contiguous(), sil=sil)
+        if workload in FAITHFUL:
+            # object-frame copy of the targets + the view parameters that map one frame to the other (dataset.py ranges)
+            d["dists"] = 1.0 + 0.5 * torch.rand(b, generator=g)
+            d["elevs"] = 20.0 + 20.0 * torch.rand(b, generator=g)
+            d["azims"] = 360.0 * torch.rand(b, generator=g)
+            d["angles"] = 360.0 * torch.rand(b, generator=g)
+            d["canon"] = (tgt * d["dists"][:, None, None]).contiguous()
+        out.append(d)
     return out
 
 
@@ -190,6 +202,8 @@ def describe(workload, world=1):
     b = per_gpu_batch(workload, world)
     what = "template vertices" if workload in VERTEX_MODE else "samples"
     s = f"{workload}: B={b}/GPU, {k} {kind} primitives x {n} {what} (P={k * n}), Chamfer vs M={m} targets + VP-diverse"
+    if workload in FAITHFUL:
+        s += " + canonical-frame Chamfer through view_to_obj_points (train.py:152-163)"
     if res:
         s += f" + {res}x{res} soft-silhouette L1"
     return s + ", fwd+bwd to (v,q,t)"
@@ -231,8 +245,12 @@ def main():
     host = synthetic(args.workload, "cpu", seed=1234 + rank, sets=nsets, batch=b)
     devsets = [{kk: (vv.to(dev) if vv is not None else None) for kk, vv in s.items()} for s in host]
     pinned = [{kk: (vv.pin_memory() if vv is not None else None) for kk, vv in s.items()} for s in host]
+    faithful = args.workload in FAITHFUL
     cfg = vpn_b200.PrimitiveLossConfig(kind=kind, l_sil=(1.0 if res else 0.0), chamfer_impl=args.chamfer_impl,
-                                       vertex_chamfer=vertex_mode)
+                                       vertex_chamfer=vertex_mode, l_can_cd=(1.0 if faithful else 0.0))
+
+    def cams_of(s):
+        return (s["dists"], s["elevs"], s["azims"], s["angles"]) if faithful else None
     step_fn = vpn_b200.PrimitiveLoss(cfg)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
     sync = vdist.GradientAllReduce(GRAD_NUMEL, dev) if world > 1 else None
@@ -241,7 +259,8 @@ def main():
     if args.graph != "off":
         try:
             d0 = devsets[0]
-            graphed = vpn_b200.GraphedPrimitiveLoss(cfg, d0["v"], d0["q"], d0["t"], d0["target"], d0["sil"], n_samples=n)
+            graphed = vpn_b200.GraphedPrimitiveLoss(cfg, d0["v"], d0["q"], d0["t"], d0["target"], d0["sil"], n_samples=n,
+                                                    canonical_points=d0.get("canon"), cameras=cams_of(d0))
         except Exception as e:                               # noqa: BLE001 - eager launches are always available
             graph_error = repr(e)[:200]
             if args.graph == "on":
@@ -249,13 +268,16 @@ def main():
 
     def one_step(s, grads_out=None):
         if graphed is not None:
-            loss, gv, gq, gt = graphed(s["v"], s["q"], s["t"], s["target"], s["sil"])
+            loss, gv, gq, gt = graphed(s["v"], s["q"], s["t"], s["target"], s["sil"], canonical_points=s.get("canon"),
+                                       cameras=cams_of(s))
             if sync is not None:
                 sync.launch()
             return loss, gv, gq, gt
         v, q, t = (s[x].detach().requires_grad_() for x in ("v", "q", "t"))
         u = None if vertex_mode else torch.rand((b, k, n, width), device=dev)      # drawn on device, like the reference
-        out = step_fn(v, q, t, u, s["target"], silhouettes=s["sil"])
+        c4 = cams_of(s) or (None, None, None, None)
+        out = step_fn(v, q, t, u, s["target"], silhouettes=s["sil"], canonical_points=s.get("canon"),
+                      dists=c4[0], elevs=c4[1], azims=c4[2], angles=c4[3])
         out["total"].backward()
         if sync is not None:
             sync.launch()

@@ -132,6 +132,27 @@ int vpn_emd_fwd(const float* xyz1, const float* xyz2, float* dist, int* assignme
 int vpn_emd_bwd(const float* xyz1, const float* xyz2, const int* assignment, const float* grad_dist,
                 float* grad_xyz1, int B, int n, void* stream);
 
+/* ---- GCN vertex-feature pooling: modules/network/gcn.py:84-164 (train_gcn.py:121)
+ * vpn_image_bounds: GCNModel.get_bound_of_images (gcn.py:90-133).  imgs (B,C,H,W) -> bounds (B,4) = [x lo, x hi, y lo,
+ *   y hi] of the pixels whose channel sum exceeds `threshold` (0.03), as x / w * 2 - 1; the lower bound skips index 0
+ *   and unset bounds stay 0 / w, as the reference's scan does.
+ * vpn_points_yz_range: the per-sample max / min of gcn.py:146-150.  range (B,4) = [min z, max z, min y, max y],
+ *   arg (B,4) int32 = first vertex attaining each (the backward pass routes the range's gradient there).
+ * vpn_feature_pool_fwd: GCNModel.perceptual_feature_pooling (gcn.py:135-164) for ONE feature map feat (B,C,H,W):
+ *   bilinear grid_sample (zeros padding, align_corners=True) at grid x = f(z), grid y = f(y), written to
+ *   out[:, :, coff : coff + C] of out (B,N,Ctot) - the reference's cat + view + permute layout.  One call per map.
+ * vpn_feature_pool_bwd: grad_feat (B,C,H,W) fully written; grad_grid (B,N,2) ACCUMULATED over the maps (zero it first).
+ * vpn_feature_pool_points_bwd: grad_grid -> grad_pts (B,N,3) (x component 0), including the arg-min / arg-max terms. */
+int vpn_image_bounds(const float* imgs, float* bounds, int B, int C, int H, int W, float threshold, void* stream);
+int vpn_points_yz_range(const float* pts, float* range, int* arg, int B, int N, void* stream);
+int vpn_feature_pool_fwd(const float* feat, const float* pts, const float* bounds, const float* range, float* out,
+                         int B, int C, int H, int W, int N, int Ctot, int coff, void* stream);
+int vpn_feature_pool_bwd(const float* feat, const float* pts, const float* bounds, const float* range,
+                         const float* grad_out, float* grad_feat, float* grad_grid,
+                         int B, int C, int H, int W, int N, int Ctot, int coff, void* stream);
+int vpn_feature_pool_points_bwd(const float* pts, const float* bounds, const float* range, const int* arg,
+                                const float* grad_grid, float* grad_pts, int B, int N, void* stream);
+
 /* ---- gradient all-reduce over NVSwitch multicast (NVLS): in-place SUM of a symmetric fp32 buffer
  * multicast_ptr: multicast virtual address of the buffer (numel % 4 == 0, 16-byte aligned).  The caller brackets the
  * call with cross-rank barriers on the stream.  The reference is single process: no counterpart. */

@@ -167,6 +167,31 @@ def main():
     comp = R.Meshing.compose_meshes([sm[0], cm[0], sm[1]])
     d["ref_ms_compose_vertices"], d["ref_ms_compose_faces"] = npy(comp.vertices), npy(comp.faces)
 
+    # ---- GCN vertex-feature pooling (modules/network/gcn.py:84-164) --------------------------
+    B, N = 3, 41
+    imgs = torch.zeros(B, 3, 20, 24)
+    imgs[0, :, 4:15, 6:19] = ru(3, 11, 13)                       # interior blob
+    imgs[1, :, 0:9, 0:11] = ru(3, 9, 11) + 0.05                  # touches row 0 / column 0 (the `== 0` quirk)
+    imgs[2, 0, 7, 23] = 0.5; imgs[2, 1, 19, 3] = 0.02            # single bright pixel in the last column + sub-threshold noise
+    feats = [rn(B, 5, 9, 11), rn(B, 7, 4, 4), rn(B, 3, 1, 6)]
+    pts = rn(B, N, 3) * 0.3
+    d["in_pool_imgs"], d["in_pool_points"] = npy(imgs), npy(pts)
+    for i, f in enumerate(feats):
+        d[f"in_pool_feat{i}"] = npy(f)
+    bounds = R.GCNModel.get_bound_of_images(imgs)
+    d["ref_pool_bounds"] = npy(bounds)
+    fg = [f.clone().requires_grad_() for f in feats]
+    pg = pts.clone().requires_grad_()
+    pooled = R.GCNModel.perceptual_feature_pooling(fg, pg, bounds)
+    d["ref_pool_out"] = npy(pooled)
+    wgt = rn(*pooled.shape)
+    (pooled * wgt).sum().backward()
+    d["in_pool_upstream"] = npy(wgt)
+    d["ref_pool_grad_points"] = npy(pg.grad)
+    for i, f in enumerate(fg):
+        d[f"ref_pool_grad_feat{i}"] = npy(f.grad)
+    d["ref_pool_local"] = npy(R.GCNModel.get_local_features(pts, imgs, feats))
+
     np.savez_compressed(os.path.join(OUT, "hotpath_golden.npz"), **d)
 
     # ---- template meshes -------------------------------------------------------------------

@@ -11,7 +11,10 @@ Accommodations (none changes arithmetic):
   * modules/transform/rotate.py:34 `.to(DEVICE)` is a no-op on CPU and leaves a leaf tensor that is
     then written in place; the source is loaded with that one token replaced by `.clone()`;
   * `kaolin.rep.TriangleMesh` (absent) is stubbed by a container with from_obj/from_tensors/to,
-    enough for modules/meshing/{sphere,cuboid,meshing}.py to run their own arithmetic.
+    enough for modules/meshing/{sphere,cuboid,meshing}.py to run their own arithmetic;
+  * modules/network/gcn.py (vertex-feature pooling) imports torch_geometric layers (absent) that
+    its static pooling methods never touch: the four names are stubbed; `get_bound_of_images` allocates its result with
+    a hard-coded `.cuda()` (gcn.py:87), loaded with that token removed.
 """
 from __future__ import annotations
 
@@ -120,7 +123,23 @@ def load_reference() -> types.SimpleNamespace:
     mesh_cuboid = importlib.import_module("modules.meshing.cuboid")
     ms_pkg.cuboid, ms_pkg.sphere = mesh_cuboid, mesh_sphere
     meshing = importlib.import_module("modules.meshing.meshing")
-    ns = types.SimpleNamespace(
+    # GCN vertex-feature pooling: only the static methods are used; torch_geometric layers are never constructed
+    tg = types.ModuleType("torch_geometric"); tg.__path__ = []
+    tgnn = types.ModuleType("torch_geometric.nn")
+    for nm in ("GCNConv", "TAGConv", "GraphUNet", "BatchNorm"):
+        setattr(tgnn, nm, type(nm, (), {}))
+    tg.nn = tgnn
+    had_tg = {k: sys.modules.get(k) for k in ("torch_geometric", "torch_geometric.nn")}
+    sys.modules["torch_geometric"], sys.modules["torch_geometric.nn"] = tg, tgnn
+    _bare_package("modules.network", os.path.join(mroot, "network"))
+    gcn = _load_patched("modules.network.gcn", os.path.join(mroot, "network", "gcn.py"),
+                        ("torch.zeros((imgs.size(0), 4)).cuda()", "torch.zeros((imgs.size(0), 4))"))
+    for k, v in had_tg.items():
+        if v is None:
+            sys.modules.pop(k, None)
+        else:
+            sys.modules[k] = v
+    ns = types.SimpleNamespace(GCNModel=gcn.GCNModel,
         root=root, config=cfg, rotate=rotate, translate=translate, transform=transform,
         sphere=sphere, cuboid=cuboid, Sampling=sampling.Sampling,
         ChamferDistanceLoss=chamfer.ChamferDistanceLoss, VPDiverseLoss=vpdiv.VPDiverseLoss,

@@ -619,6 +619,62 @@ def silhouette_loss(verts, faces, gt, dists, elevs, azims, loss_func: str = "L1"
 # --------------------------------------------------------------------------------------
 # synthetic inputs shared by tests, smoke() and bench.py
 # --------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------
+# GCN vertex-feature pooling (modules/network/gcn.py:84-164)
+# ------------------------------------------------------------------------------------------------
+def image_bounds(imgs: torch.Tensor, threshold: float = 0.03) -> torch.Tensor:
+    """gcn.py:90-133 (get_bound_of_images) without the per-pixel Python loops.  mask = channel sum > 0.03; the scan sets
+    the lower bound at the first occupied column/row whose index is NOT 0 (`bounds == 0` also means "unset", gcn.py:107,
+    :119: an occupied column 0 leaves it unset and the next occupied column overwrites it) and the upper bound at the
+    last occupied one; unset bounds stay 0 and w (h).  Normalised to [-1, 1] as x / w * 2 - 1."""
+    assert imgs.ndimension() == 4
+    b, _, h, w = imgs.shape
+    out = torch.zeros(b, 4)
+    for i in range(b):
+        mask = imgs[i].sum(0) > threshold
+        for k, (occ, size) in enumerate(((mask.any(0), w), (mask.any(1), h))):
+            idx = torch.nonzero(occ).flatten()
+            lo_c = idx[idx > 0]
+            out[i, 2 * k] = float(lo_c[0]) if lo_c.numel() else 0.0
+            out[i, 2 * k + 1] = float(idx[-1]) if idx.numel() else float(size)
+    out[:, :2] = out[:, :2] / w * 2 - 1
+    out[:, 2:4] = out[:, 2:4] / h * 2 - 1
+    return out
+
+
+def bilinear_sample(feat: torch.Tensor, gx: torch.Tensor, gy: torch.Tensor) -> torch.Tensor:
+    """torch.nn.functional.grid_sample(feat (B,C,H,W), grid (B,1,N,2), mode='bilinear', padding_mode='zeros',
+    align_corners=True) -> (B,C,N), restated: ix = (x+1)/2 (W-1); taps nw, ne, sw, se with weights
+    (ix_se-ix)(iy_se-iy), (ix-ix_sw)(iy_sw-iy), (ix_ne-ix)(iy-iy_ne), (ix-ix_nw)(iy-iy_nw); out-of-range taps add 0."""
+    b, c, h, w = feat.shape
+    ix = ((gx + 1) / 2) * (w - 1)
+    iy = ((gy + 1) / 2) * (h - 1)
+    x0, y0 = torch.floor(ix), torch.floor(iy)
+    x1, y1 = x0 + 1, y0 + 1
+    out = torch.zeros(b, c, gx.shape[1], dtype=feat.dtype)
+    flat = feat.reshape(b, c, h * w)
+    for xx, yy, wgt in ((x0, y0, (x1 - ix) * (y1 - iy)), (x1, y0, (ix - x0) * (y1 - iy)),
+                        (x0, y1, (x1 - ix) * (iy - y0)), (x1, y1, (ix - x0) * (iy - y0))):
+        ok = (xx >= 0) & (xx <= w - 1) & (yy >= 0) & (yy <= h - 1)
+        lin = (yy.clamp(0, h - 1) * w + xx.clamp(0, w - 1)).long()
+        tap = torch.gather(flat, 2, lin[:, None, :].expand(b, c, -1))
+        out = out + tap * (wgt * ok)[:, None, :]
+    return out
+
+
+def perceptual_feature_pooling(features: Sequence[torch.Tensor], points: torch.Tensor, bounds: torch.Tensor) -> torch.Tensor:
+    """gcn.py:135-164.  grid x from z, grid y from y, both flipped and rescaled by the sample's own min / max into the
+    image bounds; every feature map sampled bilinearly there; channels of all maps concatenated -> (B, N, sum C)."""
+    assert points.ndimension() == 3 and bounds.ndimension() == 2
+    mx, mn = points.max(1)[0], points.min(1)[0]                      # (B,3): differentiable through the arg-max / arg-min
+    sz = (points[..., 2] - mn[:, None, 2]) / (mx[:, None, 2] - mn[:, None, 2])
+    sy = (points[..., 1] - mn[:, None, 1]) / (mx[:, None, 1] - mn[:, None, 1])
+    gx = bounds[:, None, 0] + (1 - sz) * (bounds[:, None, 1] - bounds[:, None, 0])
+    gy = bounds[:, None, 2] + (1 - sy) * (bounds[:, None, 3] - bounds[:, None, 2])
+    pooled = [bilinear_sample(f, gx, gy) for f in features]
+    return torch.cat(pooled, 1).permute(0, 2, 1)
+
+
 def synthetic_primitives(b: int, k: int, seed: int = 1234):
     """Network-output-shaped (v, q, t): vpnet_one_resnet.py:69-85 with IS_SIGMOID and
     VOLUME_RESTRICT = [8, 10, 10] (config.py:25-26)."""

@@ -529,6 +529,45 @@ def test_step_config_shapes(vpn, O, name, kind, b, k, n, m, res, vertex):
         close(got, want, rtol=1e-3, atol=2e-4 * float(want.abs().max()), what=f"{name} grad {nm}")
 
 
+def test_step_with_canonical_frame_chamfer(vpn, O):
+    """train.py:152-163 as written: view-frame Chamfer + Chamfer of view_to_obj_points(points) against the canonical
+    targets + VP-diverse; eager step against the oracle, and the graph replay against the eager step (vertex mode: no
+    random draw)."""
+    g = torch.Generator().manual_seed(77)
+    b, k, n, m = 2, 4, 512, 1024
+    v, q, t = O.synthetic_primitives(b, k); t = t * 0.3
+    u = torch.rand(b, k, n, 3, generator=g)
+    tgt = (torch.rand(b, m, 3, generator=g) - 0.5) * 0.8
+    dists = 1.0 + 0.5 * torch.rand(b, generator=g); elevs = 40.0 * torch.rand(b, generator=g)
+    azims = 360.0 * torch.rand(b, generator=g); angles = 360.0 * torch.rand(b, generator=g)
+    canon = tgt * dists[:, None, None]
+    cfg = vpn.PrimitiveLossConfig(kind="cuboid", l_can_cd=1.0)
+    vc, qc, tc = (C(x).requires_grad_() for x in (v, q, t))
+    out = vpn.PrimitiveLoss(cfg)(vc, qc, tc, C(u), C(tgt), canonical_points=C(canon), dists=C(dists), elevs=C(elevs),
+                                 azims=C(azims), angles=C(angles))
+    out["total"].backward()
+    vo, qo, to = (x.clone().requires_grad_() for x in (v, q, t))
+    pts = O.sample_predict_points("cuboid", vo, qo, to, u)
+    ref = (O.chamfer_dense(pts, tgt) + O.chamfer_dense(O.view_to_obj_points(pts, dists, elevs, azims, angles), canon)
+           + 0.1 * O.chamfer_dense(to, tgt, w1=0.5, w2=1.0))
+    ref.backward()
+    close(out["total"], ref, rtol=RTOL, what="faithful loss")
+    for got, want, nm in ((vc.grad, vo.grad, "v"), (qc.grad, qo.grad, "q"), (tc.grad, to.grad, "t")):
+        close(got, want, rtol=1e-3, atol=2e-4 * float(want.abs().max()), what=f"faithful grad {nm}")
+    cfgv = vpn.PrimitiveLossConfig(kind="sphere", l_can_cd=1.0, vertex_chamfer=True)
+    cams = (C(dists), C(elevs), C(azims), C(angles))
+    gr = vpn.GraphedPrimitiveLoss(cfgv, C(v), C(q), C(t), C(tgt), None, canonical_points=C(canon), cameras=cams)
+    cams2 = (C(dists * 1.1), C(elevs + 3.0), C(azims), C(angles))
+    for cam, cn in ((cams, canon), (cams2, canon * 0.9)):
+        loss, gv, gq, gtt = gr(C(v), C(q), C(t), C(tgt), canonical_points=C(cn), cameras=cam)
+        ve, qe, te = (C(x).requires_grad_() for x in (v, q, t))
+        oe = vpn.PrimitiveLoss(cfgv)(ve, qe, te, None, C(tgt), canonical_points=C(cn), dists=cam[0], elevs=cam[1],
+                                     azims=cam[2], angles=cam[3])
+        oe["total"].backward()
+        close(loss, oe["total"], rtol=1e-6)
+        close(gv, ve.grad, rtol=1e-5, atol=1e-7); close(gq, qe.grad, rtol=1e-5, atol=1e-7); close(gtt, te.grad, rtol=1e-5, atol=1e-7)
+
+
 # ------------------------------------------------------------------------------------------------
 # EMD auction (modules/loss/emd): one launch per forward, deterministic; bit-exact against the restatement
 # ------------------------------------------------------------------------------------------------
@@ -628,3 +667,76 @@ def test_graphed_step_matches_eager(vpn, O):
     l1 = gs(C(v), C(q), C(t), C(tgt))[0].item()
     l2 = gs(C(v), C(q), C(t), C(tgt))[0].item()
     assert l1 > 0 and l2 > 0 and l1 != l2                      # a fresh uniform draw every replay
+
+
+# ------------------------------------------------------------------------------------------------
+# GCN vertex-feature pooling (modules/network/gcn.py:84-164)
+# ------------------------------------------------------------------------------------------------
+def test_feature_pooling_golden(vpn, golden):
+    """Against what the reference's own GCNModel.get_bound_of_images / perceptual_feature_pooling produced."""
+    g = golden
+    imgs, pts = C(g["in_pool_imgs"]), C(g["in_pool_points"])
+    feats = [C(g[f"in_pool_feat{i}"]).requires_grad_() for i in range(3)]
+    bounds = vpn.image_bounds(imgs)
+    same(bounds, g["ref_pool_bounds"], "bounds")                      # integer pixel indices, same normalisation ops
+    pg = pts.clone().requires_grad_()
+    out = vpn.perceptual_feature_pooling(feats, pg, bounds)
+    close(out, g["ref_pool_out"], rtol=RTOL, atol=1e-6, what="pooled features")
+    (out * C(g["in_pool_upstream"])).sum().backward()
+    for i, f in enumerate(feats):
+        close(f.grad, g[f"ref_pool_grad_feat{i}"], rtol=RTOL, atol=1e-5, what=f"grad feat {i}")
+    ref = g["ref_pool_grad_points"]
+    close(pg.grad, ref, rtol=1e-3, atol=1e-4 * float(np.abs(ref).max()), what="grad points")
+    import modules
+    close(modules.GCNFeaturePooling.get_local_features(pts, imgs, [f.detach() for f in feats]), g["ref_pool_local"],
+          rtol=RTOL, atol=1e-6, what="get_local_features")
+
+
+@pytest.mark.parametrize("b,n,maps", [
+    (4, 2048, [(64, 35, 35), (128, 18, 18), (256, 9, 9), (512, 5, 5)]),      # train_gcn.py: ResNet-18 maps of a 137 x 137 view
+    (2, 300, [(3, 7, 5), (33, 6, 6), (1, 1, 1)]),                             # ragged channel counts, 1 x 1 map
+    (1, 37, [(2, 200, 200)]),                                                 # plane larger than the shared-memory budget
+])
+def test_feature_pooling_vs_oracle(vpn, O, b, n, maps):
+    g = torch.Generator().manual_seed(11)
+    pts = (torch.rand(b, n, 3, generator=g) - 0.5) * 0.9
+    imgs = torch.zeros(b, 3, 137, 137)
+    for i in range(b):
+        x0, y0 = 10 + 7 * i, 20 + 5 * i
+        imgs[i, :, y0:y0 + 60, x0:x0 + 80] = torch.rand(3, 60, 80, generator=g)
+    feats = [torch.randn(b, c, h, w, generator=g) for c, h, w in maps]
+    bounds_ref = O.image_bounds(imgs)
+    bounds = vpn.image_bounds(C(imgs))
+    same(bounds, bounds_ref, "bounds")
+    fo = [f.clone().requires_grad_() for f in feats]
+    po = pts.clone().requires_grad_()
+    ref = O.perceptual_feature_pooling(fo, po, bounds_ref)
+    up = torch.randn(ref.shape, generator=g)
+    (ref * up).sum().backward()
+    fc = [C(f).requires_grad_() for f in feats]
+    pc = C(pts).requires_grad_()
+    out = vpn.perceptual_feature_pooling(fc, pc, bounds)
+    assert out.shape == (b, n, sum(c for c, _, _ in maps)) and out.is_contiguous()
+    close(out, ref, rtol=RTOL, atol=2e-6, what="pooled")
+    (out * C(up)).sum().backward()
+    for i in range(len(maps)):
+        close(fc[i].grad, fo[i].grad, rtol=RTOL, atol=1e-5 * max(1.0, float(fo[i].grad.abs().max())), what=f"grad feat {i}")
+    close(pc.grad, po.grad, rtol=1e-3, atol=2e-4 * float(po.grad.abs().max()), what="grad points")
+
+
+def test_image_bounds_edge_cases(vpn, O):
+    g = torch.Generator().manual_seed(5)
+    cases = [torch.zeros(2, 3, 16, 12)]                                        # empty masks: bounds stay (0, w, 0, h)
+    im = torch.zeros(3, 4, 9, 31)
+    im[0, :, :, 0] = 1.0; im[0, :, 4, 17] = 1.0                               # occupied column 0 is skipped as a lower bound
+    im[1, 0] = 0.0299; im[1, 1, 8, 30] = 0.001                                 # just below / above the 0.03 threshold
+    im[2] = torch.rand(4, 9, 31, generator=g)                                  # everything occupied
+    cases.append(im)
+    cases.append(torch.rand(5, 1, 137, 137, generator=g) * (torch.rand(5, 1, 137, 137, generator=g) > 0.999))
+    for imgs in cases:
+        same(vpn.image_bounds(C(imgs)), O.image_bounds(imgs), "bounds")
+    import modules
+    with pytest.raises(AssertionError):
+        modules.GCNFeaturePooling.get_bound_of_images(C(torch.zeros(3, 8, 8)))
+    with pytest.raises(AssertionError):
+        modules.GCNFeaturePooling.perceptual_feature_pooling([C(torch.zeros(1, 2, 4, 4))], C(torch.zeros(5, 3)), C(torch.zeros(1, 4)))

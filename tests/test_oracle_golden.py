@@ -198,3 +198,26 @@ def test_emd_auction_oracle_properties():
     assert (ass == np.arange(128)).all() and (dist == 0).all()
     g = O.emd_backward(a, a[::-1].copy(), ass, np.ones(128, np.float32))
     np.testing.assert_allclose(g, 2.0 * (a - a[::-1][ass]), rtol=1e-6)
+
+
+def test_gcn_feature_pooling(golden):
+    """gcn.py:84-164 (image bounds + perceptual feature pooling): the restatement against the reference's own output."""
+    g = golden
+    imgs, pts = T(g["in_pool_imgs"]), T(g["in_pool_points"])
+    feats = [T(g[f"in_pool_feat{i}"]) for i in range(3)]
+    bounds = O.image_bounds(imgs)
+    eq(bounds, g["ref_pool_bounds"])
+    fg = [f.clone().requires_grad_() for f in feats]
+    pg = pts.clone().requires_grad_()
+    out = O.perceptual_feature_pooling(fg, pg, bounds)
+    close(out, g["ref_pool_out"], 1e-5, 1e-6)
+    (out * T(g["in_pool_upstream"])).sum().backward()
+    close(pg.grad, g["ref_pool_grad_points"], 1e-4, 1e-4)
+    for i, f in enumerate(fg):
+        close(f.grad, g[f"ref_pool_grad_feat{i}"], 1e-5, 1e-6)
+    close(O.perceptual_feature_pooling(feats, pts, O.image_bounds(imgs)), g["ref_pool_local"], 1e-5, 1e-6)
+    # the `== 0` quirk of gcn.py:107: an occupied first column is skipped as a lower bound
+    im = torch.zeros(1, 3, 8, 8); im[0, :, 2:5, 0] = 1.0; im[0, :, 2:5, 3] = 1.0
+    b = O.image_bounds(im)
+    assert float(b[0, 0]) == 3 / 8 * 2 - 1 and float(b[0, 1]) == 3 / 8 * 2 - 1
+    eq(O.image_bounds(torch.zeros(1, 3, 8, 6)), np.array([[-1.0, 1.0, -1.0, 1.0]], np.float32))

@@ -488,3 +488,82 @@ def fp32_peak_tflops(device=None, reps: int = 3):
     check(lib.vpn_fp32_peak_probe(ptr(scratch), reps, ctypes.byref(a), ctypes.byref(b), stream_ptr(dev)),
           "vpn_fp32_peak_probe")
     return {"ffma": a.value, "ffma2": b.value}
+
+
+# --------------------------------------------------------------------------------------
+# GCN vertex-feature pooling (modules/network/gcn.py:84-164)
+# --------------------------------------------------------------------------------------
+def image_bounds(imgs: torch.Tensor, threshold: float = 0.03) -> torch.Tensor:
+    """GCNModel.get_bound_of_images (gcn.py:90-133): (B,C,H,W) -> (B,4) normalised [x lo, x hi, y lo, y hi].  One launch;
+    the reference walks columns and rows in Python and reads device scalars at every step."""
+    assert imgs.ndimension() == 4
+    imgs = require(imgs.contiguous(), f32, "imgs")
+    b, c, h, w = imgs.shape
+    out = torch.empty((b, 4), dtype=f32, device=imgs.device)
+    check(_lib.load().vpn_image_bounds(ptr(imgs), ptr(out), b, c, h, w, float(threshold), stream_ptr(imgs.device)),
+          "vpn_image_bounds")
+    return out
+
+
+class _FeaturePool(torch.autograd.Function):
+    """pooled (B, N, sum C) = bilinear samples of every feature map at the vertices' image positions."""
+
+    @staticmethod
+    def forward(ctx, points, bounds, *features):
+        lib = _lib.load()
+        points = require(points.contiguous(), f32, "points")
+        bounds = require(bounds.contiguous(), f32, "bounds")
+        feats = [require(f.contiguous(), f32, "features") for f in features]
+        b, n = points.shape[:2]
+        dev = points.device
+        ctot = sum(f.shape[1] for f in feats)
+        out = torch.empty((b, n, ctot), dtype=f32, device=dev)
+        rng = torch.empty((b, 4), dtype=f32, device=dev)
+        arg = torch.empty((b, 4), dtype=torch.int32, device=dev)
+        if b > 0 and n > 0:
+            check(lib.vpn_points_yz_range(ptr(points), ptr(rng), ptr(arg), b, n, stream_ptr(dev)), "vpn_points_yz_range")
+            coff = 0
+            for f in feats:
+                assert f.dim() == 4 and f.shape[0] == b, "feature maps must be (B, C, H, W)"
+                check(lib.vpn_feature_pool_fwd(ptr(f), ptr(points), ptr(bounds), ptr(rng), ptr(out), b, f.shape[1], f.shape[2],
+                                               f.shape[3], n, ctot, coff, stream_ptr(dev)), "vpn_feature_pool_fwd")
+                coff += f.shape[1]
+        ctx.save_for_backward(points, bounds, rng, arg, *feats)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        points, bounds, rng, arg, *feats = ctx.saved_tensors
+        b, n = points.shape[:2]
+        dev = points.device
+        grad_out = grad_out.contiguous()
+        ctot = grad_out.shape[2]
+        ggrid = torch.zeros((b, n, 2), dtype=f32, device=dev)
+        gfeats = []
+        coff = 0
+        for f in feats:
+            gf = torch.empty_like(f)
+            if b > 0 and n > 0:
+                check(lib.vpn_feature_pool_bwd(ptr(f), ptr(points), ptr(bounds), ptr(rng), ptr(grad_out), ptr(gf), ptr(ggrid), b,
+                                               f.shape[1], f.shape[2], f.shape[3], n, ctot, coff, stream_ptr(dev)),
+                      "vpn_feature_pool_bwd")
+            else:
+                gf.zero_()
+            gfeats.append(gf)
+            coff += f.shape[1]
+        gp = None
+        if ctx.needs_input_grad[0]:
+            gp = torch.zeros_like(points)
+            if b > 0 and n > 0:
+                check(lib.vpn_feature_pool_points_bwd(ptr(points), ptr(bounds), ptr(rng), ptr(arg), ptr(ggrid), ptr(gp), b, n,
+                                                      stream_ptr(dev)), "vpn_feature_pool_points_bwd")
+        return (gp, None, *gfeats)
+
+
+def perceptual_feature_pooling(perceptual_features, points: torch.Tensor, bounds: torch.Tensor) -> torch.Tensor:
+    """GCNModel.perceptual_feature_pooling (gcn.py:135-164): list of (B,C_l,H_l,W_l) maps, points (B,N,3), bounds (B,4)
+    -> (B, N, sum C_l).  Differentiable w.r.t. the maps and the points (through the grid and the per-sample range)."""
+    assert points.ndimension() == 3
+    assert bounds.ndimension() == 2
+    return _FeaturePool.apply(points, bounds, *perceptual_features)

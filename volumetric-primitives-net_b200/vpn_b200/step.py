@@ -122,7 +122,8 @@ class GraphedPrimitiveLoss:
         loss, gv, gq, gt = g(v, q, t, targets, silhouettes)               # static output buffers, overwritten by the next call
     """
 
-    def __init__(self, config: PrimitiveLossConfig, v, q, t, targets, silhouettes=None, n_samples: int = 0, warmup: int = 3):
+    def __init__(self, config: PrimitiveLossConfig, v, q, t, targets, silhouettes=None, n_samples: int = 0, warmup: int = 3,
+                 canonical_points=None, cameras=None):
         from . import _lib
         self.cfg = config
         self.step = PrimitiveLoss(config)
@@ -132,13 +133,18 @@ class GraphedPrimitiveLoss:
         self.t = t.detach().clone().requires_grad_()
         self.targets = targets.detach().clone()
         self.sil = None if silhouettes is None else silhouettes.detach().clone()
+        # canonical-frame Chamfer of train.py:152-163: targets in the object frame + (dists, elevs, azims, angles)
+        self.canonical = None if canonical_points is None else canonical_points.detach().clone()
+        self.cameras = None if cameras is None else tuple(c.detach().clone() for c in cameras)
         b, k = q.shape[:2]
         self.ushape = None if config.vertex_chamfer else (b, k, n_samples, 2 if config.kind == "sphere" else 3)
         assert config.vertex_chamfer or n_samples > 0, "n_samples (points per primitive) is required unless vertex_chamfer"
 
         def run():
             u = None if self.ushape is None else torch.rand(self.ushape, device=dev)      # drawn on the device, as the reference does
-            out = self.step(self.v, self.q, self.t, u, self.targets, silhouettes=self.sil)
+            cams = self.cameras or (None, None, None, None)
+            out = self.step(self.v, self.q, self.t, u, self.targets, silhouettes=self.sil, canonical_points=self.canonical,
+                            dists=cams[0], elevs=cams[1], azims=cams[2], angles=cams[3])
             gv, gq, gt = torch.autograd.grad(out["total"], (self.v, self.q, self.t))
             return out["total"], gv, gq, gt
 
@@ -156,7 +162,12 @@ class GraphedPrimitiveLoss:
             self.loss, self.gv, self.gq, self.gt = run()
         self.launches_per_step = int(lib.vpn_launch_count() - n0)      # our kernels inside one replay
 
-    def __call__(self, v, q, t, targets, silhouettes=None):
+    def __call__(self, v, q, t, targets, silhouettes=None, canonical_points=None, cameras=None):
+        if self.canonical is not None and canonical_points is not None:
+            self.canonical.copy_(canonical_points, non_blocking=True)
+        if self.cameras is not None and cameras is not None:
+            for dst, src in zip(self.cameras, cameras):
+                dst.copy_(src, non_blocking=True)
         self.v.data.copy_(v, non_blocking=True)
         self.q.data.copy_(q, non_blocking=True)
         self.t.data.copy_(t, non_blocking=True)
