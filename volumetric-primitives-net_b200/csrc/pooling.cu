@@ -122,13 +122,15 @@ __device__ __forceinline__ void make_taps(float gx, float gy, int H, int W, Taps
   }
 }
 
-// Forward.  grid: x = channel chunk (CH channels), y = sample.  dynamic smem: CH planes of `stride` floats (staged == 1).
-// A warp takes 32 vertices at a time: lane j prepares the taps of vertex j, then the warp walks the 32 vertices with the
-// lanes spread over (vertex sub-group, channel): G = 32 / CH vertices per pass, so a pass writes G rows of CH floats.
+// Forward.  grid: x = channel chunk (CH channels), y = sample, z = vertex slice.  dynamic smem: CH planes of `stride`
+// floats (staged == 1).  A warp takes 32 vertices at a time: lane j prepares the taps of vertex j, then the warp walks
+// the 32 vertices with the lanes spread over channels.  CH < 32 (large planes): G = 32 / CH vertices per pass.
+// CH = 32 KC (small planes: many channels fit): one vertex per pass, every lane owns KC channels, so the tap
+// broadcast (8 shuffles) is paid once per KC x 32 outputs; a pass writes KC rows of 128 bytes.
 __global__ void __launch_bounds__(kPoolThreads)
 feature_pool_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ pts, const float* __restrict__ bounds,
                         const float* __restrict__ range, float* __restrict__ out,
-                        int C, int H, int W, int N, int Ctot, int coff, int CH, int stride, int staged) {
+                        int C, int H, int W, int N, int Ctot, int coff, int CH, int stride, int staged, int per_slice) {
   extern __shared__ float pool_planes[];
   const int b = blockIdx.y, c0 = blockIdx.x * CH, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int HW = H * W;
@@ -142,8 +144,10 @@ feature_pool_fwd_kernel(const float* __restrict__ feat, const float* __restrict_
   const int pstride = staged ? stride : HW;
   const float* bnd = bounds + 4 * b;
   const float* rng = range + 4 * b;
-  const int G = 32 / CH, sub = lane / CH, c = lane % CH;
-  for (int base = warp * 32; base < N; base += (kPoolThreads / 32) * 32) {
+  const int LCH = min(CH, 32), KC = (CH + 31) / 32;
+  const int G = 32 / LCH, sub = lane / LCH, c = lane % LCH;
+  const int n_lo = blockIdx.z * per_slice, n_hi = min(N, n_lo + per_slice);
+  for (int base = n_lo + warp * 32; base < n_hi; base += (kPoolThreads / 32) * 32) {
     Taps mine;
     {
       const int n = min(base + lane, N - 1);
@@ -153,15 +157,22 @@ feature_pool_fwd_kernel(const float* __restrict__ feat, const float* __restrict_
     }
     for (int j0 = 0; j0 < 32; j0 += G) {
       const int j = j0 + sub;
-      float acc = 0.f;
+      int off[4]; float w[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int off = __shfl_sync(0xffffffffu, mine.off[k], j);
-        const float w = __shfl_sync(0xffffffffu, mine.w[k], j);
-        if (c < nch && w != 0.f) acc = fmaf(planes[(size_t)c * pstride + off], w, acc);
-      }
+      for (int k = 0; k < 4; ++k) { off[k] = __shfl_sync(0xffffffffu, mine.off[k], j); w[k] = __shfl_sync(0xffffffffu, mine.w[k], j); }
       const int n = base + j;
-      if (n < N && c < nch) out[((size_t)b * N + n) * Ctot + coff + c0 + c] = acc;
+      if (n >= n_hi) continue;                     // after the shuffles: every lane took part in them
+      float* orow = out + ((size_t)b * N + n) * Ctot + coff + c0;
+      for (int kc = 0; kc < KC; ++kc) {
+        const int cc = c + 32 * kc;
+        if (cc < nch) {
+          const float* pl = planes + (size_t)cc * pstride;
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) if (w[k] != 0.f) acc = fmaf(pl[off[k]], w[k], acc);
+          orow[cc] = acc;
+        }
+      }
     }
   }
 }
@@ -284,6 +295,13 @@ static int pool_chunk(int C, int HW, int planes_per_channel, int* stride) {
   return ch;
 }
 
+// forward: as above, then widened to 32 KC channels (KC <= 16) while the planes still fit
+static int pool_chunk_fwd(int C, int HW, int* stride) {
+  int ch = pool_chunk(C, HW, 1, stride);
+  if (ch == 32) while (ch < C && ch < 512 && (size_t)2 * ch * (*stride) * 4 <= (size_t)kPoolSmemBudget) ch *= 2;
+  return ch;
+}
+
 }  // namespace vpn
 
 using namespace vpn;
@@ -314,7 +332,7 @@ extern "C" int vpn_feature_pool_fwd(const float* feat, const float* pts, const f
   if (B == 0) return VPN_OK;
   if (!feat || !pts || !bounds || !range || !out) { vpn_set_error("feature pool fwd: null pointer"); return VPN_ERR_ARG; }
   int stride = 0;
-  int ch = pool_chunk(C, H * W, 1, &stride);
+  int ch = pool_chunk_fwd(C, H * W, &stride);
   const int staged = ch >= 1;
   if (!staged) ch = 32;                                            // plane larger than shared memory: taps read through L2
   const size_t smem = staged ? (size_t)ch * stride * 4 : 0;
@@ -324,9 +342,16 @@ extern "C" int vpn_feature_pool_fwd(const float* feat, const float* pts, const f
     if (e != cudaSuccess) { vpn_set_error("feature pool fwd: smem attribute: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
     attr = true;
   }
-  dim3 grid((C + ch - 1) / ch, B);
+  // enough CTAs for four per SM: split the vertices when (channel chunks x samples) alone are too few
+  const int chunks = (C + ch - 1) / ch;
+  int slices = (4 * 148 + chunks * B - 1) / (chunks * B);
+  const int max_slices = (N + kPoolThreads - 1) / kPoolThreads;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  const int per_slice = (((N + slices - 1) / slices) + 31) / 32 * 32;
+  dim3 grid(chunks, B, (N + per_slice - 1) / per_slice);
   feature_pool_fwd_kernel<<<grid, kPoolThreads, smem, (cudaStream_t)stream>>>(feat, pts, bounds, range, out, C, H, W, N, Ctot, coff,
-                                                                             ch, stride, staged);
+                                                                             ch, stride, staged, per_slice);
   return vpn_check_launch("feature_pool_fwd_kernel");
 }
 
