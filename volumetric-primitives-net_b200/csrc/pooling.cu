@@ -14,32 +14,45 @@
 namespace vpn {
 
 constexpr int kPoolThreads = 256;
-constexpr int kPoolSmemBudget = 96 * 1024;      // per CTA: two CTAs per SM
+constexpr int kPoolSmemBudget = 96 * 1024;      // backward, per CTA: two CTAs per SM
+constexpr int kPoolFwdSmemBudget = 44 * 1024;   // forward, per CTA: five CTAs (40 warps) per SM - the kernel is latency bound
 
 // ---- image bounds ---------------------------------------------------------------------------------------------
-// grid: x = sample.  dynamic smem: int flags[W + H]
-__global__ void __launch_bounds__(kPoolThreads)
+// grid: x = sample.  dynamic smem: int flags[W + H].  One CTA of 1024 threads per image, four pixels per thread in
+// flight (the kernel is latency bound: B CTAs, 4 C H W bytes each).
+constexpr int kBoundsThreads = 1024;
+__global__ void __launch_bounds__(kBoundsThreads)
 image_bounds_kernel(const float* __restrict__ imgs, float* __restrict__ bounds, int C, int H, int W, float thr) {
   extern __shared__ int pool_flags[];
   __shared__ int lohi[4];
   int* col_any = pool_flags;
   int* row_any = pool_flags + W;
   const int b = blockIdx.x, tid = threadIdx.x;
-  for (int i = tid; i < W + H; i += kPoolThreads) pool_flags[i] = 0;
+  for (int i = tid; i < W + H; i += kBoundsThreads) pool_flags[i] = 0;
   if (tid < 4) lohi[tid] = (tid & 1) ? -1 : 0x7fffffff;
   __syncthreads();
   const float* img = imgs + (size_t)b * C * H * W;
   const int HW = H * W;
-  for (int p = tid; p < HW; p += kPoolThreads) {
-    float s = 0.f;
-    for (int c = 0; c < C; ++c) s = __fadd_rn(s, img[(size_t)c * HW + p]);      // img.sum(0), channels in order
-    if (s > thr) { col_any[p % W] = 1; row_any[p / W] = 1; }
+  for (int p0 = tid; p0 < HW; p0 += 4 * kBoundsThreads) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {                                              // img.sum(0), channels in order
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u * kBoundsThreads;
+        if (p < HW) s[u] = __fadd_rn(s[u], img[(size_t)c * HW + p]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * kBoundsThreads;
+      if (p < HW && s[u] > thr) { col_any[p % W] = 1; row_any[p / W] = 1; }
+    }
   }
   __syncthreads();
   // lower bound: first occupied index that is not 0 (gcn.py:107,119: `bounds == 0` doubles as "unset");
   // upper bound: last occupied index
-  for (int i = tid; i < W; i += kPoolThreads) if (col_any[i]) { if (i > 0) atomicMin(&lohi[0], i); atomicMax(&lohi[1], i); }
-  for (int i = tid; i < H; i += kPoolThreads) if (row_any[i]) { if (i > 0) atomicMin(&lohi[2], i); atomicMax(&lohi[3], i); }
+  for (int i = tid; i < W; i += kBoundsThreads) if (col_any[i]) { if (i > 0) atomicMin(&lohi[0], i); atomicMax(&lohi[1], i); }
+  for (int i = tid; i < H; i += kBoundsThreads) if (row_any[i]) { if (i > 0) atomicMin(&lohi[2], i); atomicMax(&lohi[3], i); }
   __syncthreads();
   if (tid < 4) {
     const int size = tid < 2 ? W : H;
@@ -103,7 +116,9 @@ __device__ __forceinline__ void grid_of_vertex(const float* __restrict__ p, cons
   gy = __fadd_rn(bnd[2], __fmul_rn(__fsub_rn(1.0f, sy), __fsub_rn(bnd[3], bnd[2])));
 }
 
-__device__ __forceinline__ void make_taps(float gx, float gy, int H, int W, Taps& t) {
+// invalid taps (outside the plane) get weight 0 and offset `pad`: a word the staged planes keep at zero (index H*W), so the
+// forward loop needs no predicate; the un-staged paths pass pad = 0 and skip zero weights instead.
+__device__ __forceinline__ void make_taps(float gx, float gy, int H, int W, Taps& t, int pad = 0) {
   const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(W - 1));
   const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(H - 1));
   const float x0 = floorf(ix), y0 = floorf(iy), x1 = x0 + 1.0f, y1 = y0 + 1.0f;
@@ -115,7 +130,7 @@ __device__ __forceinline__ void make_taps(float gx, float gy, int H, int W, Taps
     // NaN coordinates (degenerate range: max == min) fail every comparison: all taps invalid, output 0 like grid_sample
     const bool ok = xs[k] >= 0.f && xs[k] <= (float)(W - 1) && ys[k] >= 0.f && ys[k] <= (float)(H - 1);
     const int xi = ok ? (int)xs[k] : 0, yi = ok ? (int)ys[k] : 0;
-    t.off[k] = yi * W + xi;
+    t.off[k] = ok ? yi * W + xi : pad;
     t.w[k] = ok ? wx[k] * wy[k] : 0.f;
     t.dx[k] = ok ? sx[k] * wy[k] : 0.f;
     t.dy[k] = ok ? sy[k] * wx[k] : 0.f;
@@ -138,6 +153,7 @@ feature_pool_fwd_kernel(const float* __restrict__ feat, const float* __restrict_
   const float* fb = feat + ((size_t)b * C + c0) * HW;
   if (staged) {
     for (int i = tid; i < nch * HW; i += kPoolThreads) pool_planes[(i / HW) * stride + (i % HW)] = fb[i];
+    for (int i = tid; i < CH; i += kPoolThreads) pool_planes[i * stride + HW] = 0.f;       // the pad word of every plane
     __syncthreads();
   }
   const float* planes = staged ? pool_planes : fb;
@@ -153,7 +169,7 @@ feature_pool_fwd_kernel(const float* __restrict__ feat, const float* __restrict_
       const int n = min(base + lane, N - 1);
       float gx, gy;
       grid_of_vertex(pts + ((size_t)b * N + n) * 3, bnd, rng, gx, gy);
-      make_taps(gx, gy, H, W, mine);
+      make_taps(gx, gy, H, W, mine, staged ? HW : 0);
     }
     for (int j0 = 0; j0 < 32; j0 += G) {
       const int j = j0 + sub;
@@ -163,14 +179,33 @@ feature_pool_fwd_kernel(const float* __restrict__ feat, const float* __restrict_
       const int n = base + j;
       if (n >= n_hi) continue;                     // after the shuffles: every lane took part in them
       float* orow = out + ((size_t)b * N + n) * Ctot + coff + c0;
-      for (int kc = 0; kc < KC; ++kc) {
-        const int cc = c + 32 * kc;
-        if (cc < nch) {
-          const float* pl = planes + (size_t)cc * pstride;
-          float acc = 0.f;
+      if (staged) {
+        // every tap is a shared-memory word (invalid ones the zero pad): no predicates, two channels in flight
+        const float* pl = planes + (size_t)c * pstride;
+        const size_t step = (size_t)32 * pstride;
+        int kc = 0;
+        for (; kc + 1 < KC; kc += 2, pl += 2 * step) {
+          const float* p2 = pl + step;
+          const float a = fmaf(pl[off[3]], w[3], fmaf(pl[off[2]], w[2], fmaf(pl[off[1]], w[1], pl[off[0]] * w[0])));
+          const float d = fmaf(p2[off[3]], w[3], fmaf(p2[off[2]], w[2], fmaf(p2[off[1]], w[1], p2[off[0]] * w[0])));
+          const int cc = c + 32 * kc;
+          if (cc < nch) orow[cc] = a;
+          if (cc + 32 < nch) orow[cc + 32] = d;
+        }
+        if (kc < KC) {
+          const int cc = c + 32 * kc;
+          if (cc < nch) orow[cc] = fmaf(pl[off[3]], w[3], fmaf(pl[off[2]], w[2], fmaf(pl[off[1]], w[1], pl[off[0]] * w[0])));
+        }
+      } else {
+        for (int kc = 0; kc < KC; ++kc) {
+          const int cc = c + 32 * kc;
+          if (cc < nch) {
+            const float* pl = planes + (size_t)cc * pstride;
+            float acc = 0.f;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) if (w[k] != 0.f) acc = fmaf(pl[off[k]], w[k], acc);
-          orow[cc] = acc;
+            for (int k = 0; k < 4; ++k) if (w[k] != 0.f) acc = fmaf(pl[off[k]], w[k], acc);
+            orow[cc] = acc;
+          }
         }
       }
     }
@@ -287,18 +322,21 @@ feature_pool_points_bwd_kernel(const float* __restrict__ pts, const float* __res
 }
 
 // channels per CTA (power of two <= 32) such that `planes_per_channel` padded planes fit the budget; 0 = does not fit
-static int pool_chunk(int C, int HW, int planes_per_channel, int* stride) {
-  *stride = HW | 1;                                  // odd plane stride: the 32 channel lanes hit 32 different banks
+static int pool_chunk_budget(int C, int HW, int planes_per_channel, int* stride, int budget) {
+  *stride = (HW + 1) | 1;                            // >= one pad word; odd: the 32 channel lanes hit 32 different banks
   int ch = 32;
   while (ch > 1 && (ch >> 1) >= C) ch >>= 1;         // no wider than the map needs
-  while (ch >= 1 && (size_t)ch * planes_per_channel * (*stride) * 4 > (size_t)kPoolSmemBudget) ch >>= 1;
+  while (ch >= 1 && (size_t)ch * planes_per_channel * (*stride) * 4 > (size_t)budget) ch >>= 1;
   return ch;
+}
+static int pool_chunk(int C, int HW, int planes_per_channel, int* stride) {
+  return pool_chunk_budget(C, HW, planes_per_channel, stride, kPoolSmemBudget);
 }
 
 // forward: as above, then widened to 32 KC channels (KC <= 16) while the planes still fit
 static int pool_chunk_fwd(int C, int HW, int* stride) {
-  int ch = pool_chunk(C, HW, 1, stride);
-  if (ch == 32) while (ch < C && ch < 512 && (size_t)2 * ch * (*stride) * 4 <= (size_t)kPoolSmemBudget) ch *= 2;
+  int ch = pool_chunk_budget(C, HW, 1, stride, kPoolFwdSmemBudget);
+  if (ch == 32) while (ch < C && ch < 512 && (size_t)2 * ch * (*stride) * 4 <= (size_t)kPoolFwdSmemBudget) ch *= 2;
   return ch;
 }
 
@@ -312,7 +350,7 @@ extern "C" int vpn_image_bounds(const float* imgs, float* bounds, int B, int C, 
   if (B == 0) return VPN_OK;
   if (!imgs || !bounds) { vpn_set_error("image bounds: null pointer"); return VPN_ERR_ARG; }
   if ((size_t)(W + H) * 4 > 48 * 1024) { vpn_set_error("image bounds: W + H too large"); return VPN_ERR_SHAPE; }
-  image_bounds_kernel<<<B, kPoolThreads, (size_t)(W + H) * 4, (cudaStream_t)stream>>>(imgs, bounds, C, H, W, threshold);
+  image_bounds_kernel<<<B, kBoundsThreads, (size_t)(W + H) * 4, (cudaStream_t)stream>>>(imgs, bounds, C, H, W, threshold);
   return vpn_check_launch("image_bounds_kernel");
 }
 
@@ -338,13 +376,13 @@ extern "C" int vpn_feature_pool_fwd(const float* feat, const float* pts, const f
   const size_t smem = staged ? (size_t)ch * stride * 4 : 0;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(feature_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(feature_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolFwdSmemBudget);
     if (e != cudaSuccess) { vpn_set_error("feature pool fwd: smem attribute: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
     attr = true;
   }
-  // enough CTAs for four per SM: split the vertices when (channel chunks x samples) alone are too few
+  // enough CTAs for two waves of five per SM: split the vertices when (channel chunks x samples) alone are too few
   const int chunks = (C + ch - 1) / ch;
-  int slices = (4 * 148 + chunks * B - 1) / (chunks * B);
+  int slices = (10 * 148 + chunks * B - 1) / (chunks * B);
   const int max_slices = (N + kPoolThreads - 1) / kPoolThreads;
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;
