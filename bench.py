@@ -87,16 +87,18 @@ def synthetic(workload, device, seed=1234, sets=1, batch=None):
 
 class ClockSampler(threading.Thread):
     """nvidia-smi-equivalent clock / throttle sampling (NVML) during the timed region: rank 0 only, first sample as soon
-    as the host has enqueued the timed steps (arm()), then one every 30 ms while the GPU executes them.
-    Every NVML query stalls the sampled GPU's work for about a millisecond (2 GPUs, r01y logs: with four samples in
-    a 60 ms region rank 0 reached every all-reduce 0.21 ms late and rank 1 waited for it, 3.15 vs 2.94 ms per step;
-    with eight ranks polling every 10 ms the 8-GPU step went from 3.2 to 3.7 ms), so the rate is kept low."""
+    as the host has enqueued the timed steps (arm()), i.e. while the GPU executes them, then one every `period_s`.
+    In a multi-rank job, sampling a GPU makes that rank reach the next all-reduces late (4 - 10 ms in total over a 60 ms
+    region, whether one or four samples fall into it; all other ranks wait: 2.94 -> 3.15 ms per step on 2 and 8 B200s,
+    profiles/r01w_*, r01y_*), while a single process on one GPU shows no cost at all (gpurun_out/nvml_cost_probe.txt);
+    warming NVML up beforehand did not help.  Multi-rank runs therefore sample at the profiling recipe's own rate
+    (nvidia-smi -lms 200), single-GPU runs every 50 ms.  VPN_BENCH_NO_CLOCKS=1 switches the sampling off."""
 
     def __init__(self, index, enabled=True, period_s=0.03):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
         self.period_s, self.nv = period_s, None
-        self.armed = threading.Event()
+        self.armed, self.ready = threading.Event(), threading.Event()
         if not enabled:
             return
         try:
@@ -110,12 +112,14 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         if self.nv is None:
+            self.ready.set()
             return
         nv = self.nv
         names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
                  nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        self.ready.set()
         self.armed.wait()
         while True:                                  # at least one sample, taken right after arm()
             try:
@@ -255,6 +259,9 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
     sync = vdist.GradientAllReduce(GRAD_NUMEL, dev) if world > 1 else None
 
+    # the bench joins the all-reduce right after launching it (nothing of this path can overlap it), so it is queued on the
+    # step's own stream: no cross-stream event waits (VPN_BENCH_AR_STREAM=side restores the dedicated stream)
+    ar_inline = os.environ.get("VPN_BENCH_AR_STREAM", "inline") != "side"
     graphed, graph_error = None, None
     if args.graph != "off":
         try:
@@ -271,7 +278,7 @@ def main():
             loss, gv, gq, gt = graphed(s["v"], s["q"], s["t"], s["target"], s["sil"], canonical_points=s.get("canon"),
                                        cameras=cams_of(s))
             if sync is not None:
-                sync.launch()
+                sync.launch(inline=ar_inline)
             return loss, gv, gq, gt
         v, q, t = (s[x].detach().requires_grad_() for x in ("v", "q", "t"))
         u = None if vertex_mode else torch.rand((b, k, n, width), device=dev)      # drawn on device, like the reference
@@ -280,7 +287,7 @@ def main():
                       dists=c4[0], elevs=c4[1], azims=c4[2], angles=c4[3])
         out["total"].backward()
         if sync is not None:
-            sync.launch()
+            sync.launch(inline=ar_inline)
         return out["total"], v.grad, q.grad, t.grad
 
     # ---- device-resident throughput ("value") ---------------------------------------------------
@@ -291,8 +298,10 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local, enabled=(rank == 0 and os.environ.get("VPN_BENCH_NO_CLOCKS", "0") != "1"))
+    sampler = ClockSampler(local, enabled=(rank == 0 and os.environ.get("VPN_BENCH_NO_CLOCKS", "0") != "1"),
+                           period_s=(0.05 if world == 1 else 0.2))
     sampler.start()
+    sampler.ready.wait(timeout=10.0)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]      # end of the rank's own compute, before the join
     do_flush = os.environ.get("VPN_BENCH_FLUSH", "1") != "0"
@@ -481,6 +490,7 @@ def main():
                            "cuda_graph": graphed is not None, "cuda_graph_error": graph_error,
                            "allreduce_numel": GRAD_NUMEL if world > 1 else 0,
                            "allreduce": (sync.mode if sync is not None else None),
+                           "allreduce_stream": (("step stream" if ar_inline else "dedicated stream") if sync is not None else None),
                            "allreduce_trial_ms": (sync.trial_ms if sync is not None else None),
                            "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
                            "rank_ms_step_and_own_kernels": rank_all, "l2_flush": do_flush},

@@ -110,11 +110,21 @@ class GradientAllReduce:
         self.buf = self._full[:numel]
         self.mode = "nvls multimem kernel (vpn_allreduce_nvls)"
 
-    def launch(self):
+    def launch(self, inline: bool = False):
+        """Start the all-reduce of `buf`.  Default: on the dedicated stream, after everything already queued on the
+        current stream, so that later work on the current stream overlaps it until join().  inline=True queues it on the
+        current stream itself - for callers that would join() immediately anyway: no cross-stream event waits at all."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
         if not self.cuda:
             dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
+            return
+        if inline:
+            self.done = None
+            if self._handle is not None:
+                self._nvls_launch()
+            else:
+                dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
             return
         self.stream.wait_stream(torch.cuda.current_stream(self.buf.device))
         with torch.cuda.stream(self.stream):
