@@ -114,3 +114,42 @@ def test_templates_match_reference_assets(golden_templates):
     tv, _ = templates.template("sphere", "cpu")
     ref = O.sphere_template(torch.from_numpy(golden_templates["sphere_vertices"]))
     assert torch.equal(tv, ref)
+
+
+def test_pooling_dropin_asserts_and_no_cpu_path(lib_path):
+    """gcn.py:91,137-138 raise AssertionError on the wrong rank; CPU tensors are refused (no fallback)."""
+    import vpn_b200
+    from modules import GCNFeaturePooling as P
+    z = torch.zeros
+    with pytest.raises(AssertionError):
+        P.get_bound_of_images(z(3, 8, 8))
+    with pytest.raises(AssertionError):
+        P.perceptual_feature_pooling([z(1, 2, 4, 4)], z(5, 3), z(1, 4))
+    with pytest.raises(AssertionError):
+        P.perceptual_feature_pooling([z(1, 2, 4, 4)], z(1, 5, 3), z(4))
+    with pytest.raises(vpn_b200.VpnError):
+        P.get_bound_of_images(z(1, 3, 8, 8))
+    with pytest.raises(vpn_b200.VpnError):
+        P.perceptual_feature_pooling([z(1, 2, 4, 4)], z(1, 5, 3), z(1, 4))
+
+
+def test_bench_host_logic():
+    """Workload table, synthetic inputs and the clock sampler's state machine (no GPU, no NVML needed)."""
+    import bench
+    for name, (kind, b, k, n, m, res) in bench.WORKLOADS.items():
+        d = bench.synthetic(name, "cpu", batch=2)[0]
+        assert d["v"].shape == (2, k, 3) and d["q"].shape == (2, k, 4) and d["t"].shape == (2, k, 3)
+        assert d["target"].shape == (2, m, 3) and (d["sil"] is None) == (res == 0)
+        assert ("canon" in d) == (name in bench.FAITHFUL)
+        assert name in bench.describe(name) and str(k * n) in bench.describe(name)
+    # network-output-shaped ranges (vpnet_one_resnet.py:69-85): v in (0.0125, 0.1375) x (0.01, 0.11)^2, q in (0, 1)
+    d = bench.synthetic("c2", "cpu", batch=4)[0]
+    assert 0.0125 < float(d["v"][..., 0].min()) and float(d["v"][..., 0].max()) < 0.1375
+    assert 0.0 < float(d["q"].min()) and float(d["q"].max()) < 1.0
+    assert bench.per_gpu_batch("c2", 8) == 32 and bench.per_gpu_batch("c4", 8) == 32 and bench.per_gpu_batch("c4", 1) == 256
+    same = bench.synthetic("c2", "cpu", seed=7, batch=1)[0]["target"]
+    assert torch.equal(same, bench.synthetic("c2", "cpu", seed=7, batch=1)[0]["target"])
+    s = bench.ClockSampler(0, enabled=False)                     # disabled sampler: starts, arms, stops, reports nothing
+    s.start(); assert s.ready.wait(5.0)
+    s.arm(); s.stop(); s.join(5.0)
+    assert not s.is_alive() and s.summary()["samples"] == 0 and s.summary()["reasons"] == []

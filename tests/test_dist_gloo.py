@@ -49,7 +49,7 @@ def _worker(rank, world, port, gb, k, n, m, out):
     loss.backward()
     sync = vd.GradientAllReduce(10, "cpu")
     sync.buf.copy_(w.grad)
-    sync.launch(); sync.join()
+    sync.launch(inline=(gb % 2 == 1)); sync.join()          # both launch modes (dedicated stream / caller's stream)
     tot = loss.detach().clone()
     dist.all_reduce(tot)
     if rank == 0:
