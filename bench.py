@@ -86,13 +86,16 @@ def synthetic(workload, device, seed=1234, sets=1, batch=None):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi-equivalent clock / throttle sampling (NVML) during the timed region: rank 0 only, first sample as soon
-    as the host has enqueued the timed steps (arm()), i.e. while the GPU executes them, then one every `period_s`.
-    In a multi-rank job, sampling a GPU makes that rank reach the next all-reduces late (4 - 10 ms in total over a 60 ms
-    region, whether one or four samples fall into it; all other ranks wait: 2.94 -> 3.15 ms per step on 2 and 8 B200s,
-    profiles/r01w_*, r01y_*), while a single process on one GPU shows no cost at all (gpurun_out/nvml_cost_probe.txt);
-    warming NVML up beforehand did not help.  Multi-rank runs therefore sample at the profiling recipe's own rate
-    (nvidia-smi -lms 200), single-GPU runs every 50 ms.  VPN_BENCH_NO_CLOCKS=1 switches the sampling off."""
+    """nvidia-smi-equivalent clock / throttle sampling (NVML) during the timed region, on rank 0 only; arm() starts it.
+    In a multi-rank job, sampling a GPU makes that rank reach the following all-reduces late and every other rank waits
+    for it; a single process on one GPU shows no cost at all (profiles/r02_nvml_cost_probe_1gpu.txt).  Measured, ms per
+    C2 step (2.94 without any sampling on 2 or 8 GPUs with the NVLS all-reduce; single runs, different boxes):
+      all ranks, every 10 ms, from before the loop   8 GPUs 3.22 - 3.72     (2 GPUs, NCCL: 2.87 vs 2.86 unsampled)
+      rank 0,    every 20 ms, from before the loop   8 GPUs 3.16, 3.16      <- what bench.py does
+      rank 0,    every 20 ms, once the steps are enqueued      8 GPUs 3.45; 2 GPUs 3.15
+      rank 0,    every 200 ms, once enqueued (one sample)      2 GPUs 3.17; with NVML warmed up first 3.34 / 4.13
+    (profiles/r01w_scale_8gpu.txt, r01y_*, r02_scale_2gpu_sampling_variants.txt).  The delay does not scale with the
+    number of samples and its mechanism is not understood; VPN_BENCH_NO_CLOCKS=1 switches the sampling off."""
 
     def __init__(self, index, enabled=True, period_s=0.03):
         super().__init__(daemon=True)
@@ -298,10 +301,13 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local, enabled=(rank == 0 and os.environ.get("VPN_BENCH_NO_CLOCKS", "0") != "1"),
-                           period_s=(0.05 if world == 1 else 0.2))
+    # clock sampling: rank 0 only, every 20 ms, started just before the timed loop (VPN_BENCH_CLOCKS=armed starts it only
+    # once the steps are enqueued; that measured worse on 2 and 8 GPUs - see the class docstring)
+    sampler = ClockSampler(local, enabled=(rank == 0 and os.environ.get("VPN_BENCH_NO_CLOCKS", "0") != "1"), period_s=0.02)
     sampler.start()
     sampler.ready.wait(timeout=10.0)
+    if os.environ.get("VPN_BENCH_CLOCKS", "early") != "armed":
+        sampler.arm()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]      # end of the rank's own compute, before the join
     do_flush = os.environ.get("VPN_BENCH_FLUSH", "1") != "0"
@@ -317,7 +323,7 @@ def main():
         if sync is not None:
             sync.join()
         evs[i][1].record()
-    sampler.arm()                       # all timed steps are enqueued; sample clocks while the GPU runs them
+    sampler.arm()                       # no-op unless VPN_BENCH_CLOCKS=armed
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
     launches = graphed.launches_per_step if graphed is not None else (lib.vpn_launch_count() - launches0) // args.steps

@@ -153,3 +153,36 @@ def test_bench_host_logic():
     s.start(); assert s.ready.wait(5.0)
     s.arm(); s.stop(); s.join(5.0)
     assert not s.is_alive() and s.summary()["samples"] == 0 and s.summary()["reasons"] == []
+
+
+def test_clock_sampler_with_fake_nvml(monkeypatch):
+    """The sampling thread against a stand-in NVML: samples only after arm(), median / reasons reported, always stops."""
+    import sys
+    import time
+    import types
+    import bench
+    fake = types.ModuleType("pynvml")
+    fake.NVML_CLOCK_SM = 1
+    fake.nvmlClocksThrottleReasonHwSlowdown, fake.nvmlClocksThrottleReasonHwThermalSlowdown = 0x8, 0x40
+    fake.nvmlClocksThrottleReasonSwThermalSlowdown, fake.nvmlClocksThrottleReasonSwPowerCap = 0x20, 0x4
+    calls = {"n": 0}
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByIndex = lambda i: ("gpu", i)
+    fake.nvmlDeviceGetMaxClockInfo = lambda h, c: 1965
+    def clock(h, c):
+        calls["n"] += 1
+        return 1965 if calls["n"] % 2 else 1900
+    fake.nvmlDeviceGetClockInfo = clock
+    fake.nvmlDeviceGetCurrentClocksThrottleReasons = lambda h: 0x4
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    s = bench.ClockSampler(0, enabled=True, period_s=0.005)
+    s.start(); assert s.ready.wait(5.0)
+    time.sleep(0.03)
+    assert s.samples == []                                        # nothing before arm()
+    s.arm(); time.sleep(0.06); s.stop(); s.join(5.0)
+    out = s.summary()
+    assert not s.is_alive() and out["samples"] >= 3 and out["sm_max_mhz"] == 1965
+    assert out["sm_mhz"] in (1900, 1965) and out["reasons"] == ["sw_power_cap"]
+    s2 = bench.ClockSampler(0, enabled=True, period_s=10.0)       # stop() before arm(): still takes its one sample and exits
+    s2.start(); s2.stop(); s2.join(5.0)
+    assert not s2.is_alive() and s2.summary()["samples"] == 1
