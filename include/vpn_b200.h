@@ -9,7 +9,9 @@
  * Conventions
  *   - every pointer is a DEVICE pointer to contiguous fp32 / int32 data unless stated otherwise;
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, stream ordered, never
- *     allocate, never synchronise (vpn_fp32_peak_probe excepted) and keep no global state;
+ *     allocate, never synchronise (the *_timed / probe measurement helpers excepted) and keep no state between calls
+ *     (process-wide: an atomic launch counter, per-device caches of immutable device properties, and the
+ *     vpn_set_tuning overrides; every device of a multi-GPU process is handled independently);
  *   - return 0 on success, negative on error (VPN_ERR_*); vpn_last_error_string() describes the last
  *     error of the calling thread;
  *   - "nprim" is B*K: one pose (v,q,t) per primitive, primitives laid out sample-major (b*K + k).
@@ -40,6 +42,9 @@ int vpn_abi_version(void);
 int vpn_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
 /* kernels launched by this library in this process so far (bench.py reports the per-step delta) */
 unsigned long long vpn_launch_count(void);
+/* Test / probe hook: force a launch-plan choice.  key "tiled_r" | "tc_nb" (4, 8, 16), "emd_cluster" (1, 2, 4, 8);
+ * value 0 restores the automatic choice.  Results never depend on it (tests check exactly that). */
+int vpn_set_tuning(const char* key, int value);
 
 /* ---- primitive instantiation: canonical sample -> scale -> rotate -> translate, one kernel ------------
  * Replaces Sampling.{sphere,cuboid}_sampling (modules/sampling/sampling.py:12-38), transform_points /
@@ -101,14 +106,16 @@ int vpn_chamfer_loss_bwd(const float* p1, const float* p2, const float* min1, co
 
 /* ---- soft silhouette (modules/loss/silhouette.py:13-23 -> render/vertex_renderer.py:15-26 -> kaolin DIB-R)
  * verts (B,V,3), faces (F,3) int32 shared topology, cam_rot (B,3,3), cam_pos (B,3), proj = (px,py,pz).
- * alpha (B,H,W); covered (B,H,W) uint8; normals (B,F,3) or NULL.  bwd needs the workspace as fwd left it. */
+ * alpha (B,H,W); covered (B,H,W) uint8; normals (B,F,3) or NULL.  bwd needs the workspace as fwd left it.
+ * soft_cull_backfaces: 0 = DIB-R as recalled in SURVEY.md 8(a-R): back faces (normal.z < 0) are skipped by the coverage
+ * (hard) pass only and still count among the first `knum` soft candidates; 1 = they are skipped by the soft pass too. */
 int vpn_silhouette_workspace_bytes(int B, int V, int F, size_t* bytes);
 int vpn_silhouette_fwd(const float* verts, const int* faces, const float* cam_rot, const float* cam_pos,
                        float proj_x, float proj_y, float proj_z, float expand, int knum, float multiplier,
-                       float delta, float* alpha, unsigned char* covered, float* normals,
+                       float delta, int soft_cull_backfaces, float* alpha, unsigned char* covered, float* normals,
                        void* workspace, size_t workspace_bytes, int B, int V, int F, int H, int W, void* stream);
 int vpn_silhouette_bwd(const int* faces, const float* cam_rot, float proj_x, float proj_y, float proj_z,
-                       float expand, int knum, float multiplier, float delta, const float* grad_alpha,
+                       float expand, int knum, float multiplier, float delta, int soft_cull_backfaces, const float* grad_alpha,
                        const unsigned char* covered, float* grad_verts, void* workspace, size_t workspace_bytes,
                        int B, int V, int F, int H, int W, void* stream);
 

@@ -207,5 +207,59 @@ def main():
     print("wrote", sorted(os.listdir(OUT)), "total bytes", tot)
 
 
+def round2():
+    """tests/golden/round2_golden.npz - added in round 2, own seed so that hotpath_golden.npz stays byte-identical:
+      * a Chamfer case large enough for the tensor-core / tiled filters (P >= 512, M >= 128), arg-mins, loss and
+        gradients from the reference's ChamferDistanceLoss + torch.min (chamfer_distance.py:14-30);
+      * obj_to_view_points / rotate_points_forward_x_axis backward (transform.py:50-94) on the transform inputs."""
+    R = ref_import.load_reference()
+    g = torch.Generator().manual_seed(4321)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    ru = lambda *s: torch.rand(*s, generator=g)
+    d = {}
+    B, P, M = 2, 1536, 640
+    # sample 0: primitive-like clusters vs a box surface; sample 1: lattice + duplicates (ties in d and in sqrt(d))
+    centres = (ru(1, 12, 3) - 0.5) * 0.8
+    p1 = torch.empty(B, P, 3); p2 = torch.empty(B, M, 3)
+    p1[0] = (centres[0, torch.randint(0, 12, (P,), generator=g)] + 0.04 * rn(P, 3))
+    s = ru(M, 3) - 0.5
+    ax = torch.randint(0, 3, (M,), generator=g)
+    s[torch.arange(M), ax] = (torch.randint(0, 2, (M,), generator=g).float() - 0.5)
+    p2[0] = s * 0.7
+    p1[1] = torch.floor(ru(P, 3) * 8) / 8 - 0.5
+    p2[1] = torch.floor(ru(M, 3) * 8) / 8 - 0.5 + 0.0625
+    p2[1, 300:340] = p2[1, 100:140]                       # duplicated targets across a 128-column chunk border
+    p1[1, 1000:1100] = p1[1, 20:120]                      # duplicated predicted points across a 128-row block border
+    d["in_cd_p1"], d["in_cd_p2"] = npy(p1), npy(p2)
+    cd = R.ChamferDistanceLoss()
+    a, b_ = p1.clone().requires_grad_(), p2.clone().requires_grad_()
+    loss = cd(a, b_)
+    loss.backward()
+    d["ref_cd_loss"], d["ref_cd_grad_p1"], d["ref_cd_grad_p2"] = npy(loss), npy(a.grad), npy(b_.grad)
+    d["ref_cd_loss_each"] = npy(cd(p1, p2, each_batch=True))
+    diff = p1[:, :, None, :] - p2[:, None, :, :]
+    dist = torch.sum(diff * diff, dim=3)
+    m1, i1 = torch.min(torch.sqrt(dist), dim=2)
+    m2, i2 = torch.min(torch.sqrt(torch.transpose(dist, 1, 2)), dim=2)
+    d["ref_cd_min1"], d["ref_cd_idx1"], d["ref_cd_min2"], d["ref_cd_idx2"] = npy(m1), npy(i1.int()), npy(m2), npy(i2.int())
+
+    old = dict(np.load(os.path.join(OUT, "hotpath_golden.npz")))
+    pts = torch.tensor(old["in_tf_points"])
+    dists, elevs, azims, angles = (torch.tensor(old["in_tf_" + k]) for k in ("dists", "elevs", "azims", "angles"))
+    wgt = torch.tensor(old["in_tf_upstream"])
+    pg = pts.clone().requires_grad_()
+    (R.transform.obj_to_view_points(pg, dists, elevs, azims) * wgt).sum().backward()
+    d["ref_tf_obj_to_view_grad_points"] = npy(pg.grad)
+    pg = pts.clone().requires_grad_()
+    (R.transform.rotate_points_forward_x_axis(pg, angles) * wgt).sum().backward()
+    d["ref_tf_rotate_x_grad_points"] = npy(pg.grad)
+    np.savez_compressed(os.path.join(OUT, "round2_golden.npz"), **d)
+    print("wrote round2_golden.npz", os.path.getsize(os.path.join(OUT, "round2_golden.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        round2()
+    else:
+        main()
+        round2()

@@ -517,8 +517,15 @@ def project_vertices(verts: torch.Tensor, rot: torch.Tensor, pos: torch.Tensor):
 
 
 def soft_silhouette(verts: torch.Tensor, faces: torch.Tensor, rot: torch.Tensor, pos: torch.Tensor,
-                    height: int, width: int) -> torch.Tensor:
+                    height: int, width: int, soft_cull_backfaces: bool = False, pixels=None) -> torch.Tensor:
     """Soft alpha channel of DIB-R's VertexColor renderer: (B,H,W).  Differentiable w.r.t. verts.
+    `pixels` (1-D LongTensor of flat pixel indices h*W+w) restricts the evaluation to those pixels and returns
+    (B, len(pixels)) - used to check BASELINE-size meshes (F = 16 128 / 32 256) on a pixel subset.
+
+    Back faces (normal.z < 0): the hard pass skips them (`if (direction < 0) continue;` in DIB-R's render kernel); the
+    soft pass does NOT (its kernel receives only the 2-D points, the expanded boxes and the coverage index - SURVEY.md
+    8(a-R) lists the back-face skip for the hard pass only).  soft_cull_backfaces=True is the other reading (skip
+    them in both passes), kept selectable because Kaolin v0.1 cannot be run here to settle it.
 
     Hard pass: a pixel centre strictly inside (barycentrics >= 0) the tight bbox of any front face
     (normal.z >= 0) is covered -> alpha 1.  Soft pass, uncovered pixels only: faces are visited in
@@ -547,7 +554,9 @@ def soft_silhouette(verts: torch.Tensor, faces: torch.Tensor, rot: torch.Tensor,
     y0 = (mult / height) * (height - 2 * hi - 1)          # (H,)
     X = x0[None, :].expand(height, width).reshape(-1)     # (HW,)
     Y = y0[:, None].expand(height, width).reshape(-1)
-    out = torch.zeros(b, height * width)
+    if pixels is not None:
+        X, Y = X[pixels], Y[pixels]
+    out = torch.zeros(b, X.numel())
     front = (normal_z >= 0)                                # direction < 0 -> skipped
     for bi in range(b):
         sb = s[bi]                                         # (F,3,2)
@@ -569,7 +578,9 @@ def soft_silhouette(verts: torch.Tensor, faces: torch.Tensor, rot: torch.Tensor,
             inside = in_tight & front[bi][None] & (w0 >= 0) & (w1 >= 0) & (w2 >= 0)
             covered = inside.any(dim=1)                    # (HW,)
             in_soft = (Xp >= bmin2[bi, :, 0][None]) & (Xp < bmax2[bi, :, 0][None]) & \
-                      (Yp >= bmin2[bi, :, 1][None]) & (Yp < bmax2[bi, :, 1][None]) & front[bi][None]
+                      (Yp >= bmin2[bi, :, 1][None]) & (Yp < bmax2[bi, :, 1][None])
+            if soft_cull_backfaces:
+                in_soft = in_soft & front[bi][None]
             rank = torch.cumsum(in_soft.to(torch.int32), dim=1)
             use = in_soft & (rank <= DIBR_KNUM) & (~covered)[:, None]
         # squared distance pixel -> triangle, 6 cases
@@ -599,10 +610,10 @@ def soft_silhouette(verts: torch.Tensor, faces: torch.Tensor, rot: torch.Tensor,
         one_minus = torch.where(use, 1 - prob, torch.ones_like(prob))
         alpha = 1 - torch.prod(one_minus, dim=1)
         out[bi] = torch.where(covered, torch.ones_like(alpha), alpha)
-    return out.view(b, height, width)
+    return out if pixels is not None else out.view(b, height, width)
 
 
-def silhouette_loss(verts, faces, gt, dists, elevs, azims, loss_func: str = "L1") -> torch.Tensor:
+def silhouette_loss(verts, faces, gt, dists, elevs, azims, loss_func: str = "L1", soft_cull_backfaces: bool = False) -> torch.Tensor:
     """loss/silhouette.py:13-23 + render/vertex_renderer.py:15-26: per-sample look-at camera,
     soft alpha (B,1,H,W), then L1Loss / MSELoss (mean over B*H*W) vs gt (B,1,H,W)."""
     b = verts.size(0)
@@ -610,7 +621,7 @@ def silhouette_loss(verts, faces, gt, dists, elevs, azims, loss_func: str = "L1"
     cams = [look_at_camera(float(azims[i]), float(elevs[i]), float(dists[i])) for i in range(b)]
     rot = torch.stack([c[0] for c in cams])
     pos = torch.stack([c[1] for c in cams])
-    alpha = soft_silhouette(verts, faces, rot, pos, h, w)[:, None]
+    alpha = soft_silhouette(verts, faces, rot, pos, h, w, soft_cull_backfaces=soft_cull_backfaces)[:, None]
     if loss_func == "L1":
         return (alpha - gt).abs().mean()
     return ((alpha - gt) ** 2).mean()

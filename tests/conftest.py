@@ -21,6 +21,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden2():
+    """Round-2 vectors (oracle/make_golden.py::round2): a Chamfer case big enough for the tensor-core filter, and the
+    backward of obj_to_view_points / rotate_points_forward_x_axis, all produced by the reference's own code."""
+    return dict(np.load(os.path.join(REPO, "tests", "golden", "round2_golden.npz")))
+
+
+@pytest.fixture(scope="session")
 def golden_templates():
     return dict(np.load(os.path.join(REPO, "tests", "golden", "templates.npz")))
 

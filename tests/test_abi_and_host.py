@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vpn_b200.h but not exported"
     lib.vpn_abi_version.restype = ctypes.c_int
-    assert lib.vpn_abi_version() == 1
+    assert lib.vpn_abi_version() == 2
 
 
 def test_python_binding_covers_header(lib_path):

@@ -1,0 +1,151 @@
+"""vpn_emd_fwd / vpn_emd_bwd against the REFERENCE's own EMD kernels (modules/loss/emd/emd_cuda.cu:23-226, :284-300).
+
+oracle/build_ref_emd.sh compiles the reference's device code, untouched, behind a raw-pointer harness into
+oracle/_ref/libemd_ref.so (test infrastructure; it travels to the GPU box as a binary).  The reference auction is racy
+by construction (GetMax / Assign, emd_cuda.cu:181-215: among bidders within 1e-6 of an object's maximum increment the
+last writer wins; calc_unass_idx orders the unassigned list with atomics), so parity is STATISTICAL, at the training
+setting of train.py:188-195 (eps 0.005, 50 iterations) and train_gcn.py:91-95:
+  * mean sqrt(dist) - the EMD loss value the training loop uses - within 1 % of the reference's;
+  * the share of distinct assigned objects (how far the assignment is from a bijection) within 1 % absolute;
+  * both at or above the exact optimum (scipy) and within the same bound above it;
+  * the backward kernel, which is deterministic given the assignment, equal to 1e-6.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(REPO, "oracle", "_ref", "libemd_ref.so")
+
+
+@pytest.fixture(scope="module")
+def ref_emd():
+    assert os.path.isfile(REF_SO), (f"{REF_SO} missing: run `make -C oracle` where /root/reference is mounted "
+                                    "(the binary is shipped to the GPU box by gpurun)")
+    lib = ctypes.CDLL(REF_SO)
+    lib.ref_emd_workspace_bytes.restype = ctypes.c_size_t
+    lib.ref_emd_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.ref_emd_forward.restype = ctypes.c_int
+    lib.ref_emd_forward.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int]
+    lib.ref_emd_backward.restype = ctypes.c_int
+    lib.ref_emd_backward.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_int]
+
+    def forward(x1, x2, eps, iters):
+        b, n, _ = x1.shape
+        dist = torch.empty(b, n, device="cuda")
+        ass = torch.empty(b, n, dtype=torch.int32, device="cuda")
+        ws = torch.empty(lib.ref_emd_workspace_bytes(b, n), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        rc = lib.ref_emd_forward(x1.data_ptr(), x2.data_ptr(), dist.data_ptr(), ass.data_ptr(), ws.data_ptr(), b, n, eps, iters)
+        assert rc == 1, f"reference emd_cuda_forward status {rc}"
+        return dist, ass
+
+    def backward(x1, x2, ass, gdist):
+        b, n, _ = x1.shape
+        g = torch.zeros_like(x1)
+        torch.cuda.synchronize()
+        rc = lib.ref_emd_backward(x1.data_ptr(), x2.data_ptr(), g.data_ptr(), gdist.data_ptr(), ass.data_ptr(), b, n)
+        assert rc == 1
+        return g
+
+    return forward, backward
+
+
+def clouds(kind, b, n, gen):
+    """xyz1 = predicted, xyz2 = ground truth, normalised to [0, 1] as emd_module.py:8 requires."""
+    if kind == "uniform":
+        return torch.rand(b, n, 3, generator=gen), torch.rand(b, n, 3, generator=gen)
+    if kind == "surface":                     # points on a box surface vs a noisy, shifted copy: what training sees late
+        p = torch.rand(b, n, 3, generator=gen)
+        axis = torch.randint(0, 3, (b, n), generator=gen)
+        side = torch.randint(0, 2, (b, n), generator=gen).float()
+        p.scatter_(2, axis[..., None], side[..., None])
+        p = 0.25 + 0.5 * p
+        perm = torch.stack([torch.randperm(n, generator=gen) for _ in range(b)])
+        q = torch.gather(p, 1, perm[..., None].expand(-1, -1, 3)) + 0.02 * torch.randn(b, n, 3, generator=gen)
+        return q.clamp(0, 1), p
+    if kind == "clustered":                   # early training: predictions collapsed near the centre, targets spread out
+        return 0.5 + 0.05 * torch.randn(b, n, 3, generator=gen), torch.rand(b, n, 3, generator=gen)
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind,b,n,eps,iters", [
+    ("uniform", 32, 2048, 0.005, 50),          # train.py:188-195 / train_gcn.py:91-95 setting, B = 32
+    ("surface", 32, 2048, 0.005, 50),
+    ("clustered", 8, 2048, 0.005, 50),
+    ("uniform", 4, 1024, 0.002, 100),
+    ("uniform", 2, 8192, 0.05, 30),            # emd_module.py:81-86 smoke shape (shorter)
+])
+def test_emd_matches_reference_kernels(ref_emd, kind, b, n, eps, iters):
+    import vpn_b200
+    fwd, _ = ref_emd
+    gen = torch.Generator().manual_seed(4242 + n + iters)
+    x1, x2 = (t.cuda().contiguous() for t in clouds(kind, b, n, gen))
+    d_ref, a_ref = fwd(x1, x2, eps, iters)
+    d_our, a_our = vpn_b200.emd_auction(x1, x2, eps, iters)
+    torch.cuda.synchronize()
+    # the assignment indexes valid objects and dist is the squared distance to it, on both sides
+    for d, a in ((d_ref, a_ref), (d_our, a_our)):
+        assert int(a.min()) >= 0 and int(a.max()) < n
+        chk = ((x1 - torch.gather(x2, 1, a.long()[..., None].expand(-1, -1, 3))) ** 2).sum(-1)
+        np.testing.assert_allclose(d.cpu().numpy(), chk.cpu().numpy(), rtol=1e-5, atol=1e-9)
+    emd_ref = torch.sqrt(d_ref).mean(1).cpu().numpy()         # per sample, the quantity train.py:194 averages
+    emd_our = torch.sqrt(d_our).mean(1).cpu().numpy()
+    # tolerance: 1 % of the loss value over the batch, 3 % for any single sample (the reference itself moves by ~1 %
+    # between two runs on the same input because of its races)
+    np.testing.assert_allclose(emd_our.mean(), emd_ref.mean(), rtol=0.01)
+    np.testing.assert_allclose(emd_our, emd_ref, rtol=0.03)
+    uniq_ref = np.array([a.unique().numel() for a in a_ref]) / n
+    uniq_our = np.array([a.unique().numel() for a in a_our]) / n
+    assert abs(uniq_our.mean() - uniq_ref.mean()) <= 0.01, (uniq_our, uniq_ref)
+
+
+def test_reference_emd_run_to_run_spread(ref_emd):
+    """How far the reference is from itself on identical input (documents the tolerance above): <= 1 % per sample."""
+    fwd, _ = ref_emd
+    gen = torch.Generator().manual_seed(7)
+    x1, x2 = (t.cuda().contiguous() for t in clouds("uniform", 8, 2048, gen))
+    runs = np.stack([torch.sqrt(fwd(x1, x2, 0.005, 50)[0]).mean(1).cpu().numpy() for _ in range(3)])
+    assert (np.abs(runs - runs[0]) / runs[0]).max() <= 0.01
+
+
+def test_emd_both_near_optimal(ref_emd):
+    """Exact optimum by scipy on n = 1024: both auctions are >= it and within the same distance of it."""
+    from scipy.optimize import linear_sum_assignment
+    import vpn_b200
+    fwd, _ = ref_emd
+    gen = torch.Generator().manual_seed(11)
+    x1, x2 = clouds("uniform", 2, 1024, gen)
+    d_ref, a_ref = fwd(x1.cuda(), x2.cuda(), 0.005, 50)
+    d_our, a_our = vpn_b200.emd_auction(x1.cuda(), x2.cuda(), 0.005, 50)
+    for i in range(2):
+        cost = torch.cdist(x1[i].double(), x2[i].double()).numpy()
+        r, c = linear_sum_assignment(cost)
+        opt = cost[r, c].mean()
+        e_ref = float(torch.sqrt(d_ref[i]).mean()); e_our = float(torch.sqrt(d_our[i]).mean())
+        # the last iteration lets unassigned bidders take their favourite object (not a bijection), which can undercut
+        # the bijective optimum slightly: allow 2 % below, and the eps-scaled slack above
+        for e in (e_ref, e_our):
+            assert opt * 0.98 <= e <= opt + 3 * 0.005 + 0.02 * opt, (e, opt)
+        assert abs(e_our - e_ref) <= 0.01 * e_ref
+
+
+def test_emd_backward_equals_reference_kernel(ref_emd):
+    """NmDistanceGradKernel (emd_cuda.cu:284-300) on the same assignment: deterministic, equal to 1e-6."""
+    import vpn_b200
+    from vpn_b200 import _lib
+    _, bwd = ref_emd
+    gen = torch.Generator().manual_seed(3)
+    b, n = 3, 2048
+    x1, x2 = (t.cuda().contiguous() for t in clouds("surface", b, n, gen))
+    x1.requires_grad_()
+    dist, ass = vpn_b200.emd_auction(x1, x2, 0.005, 50)
+    up = torch.rand(b, n, generator=gen).cuda()
+    (dist * up).sum().backward()
+    g_ref = bwd(x1.detach(), x2, ass, up)
+    np.testing.assert_allclose(x1.grad.cpu().numpy(), g_ref.cpu().numpy(), rtol=1e-6, atol=1e-7)

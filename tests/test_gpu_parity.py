@@ -608,16 +608,21 @@ def test_emd_dropin_matches_reference_call(vpn):
 
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8])
-def test_emd_auction_cluster_sizes_agree(vpn, O, cluster, monkeypatch):
+def test_emd_auction_cluster_sizes_agree(vpn, O, cluster):
     """The CTAs-per-sample choice (thread-block cluster size) must not change the result."""
-    monkeypatch.setenv("VPN_EMD_CLUSTER", str(cluster))
-    g = torch.Generator().manual_seed(77)
-    for n, iters in ((2048, 50), (600, 12), (13000, 3)):           # 13000: objects read through L2 instead of shared memory
-        x1 = torch.rand(2, n, 3, generator=g); x2 = torch.rand(2, n, 3, generator=g)
-        dist, ass = vpn.emd_auction(C(x1), C(x2), 0.005, iters)
-        d_ref, a_ref = O.emd_auction(x1[1].numpy(), x2[1].numpy(), 0.005, iters)
-        same(ass[1], a_ref, f"assignment n={n} cluster={cluster}")
-        same(dist[1], d_ref, f"dist n={n} cluster={cluster}")
+    from vpn_b200 import _lib
+    lib = _lib.load()
+    assert lib.vpn_set_tuning(b"emd_cluster", cluster) == 0
+    try:
+        g = torch.Generator().manual_seed(77)
+        for n, iters in ((2048, 50), (600, 12), (13000, 3)):           # 13000: objects read through L2 instead of shared memory
+            x1 = torch.rand(2, n, 3, generator=g); x2 = torch.rand(2, n, 3, generator=g)
+            dist, ass = vpn.emd_auction(C(x1), C(x2), 0.005, iters)
+            d_ref, a_ref = O.emd_auction(x1[1].numpy(), x2[1].numpy(), 0.005, iters)
+            same(ass[1], a_ref, f"assignment n={n} cluster={cluster}")
+            same(dist[1], d_ref, f"dist n={n} cluster={cluster}")
+    finally:
+        lib.vpn_set_tuning(b"emd_cluster", 0)
 
 
 # ------------------------------------------------------------------------------------------------

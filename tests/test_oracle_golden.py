@@ -93,6 +93,36 @@ def test_chamfer_gradients(golden):
     close(gp1, g["ref_cd_grad_p1"], 1e-4, 1e-8); close(gp2, g["ref_cd_grad_p2"], 1e-4, 1e-8)
 
 
+def test_chamfer_round2_golden(golden2, c_oracle):
+    """P = 1536, M = 640 clouds (clusters vs box surface; lattice + duplicates straddling chunk borders): the oracle's
+    arg-mins equal the reference's torch.min bit for bit, loss and gradients equal the reference's autograd."""
+    g = golden2
+    p1, p2 = T(g["in_cd_p1"]), T(g["in_cd_p2"])
+    eq(O.chamfer_dense(p1, p2), g["ref_cd_loss"])
+    eq(O.chamfer_dense(p1, p2, each_batch=True), g["ref_cd_loss_each"])
+    m1, i1, m2, i2 = O.chamfer_nn(p1, p2)
+    eq(i1, g["ref_cd_idx1"]); eq(i2, g["ref_cd_idx2"])
+    close(m1, g["ref_cd_min1"], 1.3e-7, 0); close(m2, g["ref_cd_min2"], 1.3e-7, 0)
+    c1, ci1, c2, ci2 = c_oracle(g["in_cd_p1"], g["in_cd_p2"])
+    eq(m1, c1); eq(i1, ci1); eq(m2, c2); eq(i2, ci2)
+    a, b = p1.clone().requires_grad_(), p2.clone().requires_grad_()
+    O.chamfer_dense(a, b).backward()
+    close(a.grad, g["ref_cd_grad_p1"], 1e-5, 1e-9); close(b.grad, g["ref_cd_grad_p2"], 1e-5, 1e-9)
+
+
+def test_view_transform_backward_round2(golden, golden2):
+    g = golden
+    pts = T(g["in_tf_points"])
+    d, e, a, ang = (T(g["in_tf_" + k]) for k in ("dists", "elevs", "azims", "angles"))
+    w = T(g["in_tf_upstream"])
+    pg = pts.clone().requires_grad_()
+    (O.obj_to_view_points(pg, d, e, a) * w).sum().backward()
+    close(pg.grad, golden2["ref_tf_obj_to_view_grad_points"], 1e-5, 1e-6)
+    pg = pts.clone().requires_grad_()
+    (O.rotate_points_forward_x_axis(pg, ang) * w).sum().backward()
+    close(pg.grad, golden2["ref_tf_rotate_x_grad_points"], 1e-5, 1e-6)
+
+
 def test_vp_diverse(golden):
     g = golden
     tr = T(g["in_vd_translates"])
@@ -144,6 +174,31 @@ def test_silhouette_oracle_sanity(golden_templates):
     assert torch.isfinite(verts.grad).all() and verts.grad.abs().sum() > 0
     # camera sits at (1,0,0) for dist=1, elev=azim=0
     np.testing.assert_allclose(pos.numpy(), [1, 0, 0], atol=1e-7)
+
+
+def test_silhouette_oracle_cull_modes_and_pixel_subset(golden_templates):
+    """soft_cull_backfaces: on a closed outward-wound mesh the back faces lie behind covered pixels or on the rim, so
+    culling them in the soft pass can only lower alpha; a mesh seen from inside out (all faces back-facing) is
+    invisible when culled and leaves a soft-only image otherwise.  `pixels=` returns exactly the full image's entries."""
+    tm = golden_templates
+    sph = O.sphere_template(T(tm["sphere_vertices"]))
+    faces = T(tm["sphere_faces"]).long()
+    verts = (sph * 0.3)[None] + torch.tensor([0.0, 0.1, -0.05])
+    rot, pos = O.look_at_camera(30.0, 20.0, 1.4)
+    full = O.soft_silhouette(verts, faces, rot[None], pos[None], 40, 40)
+    cull = O.soft_silhouette(verts, faces, rot[None], pos[None], 40, 40, soft_cull_backfaces=True)
+    assert ((full == 1.0) == (cull == 1.0)).all()                     # coverage pass is the same
+    assert (full >= cull - 1e-7).all() and (full > cull + 1e-6).any()
+    inward = faces[:, [0, 2, 1]]
+    inv_cull = O.soft_silhouette(verts, inward, rot[None], pos[None], 40, 40, soft_cull_backfaces=True)
+    inv_full = O.soft_silhouette(verts, inward, rot[None], pos[None], 40, 40)
+    # inside-out sphere: the far hemisphere now faces the camera (covers the disc); culled soft pass still finds it
+    assert inv_cull.max() == 1.0 and inv_full.max() == 1.0
+    pix = torch.tensor([0, 41, 20 * 40 + 20, 13 * 40 + 9, 39 * 40 + 39, 17 * 40 + 30])
+    for mode in (False, True):
+        sub = O.soft_silhouette(verts, faces, rot[None], pos[None], 40, 40, soft_cull_backfaces=mode, pixels=pix)
+        ref = O.soft_silhouette(verts, faces, rot[None], pos[None], 40, 40, soft_cull_backfaces=mode).reshape(1, -1)[:, pix]
+        eq(sub, ref.numpy())
 
 
 def test_mesh_sample_oracle_properties(golden_templates):

@@ -56,7 +56,8 @@ extern "C" int vpn_allreduce_nvls(void* multicast_ptr, size_t numel, int rank, i
   if (hi <= lo) return VPN_OK;
   const int threads = 512;
   size_t blocks = (hi - lo + (size_t)threads * 4 - 1) / ((size_t)threads * 4);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  const size_t cap = (size_t)vpn::device_sm_count() * 4;
+  if (blocks > cap) blocks = cap;
   vpn::allreduce_nvls_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(multicast_ptr), lo, hi);
   return vpn_check_launch("allreduce_nvls_kernel");
 }

@@ -12,10 +12,13 @@ void vpn_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static unsigned long long g_launches = 0;
+// The only process-wide state: a launch counter (measurement aid, atomic), per-device caches of immutable device
+// properties, and the tuning overrides of vpn_set_tuning.  No call depends on another call's state.
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_tuning[vpn::kTuneCount];
 
 int vpn_check_launch(const char* what) {
-  ++g_launches;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { vpn_set_error("%s: %s", what, cudaGetErrorString(e)); return VPN_ERR_CUDA; }
   return VPN_OK;
@@ -33,23 +36,33 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
                       int B, int P, int M, void* ws, size_t ws_bytes, int mode, cudaStream_t s, cudaEvent_t* ev);
 }
 
-static int g_sm_count = 0;
-static int sm_count() {
-  if (g_sm_count == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_sm_count = n;
-    else g_sm_count = 148;
-  }
-  return g_sm_count;
+static std::atomic<int> g_sm_count[64];
+int vpn::device_sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && (n = g_sm_count[dev].load(std::memory_order_relaxed)) > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) g_sm_count[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+static int sm_count() { return vpn::device_sm_count(); }
+int vpn::tuning_value(int key) { return (key >= 0 && key < vpn::kTuneCount) ? g_tuning[key].load(std::memory_order_relaxed) : 0; }
+
+// Test / probe hook replacing the getenv() look-ups that used to sit on the launch path.
+// key: "tiled_r" (4|8|16), "tc_nb" (4|8|16), "emd_cluster" (1|2|4|8); value 0 restores the automatic choice.
+extern "C" int vpn_set_tuning(const char* key, int value) {
+  static const char* names[vpn::kTuneCount] = {"tiled_r", "tc_nb", "emd_cluster"};
+  for (int k = 0; key && k < vpn::kTuneCount; ++k)
+    if (strcmp(key, names[k]) == 0) { g_tuning[k].store(value, std::memory_order_relaxed); return VPN_OK; }
+  vpn_set_error("vpn_set_tuning: unknown key"); return VPN_ERR_ARG;
 }
 
 extern "C" const char* vpn_last_error_string(void) { return g_err; }
 
-extern "C" int vpn_abi_version(void) { return 1; }
+extern "C" int vpn_abi_version(void) { return 2; }
 
 // Number of kernels this library has launched in this process (bench.py reports the per-step delta).
-extern "C" unsigned long long vpn_launch_count(void) { return g_launches; }
+extern "C" unsigned long long vpn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int vpn_device_info(int* sms, int* cc_major, int* cc_minor, int* clock_khz) {
   int dev = 0;

@@ -493,12 +493,11 @@ size_t chamfer_tc_smem_bytes(int NB) { return tc_smem_bytes(NB); }
 int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
                       float2* tslack, int* fallback, float* tmax, int B, int P, int M, int NB, int ntiles, int nsplit,
                       int nchunks, int cps, cudaStream_t s) {
-  static int attr_for = 0;
+  static DeviceOnce once;
   const size_t smem = tc_smem_bytes(NB);
-  if (attr_for < (int)smem) {
-    cudaError_t e = cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(16));
+  {
+    cudaError_t e = set_dyn_smem(chamfer_tc_kernel, (int)tc_smem_bytes(16), once);
     if (e != cudaSuccess) { vpn_set_error("chamfer tc: smem attribute: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
-    attr_for = (int)tc_smem_bytes(16);
   }
   chamfer_tc_bounds_kernel<<<B, 256, 0, s>>>(p2, tmax, M);
   int rc = vpn_check_launch("chamfer_tc_bounds_kernel");

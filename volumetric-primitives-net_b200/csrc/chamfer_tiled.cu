@@ -573,7 +573,7 @@ static bool make_plan(int B, int P, int M, int sm_count, TiledPlan& pl) {
     long long slots = (long long)sm_count * (R <= 8 ? 2 : 1);
     if (waste <= 1.26 && nt * B * pl.nchunks >= 2 * slots) { pick = R; break; }
   }
-  if (const char* e = getenv("VPN_TILED_R")) { int r = atoi(e); if (r == 4 || r == 8 || r == 16) pick = r; }   // tuning override
+  { int r = tuning_value(kTuneTiledR); if (r == 4 || r == 8 || r == 16) pick = r; }   // vpn_set_tuning("tiled_r")
   pl.R = pick;
   pl.TM = kTThreads * pl.R;
   pl.ntiles = (P + pl.TM - 1) / pl.TM;
@@ -594,7 +594,7 @@ static bool make_plan_tc(int B, int P, int M, int sm_count, TiledPlan& pl) {
     double waste = (double)(nt * tm) / P;
     if (waste <= 1.26 && nt * B * pl.nchunks >= 2LL * sm_count * 8) { pick = nb; break; }
   }
-  if (const char* e = getenv("VPN_TC_NB")) { int r = atoi(e); if (r == 4 || r == 8 || r == 16) pick = r; }      // tuning override
+  { int r = tuning_value(kTuneTcNb); if (r == 4 || r == 8 || r == 16) pick = r; }      // vpn_set_tuning("tc_nb")
   pl.R = pick;
   pl.TM = 128 * pl.R;
   pl.ntiles = (P + pl.TM - 1) / pl.TM;
@@ -621,10 +621,10 @@ static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   return w;
 }
 
-static const int kPlanSms = 148;   // B200; a fixed value keeps workspace queries and launches consistent
-
-// mode: -1 auto, MODE_*.  Auto prefers the tensor-core filter.
+// mode: -1 auto, MODE_*.  Auto prefers the tensor-core filter.  The plan depends on the SM count of the current
+// device: the workspace query and the launch must be made with the same device current (they are: same thread).
 static bool plan_for(int mode, int B, int P, int M, TiledPlan& pl) {
+  const int kPlanSms = device_sm_count();
   if (mode == MODE_TC) return make_plan_tc(B, P, M, kPlanSms, pl);
   if (mode >= 0) return make_plan(B, P, M, kPlanSms, pl);
   return make_plan_tc(B, P, M, kPlanSms, pl) || make_plan(B, P, M, kPlanSms, pl);
@@ -649,12 +649,11 @@ size_t chamfer_tiled_workspace_bytes(int B, int P, int M, int mode) {
 template <int R, int MODE>
 static int launch_main(const float* p1, const float* p2, char* ws, const TiledWs& wl, const TiledPlan& pl,
                        int B, int P, int M, int only_flagged, cudaStream_t s) {
-  static bool attr_set = false;
+  static DeviceOnce once;
   size_t smem = sizeof(TiledSmem<R>);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(chamfer_tiled_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = set_dyn_smem(chamfer_tiled_kernel<R, MODE>, (int)smem, once);
     if (e != cudaSuccess) { vpn_set_error("chamfer tiled: smem attribute: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
-    attr_set = true;
   }
   dim3 grid(pl.ntiles, pl.nsplit, B);
   chamfer_tiled_kernel<R, MODE><<<grid, kTThreads, smem, s>>>(
@@ -687,13 +686,10 @@ static int launch_any(int mode, const float* p1, const float* p2, char* ws, cons
 template <int R, bool TC>
 static int launch_recover_cols(const float* p1, const float* p2, const float* cb, const unsigned* cmk, const float* cthr,
                                u64* key2, int B, int P, int M, int ntiles, const int* skip, cudaStream_t s) {
-  static bool attr = false;
+  static DeviceOnce once;
   const size_t smem = (size_t)(TC ? 128 * R : kTThreads * R) * sizeof(float4);
-  if (!attr) {
-    if (cudaFuncSetAttribute(chamfer_recover_cols_kernel<R, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      vpn_set_error("chamfer tiled: smem attribute (cols recovery)"); return VPN_ERR_CUDA;
-    }
-    attr = true;
+  if (set_dyn_smem(chamfer_recover_cols_kernel<R, TC>, (int)smem, once) != cudaSuccess) {
+    vpn_set_error("chamfer tiled: smem attribute (cols recovery)"); return VPN_ERR_CUDA;
   }
   chamfer_recover_cols_kernel<R, TC><<<dim3(ntiles, B), kRecThreads, smem, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, ntiles, skip);
   return vpn_check_launch("chamfer_recover_cols_kernel");
@@ -734,14 +730,10 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   }
   if (ev) cudaEventRecord(ev[2], s);
   {
-    static bool attr_rows = false;
+    static DeviceOnce once_rows;
     const size_t smem_rows = (size_t)(pl.nchunks < kSegChunks ? pl.nchunks : kSegChunks) * kCW * sizeof(float4);
-    if (!attr_rows) {
-      if (cudaFuncSetAttribute(chamfer_recover_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(kSegChunks * kCW * sizeof(float4))) != cudaSuccess) {
-        vpn_set_error("chamfer tiled: smem attribute (rows recovery)"); return VPN_ERR_CUDA;
-      }
-      attr_rows = true;
+    if (set_dyn_smem(chamfer_recover_rows_kernel, (int)(kSegChunks * kCW * sizeof(float4)), once_rows) != cudaSuccess) {
+      vpn_set_error("chamfer tiled: smem attribute (rows recovery)"); return VPN_ERR_CUDA;
     }
     chamfer_recover_rows_kernel<<<dim3((P + kRecThreads - 1) / kRecThreads, B), kRecThreads, smem_rows, s>>>(
         p1, p2, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),

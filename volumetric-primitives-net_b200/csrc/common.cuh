@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 #define VPN_OK 0
 #define VPN_ERR_CUDA (-1)
@@ -18,6 +19,27 @@ int vpn_check_launch(const char* what);
 namespace vpn {
 
 typedef unsigned long long u64;
+
+// Per-device "done once" flag.  cudaFuncSetAttribute is a property of (kernel, device), so a process that drives several
+// GPUs must opt every one of them in to > 48 KB of dynamic shared memory; bit d = done on device ordinal d (ordinals
+// >= 64 are simply set again on every launch).
+struct DeviceOnce { std::atomic<unsigned long long> mask{0}; };
+template <typename K>
+inline cudaError_t set_dyn_smem(K kernel, int bytes, DeviceOnce& once) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = dev < 64 ? (1ull << dev) : 0ull;
+  if (bit && (once.mask.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && bit) once.mask.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+// SM count of the calling thread's current device (cached per ordinal; api.cu)
+int device_sm_count();
+// Tuning overrides set through vpn_set_tuning (tests and probes only; 0 = automatic choice)
+int tuning_value(int key);
+enum { kTuneTiledR = 0, kTuneTcNb = 1, kTuneEmdCluster = 2, kTuneCount = 3 };
 
 // Rigid pose of one primitive: row-major rotation R (from the reference's axis/turn-fraction
 // "quaternion"), plus what the backward pass needs to chain dL/dR to dL/dq.

@@ -202,7 +202,7 @@ static size_t emd_ws_bytes(int B, int n) { return (size_t)B * ((size_t)kEmdWsWor
 static int emd_cluster_size(int B, int n) {
   int c = 1;
   while (c < kEmdMaxCluster && (long long)B * c * 2 <= 160 && n / (c * 2) >= 256) c *= 2;
-  if (const char* e = getenv("VPN_EMD_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) c = v; }     // tuning override
+  { int v = tuning_value(kTuneEmdCluster); if (v == 1 || v == 2 || v == 4 || v == 8) c = v; }     // vpn_set_tuning("emd_cluster")
   return c;
 }
 
@@ -217,12 +217,9 @@ static int emd_launch(const float* xyz1, const float* xyz2, float* dist, int* as
                       int B, int n, int C, float eps, int iters, cudaStream_t s) {
   const int per = (n + C - 1) / C;
   const size_t smem = (OBJ_SMEM ? (size_t)16 * n : 0) + (size_t)12 * per;
-  static size_t attr_for = 0;
-  if (smem > 48 * 1024 && attr_for < smem) {
-    if (cudaFuncSetAttribute(emd_auction_kernel<OBJ_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) {
-      vpn_set_error("emd fwd: smem attribute"); return VPN_ERR_CUDA;
-    }
-    attr_for = 224 * 1024;
+  static DeviceOnce once;
+  if (smem > 48 * 1024 && set_dyn_smem(emd_auction_kernel<OBJ_SMEM>, 224 * 1024, once) != cudaSuccess) {
+    vpn_set_error("emd fwd: smem attribute"); return VPN_ERR_CUDA;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * C)); cfg.blockDim = dim3(kEmdThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;

@@ -374,15 +374,14 @@ extern "C" int vpn_feature_pool_fwd(const float* feat, const float* pts, const f
   const int staged = ch >= 1;
   if (!staged) ch = 32;                                            // plane larger than shared memory: taps read through L2
   const size_t smem = staged ? (size_t)ch * stride * 4 : 0;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(feature_pool_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolFwdSmemBudget);
+  static DeviceOnce once;
+  {
+    cudaError_t e = set_dyn_smem(feature_pool_fwd_kernel, kPoolFwdSmemBudget, once);
     if (e != cudaSuccess) { vpn_set_error("feature pool fwd: smem attribute: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
-    attr = true;
   }
   // enough CTAs for two waves of five per SM: split the vertices when (channel chunks x samples) alone are too few
   const int chunks = (C + ch - 1) / ch;
-  int slices = (10 * 148 + chunks * B - 1) / (chunks * B);
+  int slices = (10 * device_sm_count() + chunks * B - 1) / (chunks * B);
   const int max_slices = (N + kPoolThreads - 1) / kPoolThreads;
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;
@@ -410,11 +409,10 @@ extern "C" int vpn_feature_pool_bwd(const float* feat, const float* pts, const f
       vpn_set_error("feature pool bwd: memset failed"); return VPN_ERR_CUDA;
     }
   }
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(feature_pool_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmemBudget);
+  static DeviceOnce once;
+  {
+    cudaError_t e = set_dyn_smem(feature_pool_bwd_kernel, kPoolSmemBudget, once);
     if (e != cudaSuccess) { vpn_set_error("feature pool bwd: smem attribute: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
-    attr = true;
   }
   dim3 grid((C + ch - 1) / ch, B);
   feature_pool_bwd_kernel<<<grid, kPoolThreads, staged ? (size_t)2 * ch * stride * 4 : 0, (cudaStream_t)stream>>>(

@@ -25,6 +25,7 @@ constexpr int kKnumMax = 32;
 struct RasterParams {
   int H, W, F, knum;
   float expand, mult, delta, eps;
+  int cull_soft;      // 1: back faces (normal.z < 0) are skipped by the soft pass too; 0 (DIB-R): only by the coverage pass
 };
 
 struct __align__(16) FaceRec { float ax, ay, bx, by, cx, cy, front, pad; };
@@ -60,7 +61,8 @@ __global__ void sil_project_kernel(const float* __restrict__ verts, const float*
 __global__ void __launch_bounds__(256)
 sil_faces_kernel(const float* __restrict__ cam, const float* __restrict__ xy,
                  const int* __restrict__ faces, FaceRec* __restrict__ rec,
-                 float* __restrict__ normals, float4* __restrict__ batch_box, int V, int F, float mult, float em) {
+                 float* __restrict__ normals, float4* __restrict__ batch_box, int V, int F, float mult, float em,
+                 int cull_soft) {
   __shared__ float4 s_box[8];
   const int b = blockIdx.y;
   int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,7 +93,7 @@ sil_faces_kernel(const float* __restrict__ cam, const float* __restrict__ xy,
     float* n = normals + 3 * ((size_t)b * F + f);
     n[0] = nx / len; n[1] = ny / len; n[2] = nz / len;
   }
-  if (r.front > 0.5f)
+  if (r.front > 0.5f || !cull_soft)
     box = make_float4(__fsub_rn(min3(r.ax, r.bx, r.cx), em), __fadd_rn(max3(r.ax, r.bx, r.cx), em),
                       __fsub_rn(min3(r.ay, r.by, r.cy), em), __fadd_rn(max3(r.ay, r.by, r.cy), em));
   }
@@ -160,7 +162,7 @@ __device__ __forceinline__ bool inside_tri(const FaceRec& r, float X, float Y, f
 template <typename Fn>
 __device__ __forceinline__ void walk_tile_faces(const FaceRec* __restrict__ rec, const float4* __restrict__ batch_box,
                                                 int F, float xL, float xR, float yB, float yT,
-                                                float wxL, float wxR, float wyB, float wyT, float em, Fn fn) {
+                                                float wxL, float wxR, float wyB, float wyT, float em, int cull_soft, Fn fn) {
   __shared__ FaceRec s_rec[kRThreads];
   __shared__ float4 s_box[kRThreads];                  // tight bbox: xmin, xmax, ymin, ymax
   __shared__ int s_idx[kRThreads];
@@ -178,7 +180,7 @@ __device__ __forceinline__ void walk_tile_faces(const FaceRec* __restrict__ rec,
       tb = make_float4(min3(r.ax, r.bx, r.cx), max3(r.ax, r.bx, r.cx), min3(r.ay, r.by, r.cy), max3(r.ay, r.by, r.cy));
       float xmin = __fsub_rn(tb.x, em), xmax = __fadd_rn(tb.y, em);
       float ymin = __fsub_rn(tb.z, em), ymax = __fadd_rn(tb.w, em);
-      hit = (r.front > 0.5f) && xmin <= xR && xmax > xL && ymin <= yT && ymax > yB;
+      hit = (r.front > 0.5f || !cull_soft) && xmin <= xR && xmax > xL && ymin <= yT && ymax > yB;
     }
     unsigned bal = __ballot_sync(0xffffffffu, hit);
     if (lane == 0) s_wcount[warp] = __popc(bal);
@@ -288,11 +290,12 @@ sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
   const float em = __fmul_rn(rp.expand, rp.mult);
   bool covered = false; int cnt = 0;
   const float4* boxes = box_all + (size_t)b * ((rp.F + kRThreads - 1) / kRThreads);
-  walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, wxL, wxR, wyB, wyT, em, [&](int f, const FaceRec& r, const float4& tb) {
+  walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, wxL, wxR, wyB, wyT, em, rp.cull_soft, [&](int f, const FaceRec& r, const float4& tb) {
     if (covered) return;                                // alpha is 1 whatever follows
     const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
     if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
-    if (X >= txmin && X < txmax && Y >= tymin && Y < tymax && inside_tri(r, X, Y, rp.eps)) { covered = true; return; }
+    // coverage (hard pass): front faces only.  A back face that holds the pixel is an ordinary soft candidate.
+    if (r.front > 0.5f && X >= txmin && X < txmax && Y >= tymin && Y < tymax && inside_tri(r, X, Y, rp.eps)) { covered = true; return; }
     if (cnt < rp.knum) { tl.cand[cnt * kRThreads + tid] = (unsigned short)f; ++cnt; }
   });
   const int mine = (in_img && !covered) ? cnt : 0;
@@ -351,7 +354,7 @@ sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
   int cnt = 0;
   const float4* boxes = box_all + (size_t)b * ((rp.F + kRThreads - 1) / kRThreads);
   if (__syncthreads_or(active)) {                       // tiles without an uncovered pixel that has a gradient do nothing
-    walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, wxL, wxR, wyB, wyT, em, [&](int f, const FaceRec& r, const float4& tb) {
+    walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, wxL, wxR, wyB, wyT, em, rp.cull_soft, [&](int f, const FaceRec& r, const float4& tb) {
       if (!active || cnt >= rp.knum) return;
       const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
       if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
@@ -476,7 +479,7 @@ static int sil_check(int B, int V, int F, int H, int W, int knum) {
 // normals (B,F,3) or NULL.  The workspace keeps the projected state for the backward call.
 extern "C" int vpn_silhouette_fwd(const float* verts, const int* faces, const float* cam_rot, const float* cam_pos,
                                   float proj_x, float proj_y, float proj_z, float expand, int knum, float multiplier,
-                                  float delta, float* alpha, unsigned char* covered, float* normals,
+                                  float delta, int soft_cull_backfaces, float* alpha, unsigned char* covered, float* normals,
                                   void* workspace, size_t workspace_bytes, int B, int V, int F, int H, int W, void* stream) {
   int rc = sil_check(B, V, F, H, W, knum);
   if (rc) return rc;
@@ -493,16 +496,13 @@ extern "C" int vpn_silhouette_fwd(const float* verts, const int* faces, const fl
   if ((rc = vpn_check_launch("sil_project_kernel"))) return rc;
   float4* boxes = reinterpret_cast<float4*>(ws + wl.box);
   sil_faces_kernel<<<dim3((F + kRThreads - 1) / kRThreads, B), kRThreads, 0, s>>>(cam, xy, faces, rec, normals, boxes, V, F, multiplier,
-                                                                                  expand * multiplier);
+                                                                                  expand * multiplier, soft_cull_backfaces ? 1 : 0);
   if ((rc = vpn_check_launch("sil_faces_kernel"))) return rc;
-  RasterParams rp{H, W, F, knum, expand, multiplier, delta, 1e-15f};
+  RasterParams rp{H, W, F, knum, expand, multiplier, delta, 1e-15f, soft_cull_backfaces ? 1 : 0};
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
-  static bool attr_fwd = false;
-  if (!attr_fwd) {
-    if (cudaFuncSetAttribute(sil_raster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileListBytesFwd) != cudaSuccess) {
-      vpn_set_error("silhouette fwd: smem attribute"); return VPN_ERR_CUDA;
-    }
-    attr_fwd = true;
+  static DeviceOnce once_fwd;
+  if (set_dyn_smem(sil_raster_fwd_kernel, (int)kTileListBytesFwd, once_fwd) != cudaSuccess) {
+    vpn_set_error("silhouette fwd: smem attribute"); return VPN_ERR_CUDA;
   }
   sil_raster_fwd_kernel<<<grid, kRThreads, kTileListBytesFwd, s>>>(rec, boxes, alpha, covered, rp);
   return vpn_check_launch("sil_raster_fwd_kernel");
@@ -510,7 +510,8 @@ extern "C" int vpn_silhouette_fwd(const float* verts, const int* faces, const fl
 
 // Needs the workspace exactly as vpn_silhouette_fwd left it.  grad_verts (B,V,3) is overwritten.
 extern "C" int vpn_silhouette_bwd(const int* faces, const float* cam_rot, float proj_x, float proj_y, float proj_z,
-                                  float expand, int knum, float multiplier, float delta, const float* grad_alpha,
+                                  float expand, int knum, float multiplier, float delta, int soft_cull_backfaces,
+                                  const float* grad_alpha,
                                   const unsigned char* covered, float* grad_verts, void* workspace, size_t workspace_bytes,
                                   int B, int V, int F, int H, int W, void* stream) {
   int rc = sil_check(B, V, F, H, W, knum);
@@ -528,14 +529,11 @@ extern "C" int vpn_silhouette_bwd(const int* faces, const float* cam_rot, float 
       cudaMemsetAsync(grad_verts, 0, (size_t)B * V * 3 * 4, s) != cudaSuccess) {
     vpn_set_error("silhouette bwd: memset failed"); return VPN_ERR_CUDA;
   }
-  RasterParams rp{H, W, F, knum, expand, multiplier, delta, 1e-15f};
+  RasterParams rp{H, W, F, knum, expand, multiplier, delta, 1e-15f, soft_cull_backfaces ? 1 : 0};
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
-  static bool attr_bwd = false;
-  if (!attr_bwd) {
-    if (cudaFuncSetAttribute(sil_raster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileListBytesBwd) != cudaSuccess) {
-      vpn_set_error("silhouette bwd: smem attribute"); return VPN_ERR_CUDA;
-    }
-    attr_bwd = true;
+  static DeviceOnce once_bwd;
+  if (set_dyn_smem(sil_raster_bwd_kernel, (int)kTileListBytesBwd, once_bwd) != cudaSuccess) {
+    vpn_set_error("silhouette bwd: smem attribute"); return VPN_ERR_CUDA;
   }
   sil_raster_bwd_kernel<<<grid, kRThreads, kTileListBytesBwd, s>>>(rec, reinterpret_cast<const float4*>(ws + wl.box), grad_alpha, covered, gface, rp);
   if ((rc = vpn_check_launch("sil_raster_bwd_kernel"))) return rc;

@@ -20,6 +20,7 @@ _SIGNATURES = {
     "vpn_last_error_string": (c_char_p, []),
     "vpn_abi_version": (c_int, []),
     "vpn_launch_count": (ctypes.c_ulonglong, []),
+    "vpn_set_tuning": (c_int, [c_char_p, c_int]),
     "vpn_device_info": (c_int, [POINTER(c_int)] * 4),
     "vpn_pose_points_fwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vpn_pose_points_fwd_timed": (c_int, [c_int, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_void_p, c_int, c_int,
@@ -39,9 +40,9 @@ _SIGNATURES = {
                                      c_void_p]),
     "vpn_chamfer_loss_bwd": (c_int, [c_void_p] * 7 + [c_float, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vpn_silhouette_workspace_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
-    "vpn_silhouette_fwd": (c_int, [c_void_p] * 4 + [c_float] * 4 + [c_int, c_float, c_float] + [c_void_p] * 4
+    "vpn_silhouette_fwd": (c_int, [c_void_p] * 4 + [c_float] * 4 + [c_int, c_float, c_float, c_int] + [c_void_p] * 4
                            + [c_size_t] + [c_int] * 5 + [c_void_p]),
-    "vpn_silhouette_bwd": (c_int, [c_void_p] * 2 + [c_float] * 4 + [c_int, c_float, c_float] + [c_void_p] * 4
+    "vpn_silhouette_bwd": (c_int, [c_void_p] * 2 + [c_float] * 4 + [c_int, c_float, c_float, c_int] + [c_void_p] * 4
                            + [c_size_t] + [c_int] * 5 + [c_void_p]),
     "vpn_mesh_sample_fwd": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_void_p]),
     "vpn_mesh_sample_bwd": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
@@ -75,8 +76,36 @@ def load():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        _lib = lib
+        _lib = _DeviceGuardedLib(lib)
     return _lib
+
+
+class _StreamArg(c_void_p):
+    """cudaStream_t of torch's current stream on `device_index` (what stream_ptr returns)."""
+    device_index = -1
+
+
+class _DeviceGuardedLib:
+    """The C ABI launches on the calling thread's CURRENT device.  Calls whose stream argument belongs to another
+    device (tensors on cuda:1 while cuda:0 is current) are made with that device current, so multi-GPU single-process
+    callers work; the common case costs one integer comparison."""
+
+    def __init__(self, lib):
+        self._raw = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._raw, name)
+
+        def call(*args):
+            st = args[-1] if args else None
+            if isinstance(st, _StreamArg) and st.device_index >= 0 and st.device_index != torch.cuda.current_device():
+                with torch.cuda.device(st.device_index):
+                    return fn(*args)
+            return fn(*args)
+
+        call.__name__ = name
+        setattr(self, name, call)
+        return call
 
 
 class VpnError(RuntimeError):
@@ -94,7 +123,10 @@ def ptr(t):
 
 
 def stream_ptr(device):
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    s = _StreamArg(torch.cuda.current_stream(device).cuda_stream)
+    idx = torch.device(device).index
+    s.device_index = torch.cuda.current_device() if idx is None else idx
+    return s
 
 
 def require(t: torch.Tensor, dtype, name: str):

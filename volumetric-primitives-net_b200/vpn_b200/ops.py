@@ -315,7 +315,9 @@ def look_at_cameras(azims: torch.Tensor, elevs: torch.Tensor, dists: torch.Tenso
     d = dists.double()
     pos = torch.stack([d * torch.cos(phi) * torch.cos(theta), d * torch.sin(phi), d * torch.cos(phi) * torch.sin(theta)], 1)
     az = pos
-    ay0 = torch.tensor([0.0, 1.0, 0.0], dtype=torch.float64, device=pos.device).expand_as(pos)
+    # Y0 = (0, 1, 0) built on the device without a host-to-device copy (safe inside CUDA-graph capture)
+    ay0 = torch.zeros_like(pos)
+    ay0[:, 1] = 1.0
     ax = torch.cross(ay0, az, dim=1)
     ay = torch.cross(az, ax, dim=1)
     unit = lambda x: x / torch.linalg.norm(x, dim=1, keepdim=True)
@@ -325,7 +327,7 @@ def look_at_cameras(azims: torch.Tensor, elevs: torch.Tensor, dists: torch.Tenso
 
 class _SoftSilhouette(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, verts, faces, rot, pos, height, width, want_normals):
+    def forward(ctx, verts, faces, rot, pos, height, width, want_normals, soft_cull):
         lib = _lib.load()
         verts = require(verts.contiguous(), f32, "verts")
         faces = require(faces.contiguous(), torch.int32, "faces")
@@ -342,10 +344,10 @@ class _SoftSilhouette(torch.autograd.Function):
         ws = _scratch_bytes(nb.value, dev)
         px, py, pz = projection_vector()
         check(lib.vpn_silhouette_fwd(ptr(verts), ptr(faces), ptr(rot), ptr(pos), px, py, pz, DIBR_EXPAND, DIBR_KNUM,
-                                     DIBR_MULTIPLIER, DIBR_DELTA, ptr(alpha), ptr(covered), ptr(normals), ptr(ws),
+                                     DIBR_MULTIPLIER, DIBR_DELTA, int(soft_cull), ptr(alpha), ptr(covered), ptr(normals), ptr(ws),
                                      nb.value, b, v, f, height, width, stream_ptr(dev)), "vpn_silhouette_fwd")
         ctx.save_for_backward(faces, rot, covered, ws)
-        ctx.dims = (b, v, f, height, width, nb.value)
+        ctx.dims = (b, v, f, height, width, nb.value, int(soft_cull))
         ctx.mark_non_differentiable(covered)
         if normals is None:
             normals = torch.empty(0, device=dev)
@@ -356,22 +358,46 @@ class _SoftSilhouette(torch.autograd.Function):
     def backward(ctx, galpha, _gc, _gn):
         lib = _lib.load()
         faces, rot, covered, ws = ctx.saved_tensors
-        b, v, f, h, w, nbytes = ctx.dims
+        b, v, f, h, w, nbytes, soft_cull = ctx.dims
         dev = rot.device
         galpha = galpha.contiguous()
         gverts = torch.empty((b, v, 3), dtype=f32, device=dev)
         px, py, pz = projection_vector()
         check(lib.vpn_silhouette_bwd(ptr(faces), ptr(rot), px, py, pz, DIBR_EXPAND, DIBR_KNUM, DIBR_MULTIPLIER, DIBR_DELTA,
-                                     ptr(galpha), ptr(covered), ptr(gverts), ptr(ws), nbytes, b, v, f, h, w,
+                                     soft_cull, ptr(galpha), ptr(covered), ptr(gverts), ptr(ws), nbytes, b, v, f, h, w,
                                      stream_ptr(dev)), "vpn_silhouette_bwd")
-        return gverts, None, None, None, None, None, None
+        return gverts, None, None, None, None, None, None, None
 
 
-def soft_silhouette(verts, faces, rot, pos, height: int, width: int, want_normals: bool = False):
+def soft_silhouette(verts, faces, rot, pos, height: int, width: int, want_normals: bool = False,
+                    soft_cull_backfaces: bool = False):
     """Batched DIB-R soft alpha: verts (B,V,3), faces (F,3) int32 (shared topology), cameras (B,3,3)/(B,3).
-    Returns (alpha (B,H,W), covered (B,H,W) uint8, face_normals (B,F,3) or empty)."""
+    Returns (alpha (B,H,W), covered (B,H,W) uint8, face_normals (B,F,3) or empty).
+    soft_cull_backfaces=False is DIB-R's rule as recalled in SURVEY.md 8(a-R): the coverage pass skips back faces, the
+    soft (probability) pass does not; True skips them in both."""
     assert verts.dim() == 3 and verts.size(-1) == 3 and faces.dim() == 2 and faces.size(-1) == 3
-    return _SoftSilhouette.apply(verts, faces, rot, pos, int(height), int(width), bool(want_normals))
+    _check_face_indices(faces, verts.size(1))
+    return _SoftSilhouette.apply(verts, faces, rot, pos, int(height), int(width), bool(want_normals), bool(soft_cull_backfaces))
+
+
+_FACES_CHECKED = {}
+
+
+def _check_face_indices(faces: torch.Tensor, n_verts: int):
+    """The kernels index vertex arrays with the caller's face indices: validate each faces tensor ONCE (keyed by storage
+    pointer, shape and version; one device-to-host read the first time, none afterwards, nothing during graph capture)."""
+    key = (faces.data_ptr(), tuple(faces.shape), faces._version, int(n_verts), str(faces.device))
+    if key in _FACES_CHECKED:
+        return
+    if torch.cuda.is_current_stream_capturing():
+        return                                   # cannot read back while capturing; the eager warm-up call has checked
+    if faces.numel():
+        lo, hi = int(faces.min()), int(faces.max())
+        if lo < 0 or hi >= n_verts:
+            raise VpnError(f"faces index vertices outside [0, {n_verts}): min {lo}, max {hi}")
+    if len(_FACES_CHECKED) > 256:
+        _FACES_CHECKED.clear()
+    _FACES_CHECKED[key] = True
 
 
 # --------------------------------------------------------------------------------------
@@ -414,6 +440,7 @@ def sample_mesh_surface(verts, faces, uniforms):
     flows to the vertices through the barycentric weights."""
     assert verts.dim() == 3 and verts.size(-1) == 3 and faces.dim() == 2 and faces.size(-1) == 3
     assert uniforms.dim() == 3 and uniforms.size(-1) == 3 and uniforms.size(0) == verts.size(0)
+    _check_face_indices(faces, verts.size(1))
     return _MeshSample.apply(verts, faces, uniforms)
 
 

@@ -31,6 +31,7 @@ class PrimitiveLossConfig:
     img_size: int = 128               # config.py:46
     chamfer_impl: int = ops.CHAMFER_AUTO
     vertex_chamfer: bool = False      # train_gcn.py:127-130: the Chamfer term scores the composed mesh vertices, not samples
+    soft_cull_backfaces: bool = False  # rasteriser soft pass: False = DIB-R (back faces culled by the coverage pass only)
 
 
 class PrimitiveLoss:
@@ -60,7 +61,11 @@ class PrimitiveLoss:
     def __call__(self, v: torch.Tensor, q: torch.Tensor, t: torch.Tensor, uniforms: torch.Tensor,
                  view_center_points: torch.Tensor, silhouettes: Optional[torch.Tensor] = None,
                  canonical_points: Optional[torch.Tensor] = None, dists=None, elevs=None, azims=None,
-                 angles=None) -> Dict[str, torch.Tensor]:
+                 angles=None, sil_cameras=None) -> Dict[str, torch.Tensor]:
+        """dists / elevs / azims / angles (B,) are the view parameters of view_to_obj_points (train.py:152-163) and are
+        used by the canonical-frame Chamfer ONLY.  The silhouette is always rendered from the view-centred camera
+        dist = 1, elev = azim = 0, as the reference does under IS_VIEW_CENTER (train.py:166-176: the predicted meshes
+        live in the view-centred frame), unless sil_cameras = (dists, elevs, azims) is passed explicitly."""
         cfg = self.cfg
         out: Dict[str, torch.Tensor] = {}
         b, k = q.shape[:2]
@@ -94,14 +99,12 @@ class PrimitiveLoss:
                 verts = ops.mesh_vertices(tv, v, q, t)
             faces = self.composed_faces(k, v.device)
             h, w = silhouettes.shape[-2:]
-            if azims is None and elevs is None and dists is None:
+            if sil_cameras is None:
                 rot, pos = self.default_cameras(b, v.device)
             else:
-                one = torch.ones(b, device=v.device)
-                zero = torch.zeros(b, device=v.device)
-                rot, pos = ops.look_at_cameras(zero if azims is None else azims, zero if elevs is None else elevs,
-                                               one if dists is None else dists)
-            alpha, _, _ = ops.soft_silhouette(verts, faces, rot, pos, h, w)
+                sd, se, sa = sil_cameras
+                rot, pos = ops.look_at_cameras(sa, se, sd)
+            alpha, _, _ = ops.soft_silhouette(verts, faces, rot, pos, h, w, soft_cull_backfaces=cfg.soft_cull_backfaces)
             diff = alpha[:, None] - silhouettes
             sil = diff.abs().mean() if cfg.silhouette_loss == "L1" else (diff * diff).mean()
             out["alpha"] = alpha
