@@ -176,6 +176,22 @@ def cpu_reference_step(workload, rows_per_sample, threads, rows_per_slice=8192):
     return dt, frac, kk * n
 
 
+CPU_SAMPLE_ROWS = 32768      # ONE method for both CPU legs (cpu_baseline of our arm and --impl reference): one sample, this many
+                             # of its predicted points (whole primitives), scaled linearly to a full sample
+
+
+def cpu_sample_rows(workload):
+    kind, b, k, n, m, res = WORKLOADS[workload]
+    return min(k * n, CPU_SAMPLE_ROWS)
+
+
+def cpu_sample_text(workload, used, dt=None):
+    kind, b, k, n, m, res = WORKLOADS[workload]
+    t = f", {dt:.1f} s" if dt is not None else ""
+    return (f"1 sample, {used} of {k * n} predicted points x {m} targets per step (dense torch-CPU formulation of the "
+            f"reference, fwd+bwd, no render term){t}, scaled linearly to a full sample")
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU path (oracle port) on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -183,7 +199,7 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     kind, b, k, n, m, res = WORKLOADS[args.workload]
-    rows = min(k * n, 32768)
+    rows = cpu_sample_rows(args.workload)
     for _ in range(args.warmup):
         cpu_reference_step(args.workload, min(rows, 8192), threads)
     times = []
@@ -193,8 +209,7 @@ def run_reference(args):
     mean = sum(times) / len(times)
     per_sample = mean / frac
     value = 1.0 / per_sample
-    sample = (f"1 sample, {used} of {k * n} predicted points x {m} targets per step (dense torch-CPU formulation of the "
-              f"reference, fwd+bwd), scaled linearly to a full sample; render term not included")
+    sample = cpu_sample_text(args.workload, used)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -216,73 +231,93 @@ def describe(workload, world=1):
     return s + ", fwd+bwd to (v,q,t)"
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chamfer-impl", type=int, default=0)
-    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the step from a CUDA graph (vpn_b200.GraphedPrimitiveLoss); auto falls back to eager launches")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+class Bench:
+    """Shared state of one bench.py process: device, process group, flush buffer, gradient all-reduce."""
 
-    import vpn_b200
-    from vpn_b200 import _lib, dist as vdist
-    import torch.distributed as dist
+    def __init__(self, args):
+        import vpn_b200
+        from vpn_b200 import _lib, dist as vdist
+        import torch.distributed as dist
+        self.vpn, self.dist, self.args = vpn_b200, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = _lib.load()
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)      # > 126 MB L2
+        self.sync = vdist.GradientAllReduce(GRAD_NUMEL, self.dev) if self.world > 1 else None
+        self.do_flush = os.environ.get("VPN_BENCH_FLUSH", "1") != "0"
+        self.clocks_on = os.environ.get("VPN_BENCH_NO_CLOCKS", "0") != "1"
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-    kind, b, k, n, m, res = WORKLOADS[args.workload]
-    b = per_gpu_batch(args.workload, world)
-    vertex_mode = args.workload in VERTEX_MODE
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def new_sampler(self):
+        """NVML clock sampler thread for rank 0, fully initialised (nvmlInit, handle, first query) BEFORE the barrier that
+        starts a timed region: its set-up cost on rank 0 used to make rank 0 enter the timed loop milliseconds after the
+        other ranks, which then waited for it in their first all-reduce (the 'inter-rank skew' of round 1)."""
+        s = ClockSampler(self.local, enabled=(self.rank == 0 and self.clocks_on), period_s=0.02)
+        s.start()
+        s.ready.wait(timeout=10.0)
+        return s
+
+
+def measure_workload(B, workload, steps, warmup, chamfer_impl=0, graph="auto", with_rooflines=True, cpu_baseline=False):
+    """value (device-resident inputs), e2e (pinned host inputs, copies inside the timed region) and, on rank 0, the
+    rooflines of one workload.  Both timed regions run under the same conditions: 256 MB L2 flush before every step,
+    NVML clock sampling on rank 0, gradient all-reduce (N > 1) inside the step.  Returns a dict (rank 0) or None."""
+    vpn, dist, dev, world, rank, lib = B.vpn, B.dist, B.dev, B.world, B.rank, B.lib
+    kind, b, k, n, m, res = WORKLOADS[workload]
+    b = per_gpu_batch(workload, world)
+    vertex_mode = workload in VERTEX_MODE
+    faithful = workload in FAITHFUL
     width = 2 if kind == "sphere" else 3
     nsets = 4
-    host = synthetic(args.workload, "cpu", seed=1234 + rank, sets=nsets, batch=b)
+    host = synthetic(workload, "cpu", seed=1234 + rank, sets=nsets, batch=b)
     devsets = [{kk: (vv.to(dev) if vv is not None else None) for kk, vv in s.items()} for s in host]
     pinned = [{kk: (vv.pin_memory() if vv is not None else None) for kk, vv in s.items()} for s in host]
-    faithful = args.workload in FAITHFUL
-    cfg = vpn_b200.PrimitiveLossConfig(kind=kind, l_sil=(1.0 if res else 0.0), chamfer_impl=args.chamfer_impl,
-                                       vertex_chamfer=vertex_mode, l_can_cd=(1.0 if faithful else 0.0))
+    cfg = vpn.PrimitiveLossConfig(kind=kind, l_sil=(1.0 if res else 0.0), chamfer_impl=chamfer_impl,
+                                  vertex_chamfer=vertex_mode, l_can_cd=(1.0 if faithful else 0.0))
 
     def cams_of(s):
         return (s["dists"], s["elevs"], s["azims"], s["angles"]) if faithful else None
-    step_fn = vpn_b200.PrimitiveLoss(cfg)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    sync = vdist.GradientAllReduce(GRAD_NUMEL, dev) if world > 1 else None
-
+    step_fn = vpn.PrimitiveLoss(cfg)
+    sync, flush = B.sync, B.flush
     # the bench joins the all-reduce right after launching it (nothing of this path can overlap it), so it is queued on the
-    # step's own stream: no cross-stream event waits (VPN_BENCH_AR_STREAM=side restores the dedicated stream)
+    # step's own stream; when it is our self-synchronising NVLS kernel it is captured INSIDE the step's CUDA graph
     ar_inline = os.environ.get("VPN_BENCH_AR_STREAM", "inline") != "side"
+    ar_in_graph = (sync is not None and ar_inline and sync.graph_capturable and os.environ.get("VPN_BENCH_AR_IN_GRAPH", "1") != "0")
     graphed, graph_error = None, None
-    if args.graph != "off":
+    if graph != "off":
         try:
             d0 = devsets[0]
-            graphed = vpn_b200.GraphedPrimitiveLoss(cfg, d0["v"], d0["q"], d0["t"], d0["target"], d0["sil"], n_samples=n,
-                                                    canonical_points=d0.get("canon"), cameras=cams_of(d0))
+            graphed = vpn.GraphedPrimitiveLoss(cfg, d0["v"], d0["q"], d0["t"], d0["target"], d0["sil"], n_samples=n,
+                                               canonical_points=d0.get("canon"), cameras=cams_of(d0),
+                                               after_backward=(lambda: sync.launch(inline=True)) if ar_in_graph else None)
         except Exception as e:                               # noqa: BLE001 - eager launches are always available
             graph_error = repr(e)[:200]
-            if args.graph == "on":
+            ar_in_graph = False
+            if graph == "on":
                 raise
+    if world > 1:                                            # every rank must take the same path (graph or eager)
+        flag = torch.tensor([1 if graphed is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and graphed is not None:
+            raise RuntimeError("CUDA-graph capture succeeded on this rank but failed on another")
 
-    def one_step(s, grads_out=None):
+    def one_step(s):
         if graphed is not None:
-            loss, gv, gq, gt = graphed(s["v"], s["q"], s["t"], s["target"], s["sil"], canonical_points=s.get("canon"),
-                                       cameras=cams_of(s))
-            if sync is not None:
+            out = graphed(s["v"], s["q"], s["t"], s["target"], s["sil"], canonical_points=s.get("canon"), cameras=cams_of(s))
+            if sync is not None and not ar_in_graph:
                 sync.launch(inline=ar_inline)
-            return loss, gv, gq, gt
+            return out
         v, q, t = (s[x].detach().requires_grad_() for x in ("v", "q", "t"))
         u = None if vertex_mode else torch.rand((b, k, n, width), device=dev)      # drawn on device, like the reference
         c4 = cams_of(s) or (None, None, None, None)
@@ -294,28 +329,19 @@ def main():
         return out["total"], v.grad, q.grad, t.grad
 
     # ---- device-resident throughput ("value") ---------------------------------------------------
-    for i in range(args.warmup):
+    for i in range(warmup):
         one_step(devsets[i % nsets])
     if sync is not None:
         sync.join()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    # clock sampling: rank 0 only, every 20 ms, started just before the timed loop (VPN_BENCH_CLOCKS=armed starts it only
-    # once the steps are enqueued; that measured worse on 2 and 8 GPUs - see the class docstring)
-    sampler = ClockSampler(local, enabled=(rank == 0 and os.environ.get("VPN_BENCH_NO_CLOCKS", "0") != "1"), period_s=0.02)
-    sampler.start()
-    sampler.ready.wait(timeout=10.0)
-    if os.environ.get("VPN_BENCH_CLOCKS", "early") != "armed":
-        sampler.arm()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]      # end of the rank's own compute, before the join
-    do_flush = os.environ.get("VPN_BENCH_FLUSH", "1") != "0"
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]      # end of the rank's own compute, before the join
+    sampler = B.new_sampler()
     launches0 = lib.vpn_launch_count()
-    torch.cuda.synchronize()
+    B.barrier()                                   # barrier + synchronize immediately before the timed steps, on every rank
+    sampler.arm()
     wall0 = time.perf_counter()
-    for i in range(args.steps):
-        if do_flush:
+    for i in range(steps):
+        if B.do_flush:
             flush.zero_()                                           # L2 flush between timed iterations
         evs[i][0].record()
         one_step(devsets[i % nsets])
@@ -323,41 +349,44 @@ def main():
         if sync is not None:
             sync.join()
         evs[i][1].record()
-    sampler.arm()                       # no-op unless VPN_BENCH_CLOCKS=armed
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
-    launches = graphed.launches_per_step if graphed is not None else (lib.vpn_launch_count() - launches0) // args.steps
+    launches = (lib.vpn_launch_count() - launches0) // steps
+    if graphed is not None:
+        launches = graphed.launches_per_step + (0 if (ar_in_graph or sync is None) else (lib.vpn_launch_count() - launches0) // steps)
     sampler.stop()
     sampler.join(timeout=5.0)
+    B.barrier()
     step_ms = [a.elapsed_time(bb) for a, bb in evs]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    # per rank: mean step time and the part of it spent in the rank's own kernels (the rest is the all-reduce + waiting
-    # for the slowest rank)
-    own_ms = sum(a.elapsed_time(m_) for (a, _), m_ in zip(evs, mids)) / args.steps
-    rank_ms = torch.tensor([sum(step_ms) / args.steps, own_ms], dtype=torch.float64, device=dev)
+    # per rank: mean step time and the part of it spent before the all-reduce's completion is awaited
+    own_ms = sum(a.elapsed_time(m_) for (a, _), m_ in zip(evs, mids)) / steps
+    rank_ms = torch.tensor([sum(step_ms) / steps, own_ms], dtype=torch.float64, device=dev)
     rank_all = [rank_ms]
     if world > 1:
-        dist.barrier()
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         rank_all = [torch.zeros_like(rank_ms) for _ in range(world)]
         dist.all_gather(rank_all, rank_ms)
     rank_all = [[round(float(x), 4) for x in r_.tolist()] for r_ in rank_all]
     total_ms = float(total_ms.item())
-    value = world * b * args.steps / (total_ms * 1e-3)
+    value = world * b * steps / (total_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers ("e2e") ------------------------------
-    # results land in pinned host buffers with asynchronous copies and ONE synchronisation per step
+    # same conditions as above (flush before every step, clock sampling); inputs come from pinned host memory, results
+    # land in pinned host buffers, ONE synchronisation per step; timed over the whole loop, flushes included
     host_out = [torch.empty((), pin_memory=True), torch.empty((b, k, 3), pin_memory=True),
                 torch.empty((b, k, 4), pin_memory=True), torch.empty((b, k, 3), pin_memory=True)]
     done = torch.cuda.Event()
 
     def e2e_step(ps):
+        if B.do_flush:
+            flush.zero_()
         # with the graph the pinned inputs are copied straight into its static buffers; eager: fresh device tensors
         s = ps if graphed is not None else {kk: (vv.to(dev, non_blocking=True) if vv is not None else None) for kk, vv in ps.items()}
-        res = one_step(s)
+        out = one_step(s)
         if sync is not None:
             sync.join()
-        for h, d in zip(host_out, res):
+        for h, d in zip(host_out, out):
             h.copy_(d.detach(), non_blocking=True)
         done.record()
         done.synchronize()
@@ -365,11 +394,11 @@ def main():
 
     for i in range(2):
         e2e_step(pinned[i % nsets])
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(3, steps // 2)
+    sampler2 = B.new_sampler()
+    B.barrier()
+    sampler2.arm()
     t0 = time.perf_counter()
     e0.record()
     for i in range(e2e_steps):
@@ -377,138 +406,221 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     e2e_wall = time.perf_counter() - t0
+    sampler2.stop()
+    sampler2.join(timeout=5.0)
     e2e_ms = torch.tensor([max(e0.elapsed_time(e1), e2e_wall * 1e3)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * b * e2e_steps / (float(e2e_ms.item()) * 1e-3)
     h2d = sum(vv.numel() * vv.element_size() for vv in pinned[0].values() if vv is not None)
     d2h = 4 + b * k * 10 * 4
+    ar_timeout = bool(sync.nvls_timed_out()) if sync is not None else False
+    if rank != 0:
+        return None
 
-    line = None
-    if rank == 0:
-        # ---- roofline of the dominant kernel group: Chamfer forward (FP32 pipe) ----------------------
-        s = devsets[0]
+    out = {"workload": describe(workload, world), "value": value, "unit": "samples/s", "ms_per_step": total_ms / steps,
+           "steps": steps, "scaling": "strong" if workload in STRONG else "weak", "global_batch": world * b,
+           "gpu_launches": int(launches), "cuda_graph": graphed is not None, "cuda_graph_error": graph_error,
+           "allreduce_in_graph": bool(ar_in_graph), "allreduce_wait_timed_out": ar_timeout,
+           "wall_ms_per_step_incl_flush": wall * 1e3 / steps, "rank_ms_step_and_own_kernels": rank_all,
+           "clocks": sampler.summary(),
+           "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "steps": e2e_steps, "clocks": sampler2.summary(),
+                   "conditions": "same as value: 256 MB L2 flush before every step (inside the timed region here), NVML "
+                                 "clock sampling on rank 0, all-reduce inside the step; one host synchronisation per step"}}
+    if not with_rooflines:
+        return out
+
+    # ---- roofline of the dominant kernel group: Chamfer forward (FP32 pipe) ----------------------
+    s = devsets[0]
+    with torch.no_grad():
+        if vertex_mode:
+            from vpn_b200 import templates as _tpl
+            pts = vpn.mesh_vertices(_tpl.template(kind, dev)[0], s["v"], s["q"], s["t"])
+        else:
+            pts = vpn.sample_primitives(kind, s["v"], s["q"], s["t"], torch.rand((b, k, n, width), device=dev))
+        reps = 10
+        vpn.chamfer_nn_stage_ms(pts, s["target"], chamfer_impl, reps=3)
+        stage = vpn.chamfer_nn_stage_ms(pts, s["target"], chamfer_impl, reps=reps)
+        cham_ms = stage["total"]
+        # sampling kernel: a stream of launches over rotating uniform buffers larger than L2 in total (every
+        # launch reads cold inputs; no write-flush, whose dirty lines would be written back during the launch)
+        sbytes = b * k * n * (12 + 4 * width)
+        nrot = min(64, max(2, -(-300_000_000 // sbytes)))
+        nl = 4 * nrot
+        us = [torch.rand((b, k, n, width), device=dev) for _ in range(nrot)]
+        samp_ms = vpn.sample_primitives_ms(kind, s["v"], s["q"], s["t"], us, reps=nl)
+        del us
+    peak = vpn.fp32_peak_tflops(dev)
+    flops = 8.0 * b * (k * n) * m                      # 8 flop per (predicted, target) pair, both directions
+    main_ms = stage["main"] if stage["main"] > 0 else cham_ms
+    achieved = flops / (main_ms * 1e-3) / 1e12
+    sm_mhz_max = sampler.summary()["sm_max_mhz"] or 1965
+    nominal = 148 * 128 * 2 * sm_mhz_max * 1e6 / 1e12
+    peak_tf = max(peak["ffma2"], peak["ffma"])
+    main_kernel = vpn.chamfer_main_kernel_name(b, k * n, m, chamfer_impl)
+    traffic_db = {}
+    try:
+        traffic_db = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get(workload, {})
+    except Exception:
+        pass
+    traffic = traffic_db.get(main_kernel)
+    tsrc = "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of the same launch)"
+    roofline = {"kernel": main_kernel + " (main kernel of vpn_chamfer_fwd; both Chamfer directions in one launch)",
+                "bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "peak_source": "live FFMA2 stream probe (vpn_fp32_peak_probe), burst; MEASURED_PEAKS.json has no FP32 "
+                               "entry; nominal 148 SM x 128 lanes x 2 x max clock given beside it",
+                "peak_nominal": nominal, "frac_of_nominal": achieved / nominal, "ms": main_ms,
+                "algorithmic_flops": flops, "traffic": traffic, "traffic_source": tsrc if traffic else None,
+                "note": "achieved = 8 flop per (predicted, target) pair / kernel time, against the FP32 FMA peak the "
+                        "north star names; chamfer_tc_kernel evaluates the pairs on the tensor cores (fp16-split "
+                        "operands, fp32 accumulate) and is bounded by TMEM reads + FMNMX on the ALU pipe, see DESIGN.md 4.1",
+                "forward_total": {"ms": cham_ms, "stages_ms": stage, "achieved": flops / (cham_ms * 1e-3) / 1e12,
+                                  "frac": flops / (cham_ms * 1e-3) / 1e12 / peak_tf,
+                                  "note": "main kernel + exact recovery kernels: the time to the final min / arg-min"}}
+    hbm_peak, tensor_peak = 6536.7, None
+    try:
+        mp = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = mp["hbm_gbs"], "MEASURED_PEAKS.json"
+        tensor_peak = mp.get("bf16_tflops")
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback"
+    if main_kernel == "chamfer_tc_kernel":
+        # what the tensor pipe actually executes: a 16-term fp16 dot product per pair and direction (2 x 16 MACs = 64 flop)
+        executed = 64.0 * b * (k * n) * m / (main_ms * 1e-3) / 1e12
+        roofline["tensor_executed"] = {"tflops": executed, "peak_dense_16bit": tensor_peak,
+                                       "frac": (executed / tensor_peak) if tensor_peak else None,
+                                       "note": "fp16 operands, fp32 accumulate, K = 16; padded tiles not counted"}
+    out["roofline"] = roofline
+    if not vertex_mode:
+        pk = "pose_fwd_kernel"
+        out["roofline_sampling"] = {
+            "kernel": "pose_fwd_kernel (fused sample+pose)", "bound": "hbm",
+            "achieved": sbytes / (samp_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": sbytes / (samp_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms": samp_ms,
+            "algorithmic_bytes": sbytes, "traffic": traffic_db.get(pk), "traffic_source": tsrc if traffic_db.get(pk) else None,
+            "how": f"{nl} back-to-back launches over {nrot} rotating uniform buffers ({nrot * sbytes // 2 >> 20} MB of inputs > L2), "
+                   "one CUDA-event pair around the stream (vpn_pose_points_fwd_timed)"}
+    if res:
+        from vpn_b200 import templates
         with torch.no_grad():
-            if vertex_mode:
-                from vpn_b200 import templates as _tpl
-                pts = vpn_b200.mesh_vertices(_tpl.template(kind, dev)[0], s["v"], s["q"], s["t"])
-            else:
-                pts = vpn_b200.sample_primitives(kind, s["v"], s["q"], s["t"], torch.rand((b, k, n, width), device=dev))
-            reps = 10
-            vpn_b200.chamfer_nn_stage_ms(pts, s["target"], args.chamfer_impl, reps=3)
-            stage = vpn_b200.chamfer_nn_stage_ms(pts, s["target"], args.chamfer_impl, reps=reps)
-            cham_ms = stage["total"]
-            # sampling kernel: a stream of launches over rotating uniform buffers larger than L2 in total (every
-            # launch reads cold inputs; no write-flush, whose dirty lines would be written back during the launch)
-            sbytes = b * k * n * (12 + 4 * width)
-            nrot = min(64, max(2, -(-300_000_000 // sbytes)))
-            nl = 4 * nrot
-            us = [torch.rand((b, k, n, width), device=dev) for _ in range(nrot)]
-            samp_ms = vpn_b200.sample_primitives_ms(kind, s["v"], s["q"], s["t"], us, reps=nl)
-            del us
-        peak = vpn_b200.fp32_peak_tflops(dev)
-        flops = 8.0 * b * (k * n) * m                      # 8 flop per (predicted, target) pair, both directions
-        main_ms = stage["main"] if stage["main"] > 0 else cham_ms
-        achieved = flops / (main_ms * 1e-3) / 1e12
-        sm_mhz_max = sampler.summary()["sm_max_mhz"] or 1965
-        nominal = 148 * 128 * 2 * sm_mhz_max * 1e6 / 1e12
-        peak_tf = max(peak["ffma2"], peak["ffma"])
-        main_kernel = vpn_b200.chamfer_main_kernel_name(b, k * n, m, args.chamfer_impl)
-        traffic = None
+            tv, tf = templates.template(kind, dev)
+            verts = vpn.mesh_vertices(tv, s["v"], s["q"], s["t"])
+            faces = step_fn.composed_faces(k, dev)
+            rot, pos = vpn.look_at_cameras(torch.zeros(b, device=dev), torch.zeros(b, device=dev), torch.ones(b, device=dev))
+            for _ in range(2):
+                vpn.soft_silhouette(verts, faces, rot, pos, res, res)
+            re_ = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for i in range(reps):
+                flush.zero_()
+                re_[i][0].record()
+                vpn.soft_silhouette(verts, faces, rot, pos, res, res)
+                re_[i][1].record()
+            torch.cuda.synchronize()
+            r_ms = sum(a.elapsed_time(bb) for a, bb in re_) / reps
+        rbytes = 12 * b * verts.shape[1] + 12 * faces.shape[0] + 4 * b * res * res
+        rt = [traffic_db.get(kn) for kn in ("sil_project_kernel", "sil_faces_kernel", "sil_raster_fwd_kernel")]
+        out["roofline_raster"] = {
+            "kernel": "sil_project_kernel + sil_faces_kernel + sil_raster_fwd_kernel (vpn_silhouette_fwd, whole batch)",
+            "bound": "hbm", "achieved": rbytes / (r_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": rbytes / (r_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms": r_ms,
+            "algorithmic_bytes": rbytes, "traffic": (sum(rt) if all(x is not None for x in rt) else None),
+            "traffic_source": tsrc if all(x is not None for x in rt) else None, "faces": int(faces.shape[0]),
+            "pixel_face_tests_per_s": b * res * res * float(faces.shape[0]) / (r_ms * 1e-3),
+            "note": "algorithmic bytes are ~1 us of HBM time: the rasteriser is latency / ALU bound (DESIGN.md 4.4)"}
+    out["fp32_peak_probe_tflops"] = peak
+    if cpu_baseline:
+        threads = os.cpu_count() or 1
+        rows = cpu_sample_rows(workload)
+        cpu_reference_step(workload, min(rows, n), threads)      # warm-up on one primitive
+        dt, frac, used = cpu_reference_step(workload, rows, threads)
+        out["cpu_baseline"] = {"value": 1.0 / (dt / frac), "unit": "samples/s", "cores": threads, "kind": "port",
+                               "sample": cpu_sample_text(workload, used, dt)}
+    return out
+
+
+def compact(r):
+    """One entry of the `configs` block: what the verdict asked for per extra workload (value, ms, roofline, launches)."""
+    c = {kk: r[kk] for kk in ("workload", "value", "unit", "ms_per_step", "steps", "scaling", "global_batch", "gpu_launches",
+                              "cuda_graph", "allreduce_in_graph")}
+    c["e2e"] = {kk: r["e2e"][kk] for kk in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+    c["clocks"] = r["clocks"]
+    if "roofline" in r:
+        rf = r["roofline"]
+        c["roofline"] = {"kernel": rf["kernel"].split(" ")[0], "bound": rf["bound"], "achieved": rf["achieved"], "peak": rf["peak"],
+                         "unit": rf["unit"], "frac": rf["frac"], "ms": rf["ms"], "traffic": rf["traffic"],
+                         "forward_total_frac": rf["forward_total"]["frac"], "forward_total_ms": rf["forward_total"]["ms"]}
+    for key in ("roofline_sampling", "roofline_raster"):
+        if key in r:
+            rr = r[key]
+            c[key] = {kk: rr[kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "ms", "algorithmic_bytes", "traffic")}
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chamfer-impl", type=int, default=0)
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from a CUDA graph (vpn_b200.GraphedPrimitiveLoss); auto falls back to eager launches")
+    ap.add_argument("--configs", default="auto",
+                    help="extra workloads measured after the headline one and reported in the `configs` block of the same JSON "
+                         "line: 'auto' = c3,c5,c2f,c4 when the headline is c2, 'none', or a comma-separated list")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    B = Bench(args)
+    world, rank = B.world, B.rank
+    warm = max(3, args.warmup)
+    head = measure_workload(B, args.workload, args.steps, warm, args.chamfer_impl, args.graph, with_rooflines=True,
+                            cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+    extras = []
+    if args.configs == "auto":
+        extras = ["c3", "c5", "c2f", "c4"] if args.workload == "c2" else []
+    elif args.configs != "none":
+        extras = [w for w in args.configs.split(",") if w in WORKLOADS and w != args.workload]
+    configs = {}
+    for w in extras:
         try:
-            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))[args.workload][main_kernel]
-        except Exception:
-            pass
-        roofline = {"kernel": main_kernel + " (main kernel of vpn_chamfer_fwd; both Chamfer directions in one launch)",
-                    "bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "peak_source": "live FFMA2 stream probe (vpn_fp32_peak_probe), burst; MEASURED_PEAKS.json has no FP32 "
-                                   "entry; nominal 148 SM x 128 lanes x 2 x max clock given beside it",
-                    "peak_nominal": nominal, "frac_of_nominal": achieved / nominal, "ms": main_ms,
-                    "algorithmic_flops": flops, "traffic": traffic,
-                    "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-                                      "capture of this launch)" if traffic else None,
-                    "note": "achieved = 8 flop per (predicted, target) pair / kernel time, against the FP32 FMA peak the "
-                            "north star names; chamfer_tc_kernel evaluates the pairs on the tensor cores (fp16-split "
-                            "operands, fp32 accumulate) and is bounded by TMEM reads + FMNMX on the ALU pipe, see DESIGN.md 4.1",
-                    "forward_total": {"ms": cham_ms, "stages_ms": stage, "achieved": flops / (cham_ms * 1e-3) / 1e12,
-                                      "frac": flops / (cham_ms * 1e-3) / 1e12 / peak_tf,
-                                      "note": "main kernel + exact recovery kernels: the time to the final min / arg-min"}}
-        hbm_peak, tensor_peak = 6536.7, None
-        try:
-            mp = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-            hbm_peak, hbm_src = mp["hbm_gbs"], "MEASURED_PEAKS.json"
-            tensor_peak = mp.get("bf16_tflops")
-        except Exception:
-            hbm_peak, hbm_src = 6650.0, "fallback"
-        if main_kernel == "chamfer_tc_kernel":
-            # what the tensor pipe actually executes: a 16-term fp16 dot product per pair and direction (2 x 16 MACs = 64 flop)
-            executed = 64.0 * b * (k * n) * m / (main_ms * 1e-3) / 1e12
-            roofline["tensor_executed"] = {"tflops": executed, "peak_dense_16bit": tensor_peak,
-                                           "frac": (executed / tensor_peak) if tensor_peak else None,
-                                           "note": "fp16 operands, fp32 accumulate, K = 16; padded tiles not counted"}
-        roof_s = {"kernel": "pose_fwd_kernel (fused sample+pose)", "bound": "hbm",
-                  "achieved": sbytes / (samp_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                  "frac": sbytes / (samp_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms": samp_ms,
-                  "algorithmic_bytes": sbytes, "traffic": None,
-                  "how": f"{nl} back-to-back launches over {nrot} rotating uniform buffers ({nrot * sbytes // 2 >> 20} MB of inputs > L2), "
-                         "one CUDA-event pair around the stream (vpn_pose_points_fwd_timed)"}
-        roof_r = None
-        if res:
-            from vpn_b200 import templates
-            with torch.no_grad():
-                tv, tf = templates.template(kind, dev)
-                verts = vpn_b200.mesh_vertices(tv, s["v"], s["q"], s["t"])
-                faces = step_fn.composed_faces(k, dev)
-                rot, pos = vpn_b200.look_at_cameras(torch.zeros(b, device=dev), torch.zeros(b, device=dev), torch.ones(b, device=dev))
-                for _ in range(2):
-                    vpn_b200.soft_silhouette(verts, faces, rot, pos, res, res)
-                re_ = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-                for i in range(reps):
-                    flush.zero_()
-                    re_[i][0].record()
-                    vpn_b200.soft_silhouette(verts, faces, rot, pos, res, res)
-                    re_[i][1].record()
-                torch.cuda.synchronize()
-                r_ms = sum(a.elapsed_time(bb) for a, bb in re_) / reps
-            rbytes = 12 * b * verts.shape[1] + 12 * faces.shape[0] + 4 * b * res * res
-            roof_r = {"kernel": "sil_project_kernel + sil_faces_kernel + sil_raster_fwd_kernel (vpn_silhouette_fwd, whole batch)",
-                      "bound": "hbm", "achieved": rbytes / (r_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                      "frac": rbytes / (r_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src, "ms": r_ms,
-                      "algorithmic_bytes": rbytes, "traffic": None, "faces": int(faces.shape[0]),
-                      "pixel_face_tests_per_s": b * res * res * float(faces.shape[0]) / (r_ms * 1e-3),
-                      "note": "algorithmic bytes are ~1 us of HBM time: the rasteriser is latency / ALU bound (DESIGN.md 4.4)"}
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            rows = min(k * n, 65536)
-            cpu_reference_step(args.workload, min(rows, n), threads)      # warm-up on one primitive
-            dt, frac, used = cpu_reference_step(args.workload, rows, threads)
-            cpu = {"value": 1.0 / (dt / frac), "unit": "samples/s", "cores": threads, "kind": "port",
-                   "sample": f"1 sample, {used} of {k * n} predicted points x {m} targets, dense torch-CPU formulation "
-                             f"of the reference (fwd+bwd, no render term), {dt:.1f} s, scaled linearly to a full sample"}
-        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "strong" if args.workload in STRONG else "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": describe(args.workload, world), "global_batch": world * b,
-                           "parallelism": f"dp{world}", "l2": "256 MB L2 flush between timed iterations, outside the "
-                           "per-step CUDA-event pairs; 4 rotating input sets",
-                           "cuda_graph": graphed is not None, "cuda_graph_error": graph_error,
+            r = measure_workload(B, w, max(5, min(10, args.steps)), 3, args.chamfer_impl, args.graph, with_rooflines=True)
+            if rank == 0:
+                configs[w] = compact(r)
+        except Exception as e:                               # noqa: BLE001 - an extra workload must not cost the headline line
+            if world > 1:
+                raise                                        # ranks must stay in lock step: fail loudly
+            configs[w] = {"error": repr(e)[:200]}
+    if rank == 0:
+        sync = B.sync
+        line = {"metric": METRIC, "value": head["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+                "scaling": head["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": head["workload"], "global_batch": head["global_batch"],
+                           "parallelism": f"dp{world}", "l2": "256 MB L2 flush before every timed step (value: outside the "
+                           "per-step CUDA-event pairs; e2e: inside the timed loop); 4 rotating input sets",
+                           "cuda_graph": head["cuda_graph"], "cuda_graph_error": head["cuda_graph_error"],
                            "allreduce_numel": GRAD_NUMEL if world > 1 else 0,
                            "allreduce": (sync.mode if sync is not None else None),
-                           "allreduce_stream": (("step stream" if ar_inline else "dedicated stream") if sync is not None else None),
+                           "allreduce_in_graph": head["allreduce_in_graph"],
+                           "allreduce_wait_timed_out": head["allreduce_wait_timed_out"],
                            "allreduce_trial_ms": (sync.trial_ms if sync is not None else None),
-                           "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps,
-                           "rank_ms_step_and_own_kernels": rank_all, "l2_flush": do_flush},
-                "clocks": sampler.summary(), "gpu_launches": int(launches),
-                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps},
-                "roofline": roofline, "roofline_sampling": roof_s, "roofline_raster": roof_r, "cpu_baseline": cpu,
-                "fp32_peak_probe_tflops": peak}
+                           "wall_ms_per_step_incl_flush": head["wall_ms_per_step_incl_flush"],
+                           "rank_ms_step_and_own_kernels": head["rank_ms_step_and_own_kernels"], "l2_flush": B.do_flush,
+                           "timed_region": "barrier + synchronize on every rank immediately before the first timed step "
+                                           "(after all per-rank set-up, incl. NVML init on rank 0) and after the last"},
+                "clocks": head["clocks"], "gpu_launches": head["gpu_launches"], "e2e": head["e2e"],
+                "roofline": head.get("roofline"), "roofline_sampling": head.get("roofline_sampling"),
+                "roofline_raster": head.get("roofline_raster"), "cpu_baseline": head.get("cpu_baseline"),
+                "fp32_peak_probe_tflops": head.get("fp32_peak_probe_tflops"),
+                "configs": configs}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        B.dist.barrier()
+        B.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

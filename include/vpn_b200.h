@@ -164,6 +164,14 @@ int vpn_feature_pool_points_bwd(const float* pts, const float* bounds, const flo
  * multicast_ptr: multicast virtual address of the buffer (numel % 4 == 0, 16-byte aligned).  The caller brackets the
  * call with cross-rank barriers on the stream.  The reference is single process: no counterpart. */
 int vpn_allreduce_nvls(void* multicast_ptr, size_t numel, int rank, int world, void* stream);
+/* Self-synchronising variant: ONE launch, cross-rank barriers inside the kernel (multimem.red arrive counters in the
+ * buffer tail, bounded spins), epoch in device memory - no per-call host state, capturable in a CUDA graph.  The
+ * symmetric buffer is numel payload floats followed by vpn_allreduce_nvls_flag_floats() flag words that are zero on
+ * every rank before the first call; multicast_ptr / local_ptr address the same buffer.  A wait that times out (4 s)
+ * sets flag word vpn_allreduce_nvls_error_word() instead of hanging the GPU. */
+int vpn_allreduce_nvls_flag_floats(size_t* floats);
+int vpn_allreduce_nvls_error_word(void);
+int vpn_allreduce_nvls_sync(void* multicast_ptr, void* local_ptr, size_t numel, int rank, int world, void* stream);
 
 /* ---- measurement helper: achieved FP32 FMA throughput (the Chamfer roofline denominator) ----------------
  * scratch: >= 64 device floats, the first 16 finite and near 1.0.  Synchronises the stream. */

@@ -510,7 +510,12 @@ def projection_vector() -> torch.Tensor:
 def project_vertices(verts: torch.Tensor, rot: torch.Tensor, pos: torch.Tensor):
     """kaolin perspective_projection: camera-space points and their screen xy.
     verts (B,V,3); rot (B,3,3); pos (B,3).  Returns cam (B,V,3), xy (B,V,2)."""
-    cam = torch.matmul(verts - pos[:, None, :], rot.permute(0, 2, 1))
+    # kaolin: torch.matmul (cuBLAS batched GEMM, accumulation order unspecified).  The restatement pins ONE order,
+    # (dx r_k0 + dy r_k1) + dz r_k2 with every operation rounded separately: the rasteriser works on coordinates x 1000
+    # and cancels, so a 1-ulp difference in a projected vertex moves alpha by ~1e-4 and can flip a nearest-edge choice.
+    d = verts - pos[:, None, :]
+    cam = torch.stack([(d[..., 0] * rot[:, k, 0, None] + d[..., 1] * rot[:, k, 1, None]) + d[..., 2] * rot[:, k, 2, None]
+                       for k in range(3)], dim=-1)
     proj = projection_vector()
     xyz = cam * proj[None, None, :]
     return cam, xyz[:, :, :2] / xyz[:, :, 2:3]

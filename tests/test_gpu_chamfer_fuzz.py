@@ -1,0 +1,85 @@
+"""Property / fuzz tests (SURVEY.md section 4 layer 3) of the tensor-core Chamfer filter against the exact C oracle.
+
+The filter (chamfer_tc_kernel) only has to never drop the true arg-min; its guarantee rests on an error bound derived by
+hand.  hypothesis searches mixed-scale clouds for a counter-example: clusters of radius 1e-4 .. 1 at
+offsets 0 .. 1e3, outliers, rows / columns duplicated across the 128-wide tile borders, P and M that are not multiples
+of 128, plus the algebraic properties of the reference's definition (permutation equivariance, translation by
+power-of-two vectors, swap symmetry)."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vpn():
+    assert torch.cuda.is_available()
+    import vpn_b200
+    return vpn_b200
+
+
+def mixed_cloud(rng, n, n_clusters, log_radius, log_offset, outliers, lattice):
+    """n points: clusters of the given radius at random offsets of the given magnitude, some outliers 10-1000x away,
+    optionally snapped to a lattice (exact ties)."""
+    centres = rng.uniform(-1, 1, size=(n_clusters, 3)) * 10.0 ** log_offset
+    which = rng.integers(0, n_clusters, size=n)
+    pts = centres[which] + rng.normal(size=(n, 3)) * 10.0 ** log_radius
+    if outliers:
+        idx = rng.integers(0, n, size=outliers)
+        pts[idx] = pts[idx] * rng.uniform(10, 1000, size=(outliers, 1))
+    if lattice:
+        step = 10.0 ** log_radius / 4
+        pts = np.round(pts / step) * step
+    return pts.astype(np.float32)
+
+
+cloud_params = st.tuples(st.integers(1, 12), st.floats(-4, 0), st.floats(-2, 3), st.integers(0, 5), st.booleans())
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(seed=st.integers(0, 2 ** 31 - 1), p=st.integers(512, 3000), m=st.integers(128, 1500), b=st.integers(1, 3),
+       cp1=cloud_params, cp2=cloud_params, share_centres=st.booleans(), dup=st.booleans(), impl=st.sampled_from([5, 0, 4]))
+def test_tc_filter_never_drops_the_argmin(vpn, c_oracle, seed, p, m, b, cp1, cp2, share_centres, dup, impl):
+    rng = np.random.default_rng(seed)
+    p1 = np.stack([mixed_cloud(rng, p, *cp1) for _ in range(b)])
+    p2 = np.stack([mixed_cloud(rng, m, *(cp1 if share_centres else cp2)) for _ in range(b)])
+    if share_centres:                      # targets near the predictions: the regime training converges to
+        take = rng.integers(0, p, size=m)
+        p2 = (p1[:, take] + rng.normal(size=(b, m, 3)).astype(np.float32) * np.float32(10.0 ** cp2[1])).astype(np.float32)
+    if dup:                                # identical rows / columns on both sides of a 128-wide tile border
+        k = min(40, m // 4, p // 4)
+        p2[:, 128 - k // 2:128 - k // 2 + k] = p2[:, :k]
+        p1[:, 512 - k // 2 - k:512 - k // 2] = p1[:, :k]
+    want = c_oracle(p1, p2)
+    got = vpn.chamfer_nn(torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda(), impl)
+    m1, i1, m2, i2 = (x.cpu().numpy() for x in got)
+    np.testing.assert_array_equal(i1.astype(np.int64), want[1], err_msg="idx1")
+    np.testing.assert_array_equal(i2.astype(np.int64), want[3], err_msg="idx2")
+    np.testing.assert_array_equal(m1, want[0], err_msg="min1")
+    np.testing.assert_array_equal(m2, want[2], err_msg="min2")
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(seed=st.integers(0, 2 ** 31 - 1), p=st.integers(512, 2500), m=st.integers(128, 1200), impl=st.sampled_from([5, 4, 1]))
+def test_chamfer_properties(vpn, seed, p, m, impl):
+    """(1) permuting the targets permutes idx1 through the permutation when no ties exist, min values unchanged; with the
+    first-index rule: idx1 = the permuted position of the same target.  (2) swapping the clouds swaps the outputs.
+    (3) translating both clouds by a power-of-two vector that keeps every coordinate exactly representable changes
+    nothing (differences are exact)."""
+    gen = torch.Generator().manual_seed(seed)
+    p1 = (torch.rand(1, p, 3, generator=gen) - 0.5).cuda()
+    p2 = (torch.rand(1, m, 3, generator=gen) - 0.5).cuda()
+    m1, i1, m2, i2 = vpn.chamfer_nn(p1, p2, impl)
+    perm = torch.randperm(m, generator=gen).cuda()
+    pm1, pi1, pm2, pi2 = vpn.chamfer_nn(p1, p2[:, perm].contiguous(), impl)
+    assert torch.equal(pm1, m1) and torch.equal(perm[pi1.long()], i1.long())            # random reals: no exact ties
+    assert torch.equal(pm2, m2[:, perm]) and torch.equal(pi2, i2[:, perm])
+    s1, si1, s2, si2 = vpn.chamfer_nn(p2, p1, impl if p2.shape[1] >= 512 else 1)
+    assert torch.equal(s1, m2) and torch.equal(si1, i2) and torch.equal(s2, m1) and torch.equal(si2, i1)
+    q1 = torch.round(p1 * 4096) / 4096; q2 = torch.round(p2 * 4096) / 4096                # 12 fractional bits
+    shift = torch.tensor([4.0, -8.0, 2.0]).cuda()                                         # sums stay exact in fp32
+    a = vpn.chamfer_nn(q1, q2, impl); bb = vpn.chamfer_nn(q1 + shift, q2 + shift, impl)
+    for x, y in zip(a, bb):
+        assert torch.equal(x, y)

@@ -15,6 +15,7 @@ L_VIEW_CD = 1.0
 L_CAN_CD = 0.0
 L_SIL = 0.0
 L_VP_DIV = 0.1
+L_EMD = 1.0
 
 MANUAL_SEED = 1234
 SILHOUETTE_LOSS_FUNC = 'L1'  # L1 or MSE

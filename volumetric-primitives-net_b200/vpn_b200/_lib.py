@@ -55,6 +55,9 @@ _SIGNATURES = {
     "vpn_feature_pool_bwd": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_void_p]),
     "vpn_feature_pool_points_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),
     "vpn_allreduce_nvls": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "vpn_allreduce_nvls_flag_floats": (c_int, [POINTER(c_size_t)]),
+    "vpn_allreduce_nvls_error_word": (c_int, []),
+    "vpn_allreduce_nvls_sync": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "vpn_fp32_peak_probe": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_double), c_void_p]),
 }
 

@@ -126,7 +126,11 @@ class GraphedPrimitiveLoss:
     """
 
     def __init__(self, config: PrimitiveLossConfig, v, q, t, targets, silhouettes=None, n_samples: int = 0, warmup: int = 3,
-                 canonical_points=None, cameras=None):
+                 canonical_points=None, cameras=None, after_backward=None):
+        """after_backward: optional callable queued on the step's stream after the backward pass and captured with it -
+        e.g. GradientAllReduce.launch(inline=True) when the all-reduce is our own self-synchronising kernel, so that no
+        host launch sits between the step's tail and the collective.  It also runs in each of the `warmup` eager steps
+        (every rank makes the same number of calls)."""
         from . import _lib
         self.cfg = config
         self.step = PrimitiveLoss(config)
@@ -149,6 +153,8 @@ class GraphedPrimitiveLoss:
             out = self.step(self.v, self.q, self.t, u, self.targets, silhouettes=self.sil, canonical_points=self.canonical,
                             dists=cams[0], elevs=cams[1], azims=cams[2], angles=cams[3])
             gv, gq, gt = torch.autograd.grad(out["total"], (self.v, self.q, self.t))
+            if after_backward is not None:
+                after_backward()
             return out["total"], gv, gq, gt
 
         side = torch.cuda.Stream(device=dev)
