@@ -48,10 +48,12 @@ def test_tc_filter_never_drops_the_argmin(vpn, c_oracle, seed, p, m, b, cp1, cp2
     if share_centres:                      # targets near the predictions: the regime training converges to
         take = rng.integers(0, p, size=m)
         p2 = (p1[:, take] + rng.normal(size=(b, m, 3)).astype(np.float32) * np.float32(10.0 ** cp2[1])).astype(np.float32)
-    if dup:                                # identical rows / columns on both sides of a 128-wide tile border
-        k = min(40, m // 4, p // 4)
+    if dup and m >= 256 and p >= 1024:     # identical rows / columns on both sides of a 128-wide tile border
+        k = 40
         p2[:, 128 - k // 2:128 - k // 2 + k] = p2[:, :k]
-        p1[:, 512 - k // 2 - k:512 - k // 2] = p1[:, :k]
+        p1[:, 512 - k // 2:512 - k // 2 + k] = p1[:, :k]
+    if impl == 4 and p < 1024:             # the CUDA-core tiled kernel needs P >= 1024
+        impl = 5
     want = c_oracle(p1, p2)
     got = vpn.chamfer_nn(torch.from_numpy(p1).cuda(), torch.from_numpy(p2).cuda(), impl)
     m1, i1, m2, i2 = (x.cpu().numpy() for x in got)
@@ -68,6 +70,8 @@ def test_chamfer_properties(vpn, seed, p, m, impl):
     first-index rule: idx1 = the permuted position of the same target.  (2) swapping the clouds swaps the outputs.
     (3) translating both clouds by a power-of-two vector that keeps every coordinate exactly representable changes
     nothing (differences are exact)."""
+    if impl == 4 and p < 1024:
+        impl = 5
     gen = torch.Generator().manual_seed(seed)
     p1 = (torch.rand(1, p, 3, generator=gen) - 0.5).cuda()
     p2 = (torch.rand(1, m, 3, generator=gen) - 0.5).cuda()
@@ -76,7 +80,7 @@ def test_chamfer_properties(vpn, seed, p, m, impl):
     pm1, pi1, pm2, pi2 = vpn.chamfer_nn(p1, p2[:, perm].contiguous(), impl)
     assert torch.equal(pm1, m1) and torch.equal(perm[pi1.long()], i1.long())            # random reals: no exact ties
     assert torch.equal(pm2, m2[:, perm]) and torch.equal(pi2, i2[:, perm])
-    s1, si1, s2, si2 = vpn.chamfer_nn(p2, p1, impl if p2.shape[1] >= 512 else 1)
+    s1, si1, s2, si2 = vpn.chamfer_nn(p2, p1, impl if (p2.shape[1] >= 1024 and p1.shape[1] >= 128) else 1)
     assert torch.equal(s1, m2) and torch.equal(si1, i2) and torch.equal(s2, m1) and torch.equal(si2, i1)
     q1 = torch.round(p1 * 4096) / 4096; q2 = torch.round(p2 * 4096) / 4096                # 12 fractional bits
     shift = torch.tensor([4.0, -8.0, 2.0]).cuda()                                         # sums stay exact in fp32

