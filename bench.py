@@ -466,12 +466,21 @@ def measure_workload(B, workload, steps, warmup, chamfer_impl=0, graph="auto", w
         pass
     traffic = traffic_db.get(main_kernel)
     tsrc = "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of the same launch)"
-    roofline = {"kernel": main_kernel + " (main kernel of vpn_chamfer_fwd; both Chamfer directions in one launch)",
+    skipped_share = (stage.get("stages_skipped", 0) / stage["stages"]) if stage.get("stages") else 0.0
+    roofline = {"kernel": main_kernel + " (main kernel of vpn_chamfer_fwd; both Chamfer directions in one launch"
+                          + (", preceded by the target sort + pruning-bounds kernels, which are inside `ms`" if skipped_share else "") + ")",
                 "bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": "live FFMA2 stream probe (vpn_fp32_peak_probe), burst; MEASURED_PEAKS.json has no FP32 "
                                "entry; nominal 148 SM x 128 lanes x 2 x max clock given beside it",
                 "peak_nominal": nominal, "frac_of_nominal": achieved / nominal, "ms": main_ms,
                 "algorithmic_flops": flops, "traffic": traffic, "traffic_source": tsrc if traffic else None,
+                "pairs_skipped_share": skipped_share,
+                "pairs_skipped_note": "share of the 128 x 256 distance blocks (both directions) the spatial pruning proves "
+                                      "irrelevant and never evaluates (csrc/chamfer_prep.cu); `achieved` still counts the "
+                                      "reference's 8 flop for EVERY pair, so it can exceed what the pipes execute - "
+                                      "`executed` below is the evaluated part only",
+                "executed": {"tflops_fp32_equivalent": achieved * (1.0 - skipped_share),
+                             "frac_of_peak": achieved * (1.0 - skipped_share) / peak_tf},
                 "note": "achieved = 8 flop per (predicted, target) pair / kernel time, against the FP32 FMA peak the "
                         "north star names; chamfer_tc_kernel evaluates the pairs on the tensor cores (fp16-split "
                         "operands, fp32 accumulate) and is bounded by TMEM reads + FMNMX on the ALU pipe, see DESIGN.md 4.1",
@@ -487,7 +496,7 @@ def measure_workload(B, workload, steps, warmup, chamfer_impl=0, graph="auto", w
         hbm_peak, hbm_src = 6650.0, "fallback"
     if main_kernel == "chamfer_tc_kernel":
         # what the tensor pipe actually executes: a 16-term fp16 dot product per pair and direction (2 x 16 MACs = 64 flop)
-        executed = 64.0 * b * (k * n) * m / (main_ms * 1e-3) / 1e12
+        executed = 64.0 * b * (k * n) * m * (1.0 - skipped_share) / (main_ms * 1e-3) / 1e12
         roofline["tensor_executed"] = {"tflops": executed, "peak_dense_16bit": tensor_peak,
                                        "frac": (executed / tensor_peak) if tensor_peak else None,
                                        "note": "fp16 operands, fp32 accumulate, K = 16; padded tiles not counted"}
@@ -549,6 +558,7 @@ def compact(r):
         rf = r["roofline"]
         c["roofline"] = {"kernel": rf["kernel"].split(" ")[0], "bound": rf["bound"], "achieved": rf["achieved"], "peak": rf["peak"],
                          "unit": rf["unit"], "frac": rf["frac"], "ms": rf["ms"], "traffic": rf["traffic"],
+                         "pairs_skipped_share": rf.get("pairs_skipped_share"),
                          "forward_total_frac": rf["forward_total"]["frac"], "forward_total_ms": rf["forward_total"]["ms"]}
     for key in ("roofline_sampling", "roofline_raster"):
         if key in r:

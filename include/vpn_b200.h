@@ -90,6 +90,10 @@ const char* vpn_chamfer_main_kernel(int B, int P, int M, int impl);
 int vpn_chamfer_fwd_timed(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                           int B, int P, int M, void* workspace, size_t workspace_bytes, int impl, int reps,
                           float* stage_ms, void* stream);
+/* Pruning statistics of the last vpn_chamfer_fwd that used `workspace` (tensor-core filter only, else zeros): the sweep's
+ * 128 x 256 stages (both directions counted) and how many of them the spatial pruning skipped.  Synchronises. */
+int vpn_chamfer_prune_stats(const void* workspace, int B, int P, int M, int impl, unsigned long long* stages,
+                            unsigned long long* skipped, void* stream);
 /* g1 (B,P), g2 (B,M): upstream gradients of min1 / min2.  grad_p1 (B,P,3) overwritten; grad_p2 (B,M,3)
  * overwritten when not NULL.  Same result as autograd through the reference's dense graph. */
 int vpn_chamfer_bwd(const float* p1, const float* p2, const float* min1, const int* idx1,

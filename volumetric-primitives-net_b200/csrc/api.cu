@@ -49,9 +49,10 @@ static int sm_count() { return vpn::device_sm_count(); }
 int vpn::tuning_value(int key) { return (key >= 0 && key < vpn::kTuneCount) ? g_tuning[key].load(std::memory_order_relaxed) : 0; }
 
 // Test / probe hook replacing the getenv() look-ups that used to sit on the launch path.
-// key: "tiled_r" (4|8|16), "tc_nb" (4|8|16), "emd_cluster" (1|2|4|8); value 0 restores the automatic choice.
+// key: "tiled_r" (4|8|16), "tc_nb" (4|8|16), "emd_cluster" (1|2|4|8), "tc_prune" (2 = tensor-core filter without the
+// spatial pruning of chamfer_prep.cu); value 0 restores the automatic choice.
 extern "C" int vpn_set_tuning(const char* key, int value) {
-  static const char* names[vpn::kTuneCount] = {"tiled_r", "tc_nb", "emd_cluster"};
+  static const char* names[vpn::kTuneCount] = {"tiled_r", "tc_nb", "emd_cluster", "tc_prune"};
   for (int k = 0; key && k < vpn::kTuneCount; ++k)
     if (strcmp(key, names[k]) == 0) { g_tuning[k].store(value, std::memory_order_relaxed); return VPN_OK; }
   vpn_set_error("vpn_set_tuning: unknown key"); return VPN_ERR_ARG;
@@ -120,7 +121,22 @@ static int chamfer_fwd_impl(const float* p1, const float* p2, float* min1, int* 
   return rc;
 }
 
-namespace vpn { int chamfer_tiled_uses_tc(int B, int P, int M, int mode); }
+namespace vpn {
+int chamfer_tiled_uses_tc(int B, int P, int M, int mode);
+int chamfer_tiled_stats(int B, int P, int M, int mode, const void* ws, unsigned long long* out, cudaStream_t s);
+}
+// Share of the distance matrix the tensor-core filter skipped in the last vpn_chamfer_fwd on this workspace
+// (stages = 128 x 256 blocks of pairs, counted per direction).  Zero for the other implementations.  Synchronises.
+extern "C" int vpn_chamfer_prune_stats(const void* workspace, int B, int P, int M, int impl, unsigned long long* stages,
+                                       unsigned long long* skipped, void* stream) {
+  if (!workspace || !stages || !skipped || impl < 0 || impl > 5) { vpn_set_error("chamfer stats: bad arguments"); return VPN_ERR_ARG; }
+  unsigned long long out[2] = {0, 0};
+  int rc = VPN_OK;
+  if (impl != 1 && vpn::chamfer_tiled_supported(B, P, M, impl_mode(impl)))
+    rc = vpn::chamfer_tiled_stats(B, P, M, impl_mode(impl), workspace, out, (cudaStream_t)stream);
+  *stages = out[0]; *skipped = out[1];
+  return rc;
+}
 extern "C" const char* vpn_chamfer_main_kernel(int B, int P, int M, int impl) {
   if (impl < 0 || impl > 5 || B <= 0 || P <= 0 || M <= 0) return "invalid";
   if (impl != 1 && vpn::chamfer_tiled_supported(B, P, M, impl_mode(impl)))

@@ -1,0 +1,328 @@
+// Spatial preparation for the tensor-core Chamfer filter (chamfer_tc.cu): what lets it SKIP distance blocks.
+//
+// The filter evaluates the (P x M) distance matrix of modules/loss/chamfer_distance.py:14-23 in stages of 128 rows x
+// 256 columns.  A stage cannot hold any row's (column's) nearest neighbour when the two point sets are further apart
+// than a distance some point of the block is already known to achieve.  Two small kernels provide the ingredients:
+//
+//   chamfer_sort_targets_kernel   one CTA per sample: Morton-sorts the sample's targets (18-bit code, 64 cells per axis
+//       of the sample's bounding box, index in the low 14 key bits: a deterministic permutation), writes the sorted copy p2s, the
+//       permutation perm (sorted position -> original index), the axis-aligned box of every 128-column chunk, and the
+//       largest |coordinate| (the filter's scale).  After sorting a chunk is a compact patch of the target shape.
+//       Predicted points need no sorting: they arrive primitive-major (train.py:119 torch.cat(dim=1)), so 128
+//       consecutive rows are one patch of one primitive.
+//   chamfer_row_boxes_kernel      the box of every 128-row block.
+//   chamfer_prune_bounds_kernel   per 128-row block: T_r = max over its rows of an UPPER bound of the row's
+//       nearest-target distance (exact distance, the reference's arithmetic, to 4 representatives of each of the 8 chunks
+//       whose boxes are nearest to the block's box); per 128-column chunk: U_c likewise over 16 row blocks x 2 rows.
+//
+// chamfer_tc_kernel skips the stage (row block r, chunk c) for the row direction when gap(box_r, box_c)^2 > T_r and for
+// the column direction when gap^2 > U_c (both with a 1e-5 relative margin): every pair in the stage is then further
+// apart than a distance row i (column j) certainly achieves elsewhere, so neither its arg-min nor a tie can be there.
+// Results are unchanged bit for bit (the exact recovery kernels still decide); first-index ties survive the
+// permutation because recovery keys carry the ORIGINAL target index.
+#include "common.cuh"
+
+namespace vpn {
+
+constexpr int kSortThreads = 1024;
+constexpr int kSortMaxM = 16384;          // 14 index bits in the 32-bit sort key; 64 KB of keys in shared memory
+constexpr int kSortMinKeys = 1024;        // padded key count is at least one key per thread
+constexpr int kBlk = 128;                 // rows per block = columns per chunk
+
+__device__ __forceinline__ float prep_inf() { return __int_as_float(0x7f800000); }
+__device__ __forceinline__ unsigned spread6(unsigned x) {       // 6 bits -> every third bit
+  x = (x | (x << 8)) & 0x0000300Fu;
+  x = (x | (x << 4)) & 0x000030C3u;
+  x = (x | (x << 2)) & 0x00009249u;
+  return x;
+}
+__device__ __forceinline__ float prep_d2(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Box layout: 8 floats per block / chunk: lo.x lo.y lo.z hi.x hi.y hi.z pad pad.  An empty box is (+inf, -inf).
+// grid: x = sample.  dynamic smem: u32 keys[npow2] (npow2 = 0 when the sample is too large to sort: identity order)
+__global__ void __launch_bounds__(kSortThreads)
+chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2s, int* __restrict__ perm,
+                            float* __restrict__ cbox, float* __restrict__ tmax, int M, int npow2, int nchunks) {
+  extern __shared__ __align__(16) unsigned char prep_smem[];
+  unsigned* keys = reinterpret_cast<unsigned*>(prep_smem);
+  __shared__ float red[32][7];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* T = p2 + (size_t)b * M * 3;
+  float* Ts = p2s + (size_t)b * M * 3;
+  int* pm = perm + (size_t)b * M;
+  // ---- bounding box (finite values only: fminf / fmaxf drop NaN) and the NaN-sticky largest |coordinate|
+  float lo[3] = {prep_inf(), prep_inf(), prep_inf()}, hi[3] = {-prep_inf(), -prep_inf(), -prep_inf()}, am = 0.f;
+  for (int i = tid; i < M; i += kSortThreads) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float v = T[3 * (size_t)i + k];
+      lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v);
+      const float a = fabsf(v);
+      am = (a <= am) ? am : a;                                    // NaN sticks
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+    const float x = __shfl_xor_sync(0xffffffffu, am, o);
+    am = (x <= am) ? am : x;
+  }
+  if (lane == 0) { for (int k = 0; k < 3; ++k) { red[warp][k] = lo[k]; red[warp][3 + k] = hi[k]; } red[warp][6] = am; }
+  __syncthreads();
+  if (warp == 0) {
+    for (int k = 0; k < 3; ++k) { lo[k] = red[lane][k]; hi[k] = red[lane][3 + k]; }
+    am = red[lane][6];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+        hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+      }
+      const float x = __shfl_xor_sync(0xffffffffu, am, o);
+      am = (x <= am) ? am : x;
+    }
+    if (lane == 0) { for (int k = 0; k < 3; ++k) { red[0][k] = lo[k]; red[0][3 + k] = hi[k]; } tmax[b] = am; }
+  }
+  __syncthreads();
+  if (npow2 > 0) {
+    float q0[3], qs[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      q0[k] = red[0][k];
+      const float ext = red[0][3 + k] - red[0][k];
+      qs[k] = (ext > 0.f && ext < 1e30f) ? 63.999f / ext : 0.f;
+    }
+    for (int i = tid; i < npow2; i += kSortThreads) {
+      unsigned key = 0xffffffffu;
+      if (i < M) {
+        unsigned code = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float f = (T[3 * (size_t)i + k] - q0[k]) * qs[k];
+          const unsigned q = (f >= 0.f) ? (unsigned)fminf(f, 63.f) : 0u;            // NaN -> 0
+          code |= spread6(q) << k;
+        }
+        key = (code << 14) | (unsigned)i;
+      }
+      keys[i] = key;
+    }
+    __syncthreads();
+    // Bitonic sort, ascending; keys are unique (index in the low bits): the order is deterministic.  Warp w owns the
+    // aligned group of G = npow2 / 32 keys [w G, (w + 1) G): every compare-exchange at distance j < G stays inside one
+    // group, so those substeps need no block barrier (28 instead of 91 barriers for 8192 keys).
+    const int G = npow2 >> 5;
+    for (int k = 2; k <= npow2; k <<= 1) {
+      int j = k >> 1;
+      for (; j >= G; j >>= 1) {
+        for (int t = tid; t < (npow2 >> 1); t += kSortThreads) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const unsigned a = keys[i], c = keys[i | j];
+          const bool up = (i & k) == 0;
+          if ((a > c) == up) { keys[i] = c; keys[i | j] = a; }
+        }
+        __syncthreads();
+      }
+      for (; j > 0; j >>= 1) {
+        for (int t = lane; t < (G >> 1); t += 32) {
+          const int i = warp * G + (((t & ~(j - 1)) << 1) | (t & (j - 1)));
+          const unsigned a = keys[i], c = keys[i | j];
+          const bool up = (i & k) == 0;
+          if ((a > c) == up) { keys[i] = c; keys[i | j] = a; }
+        }
+        __syncwarp();
+      }
+      if (k >= G) __syncthreads();             // the next level starts with (or this was) a block-wide substep
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < M; i += kSortThreads) {
+    const int src = npow2 > 0 ? (int)(keys[i] & 0x3fffu) : i;
+    pm[i] = src;
+    Ts[3 * (size_t)i] = T[3 * (size_t)src]; Ts[3 * (size_t)i + 1] = T[3 * (size_t)src + 1]; Ts[3 * (size_t)i + 2] = T[3 * (size_t)src + 2];
+  }
+  __syncthreads();                                                 // the CTA's own global writes are visible to it
+  // ---- chunk boxes: one warp per chunk, 4 columns per lane
+  for (int c = warp; c < nchunks; c += kSortThreads / 32) {
+    float l[3] = {prep_inf(), prep_inf(), prep_inf()}, h[3] = {-prep_inf(), -prep_inf(), -prep_inf()};
+    for (int u = 0; u < 4; ++u) {
+      const int col = c * kBlk + u * 32 + lane;
+      if (col < M) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float v = Ts[3 * (size_t)col + k]; l[k] = fminf(l[k], v); h[k] = fmaxf(h[k], v); }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        l[k] = fminf(l[k], __shfl_xor_sync(0xffffffffu, l[k], o));
+        h[k] = fmaxf(h[k], __shfl_xor_sync(0xffffffffu, h[k], o));
+      }
+    }
+    if (lane == 0) {
+      float* o = cbox + ((size_t)b * nchunks + c) * 8;
+      o[0] = l[0]; o[1] = l[1]; o[2] = l[2]; o[3] = h[0]; o[4] = h[1]; o[5] = h[2]; o[6] = 0.f; o[7] = 0.f;
+    }
+  }
+}
+
+// ---- boxes of the 128-row blocks -------------------------------------------------------------------------------
+// grid: x = row block, y = sample; 128 threads
+__global__ void __launch_bounds__(kBlk)
+chamfer_row_boxes_kernel(const float* __restrict__ p1, float* __restrict__ rbox, int P, int nrb) {
+  __shared__ float red[4][6];
+  const int b = blockIdx.y, rb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row = rb * kBlk + tid;
+  float l[3] = {prep_inf(), prep_inf(), prep_inf()}, h[3] = {-prep_inf(), -prep_inf(), -prep_inf()};
+  if (row < P) {
+    const float* a = p1 + 3 * ((size_t)b * P + row);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { l[k] = fminf(l[k], a[k]); h[k] = fmaxf(h[k], a[k]); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      l[k] = fminf(l[k], __shfl_xor_sync(0xffffffffu, l[k], o));
+      h[k] = fmaxf(h[k], __shfl_xor_sync(0xffffffffu, h[k], o));
+    }
+  }
+  if (lane == 0) for (int k = 0; k < 3; ++k) { red[warp][k] = l[k]; red[warp][3 + k] = h[k]; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 4; ++w) for (int k = 0; k < 3; ++k) { l[k] = fminf(l[k], red[w][k]); h[k] = fmaxf(h[k], red[w][3 + k]); }
+    float* o = rbox + ((size_t)b * nrb + rb) * 8;
+    o[0] = l[0]; o[1] = l[1]; o[2] = l[2]; o[3] = h[0]; o[4] = h[1]; o[5] = h[2]; o[6] = 0.f; o[7] = 0.f;
+  }
+}
+
+// ---- upper bounds of the nearest-neighbour distances ---------------------------------------------------------------
+// For a block of 128 points of one cloud: pick the kNear blocks of the OTHER cloud whose boxes are closest to this
+// block's box, take kReps points of each as representatives, and give every point of the block the smallest exact
+// distance to a representative - an upper bound of its nearest-neighbour distance, tight when the neighbour lies in
+// one of the near blocks (the usual case) and still valid when it does not.  The block's bound is the max over its points.
+constexpr int kNearRows = 8, kRepsRows = 4;      // a row block looks at 8 chunks x 4 columns
+constexpr int kNearCols = 16, kRepsCols = 2;     // a chunk looks at 16 row blocks x 2 rows
+constexpr int kMaxNear = 16, kMaxReps = 32;
+constexpr int kGapCap = 4096;                    // boxes of the other cloud considered (strided subset beyond that)
+
+__device__ __forceinline__ float box_gap2(const float* __restrict__ a, const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float g = fmaxf(0.f, fmaxf(a[k] - b[3 + k], b[k] - a[3 + k]));
+    s = fmaf(g, g, s);
+  }
+  return s;
+}
+
+// grid: x = row blocks followed by chunks, y = sample; 128 threads.
+//   blocks [0, nrb)             row block rb : rthr[b][rb] = max_i min_rep d2(row i, rep)
+//   blocks [nrb, nrb + nchunks) chunk c      : cub[b][c]   = max_j min_rep d2(col j, rep)
+__global__ void __launch_bounds__(kBlk)
+chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restrict__ p2s,
+                            const float* __restrict__ rbox, const float* __restrict__ cbox,
+                            float* __restrict__ rthr, float* __restrict__ cub, int P, int M, int nrb, int nchunks) {
+  __shared__ float gap[kGapCap];
+  __shared__ float4 reps[kMaxReps];
+  __shared__ float red_v[4];
+  __shared__ int sel[kMaxNear];
+  __shared__ float mybox[8];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_row = (int)blockIdx.x < nrb;
+  const int blk = is_row ? blockIdx.x : blockIdx.x - nrb;
+  const int n_mine = is_row ? P : M, n_other = is_row ? M : P;
+  const float* mine = (is_row ? p1 + (size_t)b * P * 3 : p2s + (size_t)b * M * 3);
+  const float* other = (is_row ? p2s + (size_t)b * M * 3 : p1 + (size_t)b * P * 3);
+  const int nob = is_row ? nchunks : nrb;                                    // blocks of the other cloud
+  const float* obox = (is_row ? cbox + (size_t)b * nchunks * 8 : rbox + (size_t)b * nrb * 8);
+  const int near = is_row ? kNearRows : kNearCols, per = is_row ? kRepsRows : kRepsCols;
+  if (tid < 8) mybox[tid] = (is_row ? rbox + ((size_t)b * nrb + blk) * 8 : cbox + ((size_t)b * nchunks + blk) * 8)[tid];
+  const int idx = blk * kBlk + tid;
+  const bool valid = idx < n_mine;
+  float x = 0.f, y = 0.f, z = 0.f;
+  if (valid) { x = mine[3 * (size_t)idx]; y = mine[3 * (size_t)idx + 1]; z = mine[3 * (size_t)idx + 2]; }
+  __syncthreads();
+  const int stride = (nob + kGapCap - 1) / kGapCap, ncand = (nob + stride - 1) / stride;
+  for (int c = tid; c < ncand; c += kBlk) {
+    const float g = box_gap2(mybox, obox + (size_t)c * stride * 8);
+    gap[c] = (g == g) ? g : prep_inf();                                      // NaN boxes sort last
+  }
+  __syncthreads();
+  // kNear rounds of arg-min (value, index) with removal, by warp 0 alone (no block barriers inside); deterministic
+  const int nsel = min(near, ncand);
+  if (warp == 0) {
+    for (int s = 0; s < nsel; ++s) {
+      float bv = prep_inf(); int bi = 0x7fffffff;
+      for (int c = lane; c < ncand; c += 32) { const float g = gap[c]; if (g < bv || (g == bv && c < bi)) { bv = g; bi = c; } }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        sel[s] = (bi == 0x7fffffff) ? 0 : bi;
+        if (bi != 0x7fffffff) gap[bi] = __int_as_float(0x7fc00000);          // NaN: never selected again (comparisons false)
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const int nrep = nsel * per;
+  if (tid < nrep) {
+    const int ob = sel[tid / per] * stride;
+    int o = ob * kBlk + (tid % per) * (kBlk / per);
+    o = min(o, n_other - 1);                                                 // a clamped duplicate is still a real point of the cloud
+    reps[tid] = make_float4(other[3 * (size_t)o], other[3 * (size_t)o + 1], other[3 * (size_t)o + 2], 0.f);
+  }
+  __syncthreads();
+  float ub = prep_inf();
+  for (int r = 0; r < nrep; ++r) {
+    const float4 q = reps[r];
+    ub = fminf(ub, prep_d2(x, y, z, q.x, q.y, q.z));                         // NaN distances are dropped: ub stays +inf -> nothing is pruned
+  }
+  float m = valid ? ub : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncthreads();
+  if (lane == 0) red_v[warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 4; ++w) m = fmaxf(m, red_v[w]);
+    if (is_row) rthr[(size_t)b * nrb + blk] = m; else cub[(size_t)b * nchunks + blk] = m;
+  }
+}
+
+size_t chamfer_sort_smem_bytes(int M) {
+  if (M > kSortMaxM) return 0;
+  int n = kSortMinKeys;
+  while (n < M) n <<= 1;
+  return (size_t)n * 4;
+}
+
+int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, int* perm, float* cbox, float* rbox, float* rthr,
+                        float* cub, float* tmax, int B, int P, int M, cudaStream_t s) {
+  const int nchunks = (M + kBlk - 1) / kBlk, nrb = (P + kBlk - 1) / kBlk;
+  const size_t smem = chamfer_sort_smem_bytes(M);
+  static DeviceOnce once;
+  if (set_dyn_smem(chamfer_sort_targets_kernel, kSortMaxM * 4, once) != cudaSuccess) {
+    vpn_set_error("chamfer prep: smem attribute"); return VPN_ERR_CUDA;
+  }
+  chamfer_sort_targets_kernel<<<B, kSortThreads, smem, s>>>(p2, p2s, perm, cbox, tmax, M, (int)(smem / 4), nchunks);
+  int rc = vpn_check_launch("chamfer_sort_targets_kernel");
+  if (rc) return rc;
+  chamfer_row_boxes_kernel<<<dim3(nrb, B), kBlk, 0, s>>>(p1, rbox, P, nrb);
+  if ((rc = vpn_check_launch("chamfer_row_boxes_kernel"))) return rc;
+  chamfer_prune_bounds_kernel<<<dim3(nrb + nchunks, B), kBlk, 0, s>>>(p1, p2s, rbox, cbox, rthr, cub, P, M, nrb, nchunks);
+  return vpn_check_launch("chamfer_prune_bounds_kernel");
+}
+
+}  // namespace vpn

@@ -91,25 +91,71 @@ __global__ void chamfer_unpack_kernel(const u64* __restrict__ key, float* __rest
 // and the negatives into dL/dp2 when requested.  v == 0 gives inf * 0 = NaN, as in the reference.
 // Upstream gradient of min1/min2: either a full tensor g (B,n), or a per-sample gradient gl (B) of the fused
 // loss w1*mean(min1) + w2*mean(min2) times the scalar `scale` (= w1/P or w2/M).
-__global__ void chamfer_bwd_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
-                                        const float* __restrict__ min1, const int* __restrict__ idx1,
-                                        const float* __restrict__ g1, const float* __restrict__ gl, float scale,
-                                        float* __restrict__ gp1, float* __restrict__ gp2, int P, int M) {
+// One thread = 4 consecutive rows: the streamed operands (points 48 B, arg-mins 16 B, minima 16 B) and the result (48 B)
+// move as 16-byte accesses when the layout allows (vec_ok: P % 4 == 0 and 16-byte aligned bases); only the gathered
+// targets are scalar loads.  HBM bound: (12 + 4 + 4 + 12) B streamed + 12 B gathered per row.
+__global__ void __launch_bounds__(256)
+chamfer_bwd_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                        const float* __restrict__ min1, const int* __restrict__ idx1,
+                        const float* __restrict__ g1, const float* __restrict__ gl, float scale,
+                        float* __restrict__ gp1, float* __restrict__ gp2, int P, int M, int vec_ok) {
   const int b = blockIdx.y;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  size_t ri = (size_t)b * P + i;
-  int j = idx1[ri];
-  const float* a = p1 + 3 * ri;
-  const float* t = p2 + 3 * ((size_t)b * M + j);
-  float up = g1 ? g1[ri] : gl[b] * scale;
-  float coef = up / (2.0f * min1[ri]);
-  float cx = coef * (2.0f * (a[0] - t[0])), cy = coef * (2.0f * (a[1] - t[1])), cz = coef * (2.0f * (a[2] - t[2]));
-  gp1[3 * ri] = cx; gp1[3 * ri + 1] = cy; gp1[3 * ri + 2] = cz;
-  if (gp2) {
-    float* o = gp2 + 3 * ((size_t)b * M + j);
-    atomicAdd(o, -cx); atomicAdd(o + 1, -cy); atomicAdd(o + 2, -cz);
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= P) return;
+  const size_t r0 = (size_t)b * P + i0;
+  const int cnt = min(4, P - i0);
+  float a[12], mn[4], up[4], o[12];
+  int j[4];
+  if (vec_ok) {
+    const float4* a4 = reinterpret_cast<const float4*>(p1 + 3 * r0);
+    const float4 x0 = a4[0], x1 = a4[1], x2 = a4[2];
+    const int4 jj = *reinterpret_cast<const int4*>(idx1 + r0);
+    const float4 mm = *reinterpret_cast<const float4*>(min1 + r0);
+    a[0] = x0.x; a[1] = x0.y; a[2] = x0.z; a[3] = x0.w; a[4] = x1.x; a[5] = x1.y; a[6] = x1.z; a[7] = x1.w;
+    a[8] = x2.x; a[9] = x2.y; a[10] = x2.z; a[11] = x2.w;
+    j[0] = jj.x; j[1] = jj.y; j[2] = jj.z; j[3] = jj.w;
+    mn[0] = mm.x; mn[1] = mm.y; mn[2] = mm.z; mn[3] = mm.w;
+    if (g1) { const float4 gg = *reinterpret_cast<const float4*>(g1 + r0); up[0] = gg.x; up[1] = gg.y; up[2] = gg.z; up[3] = gg.w; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool ok = k < cnt;
+      j[k] = ok ? idx1[r0 + k] : 0; mn[k] = ok ? min1[r0 + k] : 1.f;
+      if (g1) up[k] = ok ? g1[r0 + k] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a[3 * k + c] = ok ? p1[3 * (r0 + k) + c] : 0.f;
+    }
   }
+  if (!g1) { const float u = gl[b] * scale; up[0] = up[1] = up[2] = up[3] = u; }
+  float t[12];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                          // the four gathers are in flight together
+    const float* tp = p2 + 3 * ((size_t)b * M + j[k]);
+    t[3 * k] = tp[0]; t[3 * k + 1] = tp[1]; t[3 * k + 2] = tp[2];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float coef = up[k] / (2.0f * mn[k]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[3 * k + c] = coef * (2.0f * (a[3 * k + c] - t[3 * k + c]));
+  }
+  if (vec_ok) {
+    float4* o4 = reinterpret_cast<float4*>(gp1 + 3 * r0);
+    o4[0] = make_float4(o[0], o[1], o[2], o[3]); o4[1] = make_float4(o[4], o[5], o[6], o[7]); o4[2] = make_float4(o[8], o[9], o[10], o[11]);
+  } else {
+    for (int k = 0; k < cnt; ++k) { gp1[3 * (r0 + k)] = o[3 * k]; gp1[3 * (r0 + k) + 1] = o[3 * k + 1]; gp1[3 * (r0 + k) + 2] = o[3 * k + 2]; }
+  }
+  if (gp2) {
+    for (int k = 0; k < cnt; ++k) {
+      float* q = gp2 + 3 * ((size_t)b * M + j[k]);
+      atomicAdd(q, -o[3 * k]); atomicAdd(q + 1, -o[3 * k + 1]); atomicAdd(q + 2, -o[3 * k + 2]);
+    }
+  }
+}
+
+static inline int bwd_rows_vec_ok(const float* p1, const float* min1, const int* idx1, const float* g1, const float* gp1, int P) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (P % 4 == 0) && al(p1) && al(min1) && al(idx1) && al(gp1) && (g1 == nullptr || al(g1));
 }
 
 constexpr int kSmallP = 256;      // clouds this small are accumulated in shared memory before the global scatter
@@ -264,7 +310,8 @@ extern "C" int vpn_chamfer_bwd(const float* p1, const float* p2, const float* mi
     cudaError_t e = cudaMemsetAsync(grad_p2, 0, (size_t)B * M * 3 * sizeof(float), s);
     if (e != cudaSuccess) { vpn_set_error("chamfer bwd: memset failed: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
   }
-  chamfer_bwd_rows_kernel<<<dim3((P + 255) / 256, B), 256, 0, s>>>(p1, p2, min1, idx1, g1, nullptr, 0.f, grad_p1, grad_p2, P, M);
+  chamfer_bwd_rows_kernel<<<dim3((P + 1023) / 1024, B), 256, 0, s>>>(p1, p2, min1, idx1, g1, nullptr, 0.f, grad_p1, grad_p2, P, M,
+                                                                     bwd_rows_vec_ok(p1, min1, idx1, g1, grad_p1, P));
   int rc = vpn_check_launch("chamfer_bwd_rows_kernel");
   if (rc) return rc;
   chamfer_bwd_cols_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(p1, p2, min2, idx2, g2, nullptr, 0.f, grad_p1, grad_p2, P, M);
@@ -300,8 +347,9 @@ extern "C" int vpn_chamfer_loss_bwd(const float* p1, const float* p2, const floa
   if (grad_p2 && cudaMemsetAsync(grad_p2, 0, (size_t)B * M * 3 * sizeof(float), s) != cudaSuccess) {
     vpn_set_error("chamfer loss bwd: memset failed"); return VPN_ERR_CUDA;
   }
-  chamfer_bwd_rows_kernel<<<dim3((P + 255) / 256, B), 256, 0, s>>>(p1, p2, min1, idx1, nullptr, grad_loss, w1 / (float)P,
-                                                                    grad_p1, grad_p2, P, M);
+  chamfer_bwd_rows_kernel<<<dim3((P + 1023) / 1024, B), 256, 0, s>>>(p1, p2, min1, idx1, nullptr, grad_loss, w1 / (float)P,
+                                                                     grad_p1, grad_p2, P, M,
+                                                                     bwd_rows_vec_ok(p1, min1, idx1, nullptr, grad_p1, P));
   int rc = vpn_check_launch("chamfer_bwd_rows_kernel");
   if (rc) return rc;
   chamfer_bwd_cols_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(p1, p2, min2, idx2, nullptr, grad_loss, w2 / (float)M,

@@ -26,6 +26,12 @@
 // 2.5e-4 rho^2 + 2^-20 + 2^-14 |x| (scaled units).  Measured error over random tiles (tools/tc_err.cu): 2^-19.85
 // relative, 2^-23.7 absolute for |P|+|T| < 1/4.
 //
+// Pruning (chamfer_prep.cu): the targets arrive Morton-sorted, so a 128-column chunk is a compact patch, and 128
+// consecutive rows are a patch of one primitive.  A stage whose two patches are further apart (box gap) than a distance
+// every row of the block (column of the chunk) is known to achieve elsewhere is not computed at all: the skip bits are
+// derived once per CTA in the prologue from the per-block boxes and bounds, and the MMA and epilogue warps walk the same
+// bit masks.  The row and the column direction prune independently (phase 0 / phase 1).
+//
 // CTA = 10 warps over one tile of NB x 128 rows, swept twice (D1 stages, then D2 stages): warps 0-7 read the
 // accumulators and keep the per-row candidate records in shared memory / emit the per-column records, warp 8
 // builds the C_j operands of the next 256 columns, warp 9 (one elected lane) issues the MMAs.  TMEM holds two
@@ -132,10 +138,14 @@ __device__ __forceinline__ float tc_make_operand(unsigned char* tile, int idx, f
 // dynamic shared memory carve-up (NB = row blocks per tile)
 struct TcSmem {
   unsigned char* rows; unsigned char* cols; float* rs_best; uint32_t* rs_mask; float* colw;
-  u64* bars; float* red; uint32_t* tmem_slot;
+  u64* bars; float* red; uint32_t* tmem_slot; uint32_t* skip;
 };
+// skip words: [0,64) row-direction prunable bits per chunk (bit r = row block r), [64,128) column-direction bits,
+// [128,160) phase-0 stage masks per chunk pair, [160,224) phase-1 stage masks per chunk (bit rp = row-block pair)
+constexpr int kTcSkipWords = 256;
 __host__ __device__ inline size_t tc_smem_bytes(int NB) {
-  return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 8 + 2 * (size_t)NB * kTcBlk * 4 + 16 * 8 + 64 * 4 + 16;
+  return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 8 + 2 * (size_t)NB * kTcBlk * 4 + 16 * 8 + 64 * 4 + 16 +
+         kTcSkipWords * 4;
 }
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
   TcSmem s;
@@ -146,7 +156,8 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
   s.colw = reinterpret_cast<float*>(p); p += 2 * (size_t)NB * kTcBlk * 4;         // [chunk parity][row block][column]
   s.bars = reinterpret_cast<u64*>(p); p += 16 * 8;
   s.red = reinterpret_cast<float*>(p); p += 64 * 4;
-  s.tmem_slot = reinterpret_cast<uint32_t*>(p);
+  s.tmem_slot = reinterpret_cast<uint32_t*>(p); p += 16;
+  s.skip = reinterpret_cast<uint32_t*>(p);
   return s;
 }
 
@@ -177,14 +188,43 @@ __device__ __forceinline__ float tc_lane_min128(uint32_t taddr, uint32_t empty_b
   return fminf(m0, m1);
 }
 
+// bit k of x -> bit 2k
+__device__ __forceinline__ u64 tc_spread32(uint32_t v) {
+  u64 x = v;
+  x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+  x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+  x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+  x = (x | (x << 2)) & 0x3333333333333333ull;
+  x = (x | (x << 1)) & 0x5555555555555555ull;
+  return x;
+}
+// squared gap between two axis-aligned boxes (8 floats: lo xyz, hi xyz); an empty box gives +inf
+__device__ __forceinline__ float tc_box_gap2(const float* __restrict__ a, const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float g = fmaxf(0.f, fmaxf(a[k] - b[3 + k], b[k] - a[3 + k]));
+    s = fmaf(g, g, s);
+  }
+  return s;
+}
+
+// Does pass (phase, chunk pair j) contain a stage that is not pruned?  (The operand builder and the MMA issuer must
+// agree on which column buffers exist.)
+__device__ __forceinline__ bool tc_pass_needed(bool phase0, int j, int nc, int NB, const uint32_t* skip0, const uint32_t* skip1) {
+  if (phase0) return ((~skip0[j]) & ((1u << NB) - 1u)) != 0u;
+  const uint32_t both = skip1[2 * j] & ((2 * j + 1 < nc) ? skip1[2 * j + 1] : 0xffffffffu);
+  return ((~both) & ((1u << (NB >> 1)) - 1u)) != 0u;
+}
+
 // grid: x = row tile (NB * 128 rows), y = column split, z = sample
 //
 // Work unit ("stage") = one 128-lane x 256-column accumulator: tcgen05.mma kind::f16 M=128 N=256 K=16, one commit.
-// TMEM (512 columns) holds two stages.  The column chunks of the split are taken in pairs (j, hc + j), hc = half
-// the chunks of the split: the 256-column operand buffer holds chunk j in its first half and chunk hc + j in its
-// second.
-//   phase 0 (row minima)   : stage (j, r) = R_r (128 rows) x [C_j C_{hc+j}]^T; TMEM lane = row, the thread of column
-//                            half h reduces the 128 values of chunk (h ? hc + j : j);
+// TMEM (512 columns) holds two stages.  The column chunks of the split are taken in ADJACENT pairs (2j, 2j + 1) - after
+// the Morton sort two neighbouring patches of the target shape: the 256-column operand buffer holds chunk 2j in its
+// first half and chunk 2j + 1 in its second.
+//   phase 0 (row minima)   : stage (j, r) = R_r (128 rows) x [C_2j C_2j+1]^T; TMEM lane = row, the thread of column
+//                            half h reduces the 128 values of chunk 2j + h;
 //   phase 1 (column minima): stage (chunk, rp) = C_chunk (128 columns) x [R_2rp R_2rp+1]^T; TMEM lane = column, the
 //                            thread of half h reduces over the 128 rows of block 2 rp + h.
 // Roles: warps 0-7 epilogue (warp = 4 h + q: TMEM lane quarter q, column half h), warp 8 builds the column operands,
@@ -196,6 +236,8 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                   float* __restrict__ rbest, u64* __restrict__ rmask,
                   float* __restrict__ cbest, unsigned* __restrict__ cmask,
                   float2* __restrict__ tslack, int* __restrict__ fallback, const float* __restrict__ tmax,
+                  const float* __restrict__ cbox, const float* __restrict__ rbox, const float* __restrict__ rthr,
+                  const float* __restrict__ cub, u64* __restrict__ stats, int nrb_total,
                   int P, int M, int NB, int nchunks, int cps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const TcSmem sm = tc_carve(smem_raw, NB);
@@ -295,26 +337,81 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   const int nc = c_last - c_first;             // chunks of this split (<= 64)
   const int hc = (nc + 1) >> 1;                // chunk pairs (<= 32)
   const int NP = NB >> 1;                      // row-block pairs
+  // ---- stage skip masks (see the header).  Without boxes (cbox == NULL) every stage is computed.
+  uint32_t* skipR = sm.skip; uint32_t* skipC = sm.skip + 64; uint32_t* skip0 = sm.skip + 128; uint32_t* skip1 = sm.skip + 160;
+  for (int i = tid; i < kTcSkipWords; i += kTcThreads) sm.skip[i] = 0u;
+  __syncthreads();
+  if (cbox != nullptr) {
+    for (int e = tid; e < NB * nc; e += kTcThreads) {
+      const int r = e % NB, c = e / NB, rb = tile_i * NB + r;
+      bool pr = true, pc = true;               // row blocks past the end of the cloud: nothing to compute
+      if (rb < nrb_total) {
+        const float gap2 = tc_box_gap2(rbox + ((size_t)b * nrb_total + rb) * 8, cbox + ((size_t)b * nchunks + c_first + c) * 8);
+        // every pair of the stage is at least sqrt(gap2) apart; T / U are distances the block's rows / the chunk's columns
+        // certainly achieve elsewhere (exact arithmetic).  1e-5 relative covers the roundings on both sides (~1e-6);
+        // a NaN gap or an infinite bound compares false: not skipped
+        pr = gap2 > __fmul_ru(rthr[(size_t)b * nrb_total + rb], 1.00001f);
+        pc = gap2 > __fmul_ru(cub[(size_t)b * nchunks + c_first + c], 1.00001f);
+      }
+      if (pr) atomicOr(&skipR[c], 1u << r);
+      if (pc) atomicOr(&skipC[c], 1u << r);
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < hc; j += kTcThreads)
+    skip0[j] = skipR[2 * j] & ((2 * j + 1 < nc) ? skipR[2 * j + 1] : 0xffffffffu);
+  for (int c = tid; c < nc; c += kTcThreads) {
+    const uint32_t both = skipC[c] & (skipC[c] >> 1);              // bit 2 rp: row blocks 2 rp and 2 rp + 1 both prunable
+    uint32_t m = 0;
+    for (int rp = 0; rp < NP; ++rp) m |= ((both >> (2 * rp)) & 1u) << rp;
+    skip1[c] = m;
+  }
+  __syncthreads();
+  if (tid == 0 && stats != nullptr) {
+    unsigned skipped = 0;
+    for (int j = 0; j < hc; ++j) skipped += __popc(skip0[j] & ((1u << NB) - 1u));
+    for (int c = 0; c < nc; ++c) skipped += __popc(skip1[c]);
+    atomicAdd(&stats[0], (u64)(hc * NB + nc * NP));
+    atomicAdd(&stats[1], (u64)skipped);
+  }
   if (warp == kTcEpiWarps) {
     // ===== column-operand builder (one pass per phase) =====
-    for (int cc = 0; cc < 2 * hc; ++cc) {
+    // Only passes that contain a live stage are built (buffer = built-pass count & 1).  The 24 coordinate loads of the
+    // NEXT pass are issued before this warp waits for that pass's buffer, so their latency hides behind the MMAs that
+    // still read it: with most stages pruned a pass is short, and an L2 round trip per pass would set the pace.
+    uint32_t seq = 0;
+    float tx[8], ty[8], tz[8];
+    auto next_needed = [&](int cc) { while (cc < 2 * hc && !tc_pass_needed(cc < hc, cc < hc ? cc : cc - hc, nc, NB, skip0, skip1)) ++cc; return cc; };
+    auto load_pass = [&](int cc) {
       const int j = cc < hc ? cc : cc - hc;
-      const int cb = cc & 1, use = cc >> 1;
-      tc_mbar_wait(bar_cempty + 8 * cb, (use & 1) ^ 1);
-      unsigned char* dst = sm.cols + cb * 2 * kTcBlkBytes;
-#pragma unroll 2
+#pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int jj = k * 32 + lane;                               // 0..255: half = jj >> 7
-        int chunk = c_first + ((jj >> 7) ? hc + j : j);
-        if (chunk >= c_last) chunk = c_first + j;                   // unpaired last chunk: duplicate, never recorded
+        int chunk = c_first + 2 * j + (jj >> 7);
+        if (chunk >= c_last) chunk = c_first + 2 * j;               // unpaired last chunk: duplicate, never recorded
         const int col = min(chunk * kTcBlk + (jj & 127), M - 1);
-        const float x = __fsub_rn(T[3 * (size_t)col], cx), y = __fsub_rn(T[3 * (size_t)col + 1], cy), z = __fsub_rn(T[3 * (size_t)col + 2], cz);
+        tx[k] = T[3 * (size_t)col]; ty[k] = T[3 * (size_t)col + 1]; tz[k] = T[3 * (size_t)col + 2];
+      }
+    };
+    int cc = next_needed(0);
+    if (cc < 2 * hc) load_pass(cc);
+    while (cc < 2 * hc) {
+      const int cb = seq & 1, use = seq >> 1;
+      ++seq;
+      tc_mbar_wait(bar_cempty + 8 * cb, (use & 1) ^ 1);
+      unsigned char* dst = sm.cols + cb * 2 * kTcBlkBytes;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int jj = k * 32 + lane;
+        const float x = __fsub_rn(tx[k], cx), y = __fsub_rn(ty[k], cy), z = __fsub_rn(tz[k], cz);
         const float n2 = tc_make_operand(dst + (jj >> 7) * kTcBlkBytes, jj & 127, x * S, y * S, z * S, false);
         if (!(n2 < 20000.f)) atomicOr(&fallback[b], 1);             // cannot happen for finite targets (|T| < 128)
       }
       tc_fence_async_smem();
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(bar_cfull + 8 * cb);
+      cc = next_needed(cc + 1);
+      if (cc < 2 * hc) load_pass(cc);
     }
   } else if (warp == kTcEpiWarps + 1) {
     // ===== MMA issuer: the whole warp walks the loop (warp-uniform operands), one elected lane issues =====
@@ -322,14 +419,19 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
     const uint64_t drows = tc_desc(rows_a);
     uint32_t it = 0;
+    uint32_t seq = 0;
     for (int cc = 0; cc < 2 * hc; ++cc) {
       const int j = cc < hc ? cc : cc - hc;
-      const int cb = cc & 1, cuse = cc >> 1;
+      if (!tc_pass_needed(cc < hc, j, nc, NB, skip0, skip1)) continue;
+      const int cb = seq & 1, cuse = seq >> 1;
+      ++seq;
       tc_mbar_wait(bar_cfull + 8 * cb, cuse & 1);
       tc_fence_after();
       const uint64_t dcols = tc_desc(cols_a + cb * 2 * kTcBlkBytes);
       if (cc < hc) {
-        for (int r = 0; r < NB; ++r, ++it) {
+        const uint32_t sk = skip0[j];
+        for (int r = 0; r < NB; ++r) {
+          if ((sk >> r) & 1u) continue;
           const uint32_t st = it & 1;
           tc_mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -340,12 +442,15 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
             tc_commit(bar_full + 8 * st);
           }
           __syncwarp();
+          ++it;
         }
       } else {
-        const int nh = (c_first + hc + j < c_last) ? 2 : 1;
+        const int nh = (2 * j + 1 < nc) ? 2 : 1;
         for (int h = 0; h < nh; ++h) {
           const uint64_t dc = dcols + (uint64_t)(h * (kTcBlkBytes >> 4));
-          for (int rp = 0; rp < NP; ++rp, ++it) {
+          const uint32_t sk = skip1[2 * j + h];
+          for (int rp = 0; rp < NP; ++rp) {
+            if ((sk >> rp) & 1u) continue;
             const uint32_t st = it & 1;
             tc_mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -356,6 +461,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
               tc_commit(bar_full + 8 * st);
             }
             __syncwarp();
+            ++it;
           }
         }
       }
@@ -372,12 +478,15 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     float* my_best = sm.rs_best + (size_t)h * TM;
     uint32_t* my_mask = sm.rs_mask + (size_t)h * TM;
     for (int j = 0; j < hc; ++j) {
-      const bool valid = c_first + (h ? hc + j : j) < c_last;
-      for (int r = 0; r < NB; ++r, ++it) {
+      const bool valid = 2 * j + h < nc;
+      const uint32_t sk = skip0[j];
+      for (int r = 0; r < NB; ++r) {
+        if ((sk >> r) & 1u) continue;
         const uint32_t st = it & 1;
         tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
         tc_fence_after();
         const float m = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
+        ++it;
         const int ri = r * kTcBlk + li;
         const float best = my_best[ri];
         if (valid && m <= tc_thr(best, slack_rel, slack_abs)) {
@@ -391,19 +500,22 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     // ---- phase 1: column minima per 128-row block, merged per chunk into (best, mask of row blocks)
     int cseq = 0;
     for (int j = 0; j < hc; ++j) {
-      const int nh = (c_first + hc + j < c_last) ? 2 : 1;
+      const int nh = (2 * j + 1 < nc) ? 2 : 1;
       for (int hh = 0; hh < nh; ++hh, ++cseq) {
         float* cw = sm.colw + (size_t)(cseq & 1) * NB * kTcBlk;
-        for (int rp = 0; rp < NP; ++rp, ++it) {
+        const uint32_t sk = skip1[2 * j + hh];
+        for (int rp = 0; rp < NP; ++rp) {
+          if ((sk >> rp) & 1u) { cw[(2 * rp + h) * kTcBlk + li] = tc_inf(); continue; }
           const uint32_t st = it & 1;
           tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
           tc_fence_after();
           cw[(2 * rp + h) * kTcBlk + li] = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
+          ++it;
         }
         // the two warps of this lane quarter meet once per chunk; they take turns merging
         asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
         if ((cseq & 1) == h) {
-          const int col = (c_first + (hh ? hc + j : j)) * kTcBlk + li;
+          const int col = (c_first + 2 * j + hh) * kTcBlk + li;
           if (col < M) {
             float best = tc_inf();
             for (int i = 0; i < NB; ++i) best = fminf(best, cw[i * kTcBlk + li]);
@@ -426,7 +538,8 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       const float b0 = sm.rs_best[i], b1 = sm.rs_best[TM + i];
       const float best = fminf(b0, b1);
       const float t = tc_thr(best, slack_rel, slack_abs);
-      const u64 mask = ((b0 <= t) ? (u64)sm.rs_mask[i] : 0ull) | ((b1 <= t) ? ((u64)sm.rs_mask[TM + i] << hc) : 0ull);
+      // record (h, row) bit j names chunk 2 j + h of the split: interleave the two 32-bit masks
+      const u64 mask = ((b0 <= t) ? tc_spread32(sm.rs_mask[i]) : 0ull) | ((b1 <= t) ? (tc_spread32(sm.rs_mask[TM + i]) << 1) : 0ull);
       const size_t o = ((size_t)b * nsplit + split) * P + row;
       rbest[o] = best * invS2; rmask[o] = mask;
     }
@@ -490,8 +603,11 @@ chamfer_tc_bounds_kernel(const float* __restrict__ p2, float* __restrict__ tmax,
 
 size_t chamfer_tc_smem_bytes(int NB) { return tc_smem_bytes(NB); }
 
+// p2: the targets the filter sweeps (Morton-sorted copy when cbox != NULL); tmax filled by the caller (chamfer_prep_launch)
+// when with_bounds == 0, by chamfer_tc_bounds_kernel here otherwise.
 int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
-                      float2* tslack, int* fallback, float* tmax, int B, int P, int M, int NB, int ntiles, int nsplit,
+                      float2* tslack, int* fallback, float* tmax, const float* cbox, const float* rbox, const float* rthr,
+                      const float* cub, u64* stats, int with_bounds, int B, int P, int M, int NB, int ntiles, int nsplit,
                       int nchunks, int cps, cudaStream_t s) {
   static DeviceOnce once;
   const size_t smem = tc_smem_bytes(NB);
@@ -499,10 +615,13 @@ int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask
     cudaError_t e = set_dyn_smem(chamfer_tc_kernel, (int)tc_smem_bytes(16), once);
     if (e != cudaSuccess) { vpn_set_error("chamfer tc: smem attribute: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
   }
-  chamfer_tc_bounds_kernel<<<B, 256, 0, s>>>(p2, tmax, M);
-  int rc = vpn_check_launch("chamfer_tc_bounds_kernel");
-  if (rc) return rc;
+  int rc;
+  if (with_bounds) {
+    chamfer_tc_bounds_kernel<<<B, 256, 0, s>>>(p2, tmax, M);
+    if ((rc = vpn_check_launch("chamfer_tc_bounds_kernel"))) return rc;
+  }
   chamfer_tc_kernel<<<dim3(ntiles, nsplit, B), kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax,
+                                                                      cbox, rbox, rthr, cub, stats, (P + kTcBlk - 1) / kTcBlk,
                                                                       P, M, NB, nchunks, cps);
   return vpn_check_launch("chamfer_tc_kernel");
 }

@@ -302,7 +302,9 @@ struct ExactBest {
 // positions (two predicated integer adds per value).  If the count is 1 the winner is that position and
 // v = sqrt(dm) - no index bookkeeping per value; otherwise (ties / near ties, rare) fall back to the
 // order-independent ExactBest walk.  Returns false when the unit holds no valid point.
-__device__ __forceinline__ bool unit_best(const float (&d)[32], float dm, int idx0, int rot, u64& key) {
+// With `orig` (the 32 staged float4 of the unit, .w = the point's ORIGINAL index as int bits) the key carries the original
+// index instead of the position: ties then resolve to the lowest original index although the points were permuted.
+__device__ __forceinline__ bool unit_best(const float (&d)[32], float dm, int idx0, int rot, u64& key, const float4* orig = nullptr) {
   if (!(dm < inf_f())) {                       // all padding, or genuinely infinite distances
     bool any = false;
 #pragma unroll
@@ -317,10 +319,17 @@ __device__ __forceinline__ bool unit_best(const float (&d)[32], float dm, int id
     cnt += in ? 1 : 0;
     pos += in ? kk : 0;
   }
-  if (cnt == 1) { key = ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)(idx0 + ((pos + rot) & 31)); return true; }
+  if (cnt == 1) {
+    const int at = (pos + rot) & 31;
+    key = ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)(orig ? __float_as_int(orig[at].w) : idx0 + at);
+    return true;
+  }
   ExactBest eb; eb.init();
 #pragma unroll
-  for (int kk = 0; kk < 32; ++kk) eb.offer(d[kk], idx0 + ((kk + rot) & 31));
+  for (int kk = 0; kk < 32; ++kk) {
+    const int at = (kk + rot) & 31;
+    eb.offer(d[kk], orig ? __float_as_int(orig[at].w) : idx0 + at);
+  }
   key = eb.key();
   return eb.i != 0x7fffffff;
 }
@@ -354,10 +363,11 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
                             const float* __restrict__ rbest, const u64* __restrict__ rmask,
                             const float2* __restrict__ tslack, float* __restrict__ min1, int* __restrict__ idx1,
                             int P, int M, int nchunks, int nsplit, int cps, int TM, int ntiles,
-                            const int* __restrict__ skip) {
+                            const int* __restrict__ skip, const int* __restrict__ perm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   if (skip && skip[blockIdx.y]) return;                  // sample redone by chamfer_flagged_kernel
   float4* cols = reinterpret_cast<float4*>(smem_raw);
+  const int* pm = perm ? perm + (size_t)blockIdx.y * M : nullptr;      // p2 is a permuted copy: sorted position -> original index
   __shared__ float4 rowc[kRecThreads];
   __shared__ u64 key[kRecThreads];
   __shared__ unsigned items[kItemCap];
@@ -382,8 +392,9 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
     const int seg_chunks = min(kSegChunks, nchunks - seg * kSegChunks);
     for (int i = tid; i < seg_chunks * kCW; i += kRecThreads) {
       int col = seg * kSegChunks * kCW + i;
-      cols[i] = col < M ? make_float4(T[3 * (size_t)col], T[3 * (size_t)col + 1], T[3 * (size_t)col + 2], 0.f)
-                        : make_float4(qnan, qnan, qnan, 0.f);
+      cols[i] = col < M ? make_float4(T[3 * (size_t)col], T[3 * (size_t)col + 1], T[3 * (size_t)col + 2],
+                                      __int_as_float(pm ? pm[col] : col))
+                        : make_float4(qnan, qnan, qnan, __int_as_float(0x7fffffff));
     }
     u64 segmask = 0ull;
     if (valid) {
@@ -419,7 +430,7 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
           dm = fminf(dm, d[kk]);
         }
         u64 kv;
-        if (unit_best(d, dm, gcol, lane, kv)) atomicMin(&key[r], kv);
+        if (unit_best(d, dm, gcol, lane, kv, src)) atomicMin(&key[r], kv);
       }
       __syncthreads();
     }
@@ -523,14 +534,17 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
   }
 }
 
+// perm (optional): key[i] belongs to sorted position i of its sample; the outputs are indexed by the original position
 __global__ void chamfer_unpack_key_kernel(const u64* __restrict__ key, float* __restrict__ mn, int* __restrict__ idx, size_t n,
-                                          const int* __restrict__ skip, int per_sample) {
+                                          const int* __restrict__ skip, int per_sample, const int* __restrict__ perm) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (skip && skip[i / (size_t)per_sample]) return;
+  const size_t smp = i / (size_t)per_sample;
+  if (skip && skip[smp]) return;
   u64 k = key[i];
-  mn[i] = __uint_as_float((unsigned)(k >> 32));
-  idx[i] = (int)(unsigned)(k & 0xffffffffu);
+  const size_t o = perm ? smp * (size_t)per_sample + (size_t)perm[i] : i;
+  mn[o] = __uint_as_float((unsigned)(k >> 32));
+  idx[o] = (int)(unsigned)(k & 0xffffffffu);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -541,8 +555,12 @@ struct TiledPlan { int R, ntiles, nchunks, nsplit, cps, tc, TM; };
 // chamfer_tc.cu
 size_t chamfer_tc_smem_bytes(int NB);
 int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
-                      float2* tslack, int* fallback, float* tmax, int B, int P, int M, int NB, int ntiles, int nsplit,
+                      float2* tslack, int* fallback, float* tmax, const float* cbox, const float* rbox, const float* rthr,
+                      const float* cub, u64* stats, int with_bounds, int B, int P, int M, int NB, int ntiles, int nsplit,
                       int nchunks, int cps, cudaStream_t s);
+// chamfer_prep.cu
+int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, int* perm, float* cbox, float* rbox, float* rthr,
+                        float* cub, float* tmax, int B, int P, int M, cudaStream_t s);
 int chamfer_flagged_launch(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                            const int* fallback, int B, int P, int M, cudaStream_t s);
 
@@ -605,7 +623,7 @@ static bool make_plan_tc(int B, int P, int M, int sm_count, TiledPlan& pl) {
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, tmax, cthr, key2, total; };
+struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, tmax, cthr, key2, p2s, perm, cbox, rbox, rthr, cub, total; };
 static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   TiledWs w; size_t o = 0;
   w.rbest = o; o += al256((size_t)B * pl.nsplit * P * 4);
@@ -613,10 +631,20 @@ static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   w.cbest = o; o += al256((size_t)B * pl.ntiles * M * 4);
   w.cmask = o; o += al256((size_t)B * pl.ntiles * M * 4);
   w.tslack = o; o += al256((size_t)B * pl.ntiles * 8);
-  w.fallback = o; o += al256((size_t)B * 4);
+  w.fallback = o; o += al256((size_t)B * 4 + 16);          // + 2 x u64 pruning statistics (stages, stages skipped), zeroed with the flags
   w.tmax = o; o += al256((size_t)B * 4);
   w.cthr = o; o += al256((size_t)B * M * 4);
   w.key2 = o; o += al256((size_t)B * M * 8);
+  w.p2s = w.perm = w.cbox = w.rbox = w.rthr = w.cub = 0;
+  if (pl.tc) {                                             // spatial preparation of the pruned tensor-core filter (chamfer_prep.cu)
+    const size_t nrb = (size_t)(P + 127) / 128;
+    w.p2s = o; o += al256((size_t)B * M * 12);
+    w.perm = o; o += al256((size_t)B * M * 4);
+    w.cbox = o; o += al256((size_t)B * pl.nchunks * 32);
+    w.rbox = o; o += al256((size_t)B * nrb * 32);
+    w.rthr = o; o += al256((size_t)B * nrb * 4);
+    w.cub = o; o += al256((size_t)B * pl.nchunks * 4);
+  }
   w.total = o;
   return w;
 }
@@ -644,6 +672,20 @@ size_t chamfer_tiled_workspace_bytes(int B, int P, int M, int mode) {
   TiledPlan pl;
   if (!plan_for(mode, B, P, M, pl)) return 0;
   return ws_layout(B, P, M, pl).total;
+}
+
+// Pruning statistics of the last tensor-core forward that used this workspace: out[0] = 128 x 256 stages in the sweep,
+// out[1] = stages skipped.  Synchronises the stream.
+int chamfer_tiled_stats(int B, int P, int M, int mode, const void* ws_, unsigned long long* out, cudaStream_t s) {
+  TiledPlan pl;
+  out[0] = out[1] = 0;
+  if (!plan_for(mode, B, P, M, pl) || !pl.tc) return VPN_OK;
+  TiledWs wl = ws_layout(B, P, M, pl);
+  const char* src = reinterpret_cast<const char*>(ws_) + wl.fallback + (((size_t)B * 4 + 7) & ~(size_t)7);
+  if (cudaMemcpyAsync(out, src, 16, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+    vpn_set_error("chamfer stats: copy failed"); return VPN_ERR_CUDA;
+  }
+  return VPN_OK;
 }
 
 template <int R, int MODE>
@@ -708,14 +750,28 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   const int* skip = nullptr;
   int rc;
   if (ev) cudaEventRecord(ev[0], s);
+  const size_t flag_bytes = (((size_t)B * 4 + 7) & ~(size_t)7) + 16;      // per-sample flags + the two u64 statistics words
   if (mode == MODE_EXPAND || mode == MODE_TC) {
-    if (cudaMemsetAsync(fallback, 0, (size_t)B * 4, s) != cudaSuccess) { vpn_set_error("chamfer tiled: memset failed"); return VPN_ERR_CUDA; }
+    if (cudaMemsetAsync(fallback, 0, flag_bytes, s) != cudaSuccess) { vpn_set_error("chamfer tiled: memset failed"); return VPN_ERR_CUDA; }
   }
+  const float* p2w = p2;                       // the targets the sweep and the recovery kernels read
+  const int* perm = nullptr;                   // sorted position -> original index (tensor-core mode)
   if (mode == MODE_TC) {
-    rc = chamfer_tc_launch(p1, p2, reinterpret_cast<float*>(ws + wl.rbest), reinterpret_cast<u64*>(ws + wl.rmask),
+    float* p2s = reinterpret_cast<float*>(ws + wl.p2s);
+    int* pm = reinterpret_cast<int*>(ws + wl.perm);
+    float* cbox = reinterpret_cast<float*>(ws + wl.cbox); float* rbox = reinterpret_cast<float*>(ws + wl.rbox);
+    float* rthr = reinterpret_cast<float*>(ws + wl.rthr); float* cub = reinterpret_cast<float*>(ws + wl.cub);
+    float* tmax = reinterpret_cast<float*>(ws + wl.tmax);
+    u64* stats = reinterpret_cast<u64*>(ws + wl.fallback + (((size_t)B * 4 + 7) & ~(size_t)7));
+    const bool prune = tuning_value(kTuneTcPrune) != 2;                      // vpn_set_tuning("tc_prune", 2): unpruned sweep
+    if (prune) {
+      if ((rc = chamfer_prep_launch(p1, p2, p2s, pm, cbox, rbox, rthr, cub, tmax, B, P, M, s))) return rc;
+      p2w = p2s; perm = pm;
+    }
+    rc = chamfer_tc_launch(p1, p2w, reinterpret_cast<float*>(ws + wl.rbest), reinterpret_cast<u64*>(ws + wl.rmask),
                            reinterpret_cast<float*>(ws + wl.cbest), reinterpret_cast<unsigned*>(ws + wl.cmask),
-                           reinterpret_cast<float2*>(ws + wl.tslack), fallback, reinterpret_cast<float*>(ws + wl.tmax), B, P, M, pl.R, pl.ntiles, pl.nsplit,
-                           pl.nchunks, pl.cps, s);
+                           reinterpret_cast<float2*>(ws + wl.tslack), fallback, tmax, prune ? cbox : nullptr, rbox, rthr, cub, stats,
+                           prune ? 0 : 1, B, P, M, pl.R, pl.ntiles, pl.nsplit, pl.nchunks, pl.cps, s);
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[1], s);
     // samples outside the filter's validity range (non-finite / huge coordinates): exact brute force, recovery skips them
@@ -736,8 +792,8 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
       vpn_set_error("chamfer tiled: smem attribute (rows recovery)"); return VPN_ERR_CUDA;
     }
     chamfer_recover_rows_kernel<<<dim3((P + kRecThreads - 1) / kRecThreads, B), kRecThreads, smem_rows, s>>>(
-        p1, p2, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
-        reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nchunks, pl.nsplit, pl.cps, pl.TM, pl.ntiles, skip);
+        p1, p2w, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
+        reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nchunks, pl.nsplit, pl.cps, pl.TM, pl.ntiles, skip, perm);
     if ((rc = vpn_check_launch("chamfer_recover_rows_kernel"))) return rc;
   }
   if (ev) cudaEventRecord(ev[3], s);
@@ -751,9 +807,9 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   if ((rc = vpn_check_launch("chamfer_col_thr_kernel"))) return rc;
   if (pl.tc) {
     switch (pl.R) {
-      case 16: rc = launch_recover_cols<16, true>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
-      case 8:  rc = launch_recover_cols<8, true>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
-      default: rc = launch_recover_cols<4, true>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
+      case 16: rc = launch_recover_cols<16, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
+      case 8:  rc = launch_recover_cols<8, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
+      default: rc = launch_recover_cols<4, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
     }
   } else {
     switch (pl.R) {
@@ -765,7 +821,7 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   if (rc) return rc;
   {
     size_t n = (size_t)B * M;
-    chamfer_unpack_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(key2, min2, idx2, n, skip, M);
+    chamfer_unpack_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(key2, min2, idx2, n, skip, M, perm);
   }
   rc = vpn_check_launch("chamfer_unpack_key_kernel");
   if (ev) cudaEventRecord(ev[4], s);

@@ -240,6 +240,10 @@ def chamfer_nn_stage_ms(points1: torch.Tensor, points2: torch.Tensor, impl: int 
                                     nb.value, impl, reps, ms, stream_ptr(dev)), "vpn_chamfer_fwd_timed")
     out = dict(zip(("main", "fallback", "rows", "cols"), [float(x) for x in ms]))
     out["total"] = sum(out.values())
+    stages, skipped = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    check(lib.vpn_chamfer_prune_stats(ptr(ws), b, p, m, impl, ctypes.byref(stages), ctypes.byref(skipped), stream_ptr(dev)),
+          "vpn_chamfer_prune_stats")
+    out["stages"], out["stages_skipped"] = int(stages.value), int(skipped.value)
     return out
 
 
