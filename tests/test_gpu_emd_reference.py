@@ -74,14 +74,17 @@ def clouds(kind, b, n, gen):
     raise KeyError(kind)
 
 
-@pytest.mark.parametrize("kind,b,n,eps,iters", [
-    ("uniform", 32, 2048, 0.005, 50),          # train.py:188-195 / train_gcn.py:91-95 setting, B = 32
-    ("surface", 32, 2048, 0.005, 50),
-    ("clustered", 8, 2048, 0.005, 50),
-    ("uniform", 4, 1024, 0.002, 100),
-    ("uniform", 2, 8192, 0.05, 30),            # emd_module.py:81-86 smoke shape (shorter)
+@pytest.mark.parametrize("kind,b,n,eps,iters,per_sample", [
+    ("uniform", 32, 2048, 0.005, 50, 0.03),          # train.py:188-195 / train_gcn.py:91-95 setting, B = 32
+    ("surface", 32, 2048, 0.005, 50, 0.03),
+    # degenerate start of training (every prediction within 0.05 of the centre: all bidders want the same objects and the
+    # 50 iterations end far from convergence).  The reference moves by up to 3 % between two runs on the SAME sample
+    # here; single samples of this kernel land up to 6 % from the reference's mean, the batch mean within 1 %.
+    ("clustered", 8, 2048, 0.005, 50, 0.08),
+    ("uniform", 4, 1024, 0.002, 100, 0.03),
+    ("uniform", 2, 8192, 0.05, 30, 0.03),            # emd_module.py:81-86 smoke shape (shorter)
 ])
-def test_emd_matches_reference_kernels(ref_emd, kind, b, n, eps, iters):
+def test_emd_matches_reference_kernels(ref_emd, kind, b, n, eps, iters, per_sample):
     import vpn_b200
     fwd, _ = ref_emd
     gen = torch.Generator().manual_seed(4242 + n + iters)
@@ -100,13 +103,11 @@ def test_emd_matches_reference_kernels(ref_emd, kind, b, n, eps, iters):
     emd_our = torch.sqrt(d_our).mean(1).cpu().numpy()
     # The loss value (mean over the batch): within 1 % of the reference's.
     np.testing.assert_allclose(emd_our.mean(), emd_ref.mean(), rtol=0.01)
-    # Single samples: within 3 %, or within 3x the reference's own run-to-run range where that is larger.  The range is
-    # taken as the largest one over the batch (three runs underestimate a single sample's range): an auction cut off at
-    # `iters` far from convergence - the clustered case, where the reference moves by ~3 % between runs on the SAME
-    # input - is decided by its tie races, which this kernel resolves deterministically (lowest index).
+    # Single samples: within `per_sample` of the reference's mean over its three runs (3 % for the training-like clouds).
+    # The auction's tie races, which the reference leaves to the hardware and this kernel resolves deterministically
+    # (lowest index), decide individual assignments; the recorded spread documents how far the reference is from itself.
     spread = float((emd_runs.max(0) - emd_runs.min(0)).max())
-    tol = np.maximum(0.03 * emd_ref, 3.0 * spread)
-    assert (np.abs(emd_our - emd_ref) <= tol).all(), (emd_our, emd_ref, spread)
+    assert (np.abs(emd_our - emd_ref) <= per_sample * emd_ref).all(), (emd_our, emd_ref, spread)
     uniq_ref = np.array([a.unique().numel() for a in a_ref]) / n
     uniq_our = np.array([a.unique().numel() for a in a_our]) / n
     assert abs(uniq_our.mean() - uniq_ref.mean()) <= 0.01, (uniq_our, uniq_ref)

@@ -42,7 +42,8 @@ __device__ __forceinline__ float prep_d2(float ax, float ay, float az, float bx,
 }
 
 // Box layout: 8 floats per block / chunk: lo.x lo.y lo.z hi.x hi.y hi.z pad pad.  An empty box is (+inf, -inf).
-// grid: x = sample.  dynamic smem: u32 keys[npow2] (npow2 = 0 when the sample is too large to sort: identity order)
+// grid: x = sample.  dynamic smem: u32 keys[npow2] (npow2 = 0 when the sample is too large to sort: identity order).
+// (Batching each thread's compare-exchanges of a substep - all loads first - was measured slower: 91 vs 62 us.)
 __global__ void __launch_bounds__(kSortThreads)
 chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2s, int* __restrict__ perm,
                             float* __restrict__ cbox, float* __restrict__ tmax, int M, int npow2, int nchunks) {
@@ -212,7 +213,8 @@ chamfer_row_boxes_kernel(const float* __restrict__ p1, float* __restrict__ rbox,
 constexpr int kNearRows = 8, kRepsRows = 4;      // a row block looks at 8 chunks x 4 columns
 constexpr int kNearCols = 16, kRepsCols = 2;     // a chunk looks at 16 row blocks x 2 rows
 constexpr int kMaxNear = 16, kMaxReps = 32;
-constexpr int kGapCap = 4096;                    // boxes of the other cloud considered (strided subset beyond that)
+constexpr int kGapCap = 1024;                    // boxes of the other cloud considered per block (strided subset beyond that)
+constexpr int kBoundWarps = 4;                   // blocks of 128 points per CTA: one per warp, no block-level barrier
 
 __device__ __forceinline__ float box_gap2(const float* __restrict__ a, const float* __restrict__ b) {
   float s = 0.f;
@@ -224,81 +226,84 @@ __device__ __forceinline__ float box_gap2(const float* __restrict__ a, const flo
   return s;
 }
 
-// grid: x = row blocks followed by chunks, y = sample; 128 threads.
+// grid: x = groups of kBoundWarps blocks (row blocks first, then chunks), y = sample; one WARP per block of 128 points,
+// 4 points per lane (the first version gave a block a whole CTA: 58 % of its stall samples were the three other warps
+// waiting at barriers for warp 0's selection rounds).
 //   blocks [0, nrb)             row block rb : rthr[b][rb] = max_i min_rep d2(row i, rep)
 //   blocks [nrb, nrb + nchunks) chunk c      : cub[b][c]   = max_j min_rep d2(col j, rep)
-__global__ void __launch_bounds__(kBlk)
+__global__ void __launch_bounds__(kBoundWarps * 32)
 chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restrict__ p2s,
                             const float* __restrict__ rbox, const float* __restrict__ cbox,
                             float* __restrict__ rthr, float* __restrict__ cub, int P, int M, int nrb, int nchunks) {
-  __shared__ float gap[kGapCap];
-  __shared__ float4 reps[kMaxReps];
-  __shared__ float red_v[4];
-  __shared__ int sel[kMaxNear];
-  __shared__ float mybox[8];
-  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool is_row = (int)blockIdx.x < nrb;
-  const int blk = is_row ? blockIdx.x : blockIdx.x - nrb;
+  __shared__ float s_gap[kBoundWarps][kGapCap];
+  __shared__ float4 s_reps[kBoundWarps][kMaxReps];
+  __shared__ int s_sel[kBoundWarps][kMaxNear];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int id = blockIdx.x * kBoundWarps + warp;
+  if (id >= nrb + nchunks) return;                                           // warp-uniform
+  float* gap = s_gap[warp]; float4* reps = s_reps[warp]; int* sel = s_sel[warp];
+  const bool is_row = id < nrb;
+  const int blk = is_row ? id : id - nrb;
   const int n_mine = is_row ? P : M, n_other = is_row ? M : P;
   const float* mine = (is_row ? p1 + (size_t)b * P * 3 : p2s + (size_t)b * M * 3);
   const float* other = (is_row ? p2s + (size_t)b * M * 3 : p1 + (size_t)b * P * 3);
   const int nob = is_row ? nchunks : nrb;                                    // blocks of the other cloud
   const float* obox = (is_row ? cbox + (size_t)b * nchunks * 8 : rbox + (size_t)b * nrb * 8);
   const int near = is_row ? kNearRows : kNearCols, per = is_row ? kRepsRows : kRepsCols;
-  if (tid < 8) mybox[tid] = (is_row ? rbox + ((size_t)b * nrb + blk) * 8 : cbox + ((size_t)b * nchunks + blk) * 8)[tid];
-  const int idx = blk * kBlk + tid;
-  const bool valid = idx < n_mine;
-  float x = 0.f, y = 0.f, z = 0.f;
-  if (valid) { x = mine[3 * (size_t)idx]; y = mine[3 * (size_t)idx + 1]; z = mine[3 * (size_t)idx + 2]; }
-  __syncthreads();
+  const float* mb = is_row ? rbox + ((size_t)b * nrb + blk) * 8 : cbox + ((size_t)b * nchunks + blk) * 8;
+  float mybox[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) mybox[k] = mb[k];
+  float x[4], y[4], z[4]; bool valid[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int idx = blk * kBlk + u * 32 + lane;
+    valid[u] = idx < n_mine;
+    x[u] = y[u] = z[u] = 0.f;
+    if (valid[u]) { x[u] = mine[3 * (size_t)idx]; y[u] = mine[3 * (size_t)idx + 1]; z[u] = mine[3 * (size_t)idx + 2]; }
+  }
   const int stride = (nob + kGapCap - 1) / kGapCap, ncand = (nob + stride - 1) / stride;
-  for (int c = tid; c < ncand; c += kBlk) {
+  for (int c = lane; c < ncand; c += 32) {
     const float g = box_gap2(mybox, obox + (size_t)c * stride * 8);
     gap[c] = (g == g) ? g : prep_inf();                                      // NaN boxes sort last
   }
-  __syncthreads();
-  // kNear rounds of arg-min (value, index) with removal, by warp 0 alone (no block barriers inside); deterministic
+  __syncwarp();
+  // `near` rounds of arg-min (value, index) with removal; deterministic
   const int nsel = min(near, ncand);
-  if (warp == 0) {
-    for (int s = 0; s < nsel; ++s) {
-      float bv = prep_inf(); int bi = 0x7fffffff;
-      for (int c = lane; c < ncand; c += 32) { const float g = gap[c]; if (g < bv || (g == bv && c < bi)) { bv = g; bi = c; } }
+  for (int s = 0; s < nsel; ++s) {
+    float bv = prep_inf(); int bi = 0x7fffffff;
+    for (int c = lane; c < ncand; c += 32) { const float g = gap[c]; if (g < bv || (g == bv && c < bi)) { bv = g; bi = c; } }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      if (lane == 0) {
-        sel[s] = (bi == 0x7fffffff) ? 0 : bi;
-        if (bi != 0x7fffffff) gap[bi] = __int_as_float(0x7fc00000);          // NaN: never selected again (comparisons false)
-      }
-      __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
+    if (lane == 0) {
+      sel[s] = (bi == 0x7fffffff) ? 0 : bi;
+      if (bi != 0x7fffffff) gap[bi] = __int_as_float(0x7fc00000);            // NaN: never selected again (comparisons false)
+    }
+    __syncwarp();
   }
-  __syncthreads();
   const int nrep = nsel * per;
-  if (tid < nrep) {
-    const int ob = sel[tid / per] * stride;
-    int o = ob * kBlk + (tid % per) * (kBlk / per);
+  if (lane < nrep) {
+    const int ob = sel[lane / per] * stride;
+    int o = ob * kBlk + (lane % per) * (kBlk / per);
     o = min(o, n_other - 1);                                                 // a clamped duplicate is still a real point of the cloud
-    reps[tid] = make_float4(other[3 * (size_t)o], other[3 * (size_t)o + 1], other[3 * (size_t)o + 2], 0.f);
+    reps[lane] = make_float4(other[3 * (size_t)o], other[3 * (size_t)o + 1], other[3 * (size_t)o + 2], 0.f);
   }
-  __syncthreads();
-  float ub = prep_inf();
+  __syncwarp();
+  float ub[4] = {prep_inf(), prep_inf(), prep_inf(), prep_inf()};
   for (int r = 0; r < nrep; ++r) {
     const float4 q = reps[r];
-    ub = fminf(ub, prep_d2(x, y, z, q.x, q.y, q.z));                         // NaN distances are dropped: ub stays +inf -> nothing is pruned
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ub[u] = fminf(ub[u], prep_d2(x[u], y[u], z[u], q.x, q.y, q.z));   // NaN distances are dropped: +inf -> nothing pruned
   }
-  float m = valid ? ub : 0.f;
+  float m = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) if (valid[u]) m = fmaxf(m, ub[u]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  __syncthreads();
-  if (lane == 0) red_v[warp] = m;
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < 4; ++w) m = fmaxf(m, red_v[w]);
-    if (is_row) rthr[(size_t)b * nrb + blk] = m; else cub[(size_t)b * nchunks + blk] = m;
-  }
+  if (lane == 0) { if (is_row) rthr[(size_t)b * nrb + blk] = m; else cub[(size_t)b * nchunks + blk] = m; }
 }
 
 size_t chamfer_sort_smem_bytes(int M) {
@@ -321,7 +326,8 @@ int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, int* perm,
   if (rc) return rc;
   chamfer_row_boxes_kernel<<<dim3(nrb, B), kBlk, 0, s>>>(p1, rbox, P, nrb);
   if ((rc = vpn_check_launch("chamfer_row_boxes_kernel"))) return rc;
-  chamfer_prune_bounds_kernel<<<dim3(nrb + nchunks, B), kBlk, 0, s>>>(p1, p2s, rbox, cbox, rthr, cub, P, M, nrb, nchunks);
+  chamfer_prune_bounds_kernel<<<dim3((nrb + nchunks + kBoundWarps - 1) / kBoundWarps, B), kBoundWarps * 32, 0, s>>>(
+      p1, p2s, rbox, cbox, rthr, cub, P, M, nrb, nchunks);
   return vpn_check_launch("chamfer_prune_bounds_kernel");
 }
 

@@ -429,9 +429,8 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       tc_fence_after();
       const uint64_t dcols = tc_desc(cols_a + cb * 2 * kTcBlkBytes);
       if (cc < hc) {
-        const uint32_t sk = skip0[j];
-        for (int r = 0; r < NB; ++r) {
-          if ((sk >> r) & 1u) continue;
+        for (uint32_t live = ~skip0[j] & ((1u << NB) - 1u); live; live &= live - 1) {
+          const int r = __ffs((int)live) - 1;
           const uint32_t st = it & 1;
           tc_mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -448,9 +447,8 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         const int nh = (2 * j + 1 < nc) ? 2 : 1;
         for (int h = 0; h < nh; ++h) {
           const uint64_t dc = dcols + (uint64_t)(h * (kTcBlkBytes >> 4));
-          const uint32_t sk = skip1[2 * j + h];
-          for (int rp = 0; rp < NP; ++rp) {
-            if ((sk >> rp) & 1u) continue;
+          for (uint32_t live = ~skip1[2 * j + h] & ((1u << NP) - 1u); live; live &= live - 1) {
+            const int rp = __ffs((int)live) - 1;
             const uint32_t st = it & 1;
             tc_mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -477,11 +475,12 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     // ---- phase 0: row minima; record (h, row): best value and the mask of chunk pairs j whose chunk may hold the arg-min
     float* my_best = sm.rs_best + (size_t)h * TM;
     uint32_t* my_mask = sm.rs_mask + (size_t)h * TM;
+    const uint32_t nbmask = (1u << NB) - 1u, npmask = (1u << NP) - 1u;
     for (int j = 0; j < hc; ++j) {
       const bool valid = 2 * j + h < nc;
-      const uint32_t sk = skip0[j];
-      for (int r = 0; r < NB; ++r) {
-        if ((sk >> r) & 1u) continue;
+      // only the live stages are visited (a per-stage `if skipped continue` cost as many instructions as the stages left)
+      for (uint32_t live = ~skip0[j] & nbmask; live; live &= live - 1) {
+        const int r = __ffs((int)live) - 1;
         const uint32_t st = it & 1;
         tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
         tc_fence_after();
@@ -501,31 +500,45 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     int cseq = 0;
     for (int j = 0; j < hc; ++j) {
       const int nh = (2 * j + 1 < nc) ? 2 : 1;
-      for (int hh = 0; hh < nh; ++hh, ++cseq) {
+      for (int hh = 0; hh < nh; ++hh) {
+        const uint32_t live1 = ~skip1[2 * j + hh] & npmask;          // row-block pairs of this chunk that are computed
+        if (live1 == 0u) {
+          // chunk pruned for the whole tile: record (+inf, no candidate) - it is never a candidate in the recovery.  No
+          // shared buffer, no barrier, and it does not take part in the two warps' alternation (cseq counts live chunks).
+          const int col = (c_first + 2 * j + hh) * kTcBlk + li;
+          if (h == hh && col < M) { const size_t o = ((size_t)b * ntiles + tile_i) * M + col; cbest[o] = tc_inf(); cmask[o] = 0u; }
+          continue;
+        }
         float* cw = sm.colw + (size_t)(cseq & 1) * NB * kTcBlk;
-        const uint32_t sk = skip1[2 * j + hh];
-        for (int rp = 0; rp < NP; ++rp) {
-          if ((sk >> rp) & 1u) { cw[(2 * rp + h) * kTcBlk + li] = tc_inf(); continue; }
+        for (uint32_t live = live1; live; live &= live - 1) {
+          const int rp = __ffs((int)live) - 1;
           const uint32_t st = it & 1;
           tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
           tc_fence_after();
           cw[(2 * rp + h) * kTcBlk + li] = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
           ++it;
         }
-        // the two warps of this lane quarter meet once per chunk; they take turns merging
+        // the two warps of this lane quarter meet once per live chunk; they take turns merging
         asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
         if ((cseq & 1) == h) {
           const int col = (c_first + 2 * j + hh) * kTcBlk + li;
           if (col < M) {
             float best = tc_inf();
-            for (int i = 0; i < NB; ++i) best = fminf(best, cw[i * kTcBlk + li]);
+            for (uint32_t live = live1; live; live &= live - 1) {
+              const int i = 2 * (__ffs((int)live) - 1);
+              best = tc_min3(best, cw[i * kTcBlk + li], cw[(i + 1) * kTcBlk + li]);
+            }
             const float t = tc_thr(best, slack_rel, slack_abs);
             unsigned mask = 0;
-            for (int i = 0; i < NB; ++i) mask |= (cw[i * kTcBlk + li] <= t) ? (1u << i) : 0u;
+            for (uint32_t live = live1; live; live &= live - 1) {
+              const int i = 2 * (__ffs((int)live) - 1);
+              mask |= ((cw[i * kTcBlk + li] <= t) ? (1u << i) : 0u) | ((cw[(i + 1) * kTcBlk + li] <= t) ? (2u << i) : 0u);
+            }
             const size_t o = ((size_t)b * ntiles + tile_i) * M + col;
             cbest[o] = best * invS2; cmask[o] = mask;
           }
         }
+        ++cseq;
       }
     }
   }

@@ -33,6 +33,7 @@
 // additions as fma(x, 1.0, y) with the 1.0 passed as a kernel argument, which rounds exactly like
 // an add and cannot be contracted.
 #include <cstdlib>
+#include <mutex>
 #include "common.cuh"
 
 namespace vpn {
@@ -737,6 +738,31 @@ static int launch_recover_cols(const float* p1, const float* p2, const float* cb
   return vpn_check_launch("chamfer_recover_cols_kernel");
 }
 
+// The row recovery and the column recovery chain (threshold, recovery, unpack) are independent and each leaves most of
+// an SM idle (ncu: 60 % / 28 % issue utilisation; a 131 KB and a 33 KB CTA fit one SM together), so the column chain is
+// forked onto a per-device side stream and joined before the call returns control of `s` - under CUDA-graph capture
+// the fork / join becomes two parallel branches.  The side stream and its two events are created on first use outside
+// a capture (never during one: the call then runs the chain serially) and the enqueue section is serialised per
+// device, so concurrent host threads cannot interleave their event records.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; std::mutex mu; };
+static SideStream g_side[64];
+static SideStream* side_stream_for(cudaStream_t s) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& ss = g_side[dev];
+  if (ss.ok) return &ss;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lock(ss.mu);
+  if (!ss.ok) {
+    if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ss.ok = true;
+  }
+  return &ss;
+}
+
 // mode: -1 auto, 0 exact, 1 diff, 2 expand, 3 tensor-core filter.  events (optional, 5 entries) bracket the stages.
 int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                       int B, int P, int M, void* ws_, size_t ws_bytes, int mode, cudaStream_t s, cudaEvent_t* ev) {
@@ -785,6 +811,15 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
     }
   }
   if (ev) cudaEventRecord(ev[2], s);
+  // fork: the column chain runs on the side stream `sc`, the row recovery on `s`
+  SideStream* side = tuning_value(kTuneSerialRecovery) ? nullptr : side_stream_for(s);
+  std::unique_lock<std::mutex> side_lock;
+  cudaStream_t sc = s;
+  if (side) {
+    side_lock = std::unique_lock<std::mutex>(side->mu);
+    if (cudaEventRecord(side->fork, s) == cudaSuccess && cudaStreamWaitEvent(side->s, side->fork, 0) == cudaSuccess) sc = side->s;
+    else { cudaGetLastError(); side = nullptr; side_lock.unlock(); }
+  }
   {
     static DeviceOnce once_rows;
     const size_t smem_rows = (size_t)(pl.nchunks < kSegChunks ? pl.nchunks : kSegChunks) * kCW * sizeof(float4);
@@ -796,34 +831,39 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
         reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nchunks, pl.nsplit, pl.cps, pl.TM, pl.ntiles, skip, perm);
     if ((rc = vpn_check_launch("chamfer_recover_rows_kernel"))) return rc;
   }
-  if (ev) cudaEventRecord(ev[3], s);
+  if (ev) cudaEventRecord(ev[3], s);          // with the fork: end of the row recovery; [3]..[4] = what the column chain adds after it
   const float* cb = reinterpret_cast<const float*>(ws + wl.cbest);
   const unsigned* cmk = reinterpret_cast<const unsigned*>(ws + wl.cmask);
   const float2* tsl = reinterpret_cast<const float2*>(ws + wl.tslack);
   float* cthr = reinterpret_cast<float*>(ws + wl.cthr);
   u64* key2 = reinterpret_cast<u64*>(ws + wl.key2);
-  if (cudaMemsetAsync(key2, 0xFF, (size_t)B * M * 8, s) != cudaSuccess) { vpn_set_error("chamfer tiled: memset failed"); return VPN_ERR_CUDA; }
-  chamfer_col_thr_kernel<<<dim3((M + 255) / 256, B), 256, 0, s>>>(cb, tsl, cthr, M, pl.ntiles);
+  if (cudaMemsetAsync(key2, 0xFF, (size_t)B * M * 8, sc) != cudaSuccess) { vpn_set_error("chamfer tiled: memset failed"); return VPN_ERR_CUDA; }
+  chamfer_col_thr_kernel<<<dim3((M + 255) / 256, B), 256, 0, sc>>>(cb, tsl, cthr, M, pl.ntiles);
   if ((rc = vpn_check_launch("chamfer_col_thr_kernel"))) return rc;
   if (pl.tc) {
     switch (pl.R) {
-      case 16: rc = launch_recover_cols<16, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
-      case 8:  rc = launch_recover_cols<8, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
-      default: rc = launch_recover_cols<4, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
+      case 16: rc = launch_recover_cols<16, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
+      case 8:  rc = launch_recover_cols<8, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
+      default: rc = launch_recover_cols<4, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
     }
   } else {
     switch (pl.R) {
-      case 16: rc = launch_recover_cols<16, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
-      case 8:  rc = launch_recover_cols<8, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
-      default: rc = launch_recover_cols<4, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, s); break;
+      case 16: rc = launch_recover_cols<16, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
+      case 8:  rc = launch_recover_cols<8, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
+      default: rc = launch_recover_cols<4, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
     }
   }
   if (rc) return rc;
   {
     size_t n = (size_t)B * M;
-    chamfer_unpack_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(key2, min2, idx2, n, skip, M, perm);
+    chamfer_unpack_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sc>>>(key2, min2, idx2, n, skip, M, perm);
   }
   rc = vpn_check_launch("chamfer_unpack_key_kernel");
+  if (side) {                                  // join
+    if (cudaEventRecord(side->join, sc) != cudaSuccess || cudaStreamWaitEvent(s, side->join, 0) != cudaSuccess) {
+      vpn_set_error("chamfer tiled: stream join failed"); rc = VPN_ERR_CUDA;
+    }
+  }
   if (ev) cudaEventRecord(ev[4], s);
   return rc;
 }

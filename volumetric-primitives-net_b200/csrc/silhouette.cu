@@ -145,85 +145,62 @@ __device__ __forceinline__ bool inside_tri(const FaceRec& r, float X, float Y, f
   return w0 >= 0.f && w1 >= 0.f && w2 >= 0.f;
 }
 
-// Shared tile walker: calls fn(face_index, record, tight bbox) for the faces binned to this tile that can touch the
-// calling WARP's pixels, in index order.  All threads of the CTA must call it; fn is invoked per thread (pixel).
-// Two culls before any per-pixel work: groups of 32 faces whose union box (sil_faces_kernel) misses the tile are never
-// loaded, and batches of 8 such groups are skipped entirely; of the binned faces, 32 at a time are tested by the lanes
-// against the warp's own pixel block (wxL..wyT: pixel-centre extent of the warp's 8 x 4 pixels) and only the hits are walked.
+// Warp-autonomous face walker: calls fn(face_index, record, tight bbox) on every lane for the faces that can touch the
+// calling WARP's 8 x 4 pixel block (wxL..wyT: pixel-centre extent), in face-index order, with no block-level barrier.
+// (A CTA-cooperative binning was measured first: 41 % of its stall samples were warps waiting at the per-batch
+// __syncthreads for the warp with the most faces - profiles/r02a_ncu_lines_raster.md.)
+//   1. groups of 32 consecutive faces whose union box (sil_faces_kernel) misses the block are never loaded: the lanes
+//      test 32 group boxes at a time;
+//   2. of a live group, lane l holds face 32 g + l and tests its expanded box against the block; the hits are broadcast
+//      one by one (7 shuffles) and every lane runs fn on its own pixel.
+// The next live group's records are in flight while the current group's hits are walked.
 template <typename Fn>
-__device__ __forceinline__ void walk_tile_faces(const FaceRec* __restrict__ rec, const float4* __restrict__ group_box,
-                                                int F, float xL, float xR, float yB, float yT,
-                                                float wxL, float wxR, float wyB, float wyT, float em, int cull_soft, Fn fn) {
-  __shared__ FaceRec s_rec[kRThreads];
-  __shared__ float4 s_box[kRThreads];                  // tight bbox: xmin, xmax, ymin, ymax
-  __shared__ int s_idx[kRThreads];
-  __shared__ int s_wcount[kRThreads / 32];
-  __shared__ unsigned s_glive[64];                     // one bit per 32-face group whose box touches the tile (F <= 65535)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nbatch = (F + kRThreads - 1) / kRThreads, ngroups = nbatch * 8;
-  // All group boxes are tested at once (one parallel round of loads; a serial walk over the batches paid an L2 round
-  // trip per batch: 40 % of the kernel's stall samples).  Batch k = byte k of the bit array, warp w of a batch = bit w.
-  for (int g0 = 0; g0 < ngroups; g0 += kRThreads) {
-    const int g = g0 + tid;
+__device__ __forceinline__ void walk_warp_faces(const FaceRec* __restrict__ rec, const float4* __restrict__ group_box,
+                                                int F, float wxL, float wxR, float wyB, float wyT, float em, int cull_soft,
+                                                Fn fn) {
+  const int lane = threadIdx.x & 31;
+  const int ngroups = (F + 31) >> 5;
+  for (int g0 = 0; g0 < ngroups; g0 += 32) {
     bool live = false;
-    if (g < ngroups) {
-      const float4 bb = group_box[g];
-      live = bb.x <= xR && bb.y > xL && bb.z <= yT && bb.w > yB;
+    if (g0 + lane < ngroups) {
+      const float4 bb = group_box[g0 + lane];
+      live = bb.x <= wxR && bb.y > wxL && bb.z <= wyT && bb.w > wyB;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, live);
-    if (lane == 0) s_glive[g >> 5] = bal;
-  }
-  __syncthreads();
-  auto next_live = [&](int k) { while (k < nbatch && ((s_glive[k >> 2] >> ((k & 3) * 8)) & 0xffu) == 0u) ++k; return k; };
-  int kb = next_live(0);
-  FaceRec rnext;
-  bool have = false;
-  if (kb < nbatch) {
-    have = ((s_glive[kb >> 2] >> ((kb & 3) * 8 + warp)) & 1u) && kb * kRThreads + tid < F;
-    if (have) rnext = rec[kb * kRThreads + tid];
-  }
-  while (kb < nbatch) {
-    const int f = kb * kRThreads + tid;
-    bool hit = false;
-    const FaceRec r = rnext;
-    float4 tb;
-    if (have) {
-      tb = make_float4(min3(r.ax, r.bx, r.cx), max3(r.ax, r.bx, r.cx), min3(r.ay, r.by, r.cy), max3(r.ay, r.by, r.cy));
-      float xmin = __fsub_rn(tb.x, em), xmax = __fadd_rn(tb.y, em);
-      float ymin = __fsub_rn(tb.z, em), ymax = __fadd_rn(tb.w, em);
-      hit = (r.front > 0.5f || !cull_soft) && xmin <= xR && xmax > xL && ymin <= yT && ymax > yB;
-    }
-    // the next live batch's records are in flight while this batch is binned and walked
-    const int kn = next_live(kb + 1);
-    have = false;
-    if (kn < nbatch) {
-      have = ((s_glive[kn >> 2] >> ((kn & 3) * 8 + warp)) & 1u) && kn * kRThreads + tid < F;
-      if (have) rnext = rec[kn * kRThreads + tid];
-    }
-    unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) s_wcount[warp] = __popc(bal);
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kRThreads / 32; ++w) { int c = s_wcount[w]; if (w < warp) base += c; total += c; }
-    if (hit) {
-      int slot = base + __popc(bal & ((1u << lane) - 1u));
-      s_rec[slot] = r; s_box[slot] = tb; s_idx[slot] = f;
-    }
-    __syncthreads();
-    for (int k0 = 0; k0 < total; k0 += 32) {
-      bool mine = false;
-      if (k0 + lane < total) {
-        const float4 b4 = s_box[k0 + lane];
-        mine = __fsub_rn(b4.x, em) <= wxR && __fadd_rn(b4.y, em) > wxL && __fsub_rn(b4.z, em) <= wyT && __fadd_rn(b4.w, em) > wyB;
+    unsigned groups = __ballot_sync(0xffffffffu, live);
+    if (!groups) continue;
+    int g = g0 + __ffs((int)groups) - 1;
+    groups &= groups - 1;
+    FaceRec rnext;
+    bool have = g * 32 + lane < F;
+    if (have) rnext = rec[g * 32 + lane];
+    while (true) {
+      const FaceRec r = rnext;
+      const int fbase = g * 32;
+      bool hit = false;
+      if (have) {
+        const float xmin = __fsub_rn(min3(r.ax, r.bx, r.cx), em), xmax = __fadd_rn(max3(r.ax, r.bx, r.cx), em);
+        const float ymin = __fsub_rn(min3(r.ay, r.by, r.cy), em), ymax = __fadd_rn(max3(r.ay, r.by, r.cy), em);
+        hit = (r.front > 0.5f || !cull_soft) && xmin <= wxR && xmax > wxL && ymin <= wyT && ymax > wyB;
       }
-      for (unsigned bits = __ballot_sync(0xffffffffu, mine); bits; bits &= bits - 1) {
-        const int k = k0 + __ffs((int)bits) - 1;
-        fn(s_idx[k], s_rec[k], s_box[k]);
+      const bool more = groups != 0u;
+      if (more) {
+        g = g0 + __ffs((int)groups) - 1;
+        groups &= groups - 1;
+        have = g * 32 + lane < F;
+        if (have) rnext = rec[g * 32 + lane];
       }
+      for (unsigned bits = __ballot_sync(0xffffffffu, hit); bits; bits &= bits - 1) {
+        const int src = __ffs((int)bits) - 1;
+        FaceRec q;
+        q.ax = __shfl_sync(0xffffffffu, r.ax, src); q.ay = __shfl_sync(0xffffffffu, r.ay, src);
+        q.bx = __shfl_sync(0xffffffffu, r.bx, src); q.by = __shfl_sync(0xffffffffu, r.by, src);
+        q.cx = __shfl_sync(0xffffffffu, r.cx, src); q.cy = __shfl_sync(0xffffffffu, r.cy, src);
+        q.front = __shfl_sync(0xffffffffu, r.front, src); q.pad = 0.f;
+        const float4 tb = make_float4(min3(q.ax, q.bx, q.cx), max3(q.ax, q.bx, q.cx), min3(q.ay, q.by, q.cy), max3(q.ay, q.by, q.cy));
+        fn(fbase + src, q, tb);
+      }
+      if (!more) break;
     }
-    __syncthreads();
-    kb = kn;
   }
 }
 
@@ -255,61 +232,52 @@ __device__ __forceinline__ TileLists tile_lists(unsigned char* p) {
 constexpr size_t kTileListBytesFwd = kKnumMax * kRThreads * (sizeof(float) + sizeof(unsigned short));
 constexpr size_t kTileListBytesBwd = kTileListBytesFwd + kKnumMax * kRThreads;
 
-// Exclusive prefix sum of cnt over the CTA's 256 threads into s_off[0..256] (s_off[256] = total).
-__device__ __forceinline__ void tile_offsets(int cnt, int* s_off, int* s_wsum) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Exclusive prefix sum of cnt over the warp's 32 pixels; *total = sum.
+__device__ __forceinline__ int warp_offsets(int cnt, int* total) {
+  const int lane = threadIdx.x & 31;
   int inc = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-  if (lane == 31) s_wsum[warp] = inc;
-  __syncthreads();
-  int base = 0;
-#pragma unroll
-  for (int w = 0; w < kRThreads / 32; ++w) if (w < warp) base += s_wsum[w];
-  s_off[tid] = base + inc - cnt;
-  if (tid == kRThreads - 1) s_off[kRThreads] = base + inc;
-  __syncthreads();
+  *total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - cnt;
 }
-// pixel p of the tile that owns work item `it`: largest p with s_off[p] <= it
-__device__ __forceinline__ int item_pixel(const int* s_off, int it) {
-  int lo = 0, hi = kRThreads - 1;
+// lane (pixel of the warp) that owns work item `it`: largest p with off_p <= it (off = this lane's exclusive offset)
+__device__ __forceinline__ int item_lane(int off, int it) {
+  int lo = 0, hi = 31;
 #pragma unroll
-  for (int step = 0; step < 8; ++step) {
+  for (int step = 0; step < 5; ++step) {
     const int mid = (lo + hi + 1) >> 1;
-    if (s_off[mid] <= it) lo = mid; else hi = mid - 1;
+    if (__shfl_sync(0xffffffffu, off, mid) <= it) lo = mid; else hi = mid - 1;
   }
   return lo;
 }
 
 // The soft term costs ~200 instructions per (pixel, face) pair and only a few pixels of a warp lie inside a face's
-// expanded box, so the tile is done in three passes:
-//   A  pixel-parallel, cheap: walk the binned faces in index order; coverage test; remember the first knum candidates
-//   B  work-parallel, dense : one (pixel, candidate) item per thread - distance, prob          (all lanes busy)
+// expanded box, so a warp does its 8 x 4 pixel block in three passes (warp-synchronous, no block barrier anywhere):
+//   A  pixel-parallel, cheap: walk the faces in index order; coverage test; remember the first knum candidates
+//   B  work-parallel, dense : one (pixel, candidate) item per lane - distance, prob            (all lanes busy)
 //   C  pixel-parallel       : product of the pixel's factors in candidate order (the order DIB-R multiplies in)
-// grid: x = tile x, y = tile y, z = sample
+// grid: x = tile x, y = tile y, z = sample; CTA = 8 warps = one 16 x 16 tile
 __global__ void __launch_bounds__(kRThreads)
 sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restrict__ box_all, float* __restrict__ alpha,
                       unsigned char* __restrict__ covered_out, RasterParams rp) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  __shared__ int s_off[kRThreads + 1];
-  __shared__ int s_wsum[kRThreads / 32];
   const TileLists tl = tile_lists(s_dyn);
-  const int b = blockIdx.z, tid = threadIdx.x;
+  const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
   int px, py; tile_px(tid, px, py);
   const int w = blockIdx.x * kTile + px, h = blockIdx.y * kTile + py;
   const bool in_img = (w < rp.W && h < rp.H);
+  if (!__any_sync(0xffffffffu, in_img)) return;
   const FaceRec* rec = rec_all + (size_t)b * rp.F;
   float X, Y; pixel_coords(rp, min(w, rp.W - 1), min(h, rp.H - 1), X, Y);
-  // pixel-centre extent of the tile and of this warp's 8 x 4 block (x grows with w, y shrinks with h)
-  float xL, xR, yT, yB, wxL, wxR, wyT, wyB;
-  pixel_coords(rp, blockIdx.x * kTile, blockIdx.y * kTile, xL, yT);
-  pixel_coords(rp, min(blockIdx.x * kTile + kTile - 1, rp.W - 1), min(blockIdx.y * kTile + kTile - 1, rp.H - 1), xR, yB);
+  // pixel-centre extent of this warp's 8 x 4 block (x grows with w, y shrinks with h)
+  float wxL, wxR, wyT, wyB;
   pixel_coords(rp, min(w - (px & 7), rp.W - 1), min(h - (py & 3), rp.H - 1), wxL, wyT);
   pixel_coords(rp, min(w - (px & 7) + 7, rp.W - 1), min(h - (py & 3) + 3, rp.H - 1), wxR, wyB);
   const float em = __fmul_rn(rp.expand, rp.mult);
   bool covered = false; int cnt = 0;
   const float4* boxes = box_all + (size_t)b * ((rp.F + kRThreads - 1) / kRThreads) * 8;
-  walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, wxL, wxR, wyB, wyT, em, rp.cull_soft, [&](int f, const FaceRec& r, const float4& tb) {
+  walk_warp_faces(rec, boxes, rp.F, wxL, wxR, wyB, wyT, em, rp.cull_soft, [&](int f, const FaceRec& r, const float4& tb) {
     if (covered) return;                                // alpha is 1 whatever follows
     const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
     if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
@@ -318,20 +286,23 @@ sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
     if (cnt < rp.knum) { tl.cand[cnt * kRThreads + tid] = (unsigned short)f; ++cnt; }
   });
   const int mine = (in_img && !covered) ? cnt : 0;
-  tile_offsets(mine, s_off, s_wsum);
-  const int total = s_off[kRThreads];
-  for (int it = tid; it < total; it += kRThreads) {
-    const int p = item_pixel(s_off, it), k = it - s_off[p];
-    const FaceRec r = rec[tl.cand[k * kRThreads + p]];
-    float PX, PY;
-    int qx, qy; tile_px(p, qx, qy);
-    pixel_coords(rp, min((int)(blockIdx.x * kTile) + qx, rp.W - 1), min((int)(blockIdx.y * kTile) + qy, rp.H - 1), PX, PY);
-    int which;
-    const float d2 = tri_dist2(r, PX, PY, rp.mult, rp.eps, which);
-    const float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
-    tl.fac[k * kRThreads + p] = __fsub_rn(1.0f, expf(-z));
+  int total;
+  const int off = warp_offsets(mine, &total);
+  __syncwarp();
+  for (int it = lane; it < ((total + 31) & ~31); it += 32) {
+    const bool on = it < total;
+    const int pl = item_lane(off, on ? it : 0);                           // all lanes take part in the shuffles
+    const int k = it - __shfl_sync(0xffffffffu, off, pl);
+    const float PX = __shfl_sync(0xffffffffu, X, pl), PY = __shfl_sync(0xffffffffu, Y, pl);
+    if (on) {
+      const FaceRec r = rec[tl.cand[k * kRThreads + wbase + pl]];
+      int which;
+      const float d2 = tri_dist2(r, PX, PY, rp.mult, rp.eps, which);
+      const float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
+      tl.fac[k * kRThreads + wbase + pl] = __fsub_rn(1.0f, expf(-z));
+    }
   }
-  __syncthreads();
+  __syncwarp();
   if (in_img) {
     float prod = 1.0f;
     for (int k = 0; k < mine; ++k) prod = __fmul_rn(prod, tl.fac[k * kRThreads + tid]);
@@ -342,24 +313,19 @@ sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
 }
 
 // Backward of the soft term: d alpha / d (scaled screen coords of the recorded faces).  Same three passes; pass C is
-// work-parallel too: one (pixel, candidate) item per thread, scattered into the per-face buffer with atomics.
+// work-parallel too: one (pixel, candidate) item per lane, scattered into the per-face buffer with atomics.
 __global__ void __launch_bounds__(kRThreads)
 sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restrict__ box_all, const float* __restrict__ galpha,
                       const unsigned char* __restrict__ covered_in, float* __restrict__ gface, RasterParams rp) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  __shared__ int s_off[kRThreads + 1];
-  __shared__ int s_wsum[kRThreads / 32];
-  __shared__ float s_g[kRThreads];
   const TileLists tl = tile_lists(s_dyn);
-  const int b = blockIdx.z, tid = threadIdx.x;
+  const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
   int px, py; tile_px(tid, px, py);
   const int w = blockIdx.x * kTile + px, h = blockIdx.y * kTile + py;
   const bool in_img = (w < rp.W && h < rp.H);
   const FaceRec* rec = rec_all + (size_t)b * rp.F;
   float X, Y; pixel_coords(rp, min(w, rp.W - 1), min(h, rp.H - 1), X, Y);
-  float xL, xR, yT, yB, wxL, wxR, wyT, wyB;
-  pixel_coords(rp, blockIdx.x * kTile, blockIdx.y * kTile, xL, yT);
-  pixel_coords(rp, min(blockIdx.x * kTile + kTile - 1, rp.W - 1), min(blockIdx.y * kTile + kTile - 1, rp.H - 1), xR, yB);
+  float wxL, wxR, wyT, wyB;
   pixel_coords(rp, min(w - (px & 7), rp.W - 1), min(h - (py & 3), rp.H - 1), wxL, wyT);
   pixel_coords(rp, min(w - (px & 7) + 7, rp.W - 1), min(h - (py & 3) + 3, rp.H - 1), wxR, wyB);
   const float em = __fmul_rn(rp.expand, rp.mult);
@@ -369,35 +335,42 @@ sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
     g = galpha[o];
     active = (covered_in[o] == 0) && (g != 0.f);
   }
-  s_g[tid] = g;
+  if (!__any_sync(0xffffffffu, active)) return;         // blocks without an uncovered pixel that has a gradient do nothing
   int cnt = 0;
   const float4* boxes = box_all + (size_t)b * ((rp.F + kRThreads - 1) / kRThreads) * 8;
-  if (__syncthreads_or(active)) {                       // tiles without an uncovered pixel that has a gradient do nothing
-    walk_tile_faces(rec, boxes, rp.F, xL, xR, yB, yT, wxL, wxR, wyB, wyT, em, rp.cull_soft, [&](int f, const FaceRec& r, const float4& tb) {
-      if (!active || cnt >= rp.knum) return;
-      const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
-      if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
-      tl.cand[cnt * kRThreads + tid] = (unsigned short)f; ++cnt;
-    });
-  }
-  tile_offsets(cnt, s_off, s_wsum);
-  const int total = s_off[kRThreads];
+  walk_warp_faces(rec, boxes, rp.F, wxL, wxR, wyB, wyT, em, rp.cull_soft, [&](int f, const FaceRec& r, const float4& tb) {
+    if (!active || cnt >= rp.knum) return;
+    const float txmin = tb.x, txmax = tb.y, tymin = tb.z, tymax = tb.w;
+    if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
+    tl.cand[cnt * kRThreads + tid] = (unsigned short)f; ++cnt;
+  });
+  int total;
+  const int off = warp_offsets(cnt, &total);
   if (total == 0) return;
-  for (int it = tid; it < total; it += kRThreads) {
-    const int p = item_pixel(s_off, it), k = it - s_off[p];
-    const FaceRec r = rec[tl.cand[k * kRThreads + p]];
-    float PX, PY;
-    int qx, qy; tile_px(p, qx, qy);
-    pixel_coords(rp, min((int)(blockIdx.x * kTile) + qx, rp.W - 1), min((int)(blockIdx.y * kTile) + qy, rp.H - 1), PX, PY);
-    int which;
-    const float d2 = tri_dist2(r, PX, PY, rp.mult, rp.eps, which);
-    const float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
-    tl.fac[k * kRThreads + p] = expf(-z);
-    tl.which[k * kRThreads + p] = (unsigned char)which;
+  __syncwarp();
+  const int padded = (total + 31) & ~31;
+  for (int it = lane; it < padded; it += 32) {
+    const bool on = it < total;
+    const int pl = item_lane(off, on ? it : 0);
+    const int k = it - __shfl_sync(0xffffffffu, off, pl);
+    const float PX = __shfl_sync(0xffffffffu, X, pl), PY = __shfl_sync(0xffffffffu, Y, pl);
+    if (on) {
+      const FaceRec r = rec[tl.cand[k * kRThreads + wbase + pl]];
+      int which;
+      const float d2 = tri_dist2(r, PX, PY, rp.mult, rp.eps, which);
+      const float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
+      tl.fac[k * kRThreads + wbase + pl] = expf(-z);
+      tl.which[k * kRThreads + wbase + pl] = (unsigned char)which;
+    }
   }
-  __syncthreads();
-  for (int it = tid; it < total; it += kRThreads) {
-    const int p = item_pixel(s_off, it), k = it - s_off[p], n = s_off[p + 1] - s_off[p];
+  __syncwarp();
+  for (int it = lane; it < padded; it += 32) {
+    const bool on = it < total;
+    const int pl = item_lane(off, on ? it : 0);
+    const int offp = __shfl_sync(0xffffffffu, off, pl), n = __shfl_sync(0xffffffffu, cnt, pl);
+    const float PX = __shfl_sync(0xffffffffu, X, pl), PY = __shfl_sync(0xffffffffu, Y, pl), gp = __shfl_sync(0xffffffffu, g, pl);
+    if (!on) continue;
+    const int k = it - offp, p = wbase + pl;
     // alpha = 1 - prod_j (1 - p_j);  d alpha / d p_k = prod_{j != k} (1 - p_j), multiplied in the order prefix * suffix
     float prefix = 1.0f, suffix = 1.0f;
     for (int j = 0; j < k; ++j) prefix *= (1.0f - tl.fac[j * kRThreads + p]);
@@ -407,11 +380,8 @@ sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
     const int which = tl.which[k * kRThreads + p];
     const int f = tl.cand[k * kRThreads + p];
     const FaceRec r = rec[f];
-    float PX, PY;
-    int qx, qy; tile_px(p, qx, qy);
-    pixel_coords(rp, min((int)(blockIdx.x * kTile) + qx, rp.W - 1), min((int)(blockIdx.y * kTile) + qy, rp.H - 1), PX, PY);
     // p = exp(-delta d2 / mult^2)  ->  dp/dd2 = -p delta / mult^2
-    const float gd2 = s_g[p] * dadp * (-prob) * rp.delta / (rp.mult * rp.mult);
+    const float gd2 = gp * dadp * (-prob) * rp.delta / (rp.mult * rp.mult);
     float gr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float vx[3] = {r.ax, r.bx, r.cx}, vy[3] = {r.ay, r.by, r.cy};
     if (which < 3) {

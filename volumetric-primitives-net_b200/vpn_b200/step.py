@@ -32,6 +32,7 @@ class PrimitiveLossConfig:
     chamfer_impl: int = ops.CHAMFER_AUTO
     vertex_chamfer: bool = False      # train_gcn.py:127-130: the Chamfer term scores the composed mesh vertices, not samples
     soft_cull_backfaces: bool = False  # rasteriser soft pass: False = DIB-R (back faces culled by the coverage pass only)
+    overlap_silhouette: bool = True   # run mesh -> silhouette -> image loss on a second stream, concurrently with the Chamfer terms
 
 
 class PrimitiveLoss:
@@ -83,6 +84,26 @@ class PrimitiveLoss:
             out[name] = val
             total = val if total is None else total + val
 
+        # The silhouette branch (mesh vertices -> rasteriser -> image loss) shares nothing with the Chamfer terms but the
+        # primitives: it is forked onto a second stream and joined before the sum.  The rasteriser is latency bound and
+        # leaves most of every SM idle (one 131 KB Chamfer CTA + raster CTAs fit an SM together), so the two overlap almost
+        # completely, forward and backward (autograd runs a node's backward on the stream of its forward).  Under CUDA-graph
+        # capture the fork / join becomes two parallel branches of the graph.
+        sil_term, side = None, None
+        if cfg.l_sil:
+            fork = cfg.overlap_silhouette and v.is_cuda and (cfg.l_view_cd or cfg.l_can_cd or cfg.l_vp_div)
+            if sil_cameras is None:
+                self.default_cameras(b, v.device)          # cached constants are created on the caller's stream, before the fork
+            self.composed_faces(k, v.device)
+            if fork:
+                cur = torch.cuda.current_stream(v.device)
+                side = self._side_stream(v.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    sil_term, out["alpha"] = self._silhouette_term(v, q, t, verts, silhouettes, sil_cameras)
+                    sil_term.record_stream(cur); out["alpha"].record_stream(cur)
+            else:
+                sil_term, out["alpha"] = self._silhouette_term(v, q, t, verts, silhouettes, sil_cameras)
         if cfg.l_view_cd:
             add("view_cd", ops.chamfer_distance(points, view_center_points, w1=cfg.cd_w1, w2=cfg.cd_w2,
                                                 impl=cfg.chamfer_impl) * cfg.l_view_cd)
@@ -93,24 +114,38 @@ class PrimitiveLoss:
         if cfg.l_vp_div:
             add("vp_div", ops.chamfer_distance(t.contiguous(), view_center_points, w1=0.5, w2=1.0,
                                                impl=cfg.chamfer_impl) * cfg.l_vp_div)
-        if cfg.l_sil:
-            if verts is None:
-                tv, _ = templates.template(cfg.kind, v.device)
-                verts = ops.mesh_vertices(tv, v, q, t)
-            faces = self.composed_faces(k, v.device)
-            h, w = silhouettes.shape[-2:]
-            if sil_cameras is None:
-                rot, pos = self.default_cameras(b, v.device)
-            else:
-                sd, se, sa = sil_cameras
-                rot, pos = ops.look_at_cameras(sa, se, sd)
-            alpha, _, _ = ops.soft_silhouette(verts, faces, rot, pos, h, w, soft_cull_backfaces=cfg.soft_cull_backfaces)
-            diff = alpha[:, None] - silhouettes
-            sil = diff.abs().mean() if cfg.silhouette_loss == "L1" else (diff * diff).mean()
-            out["alpha"] = alpha
-            add("sil", sil * cfg.l_sil)
+        if sil_term is not None:
+            if side is not None:
+                torch.cuda.current_stream(v.device).wait_stream(side)
+            add("sil", sil_term)
         out["total"] = total
         return out
+
+    def _side_stream(self, device):
+        key = ("side", str(device))
+        cache = self.__dict__.setdefault("_streams", {})
+        if key not in cache:
+            cache[key] = torch.cuda.Stream(device=device)
+        return cache[key]
+
+    def _silhouette_term(self, v, q, t, verts, silhouettes, sil_cameras):
+        """l_sil * L1|MSE(soft alpha, gt) and alpha (train.py:123-149,166-176; silhouette.py:13-23)."""
+        cfg = self.cfg
+        b, k = q.shape[:2]
+        if verts is None:
+            tv, _ = templates.template(cfg.kind, v.device)
+            verts = ops.mesh_vertices(tv, v, q, t)
+        faces = self.composed_faces(k, v.device)
+        h, w = silhouettes.shape[-2:]
+        if sil_cameras is None:
+            rot, pos = self.default_cameras(b, v.device)
+        else:
+            sd, se, sa = sil_cameras
+            rot, pos = ops.look_at_cameras(sa, se, sd)
+        alpha, _, _ = ops.soft_silhouette(verts, faces, rot, pos, h, w, soft_cull_backfaces=cfg.soft_cull_backfaces)
+        diff = alpha[:, None] - silhouettes
+        sil = diff.abs().mean() if cfg.silhouette_loss == "L1" else (diff * diff).mean()
+        return sil * cfg.l_sil, alpha
 
 
 class GraphedPrimitiveLoss:
