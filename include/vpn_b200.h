@@ -94,6 +94,9 @@ int vpn_chamfer_fwd_timed(const float* p1, const float* p2, float* min1, int* id
  * 128 x 256 stages (both directions counted) and how many of them the spatial pruning skipped.  Synchronises. */
 int vpn_chamfer_prune_stats(const void* workspace, int B, int P, int M, int impl, unsigned long long* stages,
                             unsigned long long* skipped, void* stream);
+/* Probe: the filter's 16 counters - [0] stages, [1] skipped, [2..5] cycles of one epilogue warp summed over the CTAs
+ * (prologue, row phase, column phase, tail), [6] / [7] live stages per phase, [8] live chunks, [9] operand passes built. */
+int vpn_chamfer_tc_counters(const void* workspace, int B, int P, int M, int impl, unsigned long long* out16, void* stream);
 /* g1 (B,P), g2 (B,M): upstream gradients of min1 / min2.  grad_p1 (B,P,3) overwritten; grad_p2 (B,M,3)
  * overwritten when not NULL.  Same result as autograd through the reference's dense graph. */
 int vpn_chamfer_bwd(const float* p1, const float* p2, const float* min1, const int* idx1,

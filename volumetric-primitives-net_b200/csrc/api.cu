@@ -130,12 +130,21 @@ int chamfer_tiled_stats(int B, int P, int M, int mode, const void* ws, unsigned 
 extern "C" int vpn_chamfer_prune_stats(const void* workspace, int B, int P, int M, int impl, unsigned long long* stages,
                                        unsigned long long* skipped, void* stream) {
   if (!workspace || !stages || !skipped || impl < 0 || impl > 5) { vpn_set_error("chamfer stats: bad arguments"); return VPN_ERR_ARG; }
-  unsigned long long out[2] = {0, 0};
+  unsigned long long out[16] = {0};
   int rc = VPN_OK;
   if (impl != 1 && vpn::chamfer_tiled_supported(B, P, M, impl_mode(impl)))
     rc = vpn::chamfer_tiled_stats(B, P, M, impl_mode(impl), workspace, out, (cudaStream_t)stream);
   *stages = out[0]; *skipped = out[1];
   return rc;
+}
+// All 16 counters of the tensor-core filter (probe): [0] stages, [1] skipped, [2..5] cycles of epilogue warp 0 summed over
+// the CTAs (prologue, phase 0, phase 1, tail), [6] / [7] live stages of phase 0 / 1, [8] live chunks, [9] operand passes.
+extern "C" int vpn_chamfer_tc_counters(const void* workspace, int B, int P, int M, int impl, unsigned long long* out16, void* stream) {
+  if (!workspace || !out16 || impl < 0 || impl > 5) { vpn_set_error("chamfer counters: bad arguments"); return VPN_ERR_ARG; }
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  if (impl != 1 && vpn::chamfer_tiled_supported(B, P, M, impl_mode(impl)))
+    return vpn::chamfer_tiled_stats(B, P, M, impl_mode(impl), workspace, out16, (cudaStream_t)stream);
+  return VPN_OK;
 }
 extern "C" const char* vpn_chamfer_main_kernel(int B, int P, int M, int impl) {
   if (impl < 0 || impl > 5 || B <= 0 || P <= 0 || M <= 0) return "invalid";

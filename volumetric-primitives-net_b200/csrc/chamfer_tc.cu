@@ -240,6 +240,9 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                   const float* __restrict__ cub, u64* __restrict__ stats, int nrb_total,
                   int P, int M, int NB, int nchunks, int cps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+#ifdef VPN_TC_COUNTERS
+  const long long t_start = clock64();
+#endif
   const TcSmem sm = tc_carve(smem_raw, NB);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_i = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
@@ -367,13 +370,40 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     skip1[c] = m;
   }
   __syncthreads();
-  if (tid == 0 && stats != nullptr) {
-    unsigned skipped = 0;
-    for (int j = 0; j < hc; ++j) skipped += __popc(skip0[j] & ((1u << NB) - 1u));
-    for (int c = 0; c < nc; ++c) skipped += __popc(skip1[c]);
-    atomicAdd(&stats[0], (u64)(hc * NB + nc * NP));
-    atomicAdd(&stats[1], (u64)skipped);
+  // statistics: stats[0] stages, stats[1] stages skipped - counted by the MMA warp's lanes in parallel, two atomics per CTA
+  // (thread 0 doing it alone, plus cycle counters, delayed epilogue warp 0 and with it every stage: +3 %).  A probe build
+  // (-DVPN_TC_COUNTERS) adds the cycle counters of epilogue warp 0: [2] prologue, [3] row phase, [4] column phase, [5]
+  // tail, and [6] / [7] live stages per phase, [8] live chunks, [9] operand passes built.
+  if (warp == kTcEpiWarps + 1 && stats != nullptr) {
+    unsigned s0 = 0, s1 = 0;
+    for (int j = lane; j < hc; j += 32) s0 += __popc(skip0[j] & ((1u << NB) - 1u));
+    for (int c = lane; c < nc; c += 32) s1 += __popc(skip1[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (lane == 0) {
+      atomicAdd(&stats[0], (u64)(hc * NB + nc * NP));
+      atomicAdd(&stats[1], (u64)(s0 + s1));
+#ifdef VPN_TC_COUNTERS
+      atomicAdd(&stats[6], (u64)(hc * NB - s0));
+      atomicAdd(&stats[7], (u64)(nc * NP - s1));
+#endif
+    }
   }
+#ifdef VPN_TC_COUNTERS
+  long long t_mark = 0;
+  if (tid == 0 && stats != nullptr) {
+    unsigned livechunks = 0, passes = 0;
+    for (int c = 0; c < nc; ++c) livechunks += (skip1[c] != ((1u << NP) - 1u)) ? 1u : 0u;
+    for (int cc = 0; cc < 2 * hc; ++cc) passes += tc_pass_needed(cc < hc, cc < hc ? cc : cc - hc, nc, NB, skip0, skip1) ? 1u : 0u;
+    atomicAdd(&stats[8], (u64)livechunks);
+    atomicAdd(&stats[9], (u64)passes);
+    t_mark = clock64();
+    atomicAdd(&stats[2], (u64)(t_mark - t_start));
+  }
+#define TC_MARK(slot) if (tid == 0 && stats != nullptr) { const long long t_ = clock64(); atomicAdd(&stats[slot], (u64)(t_ - t_mark)); t_mark = t_; }
+#else
+#define TC_MARK(slot)
+#endif
   if (warp == kTcEpiWarps) {
     // ===== column-operand builder (one pass per phase) =====
     // Only passes that contain a live stage are built (buffer = built-pass count & 1).  The 24 coordinate loads of the
@@ -496,52 +526,59 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         }
       }
     }
-    // ---- phase 1: column minima per 128-row block, merged per chunk into (best, mask of row blocks)
+    TC_MARK(3)
+    // ---- phase 1: column minima.  Thread = one column of the chunk; it keeps a running record (best, mask of row
+    // blocks) of the row blocks 2 rp + h it sees, in REGISTERS, with the same update rule as the row records; at the end
+    // of a chunk the two warps of a lane quarter (h = 0 / 1) exchange their records through shared memory (8 bytes per
+    // column) and the warp whose turn it is merges the two and writes the (tile, column) record.  (A per-block value
+    // array in shared memory merged in two passes per chunk cost ~400 clk per chunk on the critical path.)
     int cseq = 0;
+    float2* xch = reinterpret_cast<float2*>(sm.colw);                 // [parity][h][128] exchange slots
     for (int j = 0; j < hc; ++j) {
       const int nh = (2 * j + 1 < nc) ? 2 : 1;
       for (int hh = 0; hh < nh; ++hh) {
         const uint32_t live1 = ~skip1[2 * j + hh] & npmask;          // row-block pairs of this chunk that are computed
         if (live1 == 0u) {
           // chunk pruned for the whole tile: record (+inf, no candidate) - it is never a candidate in the recovery.  No
-          // shared buffer, no barrier, and it does not take part in the two warps' alternation (cseq counts live chunks).
+          // exchange, no barrier, and it does not take part in the two warps' alternation (cseq counts live chunks).
           const int col = (c_first + 2 * j + hh) * kTcBlk + li;
           if (h == hh && col < M) { const size_t o = ((size_t)b * ntiles + tile_i) * M + col; cbest[o] = tc_inf(); cmask[o] = 0u; }
           continue;
         }
-        float* cw = sm.colw + (size_t)(cseq & 1) * NB * kTcBlk;
+        float best = tc_inf(); uint32_t mask = 0u;
         for (uint32_t live = live1; live; live &= live - 1) {
           const int rp = __ffs((int)live) - 1;
           const uint32_t st = it & 1;
           tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
           tc_fence_after();
-          cw[(2 * rp + h) * kTcBlk + li] = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
+          const float m = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
           ++it;
+          if (m <= tc_thr(best, slack_rel, slack_abs)) {
+            const float tm = tc_thr(m, slack_rel, slack_abs);
+            mask = ((tm < best) ? 0u : mask) | (1u << (2 * rp + h));
+            best = fminf(best, m);
+          }
         }
+        float2* slot = xch + (size_t)(cseq & 1) * 2 * kTcBlk;
+        slot[h * kTcBlk + li] = make_float2(best, __uint_as_float(mask));
         // the two warps of this lane quarter meet once per live chunk; they take turns merging
         asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
         if ((cseq & 1) == h) {
           const int col = (c_first + 2 * j + hh) * kTcBlk + li;
           if (col < M) {
-            float best = tc_inf();
-            for (uint32_t live = live1; live; live &= live - 1) {
-              const int i = 2 * (__ffs((int)live) - 1);
-              best = tc_min3(best, cw[i * kTcBlk + li], cw[(i + 1) * kTcBlk + li]);
-            }
-            const float t = tc_thr(best, slack_rel, slack_abs);
-            unsigned mask = 0;
-            for (uint32_t live = live1; live; live &= live - 1) {
-              const int i = 2 * (__ffs((int)live) - 1);
-              mask |= ((cw[i * kTcBlk + li] <= t) ? (1u << i) : 0u) | ((cw[(i + 1) * kTcBlk + li] <= t) ? (2u << i) : 0u);
-            }
+            const float2 other = slot[(h ^ 1) * kTcBlk + li];
+            const float b2 = fminf(best, other.x);
+            const float t = tc_thr(b2, slack_rel, slack_abs);
+            const uint32_t m2 = ((best <= t) ? mask : 0u) | ((other.x <= t) ? __float_as_uint(other.y) : 0u);
             const size_t o = ((size_t)b * ntiles + tile_i) * M + col;
-            cbest[o] = best * invS2; cmask[o] = mask;
+            cbest[o] = b2 * invS2; cmask[o] = m2;
           }
         }
         ++cseq;
       }
     }
   }
+  TC_MARK(4)
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
@@ -557,6 +594,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       rbest[o] = best * invS2; rmask[o] = mask;
     }
   }
+  TC_MARK(5)
 }
 
 // Samples whose coordinates are not finite or too large for the centred expansion (fallback[b] != 0) are

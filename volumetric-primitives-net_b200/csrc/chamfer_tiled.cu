@@ -298,19 +298,18 @@ struct ExactBest {
   __device__ __forceinline__ u64 key() const { return ((u64)__float_as_uint(v) << 32) | (unsigned)i; }
 };
 
-// Scan of 32 squared distances held in registers (d[kk] belongs to index idx0 + ((kk + rot) & 31)).
+// Scan of 32 squared distances held in registers (d[kk] belongs to position (kk + rot) & 31 of the unit).
 // Phase 1 found dm = min d.  One more pass counts the values within dm's sqrt rounding class and sums their
-// positions (two predicated integer adds per value).  If the count is 1 the winner is that position and
-// v = sqrt(dm) - no index bookkeeping per value; otherwise (ties / near ties, rare) fall back to the
-// order-independent ExactBest walk.  Returns false when the unit holds no valid point.
-// With `orig` (the 32 staged float4 of the unit, .w = the point's ORIGINAL index as int bits) the key carries the original
-// index instead of the position: ties then resolve to the lowest original index although the points were permuted.
-__device__ __forceinline__ bool unit_best(const float (&d)[32], float dm, int idx0, int rot, u64& key, const float4* orig = nullptr) {
+// positions (two predicated integer adds per value).  Returns 1 with *at = the winner's position when the count is 1
+// (v = sqrt(dm), no index bookkeeping per value), 2 when several values share the class (ties / near ties, rare: the
+// caller takes the out-of-line exact walk), 0 when the unit holds no valid point.
+__device__ __forceinline__ int unit_scan(const float (&d)[32], float dm, int rot, int* at) {
   if (!(dm < inf_f())) {                       // all padding, or genuinely infinite distances
     bool any = false;
 #pragma unroll
     for (int kk = 0; kk < 32; ++kk) any |= (d[kk] == inf_f());
-    if (!any) return false;
+    if (!any) return 0;
+    return 2;
   }
   const float hi = thr_of(dm, 9.5367431640625e-07f, 1e-36f);
   int cnt = 0, pos = 0;
@@ -320,19 +319,19 @@ __device__ __forceinline__ bool unit_best(const float (&d)[32], float dm, int id
     cnt += in ? 1 : 0;
     pos += in ? kk : 0;
   }
-  if (cnt == 1) {
-    const int at = (pos + rot) & 31;
-    key = ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)(orig ? __float_as_int(orig[at].w) : idx0 + at);
-    return true;
-  }
+  *at = (pos + rot) & 31;
+  return cnt == 1 ? 1 : 2;
+}
+
+// Out-of-line exact walk over a unit's 32 points (rare path: kept out of the scan's register budget).  pts: the 32
+// staged points; index of point k = w-component as int bits (use_w: original index of a permuted cloud) or idx0 + k.
+__device__ __noinline__ u64 unit_exact_walk(float ax, float ay, float az, const float4* __restrict__ pts, int idx0, int use_w) {
   ExactBest eb; eb.init();
-#pragma unroll
-  for (int kk = 0; kk < 32; ++kk) {
-    const int at = (kk + rot) & 31;
-    eb.offer(d[kk], orig ? __float_as_int(orig[at].w) : idx0 + at);
+  for (int k = 0; k < 32; ++k) {
+    const float4 q = pts[k];
+    eb.offer(exact_d2s(ax, ay, az, q.x, q.y, q.z), use_w ? __float_as_int(q.w) : idx0 + k);
   }
-  key = eb.key();
-  return eb.i != 0x7fffffff;
+  return eb.i != 0x7fffffff ? eb.key() : ~0ull;
 }
 
 // exclusive prefix sum of `cnt` over the CTA (kRecThreads threads); returns the offset, *total gets the sum
@@ -430,8 +429,10 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
           d[kk] = exact_d2s(rc.x, rc.y, rc.z, q.x, q.y, q.z);
           dm = fminf(dm, d[kk]);
         }
-        u64 kv;
-        if (unit_best(d, dm, gcol, lane, kv, src)) atomicMin(&key[r], kv);
+        int at;
+        const int st = unit_scan(d, dm, lane, &at);
+        if (st == 1) atomicMin(&key[r], ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)__float_as_int(src[at].w));
+        else if (st == 2) { const u64 kv = unit_exact_walk(rc.x, rc.y, rc.z, src, gcol, 1); if (kv != ~0ull) atomicMin(&key[r], kv); }
       }
       __syncthreads();
     }
@@ -525,8 +526,12 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
             d[kk] = exact_d2s(a.x, a.y, a.z, tx, ty, tz);
             dm = fminf(dm, d[kk]);
           }
-          u64 kv;
-          if (unit_best(d, dm, ti * TM + base_row, lane, kv)) best = kv < best ? kv : best;
+          int at;
+          const int st = unit_scan(d, dm, lane, &at);
+          u64 kv = ~0ull;
+          if (st == 1) kv = ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)(ti * TM + base_row + at);
+          else if (st == 2) kv = unit_exact_walk(tx, ty, tz, rows + base_row, ti * TM + base_row, 0);
+          best = kv < best ? kv : best;
         }
         if (best != ~0ull) atomicMin(&key2[(size_t)b * M + col], best);
       }
@@ -632,7 +637,7 @@ static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   w.cbest = o; o += al256((size_t)B * pl.ntiles * M * 4);
   w.cmask = o; o += al256((size_t)B * pl.ntiles * M * 4);
   w.tslack = o; o += al256((size_t)B * pl.ntiles * 8);
-  w.fallback = o; o += al256((size_t)B * 4 + 16);          // + 2 x u64 pruning statistics (stages, stages skipped), zeroed with the flags
+  w.fallback = o; o += al256((size_t)B * 4 + 8 + 128);     // + 16 x u64 statistics / cycle counters of the tensor-core filter, zeroed with the flags
   w.tmax = o; o += al256((size_t)B * 4);
   w.cthr = o; o += al256((size_t)B * M * 4);
   w.key2 = o; o += al256((size_t)B * M * 8);
@@ -675,15 +680,15 @@ size_t chamfer_tiled_workspace_bytes(int B, int P, int M, int mode) {
   return ws_layout(B, P, M, pl).total;
 }
 
-// Pruning statistics of the last tensor-core forward that used this workspace: out[0] = 128 x 256 stages in the sweep,
-// out[1] = stages skipped.  Synchronises the stream.
+// Statistics of the last tensor-core forward that used this workspace: out[0] = 128 x 256 stages in the sweep,
+// out[1] = stages skipped, out[2..9] = cycle / work counters (chamfer_tc.cu), out[10..15] = 0.  Synchronises the stream.
 int chamfer_tiled_stats(int B, int P, int M, int mode, const void* ws_, unsigned long long* out, cudaStream_t s) {
   TiledPlan pl;
-  out[0] = out[1] = 0;
+  for (int i = 0; i < 16; ++i) out[i] = 0;
   if (!plan_for(mode, B, P, M, pl) || !pl.tc) return VPN_OK;
   TiledWs wl = ws_layout(B, P, M, pl);
   const char* src = reinterpret_cast<const char*>(ws_) + wl.fallback + (((size_t)B * 4 + 7) & ~(size_t)7);
-  if (cudaMemcpyAsync(out, src, 16, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+  if (cudaMemcpyAsync(out, src, 128, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
     vpn_set_error("chamfer stats: copy failed"); return VPN_ERR_CUDA;
   }
   return VPN_OK;
@@ -776,7 +781,7 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   const int* skip = nullptr;
   int rc;
   if (ev) cudaEventRecord(ev[0], s);
-  const size_t flag_bytes = (((size_t)B * 4 + 7) & ~(size_t)7) + 16;      // per-sample flags + the two u64 statistics words
+  const size_t flag_bytes = (((size_t)B * 4 + 7) & ~(size_t)7) + 128;     // per-sample flags + the 16 u64 statistics words
   if (mode == MODE_EXPAND || mode == MODE_TC) {
     if (cudaMemsetAsync(fallback, 0, flag_bytes, s) != cudaSuccess) { vpn_set_error("chamfer tiled: memset failed"); return VPN_ERR_CUDA; }
   }

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "vpn_chamfer_fwd_timed": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_int,
                                       POINTER(c_float), c_void_p]),
     "vpn_chamfer_bwd": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_void_p]),
+    "vpn_chamfer_tc_counters": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(ctypes.c_ulonglong), c_void_p]),
     "vpn_chamfer_prune_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(ctypes.c_ulonglong), POINTER(ctypes.c_ulonglong),
                                         c_void_p]),
     "vpn_chamfer_loss_fwd": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -244,6 +244,9 @@ def chamfer_nn_stage_ms(points1: torch.Tensor, points2: torch.Tensor, impl: int 
     check(lib.vpn_chamfer_prune_stats(ptr(ws), b, p, m, impl, ctypes.byref(stages), ctypes.byref(skipped), stream_ptr(dev)),
           "vpn_chamfer_prune_stats")
     out["stages"], out["stages_skipped"] = int(stages.value), int(skipped.value)
+    cnt = (ctypes.c_ulonglong * 16)()
+    check(lib.vpn_chamfer_tc_counters(ptr(ws), b, p, m, impl, cnt, stream_ptr(dev)), "vpn_chamfer_tc_counters")
+    out["tc_counters"] = [int(x) for x in cnt[:10]]
     return out
 
 
