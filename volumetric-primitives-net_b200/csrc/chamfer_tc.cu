@@ -140,9 +140,10 @@ struct TcSmem {
   unsigned char* rows; unsigned char* cols; float* rs_best; uint32_t* rs_mask; float* colw;
   u64* bars; float* red; uint32_t* tmem_slot; uint32_t* skip;
 };
-// skip words: [0,64) row-direction prunable bits per chunk (bit r = row block r), [64,128) column-direction bits,
-// [128,160) phase-0 stage masks per chunk pair, [160,224) phase-1 stage masks per chunk (bit rp = row-block pair)
-constexpr int kTcSkipWords = 256;
+// skip words of a tile: [0,32) phase-0 stage masks per chunk pair (bit r = row block r), [32,96) phase-1 stage masks per
+// chunk (bit rp = row-block pair)
+constexpr int kTcPlanWords = 96;
+constexpr int kTcSkipWords = 128;
 __host__ __device__ inline size_t tc_smem_bytes(int NB) {
   return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 8 + 2 * (size_t)NB * kTcBlk * 4 + 16 * 8 + 64 * 4 + 16 +
          kTcSkipWords * 4;
@@ -217,7 +218,83 @@ __device__ __forceinline__ bool tc_pass_needed(bool phase0, int j, int nc, int N
   return ((~both) & ((1u << (NB >> 1)) - 1u)) != 0u;
 }
 
-// grid: x = row tile (NB * 128 rows), y = column split, z = sample
+// ---- plan: which stages of which tile are pruned, and the order the tiles are run in ---------------------------------
+// One warp per tile (tile_i, split, b).  Stage (row block r, chunk c) is prunable for the row direction when
+// gap(box_r, box_c)^2 > T_r and for the column direction when gap^2 > U_c (chamfer_prep.cu): every pair of the stage is
+// then at least sqrt(gap2) apart while T / U are distances the block's rows / the chunk's columns certainly achieve
+// elsewhere (exact arithmetic).  1e-5 relative covers the roundings on both sides (~1e-6); a NaN gap or an infinite
+// bound compares false: not skipped.  Row blocks past the end of the cloud are always prunable.
+// Output per tile: kTcPlanWords mask words + the number of live stages (the tile's work).
+constexpr int kPlanWarps = 4;
+__global__ void __launch_bounds__(kPlanWarps * 32)
+chamfer_tc_plan_kernel(const float* __restrict__ cbox, const float* __restrict__ rbox, const float* __restrict__ rthr,
+                       const float* __restrict__ cub, uint32_t* __restrict__ plan_masks, int* __restrict__ plan_work,
+                       int ncta, int ntiles, int nsplit, int nrb_total, int NB, int nchunks, int cps) {
+  __shared__ uint32_t s_r[kPlanWarps][64], s_c[kPlanWarps][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cta = blockIdx.x * kPlanWarps + warp;
+  if (cta >= ncta) return;                                            // warp-uniform; no block barrier below
+  const int tile_i = cta % ntiles, split = (cta / ntiles) % nsplit, b = cta / (ntiles * nsplit);
+  const int c_first = split * cps, nc = min(nchunks, c_first + cps) - c_first;
+  const int hc = (nc + 1) >> 1, NP = NB >> 1;
+  uint32_t* skipR = s_r[warp]; uint32_t* skipC = s_c[warp];
+  skipR[lane] = 0u; skipR[lane + 32] = 0u; skipC[lane] = 0u; skipC[lane + 32] = 0u;
+  __syncwarp();
+  for (int e = lane; e < NB * nc; e += 32) {
+    const int r = e % NB, c = e / NB, rb = tile_i * NB + r;
+    bool pr = true, pc = true;
+    if (rb < nrb_total) {
+      const float gap2 = tc_box_gap2(rbox + ((size_t)b * nrb_total + rb) * 8, cbox + ((size_t)b * nchunks + c_first + c) * 8);
+      pr = gap2 > __fmul_ru(rthr[(size_t)b * nrb_total + rb], 1.00001f);
+      pc = gap2 > __fmul_ru(cub[(size_t)b * nchunks + c_first + c], 1.00001f);
+    }
+    if (pr) atomicOr(&skipR[c], 1u << r);
+    if (pc) atomicOr(&skipC[c], 1u << r);
+  }
+  __syncwarp();
+  uint32_t* out = plan_masks + (size_t)cta * kTcPlanWords;
+  int live = 0;
+  {
+    const int j = lane;                                               // hc <= 32
+    uint32_t m = 0xffffffffu;
+    if (j < hc) { m = skipR[2 * j] & ((2 * j + 1 < nc) ? skipR[2 * j + 1] : 0xffffffffu); live += NB - __popc(m & ((1u << NB) - 1u)); }
+    out[j] = m;
+  }
+  for (int c = lane; c < 64; c += 32) {
+    uint32_t m = 0xffffffffu;
+    if (c < nc) {
+      const uint32_t both = skipC[c] & (skipC[c] >> 1);              // bit 2 rp: row blocks 2 rp and 2 rp + 1 both prunable
+      m = 0u;
+      for (int rp = 0; rp < NP; ++rp) m |= ((both >> (2 * rp)) & 1u) << rp;
+      live += NP - __popc(m);
+    }
+    out[32 + c] = m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
+  if (lane == 0) plan_work[cta] = live;
+}
+
+// Counting sort of the tiles by work, heaviest first (work <= 1024 stages).  One CTA.  The order among tiles of equal
+// work depends on atomics; it only affects which SM runs which tile, never a result.
+constexpr int kOrderThreads = 1024, kOrderBins = 1056;
+__global__ void __launch_bounds__(kOrderThreads)
+chamfer_tc_order_kernel(const int* __restrict__ plan_work, int* __restrict__ plan_order, int ncta) {
+  __shared__ int hist[kOrderBins];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kOrderBins; i += kOrderThreads) hist[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < ncta; i += kOrderThreads) atomicAdd(&hist[min(max(plan_work[i], 0), kOrderBins - 1)], 1);
+  __syncthreads();
+  if (tid == 0) {                                                     // exclusive prefix over the bins, heaviest bin first
+    int run = 0;
+    for (int w = kOrderBins - 1; w >= 0; --w) { const int n = hist[w]; hist[w] = run; run += n; }
+  }
+  __syncthreads();
+  for (int i = tid; i < ncta; i += kOrderThreads) plan_order[atomicAdd(&hist[min(max(plan_work[i], 0), kOrderBins - 1)], 1)] = i;
+}
+
+// grid: x = tile (row tile NB * 128 rows, column split, sample) in the order of the plan
 //
 // Work unit ("stage") = one 128-lane x 256-column accumulator: tcgen05.mma kind::f16 M=128 N=256 K=16, one commit.
 // TMEM (512 columns) holds two stages.  The column chunks of the split are taken in ADJACENT pairs (2j, 2j + 1) - after
@@ -236,17 +313,19 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                   float* __restrict__ rbest, u64* __restrict__ rmask,
                   float* __restrict__ cbest, unsigned* __restrict__ cmask,
                   float2* __restrict__ tslack, int* __restrict__ fallback, const float* __restrict__ tmax,
-                  const float* __restrict__ cbox, const float* __restrict__ rbox, const float* __restrict__ rthr,
-                  const float* __restrict__ cub, u64* __restrict__ stats, int nrb_total,
-                  int P, int M, int NB, int nchunks, int cps) {
+                  const uint32_t* __restrict__ plan_masks, const int* __restrict__ plan_order, u64* __restrict__ stats,
+                  int ntiles, int nsplit, int P, int M, int NB, int nchunks, int cps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
 #ifdef VPN_TC_COUNTERS
   const long long t_start = clock64();
 #endif
   const TcSmem sm = tc_carve(smem_raw, NB);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile_i = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
-  const int ntiles = gridDim.x, nsplit = gridDim.y;
+  // 1-D grid.  With a plan (chamfer_tc_plan_kernel + chamfer_tc_order_kernel) block x runs the x-th heaviest tile: CTAs
+  // are dispatched in block order, so the heavy ones start first and the light ones fill the tail (without it the SMs
+  // idled 13 % of the kernel waiting for late heavy tiles).
+  const int cta = plan_order ? plan_order[blockIdx.x] : (int)blockIdx.x;
+  const int tile_i = cta % ntiles, split = (cta / ntiles) % nsplit, b = cta / (ntiles * nsplit);
   const int TM = NB * kTcBlk;
   const float* A = p1 + (size_t)b * P * 3;
   const float* T = p2 + (size_t)b * M * 3;
@@ -340,35 +419,9 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   const int nc = c_last - c_first;             // chunks of this split (<= 64)
   const int hc = (nc + 1) >> 1;                // chunk pairs (<= 32)
   const int NP = NB >> 1;                      // row-block pairs
-  // ---- stage skip masks (see the header).  Without boxes (cbox == NULL) every stage is computed.
-  uint32_t* skipR = sm.skip; uint32_t* skipC = sm.skip + 64; uint32_t* skip0 = sm.skip + 128; uint32_t* skip1 = sm.skip + 160;
-  for (int i = tid; i < kTcSkipWords; i += kTcThreads) sm.skip[i] = 0u;
-  __syncthreads();
-  if (cbox != nullptr) {
-    for (int e = tid; e < NB * nc; e += kTcThreads) {
-      const int r = e % NB, c = e / NB, rb = tile_i * NB + r;
-      bool pr = true, pc = true;               // row blocks past the end of the cloud: nothing to compute
-      if (rb < nrb_total) {
-        const float gap2 = tc_box_gap2(rbox + ((size_t)b * nrb_total + rb) * 8, cbox + ((size_t)b * nchunks + c_first + c) * 8);
-        // every pair of the stage is at least sqrt(gap2) apart; T / U are distances the block's rows / the chunk's columns
-        // certainly achieve elsewhere (exact arithmetic).  1e-5 relative covers the roundings on both sides (~1e-6);
-        // a NaN gap or an infinite bound compares false: not skipped
-        pr = gap2 > __fmul_ru(rthr[(size_t)b * nrb_total + rb], 1.00001f);
-        pc = gap2 > __fmul_ru(cub[(size_t)b * nchunks + c_first + c], 1.00001f);
-      }
-      if (pr) atomicOr(&skipR[c], 1u << r);
-      if (pc) atomicOr(&skipC[c], 1u << r);
-    }
-  }
-  __syncthreads();
-  for (int j = tid; j < hc; j += kTcThreads)
-    skip0[j] = skipR[2 * j] & ((2 * j + 1 < nc) ? skipR[2 * j + 1] : 0xffffffffu);
-  for (int c = tid; c < nc; c += kTcThreads) {
-    const uint32_t both = skipC[c] & (skipC[c] >> 1);              // bit 2 rp: row blocks 2 rp and 2 rp + 1 both prunable
-    uint32_t m = 0;
-    for (int rp = 0; rp < NP; ++rp) m |= ((both >> (2 * rp)) & 1u) << rp;
-    skip1[c] = m;
-  }
+  // ---- stage skip masks of this tile (computed by chamfer_tc_plan_kernel).  Without a plan every stage is computed.
+  uint32_t* skip0 = sm.skip; uint32_t* skip1 = sm.skip + 32;
+  for (int i = tid; i < kTcPlanWords; i += kTcThreads) sm.skip[i] = plan_masks ? plan_masks[(size_t)cta * kTcPlanWords + i] : 0u;
   __syncthreads();
   // statistics: stats[0] stages, stats[1] stages skipped - counted by the MMA warp's lanes in parallel, two atomics per CTA
   // (thread 0 doing it alone, plus cycle counters, delayed epilogue warp 0 and with it every stage: +3 %).  A probe build
@@ -656,10 +709,11 @@ size_t chamfer_tc_smem_bytes(int NB) { return tc_smem_bytes(NB); }
 
 // p2: the targets the filter sweeps (Morton-sorted copy when cbox != NULL); tmax filled by the caller (chamfer_prep_launch)
 // when with_bounds == 0, by chamfer_tc_bounds_kernel here otherwise.
+// cbox != NULL: the pruned sweep; plan_masks (ncta x kTcPlanWords words), plan_work and plan_order (ncta ints) are scratch.
 int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
                       float2* tslack, int* fallback, float* tmax, const float* cbox, const float* rbox, const float* rthr,
-                      const float* cub, u64* stats, int with_bounds, int B, int P, int M, int NB, int ntiles, int nsplit,
-                      int nchunks, int cps, cudaStream_t s) {
+                      const float* cub, u64* stats, uint32_t* plan_masks, int* plan_work, int* plan_order, int with_bounds,
+                      int B, int P, int M, int NB, int ntiles, int nsplit, int nchunks, int cps, cudaStream_t s) {
   static DeviceOnce once;
   const size_t smem = tc_smem_bytes(NB);
   {
@@ -671,9 +725,19 @@ int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask
     chamfer_tc_bounds_kernel<<<B, 256, 0, s>>>(p2, tmax, M);
     if ((rc = vpn_check_launch("chamfer_tc_bounds_kernel"))) return rc;
   }
-  chamfer_tc_kernel<<<dim3(ntiles, nsplit, B), kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax,
-                                                                      cbox, rbox, rthr, cub, stats, (P + kTcBlk - 1) / kTcBlk,
-                                                                      P, M, NB, nchunks, cps);
+  const long long ncta_ll = (long long)ntiles * nsplit * B;
+  if (ncta_ll > 0x7fffffffLL) { vpn_set_error("chamfer tc: too many tiles"); return VPN_ERR_SHAPE; }
+  const int ncta = (int)ncta_ll;
+  if (cbox != nullptr) {
+    chamfer_tc_plan_kernel<<<(ncta + kPlanWarps - 1) / kPlanWarps, kPlanWarps * 32, 0, s>>>(
+        cbox, rbox, rthr, cub, plan_masks, plan_work, ncta, ntiles, nsplit, (P + kTcBlk - 1) / kTcBlk, NB, nchunks, cps);
+    if ((rc = vpn_check_launch("chamfer_tc_plan_kernel"))) return rc;
+    chamfer_tc_order_kernel<<<1, kOrderThreads, 0, s>>>(plan_work, plan_order, ncta);
+    if ((rc = vpn_check_launch("chamfer_tc_order_kernel"))) return rc;
+  }
+  chamfer_tc_kernel<<<ncta, kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax,
+                                                   cbox ? plan_masks : nullptr, cbox ? plan_order : nullptr, stats,
+                                                   ntiles, nsplit, P, M, NB, nchunks, cps);
   return vpn_check_launch("chamfer_tc_kernel");
 }
 

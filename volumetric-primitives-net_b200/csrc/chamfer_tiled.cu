@@ -562,8 +562,8 @@ struct TiledPlan { int R, ntiles, nchunks, nsplit, cps, tc, TM; };
 size_t chamfer_tc_smem_bytes(int NB);
 int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
                       float2* tslack, int* fallback, float* tmax, const float* cbox, const float* rbox, const float* rthr,
-                      const float* cub, u64* stats, int with_bounds, int B, int P, int M, int NB, int ntiles, int nsplit,
-                      int nchunks, int cps, cudaStream_t s);
+                      const float* cub, u64* stats, unsigned* plan_masks, int* plan_work, int* plan_order, int with_bounds,
+                      int B, int P, int M, int NB, int ntiles, int nsplit, int nchunks, int cps, cudaStream_t s);
 // chamfer_prep.cu
 int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, int* perm, float* cbox, float* rbox, float* rthr,
                         float* cub, float* tmax, int B, int P, int M, cudaStream_t s);
@@ -629,7 +629,7 @@ static bool make_plan_tc(int B, int P, int M, int sm_count, TiledPlan& pl) {
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, tmax, cthr, key2, p2s, perm, cbox, rbox, rthr, cub, total; };
+struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, tmax, cthr, key2, p2s, perm, cbox, rbox, rthr, cub, pmask, pwork, porder, total; };
 static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   TiledWs w; size_t o = 0;
   w.rbest = o; o += al256((size_t)B * pl.nsplit * P * 4);
@@ -641,7 +641,7 @@ static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   w.tmax = o; o += al256((size_t)B * 4);
   w.cthr = o; o += al256((size_t)B * M * 4);
   w.key2 = o; o += al256((size_t)B * M * 8);
-  w.p2s = w.perm = w.cbox = w.rbox = w.rthr = w.cub = 0;
+  w.p2s = w.perm = w.cbox = w.rbox = w.rthr = w.cub = w.pmask = w.pwork = w.porder = 0;
   if (pl.tc) {                                             // spatial preparation of the pruned tensor-core filter (chamfer_prep.cu)
     const size_t nrb = (size_t)(P + 127) / 128;
     w.p2s = o; o += al256((size_t)B * M * 12);
@@ -650,6 +650,10 @@ static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
     w.rbox = o; o += al256((size_t)B * nrb * 32);
     w.rthr = o; o += al256((size_t)B * nrb * 4);
     w.cub = o; o += al256((size_t)B * pl.nchunks * 4);
+    const size_t ncta = (size_t)pl.ntiles * pl.nsplit * B;         // tiles of the filter: skip masks, work, run order
+    w.pmask = o; o += al256(ncta * 96 * 4);
+    w.pwork = o; o += al256(ncta * 4);
+    w.porder = o; o += al256(ncta * 4);
   }
   w.total = o;
   return w;
@@ -802,7 +806,9 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
     rc = chamfer_tc_launch(p1, p2w, reinterpret_cast<float*>(ws + wl.rbest), reinterpret_cast<u64*>(ws + wl.rmask),
                            reinterpret_cast<float*>(ws + wl.cbest), reinterpret_cast<unsigned*>(ws + wl.cmask),
                            reinterpret_cast<float2*>(ws + wl.tslack), fallback, tmax, prune ? cbox : nullptr, rbox, rthr, cub, stats,
-                           prune ? 0 : 1, B, P, M, pl.R, pl.ntiles, pl.nsplit, pl.nchunks, pl.cps, s);
+                           reinterpret_cast<unsigned*>(ws + wl.pmask), reinterpret_cast<int*>(ws + wl.pwork),
+                           reinterpret_cast<int*>(ws + wl.porder), prune ? 0 : 1, B, P, M, pl.R, pl.ntiles, pl.nsplit, pl.nchunks,
+                           pl.cps, s);
     if (rc) return rc;
     if (ev) cudaEventRecord(ev[1], s);
     // samples outside the filter's validity range (non-finite / huge coordinates): exact brute force, recovery skips them
