@@ -467,26 +467,31 @@ def measure_workload(B, workload, steps, warmup, chamfer_impl=0, graph="auto", w
     traffic = traffic_db.get(main_kernel)
     tsrc = "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of the same launch)"
     skipped_share = (stage.get("stages_skipped", 0) / stage["stages"]) if stage.get("stages") else 0.0
+    executed_tf = achieved * (1.0 - skipped_share)      # 8 flop per pair the filter actually evaluates
     roofline = {"kernel": main_kernel + " (main kernel of vpn_chamfer_fwd; both Chamfer directions in one launch"
-                          + (", preceded by the target sort + pruning-bounds kernels, which are inside `ms`" if skipped_share else "") + ")",
-                "bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                          + (", preceded by the target sort, pruning-bounds and plan kernels, which are inside `ms`" if skipped_share else "") + ")",
+                "bound": "fp32", "achieved": executed_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": executed_tf / peak_tf,
                 "peak_source": "live FFMA2 stream probe (vpn_fp32_peak_probe), burst; MEASURED_PEAKS.json has no FP32 "
                                "entry; nominal 148 SM x 128 lanes x 2 x max clock given beside it",
-                "peak_nominal": nominal, "frac_of_nominal": achieved / nominal, "ms": main_ms,
-                "algorithmic_flops": flops, "traffic": traffic, "traffic_source": tsrc if traffic else None,
+                "peak_nominal": nominal, "frac_of_nominal": executed_tf / nominal, "ms": main_ms,
+                "algorithmic_flops": flops * (1.0 - skipped_share), "traffic": traffic, "traffic_source": tsrc if traffic else None,
                 "pairs_skipped_share": skipped_share,
                 "pairs_skipped_note": "share of the 128 x 256 distance blocks (both directions) the spatial pruning proves "
-                                      "irrelevant and never evaluates (csrc/chamfer_prep.cu); `achieved` still counts the "
-                                      "reference's 8 flop for EVERY pair, so it can exceed what the pipes execute - "
-                                      "`executed` below is the evaluated part only",
-                "executed": {"tflops_fp32_equivalent": achieved * (1.0 - skipped_share),
-                             "frac_of_peak": achieved * (1.0 - skipped_share) / peak_tf},
+                                      "irrelevant and never evaluates (csrc/chamfer_prep.cu).  `achieved` / `frac` count 8 flop "
+                                      "for the EVALUATED pairs only (the kernel's own work over its time, prep kernels included "
+                                      "in the time); `all_pairs` is the same time against the reference's full pair count",
+                "all_pairs": {"flops": flops, "tflops": achieved, "x_peak": achieved / peak_tf,
+                              "note": "8 flop x B x P x M / ms: what a kernel evaluating every pair would have to sustain to "
+                                      "finish in this time; above the FP32 peak because most pairs are never evaluated"},
                 "note": "achieved = 8 flop per (predicted, target) pair / kernel time, against the FP32 FMA peak the "
                         "north star names; chamfer_tc_kernel evaluates the pairs on the tensor cores (fp16-split "
                         "operands, fp32 accumulate) and is bounded by TMEM reads + FMNMX on the ALU pipe, see DESIGN.md 4.1",
-                "forward_total": {"ms": cham_ms, "stages_ms": stage, "achieved": flops / (cham_ms * 1e-3) / 1e12,
-                                  "frac": flops / (cham_ms * 1e-3) / 1e12 / peak_tf,
-                                  "note": "main kernel + exact recovery kernels: the time to the final min / arg-min"}}
+                "forward_total": {"ms": cham_ms, "stages_ms": stage,
+                                  "achieved": flops * (1.0 - skipped_share) / (cham_ms * 1e-3) / 1e12,
+                                  "frac": flops * (1.0 - skipped_share) / (cham_ms * 1e-3) / 1e12 / peak_tf,
+                                  "all_pairs_tflops": flops / (cham_ms * 1e-3) / 1e12,
+                                  "note": "main kernel + exact recovery kernels: the time to the final min / arg-min; "
+                                          "achieved / frac count the evaluated pairs only"}}
     hbm_peak, tensor_peak = 6536.7, None
     try:
         mp = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -558,7 +563,7 @@ def compact(r):
         rf = r["roofline"]
         c["roofline"] = {"kernel": rf["kernel"].split(" ")[0], "bound": rf["bound"], "achieved": rf["achieved"], "peak": rf["peak"],
                          "unit": rf["unit"], "frac": rf["frac"], "ms": rf["ms"], "traffic": rf["traffic"],
-                         "pairs_skipped_share": rf.get("pairs_skipped_share"),
+                         "pairs_skipped_share": rf.get("pairs_skipped_share"), "all_pairs_tflops": rf["all_pairs"]["tflops"],
                          "forward_total_frac": rf["forward_total"]["frac"], "forward_total_ms": rf["forward_total"]["ms"]}
     for key in ("roofline_sampling", "roofline_raster"):
         if key in r:

@@ -219,28 +219,27 @@ __device__ __forceinline__ bool tc_pass_needed(bool phase0, int j, int nc, int N
 }
 
 // ---- plan: which stages of which tile are pruned, and the order the tiles are run in ---------------------------------
-// One warp per tile (tile_i, split, b).  Stage (row block r, chunk c) is prunable for the row direction when
+// One CTA per tile (tile_i, split, b).  Stage (row block r, chunk c) is prunable for the row direction when
 // gap(box_r, box_c)^2 > T_r and for the column direction when gap^2 > U_c (chamfer_prep.cu): every pair of the stage is
 // then at least sqrt(gap2) apart while T / U are distances the block's rows / the chunk's columns certainly achieve
 // elsewhere (exact arithmetic).  1e-5 relative covers the roundings on both sides (~1e-6); a NaN gap or an infinite
 // bound compares false: not skipped.  Row blocks past the end of the cloud are always prunable.
 // Output per tile: kTcPlanWords mask words + the number of live stages (the tile's work).
-constexpr int kPlanWarps = 4;
-__global__ void __launch_bounds__(kPlanWarps * 32)
+constexpr int kPlanThreads = 128;
+__global__ void __launch_bounds__(kPlanThreads)
 chamfer_tc_plan_kernel(const float* __restrict__ cbox, const float* __restrict__ rbox, const float* __restrict__ rthr,
                        const float* __restrict__ cub, uint32_t* __restrict__ plan_masks, int* __restrict__ plan_work,
                        int ncta, int ntiles, int nsplit, int nrb_total, int NB, int nchunks, int cps) {
-  __shared__ uint32_t s_r[kPlanWarps][64], s_c[kPlanWarps][64];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cta = blockIdx.x * kPlanWarps + warp;
-  if (cta >= ncta) return;                                            // warp-uniform; no block barrier below
+  __shared__ uint32_t skipR[64], skipC[64];
+  __shared__ int s_live[kPlanThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x;                                         // one CTA per tile (the box loads of its NB x nc pairs in parallel)
   const int tile_i = cta % ntiles, split = (cta / ntiles) % nsplit, b = cta / (ntiles * nsplit);
   const int c_first = split * cps, nc = min(nchunks, c_first + cps) - c_first;
   const int hc = (nc + 1) >> 1, NP = NB >> 1;
-  uint32_t* skipR = s_r[warp]; uint32_t* skipC = s_c[warp];
-  skipR[lane] = 0u; skipR[lane + 32] = 0u; skipC[lane] = 0u; skipC[lane + 32] = 0u;
-  __syncwarp();
-  for (int e = lane; e < NB * nc; e += 32) {
+  if (tid < 64) { skipR[tid] = 0u; skipC[tid] = 0u; }
+  __syncthreads();
+  for (int e = tid; e < NB * nc; e += kPlanThreads) {
     const int r = e % NB, c = e / NB, rb = tile_i * NB + r;
     bool pr = true, pc = true;
     if (rb < nrb_total) {
@@ -251,16 +250,16 @@ chamfer_tc_plan_kernel(const float* __restrict__ cbox, const float* __restrict__
     if (pr) atomicOr(&skipR[c], 1u << r);
     if (pc) atomicOr(&skipC[c], 1u << r);
   }
-  __syncwarp();
+  __syncthreads();
   uint32_t* out = plan_masks + (size_t)cta * kTcPlanWords;
   int live = 0;
-  {
-    const int j = lane;                                               // hc <= 32
+  if (tid < 32) {                                                     // phase-0 words (hc <= 32)
+    const int j = tid;
     uint32_t m = 0xffffffffu;
     if (j < hc) { m = skipR[2 * j] & ((2 * j + 1 < nc) ? skipR[2 * j + 1] : 0xffffffffu); live += NB - __popc(m & ((1u << NB) - 1u)); }
     out[j] = m;
-  }
-  for (int c = lane; c < 64; c += 32) {
+  } else if (tid < 96) {                                              // phase-1 words
+    const int c = tid - 32;
     uint32_t m = 0xffffffffu;
     if (c < nc) {
       const uint32_t both = skipC[c] & (skipC[c] >> 1);              // bit 2 rp: row blocks 2 rp and 2 rp + 1 both prunable
@@ -272,7 +271,9 @@ chamfer_tc_plan_kernel(const float* __restrict__ cbox, const float* __restrict__
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
-  if (lane == 0) plan_work[cta] = live;
+  if (lane == 0) s_live[warp] = live;
+  __syncthreads();
+  if (tid == 0) plan_work[cta] = s_live[0] + s_live[1] + s_live[2] + s_live[3];
 }
 
 // Counting sort of the tiles by work, heaviest first (work <= 1024 stages).  One CTA.  The order among tiles of equal
@@ -729,7 +730,7 @@ int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask
   if (ncta_ll > 0x7fffffffLL) { vpn_set_error("chamfer tc: too many tiles"); return VPN_ERR_SHAPE; }
   const int ncta = (int)ncta_ll;
   if (cbox != nullptr) {
-    chamfer_tc_plan_kernel<<<(ncta + kPlanWarps - 1) / kPlanWarps, kPlanWarps * 32, 0, s>>>(
+    chamfer_tc_plan_kernel<<<ncta, kPlanThreads, 0, s>>>(
         cbox, rbox, rthr, cub, plan_masks, plan_work, ncta, ntiles, nsplit, (P + kTcBlk - 1) / kTcBlk, NB, nchunks, cps);
     if ((rc = vpn_check_launch("chamfer_tc_plan_kernel"))) return rc;
     chamfer_tc_order_kernel<<<1, kOrderThreads, 0, s>>>(plan_work, plan_order, ncta);
