@@ -71,6 +71,33 @@ __device__ __forceinline__ void reduce_slice(float4* __restrict__ mc, size_t lo,
   for (; i < hi; i += stride) multimem_st(mc + i, multimem_ld_reduce_add(mc + i));
 }
 
+// Pipelined form of the same slice reduction: every thread walks its elements with the store of batch i issued AFTER the
+// load of batch i + 1, so that the switch carries reduced data towards this GPU and broadcast data away from it at the
+// same time.  (In reduce_slice a thread issues all its loads and then all its stores; with one batch per thread the
+// whole GPU first only reads - link egress busy serving the peers' reads, ingress nearly idle - and then only writes.)
+template <int U>
+__device__ __forceinline__ void reduce_slice_pipelined(float4* __restrict__ mc, size_t lo, size_t hi) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float4 cur[U]; size_t at[U];
+  int n = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) { at[u] = i + (size_t)u * stride; if (at[u] < hi) { cur[u] = multimem_ld_reduce_add(mc + at[u]); n = u + 1; } }
+  i += (size_t)U * stride;
+  while (n > 0) {
+    float4 nxt[U]; size_t nat[U];
+    int nn = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) { nat[u] = i + (size_t)u * stride; if (nat[u] < hi) { nxt[u] = multimem_ld_reduce_add(mc + nat[u]); nn = u + 1; } }
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (u < n) multimem_st(mc + at[u], cur[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) { cur[u] = nxt[u]; at[u] = nat[u]; }
+    n = nn;
+    i += (size_t)U * stride;
+  }
+}
+
 __global__ void __launch_bounds__(512)
 allreduce_nvls_kernel(float4* __restrict__ mc, size_t lo, size_t hi) {
   reduce_slice(mc, lo, hi);
@@ -88,7 +115,9 @@ enum { kArrive = 0, kDone = 32, kEpoch = 64, kCtas = 96, kError = 97, kFlagWords
 // Start: every rank's input is complete (stream order on each rank, then arrive + wait).  End: the LAST CTA of the
 // rank - after every CTA has fenced its stores at system scope - announces the rank done and waits for all ranks, so
 // that the kernel's completion on a GPU means every rank's sums have landed in that GPU's copy.
-__global__ void __launch_bounds__(512, 4)
+// V: 0 = all loads then all stores per thread, 1 / 2 / 4 = pipelined with that many elements per batch
+template <int V>
+__global__ void __launch_bounds__(512, (V == 4 ? 2 : 4))
 allreduce_nvls_sync_kernel(float4* __restrict__ mc, float* __restrict__ local, size_t flag_off, size_t lo, size_t hi, int world) {
   unsigned* fl_local = reinterpret_cast<unsigned*>(local + flag_off);
   unsigned* fl_mc = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(mc) + flag_off);
@@ -101,7 +130,7 @@ allreduce_nvls_sync_kernel(float4* __restrict__ mc, float* __restrict__ local, s
     s_target = target;
   }
   __syncthreads();
-  reduce_slice(mc, lo, hi);
+  if (V == 0) reduce_slice(mc, lo, hi); else reduce_slice_pipelined<(V == 0 ? 1 : V)>(mc, lo, hi);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();                                     // this CTA's multimem stores are ordered before the count
@@ -125,9 +154,9 @@ static int slice_of(size_t numel, int rank, int world, size_t* lo, size_t* hi) {
   return 0;
 }
 
-static unsigned grid_for(size_t nvec_slice, int threads) {
+static unsigned grid_for(size_t nvec_slice, int threads, int ctas_per_sm = 4) {
   size_t blocks = (nvec_slice + (size_t)threads * 4 - 1) / ((size_t)threads * 4);
-  const size_t cap = (size_t)device_sm_count() * 4;            // 4 x 512 threads: all CTAs co-resident
+  const size_t cap = (size_t)device_sm_count() * ctas_per_sm;  // <= 4 x 512 threads per SM: all CTAs co-resident
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
@@ -170,8 +199,30 @@ extern "C" int vpn_allreduce_nvls_sync(void* multicast_ptr, void* local_ptr, siz
   }
   size_t lo, hi;
   vpn::slice_of(numel, rank, world, &lo, &hi);
-  const int threads = 512;
-  vpn::allreduce_nvls_sync_kernel<<<vpn::grid_for(hi > lo ? hi - lo : 0, threads), threads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<float4*>(multicast_ptr), reinterpret_cast<float*>(local_ptr), numel, lo, hi, world);
+  // Launch shape.  Measured on 8 B200s, 91.5 MB (tools/allreduce_sweep.py -> profiles/r02u_allreduce_sweep_8gpu.txt): the
+  // switch is saturated by ~19 000 threads with one load and one store in flight each; more threads only add contention
+  // (4 CTAs x 512 threads per SM, loads-then-stores: 0.267 ms; 1 CTA x 512: 0.237; pipelined: 0.222; pipelined, 256
+  // threads on every second SM: 0.2095 ms = 765 GB/s bus bandwidth; NCCL 2.28.9: 0.355 ms).  Probe knobs
+  // (vpn_set_tuning): "ar_variant" 0 = loads then stores, 1 / 2 / 4 = pipelined with that batch (default 1, passed as 8
+  // for variant 0); "ar_threads" 128 | 256 | 512; "ar_ctas" CTAs per SM; "ar_grid_div" use 1 / div of the SMs.
+  int threads = vpn::tuning_value(vpn::kTuneArThreads);
+  if (threads != 128 && threads != 512) threads = 256;
+  int variant = vpn::tuning_value(vpn::kTuneArVariant);
+  if (variant == 0) variant = 1; else if (variant == 8) variant = 0;
+  int cps = vpn::tuning_value(vpn::kTuneArCtas);
+  if (cps < 1 || cps > 4) cps = 1;
+  if (variant == 4 && cps > 2) cps = 2;                        // that variant is built for two resident CTAs per SM
+  unsigned grid = vpn::grid_for(hi > lo ? hi - lo : 0, threads, cps);
+  int div = vpn::tuning_value(vpn::kTuneArGridDiv);
+  if (div < 1) div = 2;
+  if (cps == 1) grid = (grid + div - 1) / div;
+  float4* mc = reinterpret_cast<float4*>(multicast_ptr); float* lp = reinterpret_cast<float*>(local_ptr);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (variant) {
+    case 1:  vpn::allreduce_nvls_sync_kernel<1><<<grid, threads, 0, s>>>(mc, lp, numel, lo, hi, world); break;
+    case 2:  vpn::allreduce_nvls_sync_kernel<2><<<grid, threads, 0, s>>>(mc, lp, numel, lo, hi, world); break;
+    case 4:  vpn::allreduce_nvls_sync_kernel<4><<<grid, threads, 0, s>>>(mc, lp, numel, lo, hi, world); break;
+    default: vpn::allreduce_nvls_sync_kernel<0><<<grid, threads, 0, s>>>(mc, lp, numel, lo, hi, world); break;
+  }
   return vpn_check_launch("allreduce_nvls_sync_kernel");
 }
