@@ -284,7 +284,8 @@ def measure_workload(B, workload, steps, warmup, chamfer_impl=0, graph="auto", w
     devsets = [{kk: (vv.to(dev) if vv is not None else None) for kk, vv in s.items()} for s in host]
     pinned = [{kk: (vv.pin_memory() if vv is not None else None) for kk, vv in s.items()} for s in host]
     cfg = vpn.PrimitiveLossConfig(kind=kind, l_sil=(1.0 if res else 0.0), chamfer_impl=chamfer_impl,
-                                  vertex_chamfer=vertex_mode, l_can_cd=(1.0 if faithful else 0.0))
+                                  vertex_chamfer=vertex_mode, l_can_cd=(1.0 if faithful else 0.0),
+                                  overlap_silhouette=os.environ.get("VPN_BENCH_NO_SIL_OVERLAP", "0") != "1")
 
     def cams_of(s):
         return (s["dists"], s["elevs"], s["azims"], s["angles"]) if faithful else None

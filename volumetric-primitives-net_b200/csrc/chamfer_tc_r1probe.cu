@@ -1,3 +1,4 @@
+// PROBE ONLY (not part of the default build): round 1's tensor-core filter kernel, for A/B timing inside the current library.
 // Chamfer nearest-neighbour search: tensor-core candidate filter for sm_100a (tcgen05 + TMEM).
 //
 // Same contract as chamfer_tiled_kernel (chamfer_tiled.cu): ONE pass over the (P x M) squared-distance matrix
@@ -26,12 +27,6 @@
 // 2.5e-4 rho^2 + 2^-20 + 2^-14 |x| (scaled units).  Measured error over random tiles (tools/tc_err.cu): 2^-19.85
 // relative, 2^-23.7 absolute for |P|+|T| < 1/4.
 //
-// Pruning (chamfer_prep.cu): the targets arrive Morton-sorted, so a 128-column chunk is a compact patch, and 128
-// consecutive rows are a patch of one primitive.  A stage whose two patches are further apart (box gap) than a distance
-// every row of the block (column of the chunk) is known to achieve elsewhere is not computed at all: the skip bits are
-// derived once per CTA in the prologue from the per-block boxes and bounds, and the MMA and epilogue warps walk the same
-// bit masks.  The row and the column direction prune independently (phase 0 / phase 1).
-//
 // CTA = 10 warps over one tile of NB x 128 rows, swept twice (D1 stages, then D2 stages): warps 0-7 read the
 // accumulators and keep the per-row candidate records in shared memory / emit the per-column records, warp 8
 // builds the C_j operands of the next 256 columns, warp 9 (one elected lane) issues the MMAs.  TMEM holds two
@@ -39,7 +34,8 @@
 #include <cuda_fp16.h>
 #include "common.cuh"
 
-namespace vpn {
+namespace vpn_r1 {
+using vpn::u64; using vpn::warp_sum;
 
 constexpr int kTcBlk = 128;                    // rows per block = columns per chunk = MMA M = MMA N
 constexpr int kTcEpiWarps = 8;
@@ -138,15 +134,10 @@ __device__ __forceinline__ float tc_make_operand(unsigned char* tile, int idx, f
 // dynamic shared memory carve-up (NB = row blocks per tile)
 struct TcSmem {
   unsigned char* rows; unsigned char* cols; float* rs_best; uint32_t* rs_mask; float* colw;
-  u64* bars; float* red; uint32_t* tmem_slot; uint32_t* skip;
+  u64* bars; float* red; uint32_t* tmem_slot;
 };
-// skip words of a tile: [0,32) phase-0 stage masks per chunk pair (bit r = row block r), [32,96) phase-1 stage masks per
-// chunk (bit rp = row-block pair)
-constexpr int kTcPlanWords = 96;
-constexpr int kTcSkipWords = 128;
 __host__ __device__ inline size_t tc_smem_bytes(int NB) {
-  return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 8 + 2 * (size_t)NB * kTcBlk * 4 + 16 * 8 + 64 * 4 + 16 +
-         kTcSkipWords * 4;
+  return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 8 + 2 * (size_t)NB * kTcBlk * 4 + 16 * 8 + 64 * 4 + 16;
 }
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
   TcSmem s;
@@ -157,8 +148,7 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
   s.colw = reinterpret_cast<float*>(p); p += 2 * (size_t)NB * kTcBlk * 4;         // [chunk parity][row block][column]
   s.bars = reinterpret_cast<u64*>(p); p += 16 * 8;
   s.red = reinterpret_cast<float*>(p); p += 64 * 4;
-  s.tmem_slot = reinterpret_cast<uint32_t*>(p); p += 16;
-  s.skip = reinterpret_cast<uint32_t*>(p);
+  s.tmem_slot = reinterpret_cast<uint32_t*>(p);
   return s;
 }
 
@@ -189,120 +179,14 @@ __device__ __forceinline__ float tc_lane_min128(uint32_t taddr, uint32_t empty_b
   return fminf(m0, m1);
 }
 
-// bit k of x -> bit 2k
-__device__ __forceinline__ u64 tc_spread32(uint32_t v) {
-  u64 x = v;
-  x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
-  x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
-  x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
-  x = (x | (x << 2)) & 0x3333333333333333ull;
-  x = (x | (x << 1)) & 0x5555555555555555ull;
-  return x;
-}
-// squared gap between two axis-aligned boxes (8 floats: lo xyz, hi xyz); an empty box gives +inf
-__device__ __forceinline__ float tc_box_gap2(const float* __restrict__ a, const float* __restrict__ b) {
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float g = fmaxf(0.f, fmaxf(a[k] - b[3 + k], b[k] - a[3 + k]));
-    s = fmaf(g, g, s);
-  }
-  return s;
-}
-
-// Does pass (phase, chunk pair j) contain a stage that is not pruned?  (The operand builder and the MMA issuer must
-// agree on which column buffers exist.)
-__device__ __forceinline__ bool tc_pass_needed(bool phase0, int j, int nc, int NB, const uint32_t* skip0, const uint32_t* skip1) {
-  if (phase0) return ((~skip0[j]) & ((1u << NB) - 1u)) != 0u;
-  const uint32_t both = skip1[2 * j] & ((2 * j + 1 < nc) ? skip1[2 * j + 1] : 0xffffffffu);
-  return ((~both) & ((1u << (NB >> 1)) - 1u)) != 0u;
-}
-
-// ---- plan: which stages of which tile are pruned, and the order the tiles are run in ---------------------------------
-// One CTA per tile (tile_i, split, b).  Stage (row block r, chunk c) is prunable for the row direction when
-// gap(box_r, box_c)^2 > T_r and for the column direction when gap^2 > U_c (chamfer_prep.cu): every pair of the stage is
-// then at least sqrt(gap2) apart while T / U are distances the block's rows / the chunk's columns certainly achieve
-// elsewhere (exact arithmetic).  1e-5 relative covers the roundings on both sides (~1e-6); a NaN gap or an infinite
-// bound compares false: not skipped.  Row blocks past the end of the cloud are always prunable.
-// Output per tile: kTcPlanWords mask words + the number of live stages (the tile's work).
-constexpr int kPlanThreads = 128;
-__global__ void __launch_bounds__(kPlanThreads)
-chamfer_tc_plan_kernel(const float* __restrict__ cbox, const float* __restrict__ rbox, const float* __restrict__ rthr,
-                       const float* __restrict__ cub, uint32_t* __restrict__ plan_masks, int* __restrict__ plan_work,
-                       int ncta, int ntiles, int nsplit, int nrb_total, int NB, int nchunks, int cps) {
-  __shared__ uint32_t skipR[64], skipC[64];
-  __shared__ int s_live[kPlanThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cta = blockIdx.x;                                         // one CTA per tile (the box loads of its NB x nc pairs in parallel)
-  const int tile_i = cta % ntiles, split = (cta / ntiles) % nsplit, b = cta / (ntiles * nsplit);
-  const int c_first = split * cps, nc = min(nchunks, c_first + cps) - c_first;
-  const int hc = (nc + 1) >> 1, NP = NB >> 1;
-  if (tid < 64) { skipR[tid] = 0u; skipC[tid] = 0u; }
-  __syncthreads();
-  for (int e = tid; e < NB * nc; e += kPlanThreads) {
-    const int r = e % NB, c = e / NB, rb = tile_i * NB + r;
-    bool pr = true, pc = true;
-    if (rb < nrb_total) {
-      const float gap2 = tc_box_gap2(rbox + ((size_t)b * nrb_total + rb) * 8, cbox + ((size_t)b * nchunks + c_first + c) * 8);
-      pr = gap2 > __fmul_ru(rthr[(size_t)b * nrb_total + rb], 1.00001f);
-      pc = gap2 > __fmul_ru(cub[(size_t)b * nchunks + c_first + c], 1.00001f);
-    }
-    if (pr) atomicOr(&skipR[c], 1u << r);
-    if (pc) atomicOr(&skipC[c], 1u << r);
-  }
-  __syncthreads();
-  uint32_t* out = plan_masks + (size_t)cta * kTcPlanWords;
-  int live = 0;
-  if (tid < 32) {                                                     // phase-0 words (hc <= 32)
-    const int j = tid;
-    uint32_t m = 0xffffffffu;
-    if (j < hc) { m = skipR[2 * j] & ((2 * j + 1 < nc) ? skipR[2 * j + 1] : 0xffffffffu); live += NB - __popc(m & ((1u << NB) - 1u)); }
-    out[j] = m;
-  } else if (tid < 96) {                                              // phase-1 words
-    const int c = tid - 32;
-    uint32_t m = 0xffffffffu;
-    if (c < nc) {
-      const uint32_t both = skipC[c] & (skipC[c] >> 1);              // bit 2 rp: row blocks 2 rp and 2 rp + 1 both prunable
-      m = 0u;
-      for (int rp = 0; rp < NP; ++rp) m |= ((both >> (2 * rp)) & 1u) << rp;
-      live += NP - __popc(m);
-    }
-    out[32 + c] = m;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
-  if (lane == 0) s_live[warp] = live;
-  __syncthreads();
-  if (tid == 0) plan_work[cta] = s_live[0] + s_live[1] + s_live[2] + s_live[3];
-}
-
-// Counting sort of the tiles by work, heaviest first (work <= 1024 stages).  One CTA.  The order among tiles of equal
-// work depends on atomics; it only affects which SM runs which tile, never a result.
-constexpr int kOrderThreads = 1024, kOrderBins = 1056;
-__global__ void __launch_bounds__(kOrderThreads)
-chamfer_tc_order_kernel(const int* __restrict__ plan_work, int* __restrict__ plan_order, int ncta) {
-  __shared__ int hist[kOrderBins];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < kOrderBins; i += kOrderThreads) hist[i] = 0;
-  __syncthreads();
-  for (int i = tid; i < ncta; i += kOrderThreads) atomicAdd(&hist[min(max(plan_work[i], 0), kOrderBins - 1)], 1);
-  __syncthreads();
-  if (tid == 0) {                                                     // exclusive prefix over the bins, heaviest bin first
-    int run = 0;
-    for (int w = kOrderBins - 1; w >= 0; --w) { const int n = hist[w]; hist[w] = run; run += n; }
-  }
-  __syncthreads();
-  for (int i = tid; i < ncta; i += kOrderThreads) plan_order[atomicAdd(&hist[min(max(plan_work[i], 0), kOrderBins - 1)], 1)] = i;
-}
-
-// grid: x = tile (row tile NB * 128 rows, column split, sample) in the order of the plan
+// grid: x = row tile (NB * 128 rows), y = column split, z = sample
 //
 // Work unit ("stage") = one 128-lane x 256-column accumulator: tcgen05.mma kind::f16 M=128 N=256 K=16, one commit.
-// TMEM (512 columns) holds two stages.  The column chunks of the split are taken in ADJACENT pairs (2j, 2j + 1) - after
-// the Morton sort two neighbouring patches of the target shape: the 256-column operand buffer holds chunk 2j in its
-// first half and chunk 2j + 1 in its second.
-//   phase 0 (row minima)   : stage (j, r) = R_r (128 rows) x [C_2j C_2j+1]^T; TMEM lane = row, the thread of column
-//                            half h reduces the 128 values of chunk 2j + h;
+// TMEM (512 columns) holds two stages.  The column chunks of the split are taken in pairs (j, hc + j), hc = half
+// the chunks of the split: the 256-column operand buffer holds chunk j in its first half and chunk hc + j in its
+// second.
+//   phase 0 (row minima)   : stage (j, r) = R_r (128 rows) x [C_j C_{hc+j}]^T; TMEM lane = row, the thread of column
+//                            half h reduces the 128 values of chunk (h ? hc + j : j);
 //   phase 1 (column minima): stage (chunk, rp) = C_chunk (128 columns) x [R_2rp R_2rp+1]^T; TMEM lane = column, the
 //                            thread of half h reduces over the 128 rows of block 2 rp + h.
 // Roles: warps 0-7 epilogue (warp = 4 h + q: TMEM lane quarter q, column half h), warp 8 builds the column operands,
@@ -314,19 +198,12 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                   float* __restrict__ rbest, u64* __restrict__ rmask,
                   float* __restrict__ cbest, unsigned* __restrict__ cmask,
                   float2* __restrict__ tslack, int* __restrict__ fallback, const float* __restrict__ tmax,
-                  const uint32_t* __restrict__ plan_masks, const int* __restrict__ plan_order, u64* __restrict__ stats,
-                  int ntiles, int nsplit, int P, int M, int NB, int nchunks, int cps) {
+                  int P, int M, int NB, int nchunks, int cps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-#ifdef VPN_TC_COUNTERS
-  const long long t_start = clock64();
-#endif
   const TcSmem sm = tc_carve(smem_raw, NB);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // 1-D grid.  With a plan (chamfer_tc_plan_kernel + chamfer_tc_order_kernel) block x runs the x-th heaviest tile: CTAs
-  // are dispatched in block order, so the heavy ones start first and the light ones fill the tail (without it the SMs
-  // idled 13 % of the kernel waiting for late heavy tiles).
-  const int cta = plan_order ? plan_order[blockIdx.x] : (int)blockIdx.x;
-  const int tile_i = cta % ntiles, split = (cta / ntiles) % nsplit, b = cta / (ntiles * nsplit);
+  const int tile_i = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
+  const int ntiles = gridDim.x, nsplit = gridDim.y;
   const int TM = NB * kTcBlk;
   const float* A = p1 + (size_t)b * P * 3;
   const float* T = p2 + (size_t)b * M * 3;
@@ -420,82 +297,26 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   const int nc = c_last - c_first;             // chunks of this split (<= 64)
   const int hc = (nc + 1) >> 1;                // chunk pairs (<= 32)
   const int NP = NB >> 1;                      // row-block pairs
-  // ---- stage skip masks of this tile (computed by chamfer_tc_plan_kernel).  Without a plan every stage is computed.
-  uint32_t* skip0 = sm.skip; uint32_t* skip1 = sm.skip + 32;
-  for (int i = tid; i < kTcPlanWords; i += kTcThreads) sm.skip[i] = plan_masks ? plan_masks[(size_t)cta * kTcPlanWords + i] : 0u;
-  __syncthreads();
-  // statistics: stats[0] stages, stats[1] stages skipped - counted by the MMA warp's lanes in parallel, two atomics per CTA
-  // (thread 0 doing it alone, plus cycle counters, delayed epilogue warp 0 and with it every stage: +3 %).  A probe build
-  // (-DVPN_TC_COUNTERS) adds the cycle counters of epilogue warp 0: [2] prologue, [3] row phase, [4] column phase, [5]
-  // tail, and [6] / [7] live stages per phase, [8] live chunks, [9] operand passes built.
-  if (warp == kTcEpiWarps + 1 && stats != nullptr) {
-    unsigned s0 = 0, s1 = 0;
-    for (int j = lane; j < hc; j += 32) s0 += __popc(skip0[j] & ((1u << NB) - 1u));
-    for (int c = lane; c < nc; c += 32) s1 += __popc(skip1[c]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-    if (lane == 0) {
-      atomicAdd(&stats[0], (u64)(hc * NB + nc * NP));
-      atomicAdd(&stats[1], (u64)(s0 + s1));
-#ifdef VPN_TC_COUNTERS
-      atomicAdd(&stats[6], (u64)(hc * NB - s0));
-      atomicAdd(&stats[7], (u64)(nc * NP - s1));
-#endif
-    }
-  }
-#ifdef VPN_TC_COUNTERS
-  long long t_mark = 0;
-  if (tid == 0 && stats != nullptr) {
-    unsigned livechunks = 0, passes = 0;
-    for (int c = 0; c < nc; ++c) livechunks += (skip1[c] != ((1u << NP) - 1u)) ? 1u : 0u;
-    for (int cc = 0; cc < 2 * hc; ++cc) passes += tc_pass_needed(cc < hc, cc < hc ? cc : cc - hc, nc, NB, skip0, skip1) ? 1u : 0u;
-    atomicAdd(&stats[8], (u64)livechunks);
-    atomicAdd(&stats[9], (u64)passes);
-    t_mark = clock64();
-    atomicAdd(&stats[2], (u64)(t_mark - t_start));
-  }
-#define TC_MARK(slot) if (tid == 0 && stats != nullptr) { const long long t_ = clock64(); atomicAdd(&stats[slot], (u64)(t_ - t_mark)); t_mark = t_; }
-#else
-#define TC_MARK(slot)
-#endif
   if (warp == kTcEpiWarps) {
     // ===== column-operand builder (one pass per phase) =====
-    // Only passes that contain a live stage are built (buffer = built-pass count & 1).  The 24 coordinate loads of the
-    // NEXT pass are issued before this warp waits for that pass's buffer, so their latency hides behind the MMAs that
-    // still read it: with most stages pruned a pass is short, and an L2 round trip per pass would set the pace.
-    uint32_t seq = 0;
-    float tx[8], ty[8], tz[8];
-    auto next_needed = [&](int cc) { while (cc < 2 * hc && !tc_pass_needed(cc < hc, cc < hc ? cc : cc - hc, nc, NB, skip0, skip1)) ++cc; return cc; };
-    auto load_pass = [&](int cc) {
+    for (int cc = 0; cc < 2 * hc; ++cc) {
       const int j = cc < hc ? cc : cc - hc;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int jj = k * 32 + lane;                               // 0..255: half = jj >> 7
-        int chunk = c_first + 2 * j + (jj >> 7);
-        if (chunk >= c_last) chunk = c_first + 2 * j;               // unpaired last chunk: duplicate, never recorded
-        const int col = min(chunk * kTcBlk + (jj & 127), M - 1);
-        tx[k] = T[3 * (size_t)col]; ty[k] = T[3 * (size_t)col + 1]; tz[k] = T[3 * (size_t)col + 2];
-      }
-    };
-    int cc = next_needed(0);
-    if (cc < 2 * hc) load_pass(cc);
-    while (cc < 2 * hc) {
-      const int cb = seq & 1, use = seq >> 1;
-      ++seq;
+      const int cb = cc & 1, use = cc >> 1;
       tc_mbar_wait(bar_cempty + 8 * cb, (use & 1) ^ 1);
       unsigned char* dst = sm.cols + cb * 2 * kTcBlkBytes;
-#pragma unroll
+#pragma unroll 2
       for (int k = 0; k < 8; ++k) {
-        const int jj = k * 32 + lane;
-        const float x = __fsub_rn(tx[k], cx), y = __fsub_rn(ty[k], cy), z = __fsub_rn(tz[k], cz);
+        const int jj = k * 32 + lane;                               // 0..255: half = jj >> 7
+        int chunk = c_first + ((jj >> 7) ? hc + j : j);
+        if (chunk >= c_last) chunk = c_first + j;                   // unpaired last chunk: duplicate, never recorded
+        const int col = min(chunk * kTcBlk + (jj & 127), M - 1);
+        const float x = __fsub_rn(T[3 * (size_t)col], cx), y = __fsub_rn(T[3 * (size_t)col + 1], cy), z = __fsub_rn(T[3 * (size_t)col + 2], cz);
         const float n2 = tc_make_operand(dst + (jj >> 7) * kTcBlkBytes, jj & 127, x * S, y * S, z * S, false);
         if (!(n2 < 20000.f)) atomicOr(&fallback[b], 1);             // cannot happen for finite targets (|T| < 128)
       }
       tc_fence_async_smem();
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(bar_cfull + 8 * cb);
-      cc = next_needed(cc + 1);
-      if (cc < 2 * hc) load_pass(cc);
     }
   } else if (warp == kTcEpiWarps + 1) {
     // ===== MMA issuer: the whole warp walks the loop (warp-uniform operands), one elected lane issues =====
@@ -503,18 +324,14 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
     const uint64_t drows = tc_desc(rows_a);
     uint32_t it = 0;
-    uint32_t seq = 0;
     for (int cc = 0; cc < 2 * hc; ++cc) {
       const int j = cc < hc ? cc : cc - hc;
-      if (!tc_pass_needed(cc < hc, j, nc, NB, skip0, skip1)) continue;
-      const int cb = seq & 1, cuse = seq >> 1;
-      ++seq;
+      const int cb = cc & 1, cuse = cc >> 1;
       tc_mbar_wait(bar_cfull + 8 * cb, cuse & 1);
       tc_fence_after();
       const uint64_t dcols = tc_desc(cols_a + cb * 2 * kTcBlkBytes);
       if (cc < hc) {
-        for (uint32_t live = ~skip0[j] & ((1u << NB) - 1u); live; live &= live - 1) {
-          const int r = __ffs((int)live) - 1;
+        for (int r = 0; r < NB; ++r, ++it) {
           const uint32_t st = it & 1;
           tc_mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -525,14 +342,12 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
             tc_commit(bar_full + 8 * st);
           }
           __syncwarp();
-          ++it;
         }
       } else {
-        const int nh = (2 * j + 1 < nc) ? 2 : 1;
+        const int nh = (c_first + hc + j < c_last) ? 2 : 1;
         for (int h = 0; h < nh; ++h) {
           const uint64_t dc = dcols + (uint64_t)(h * (kTcBlkBytes >> 4));
-          for (uint32_t live = ~skip1[2 * j + h] & ((1u << NP) - 1u); live; live &= live - 1) {
-            const int rp = __ffs((int)live) - 1;
+          for (int rp = 0; rp < NP; ++rp, ++it) {
             const uint32_t st = it & 1;
             tc_mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -543,7 +358,6 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
               tc_commit(bar_full + 8 * st);
             }
             __syncwarp();
-            ++it;
           }
         }
       }
@@ -559,17 +373,13 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     // ---- phase 0: row minima; record (h, row): best value and the mask of chunk pairs j whose chunk may hold the arg-min
     float* my_best = sm.rs_best + (size_t)h * TM;
     uint32_t* my_mask = sm.rs_mask + (size_t)h * TM;
-    const uint32_t nbmask = (1u << NB) - 1u, npmask = (1u << NP) - 1u;
     for (int j = 0; j < hc; ++j) {
-      const bool valid = 2 * j + h < nc;
-      // only the live stages are visited (a per-stage `if skipped continue` cost as many instructions as the stages left)
-      for (uint32_t live = ~skip0[j] & nbmask; live; live &= live - 1) {
-        const int r = __ffs((int)live) - 1;
+      const bool valid = c_first + (h ? hc + j : j) < c_last;
+      for (int r = 0; r < NB; ++r, ++it) {
         const uint32_t st = it & 1;
         tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
         tc_fence_after();
         const float m = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
-        ++it;
         const int ri = r * kTcBlk + li;
         const float best = my_best[ri];
         if (valid && m <= tc_thr(best, slack_rel, slack_abs)) {
@@ -580,59 +390,35 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         }
       }
     }
-    TC_MARK(3)
-    // ---- phase 1: column minima.  Thread = one column of the chunk; it keeps a running record (best, mask of row
-    // blocks) of the row blocks 2 rp + h it sees, in REGISTERS, with the same update rule as the row records; at the end
-    // of a chunk the two warps of a lane quarter (h = 0 / 1) exchange their records through shared memory (8 bytes per
-    // column) and the warp whose turn it is merges the two and writes the (tile, column) record.  (A per-block value
-    // array in shared memory merged in two passes per chunk cost ~400 clk per chunk on the critical path.)
+    // ---- phase 1: column minima per 128-row block, merged per chunk into (best, mask of row blocks)
     int cseq = 0;
-    float2* xch = reinterpret_cast<float2*>(sm.colw);                 // [parity][h][128] exchange slots
     for (int j = 0; j < hc; ++j) {
-      const int nh = (2 * j + 1 < nc) ? 2 : 1;
-      for (int hh = 0; hh < nh; ++hh) {
-        const uint32_t live1 = ~skip1[2 * j + hh] & npmask;          // row-block pairs of this chunk that are computed
-        if (live1 == 0u) {
-          // chunk pruned for the whole tile: record (+inf, no candidate) - it is never a candidate in the recovery.  No
-          // exchange, no barrier, and it does not take part in the two warps' alternation (cseq counts live chunks).
-          const int col = (c_first + 2 * j + hh) * kTcBlk + li;
-          if (h == hh && col < M) { const size_t o = ((size_t)b * ntiles + tile_i) * M + col; cbest[o] = tc_inf(); cmask[o] = 0u; }
-          continue;
-        }
-        float best = tc_inf(); uint32_t mask = 0u;
-        for (uint32_t live = live1; live; live &= live - 1) {
-          const int rp = __ffs((int)live) - 1;
+      const int nh = (c_first + hc + j < c_last) ? 2 : 1;
+      for (int hh = 0; hh < nh; ++hh, ++cseq) {
+        float* cw = sm.colw + (size_t)(cseq & 1) * NB * kTcBlk;
+        for (int rp = 0; rp < NP; ++rp, ++it) {
           const uint32_t st = it & 1;
           tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
           tc_fence_after();
-          const float m = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
-          ++it;
-          if (m <= tc_thr(best, slack_rel, slack_abs)) {
-            const float tm = tc_thr(m, slack_rel, slack_abs);
-            mask = ((tm < best) ? 0u : mask) | (1u << (2 * rp + h));
-            best = fminf(best, m);
-          }
+          cw[(2 * rp + h) * kTcBlk + li] = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
         }
-        float2* slot = xch + (size_t)(cseq & 1) * 2 * kTcBlk;
-        slot[h * kTcBlk + li] = make_float2(best, __uint_as_float(mask));
-        // the two warps of this lane quarter meet once per live chunk; they take turns merging
+        // the two warps of this lane quarter meet once per chunk; they take turns merging
         asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
         if ((cseq & 1) == h) {
-          const int col = (c_first + 2 * j + hh) * kTcBlk + li;
+          const int col = (c_first + (hh ? hc + j : j)) * kTcBlk + li;
           if (col < M) {
-            const float2 other = slot[(h ^ 1) * kTcBlk + li];
-            const float b2 = fminf(best, other.x);
-            const float t = tc_thr(b2, slack_rel, slack_abs);
-            const uint32_t m2 = ((best <= t) ? mask : 0u) | ((other.x <= t) ? __float_as_uint(other.y) : 0u);
+            float best = tc_inf();
+            for (int i = 0; i < NB; ++i) best = fminf(best, cw[i * kTcBlk + li]);
+            const float t = tc_thr(best, slack_rel, slack_abs);
+            unsigned mask = 0;
+            for (int i = 0; i < NB; ++i) mask |= (cw[i * kTcBlk + li] <= t) ? (1u << i) : 0u;
             const size_t o = ((size_t)b * ntiles + tile_i) * M + col;
-            cbest[o] = b2 * invS2; cmask[o] = m2;
+            cbest[o] = best * invS2; cmask[o] = mask;
           }
         }
-        ++cseq;
       }
     }
   }
-  TC_MARK(4)
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
@@ -642,121 +428,18 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       const float b0 = sm.rs_best[i], b1 = sm.rs_best[TM + i];
       const float best = fminf(b0, b1);
       const float t = tc_thr(best, slack_rel, slack_abs);
-      // record (h, row) bit j names chunk 2 j + h of the split: interleave the two 32-bit masks
-      const u64 mask = ((b0 <= t) ? tc_spread32(sm.rs_mask[i]) : 0ull) | ((b1 <= t) ? (tc_spread32(sm.rs_mask[TM + i]) << 1) : 0ull);
+      const u64 mask = ((b0 <= t) ? (u64)sm.rs_mask[i] : 0ull) | ((b1 <= t) ? ((u64)sm.rs_mask[TM + i] << hc) : 0ull);
       const size_t o = ((size_t)b * nsplit + split) * P + row;
       rbest[o] = best * invS2; rmask[o] = mask;
     }
   }
-  TC_MARK(5)
 }
 
-// Samples whose coordinates are not finite or too large for the centred expansion (fallback[b] != 0) are
-// redone here with the reference's arithmetic, thread per point, no candidate filter: correct, not fast.
-// grid: x = slice, y = sample
-__global__ void __launch_bounds__(256)
-chamfer_flagged_kernel(const float* __restrict__ p1, const float* __restrict__ p2, float* __restrict__ min1,
-                       int* __restrict__ idx1, float* __restrict__ min2, int* __restrict__ idx2,
-                       const int* __restrict__ fallback, int P, int M) {
-  const int b = blockIdx.y;
-  if (fallback[b] == 0) return;
-  const float* A = p1 + (size_t)b * P * 3;
-  const float* T = p2 + (size_t)b * M * 3;
-  for (int dir = 0; dir < 2; ++dir) {
-    const float* X = dir ? T : A; const float* Y = dir ? A : T;
-    const int nx = dir ? M : P, ny = dir ? P : M;
-    float* mn = (dir ? min2 + (size_t)b * M : min1 + (size_t)b * P);
-    int* ix = (dir ? idx2 + (size_t)b * M : idx1 + (size_t)b * P);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
-      const float x = X[3 * (size_t)i], y = X[3 * (size_t)i + 1], z = X[3 * (size_t)i + 2];
-      float bv = tc_inf(); int bj = 0;
-      // torch.min over sqrt(d): first index of the smallest value; NaN propagates as in torch (first NaN wins)
-      bool nan_seen = false;
-      for (int j = 0; j < ny; ++j) {
-        // (x - y)^2 == (y - x)^2 bit for bit, so the direction of the difference does not matter
-        const float dx = __fsub_rn(x, Y[3 * (size_t)j]), dy = __fsub_rn(y, Y[3 * (size_t)j + 1]), dz = __fsub_rn(z, Y[3 * (size_t)j + 2]);
-        const float v = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-        if (!nan_seen) {
-          if (v != v) { bv = v; bj = j; nan_seen = true; }
-          else if (v < bv || j == 0) { bv = v; bj = j; }
-        }
-      }
-      mn[i] = bv; ix[i] = bj;
-    }
-  }
+int launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask, float2* tslack, int* fallback,
+           const float* tmax, int B, int P, int M, int NB, int ntiles, int nsplit, int nchunks, int cps, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(chamfer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(16)); attr = true; }
+  chamfer_tc_kernel<<<dim3(ntiles, nsplit, B), kTcThreads, tc_smem_bytes(NB), s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax, P, M, NB, nchunks, cps);
+  return 0;
 }
-
-// largest |coordinate| of every sample's targets (the tensor-core kernel scales by it).  grid: x = sample
-__global__ void __launch_bounds__(256)
-chamfer_tc_bounds_kernel(const float* __restrict__ p2, float* __restrict__ tmax, int M) {
-  __shared__ float red[8];
-  const float* T = p2 + (size_t)blockIdx.x * M * 3;
-  float m = 0.f;
-  for (int i = threadIdx.x; i < 3 * M; i += 256) {
-    const float v = fabsf(T[i]);
-    m = (v <= m) ? m : v;                                           // NaN sticks
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { const float x = __shfl_xor_sync(0xffffffffu, m, o); m = (x <= m) ? m : x; }
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) m = (red[w] <= m) ? m : red[w];
-    tmax[blockIdx.x] = m;
-  }
-}
-
-size_t chamfer_tc_smem_bytes(int NB) { return tc_smem_bytes(NB); }
-}  // namespace vpn
-#ifdef VPN_TC_R1PROBE
-namespace vpn_r1 { int launch(const float*, const float*, float*, vpn::u64*, float*, unsigned*, float2*, int*, const float*, int, int, int, int, int, int, int, int, cudaStream_t); }
-#endif
-namespace vpn {
-
-// p2: the targets the filter sweeps (Morton-sorted copy when cbox != NULL); tmax filled by the caller (chamfer_prep_launch)
-// when with_bounds == 0, by chamfer_tc_bounds_kernel here otherwise.
-// cbox != NULL: the pruned sweep; plan_masks (ncta x kTcPlanWords words), plan_work and plan_order (ncta ints) are scratch.
-int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
-                      float2* tslack, int* fallback, float* tmax, const float* cbox, const float* rbox, const float* rthr,
-                      const float* cub, u64* stats, uint32_t* plan_masks, int* plan_work, int* plan_order, int with_bounds,
-                      int B, int P, int M, int NB, int ntiles, int nsplit, int nchunks, int cps, cudaStream_t s) {
-  static DeviceOnce once;
-  const size_t smem = tc_smem_bytes(NB);
-  {
-    cudaError_t e = set_dyn_smem(chamfer_tc_kernel, (int)tc_smem_bytes(16), once);
-    if (e != cudaSuccess) { vpn_set_error("chamfer tc: smem attribute: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
-  }
-  int rc;
-  if (with_bounds) {
-    chamfer_tc_bounds_kernel<<<B, 256, 0, s>>>(p2, tmax, M);
-    if ((rc = vpn_check_launch("chamfer_tc_bounds_kernel"))) return rc;
-  }
-  const long long ncta_ll = (long long)ntiles * nsplit * B;
-  if (ncta_ll > 0x7fffffffLL) { vpn_set_error("chamfer tc: too many tiles"); return VPN_ERR_SHAPE; }
-  const int ncta = (int)ncta_ll;
-  if (cbox != nullptr) {
-    chamfer_tc_plan_kernel<<<ncta, kPlanThreads, 0, s>>>(
-        cbox, rbox, rthr, cub, plan_masks, plan_work, ncta, ntiles, nsplit, (P + kTcBlk - 1) / kTcBlk, NB, nchunks, cps);
-    if ((rc = vpn_check_launch("chamfer_tc_plan_kernel"))) return rc;
-    chamfer_tc_order_kernel<<<1, kOrderThreads, 0, s>>>(plan_work, plan_order, ncta);
-    if ((rc = vpn_check_launch("chamfer_tc_order_kernel"))) return rc;
-  }
-#ifdef VPN_TC_R1PROBE
-  if (cbox == nullptr && tuning_value(kTuneTcNb) == 99) {        // probe: round 1's kernel (NB 16 plan only)
-    vpn_r1::launch(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax, B, P, M, NB, ntiles, nsplit, nchunks, cps, s);
-    return vpn_check_launch("chamfer_tc_kernel_r1");
-  }
-#endif
-  chamfer_tc_kernel<<<ncta, kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax,
-                                                   cbox ? plan_masks : nullptr, cbox ? plan_order : nullptr, stats,
-                                                   ntiles, nsplit, P, M, NB, nchunks, cps);
-  return vpn_check_launch("chamfer_tc_kernel");
-}
-
-int chamfer_flagged_launch(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
-                           const int* fallback, int B, int P, int M, cudaStream_t s) {
-  chamfer_flagged_kernel<<<dim3(32, B), 256, 0, s>>>(p1, p2, min1, idx1, min2, idx2, fallback, P, M);
-  return vpn_check_launch("chamfer_flagged_kernel");
-}
-
-}  // namespace vpn
+}  // namespace vpn_r1

@@ -166,7 +166,7 @@ pose_fwd_kernel(const float* __restrict__ v, const float* __restrict__ q, const 
 //   [12..14] sum_n (R^T g_n) (.) d_n   (dL/dv)
 // KIND_POINTS also writes dL/dpoints = R^T g.
 template <int KIND>
-__global__ void __launch_bounds__(kPoseThreads)
+__global__ void __launch_bounds__(kPoseThreads, 3)
 pose_bwd_partial_kernel(const float* __restrict__ v, const float* __restrict__ q,
                         const float* __restrict__ src, const float* __restrict__ gout,
                         float* __restrict__ partial, float* __restrict__ gpts, int N, int vec_ok) {
