@@ -32,10 +32,4 @@ for path in sys.argv[1:]:
             lib.vpn_chamfer_fwd_timed(pts.data_ptr(), tgt.data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(),
                                       b, P, m, ws.data_ptr(), nb.value, 5, reps, ms, None)
         print(os.path.basename(path), "unpruned: main %.3f fallback %.3f rows %.3f cols %.3f" % tuple(ms), flush=True)
-        lib.vpn_set_tuning(b"tc_nb", 99)
-        for reps in (2, 10):
-            lib.vpn_chamfer_fwd_timed(pts.data_ptr(), tgt.data_ptr(), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(),
-                                      b, P, m, ws.data_ptr(), nb.value, 5, reps, ms, None)
-        print(os.path.basename(path), "unpruned, tc_nb=99 (round-1 kernel in probe builds): main %.3f" % ms[0], flush=True)
-        lib.vpn_set_tuning(b"tc_nb", 0)
         lib.vpn_set_tuning(b"tc_prune", 0)

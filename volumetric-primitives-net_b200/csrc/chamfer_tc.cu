@@ -707,11 +707,7 @@ chamfer_tc_bounds_kernel(const float* __restrict__ p2, float* __restrict__ tmax,
 }
 
 size_t chamfer_tc_smem_bytes(int NB) { return tc_smem_bytes(NB); }
-}  // namespace vpn
-#ifdef VPN_TC_R1PROBE
-namespace vpn_r1 { int launch(const float*, const float*, float*, vpn::u64*, float*, unsigned*, float2*, int*, const float*, int, int, int, int, int, int, int, int, cudaStream_t); }
-#endif
-namespace vpn {
+
 
 // p2: the targets the filter sweeps (Morton-sorted copy when cbox != NULL); tmax filled by the caller (chamfer_prep_launch)
 // when with_bounds == 0, by chamfer_tc_bounds_kernel here otherwise.
@@ -741,12 +737,6 @@ int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask
     chamfer_tc_order_kernel<<<1, kOrderThreads, 0, s>>>(plan_work, plan_order, ncta);
     if ((rc = vpn_check_launch("chamfer_tc_order_kernel"))) return rc;
   }
-#ifdef VPN_TC_R1PROBE
-  if (cbox == nullptr && tuning_value(kTuneTcNb) == 99) {        // probe: round 1's kernel (NB 16 plan only)
-    vpn_r1::launch(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax, B, P, M, NB, ntiles, nsplit, nchunks, cps, s);
-    return vpn_check_launch("chamfer_tc_kernel_r1");
-  }
-#endif
   chamfer_tc_kernel<<<ncta, kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax,
                                                    cbox ? plan_masks : nullptr, cbox ? plan_order : nullptr, stats,
                                                    ntiles, nsplit, P, M, NB, nchunks, cps);
