@@ -164,6 +164,14 @@ int vpn_feature_pool_fwd(const float* feat, const float* pts, const float* bound
 int vpn_feature_pool_bwd(const float* feat, const float* pts, const float* bounds, const float* range,
                          const float* grad_out, float* grad_feat, float* grad_grid,
                          int B, int C, int H, int W, int N, int Ctot, int coff, void* stream);
+/* The same gradient through the cell-sorted kernels (what the autograd Function uses): the vertices are counting-sorted by
+ * bilinear cell once per map, a warp accumulates a cell's four texel gradients in registers and flushes them with global
+ * float atomics into the zero-filled grad_feat (so the summation order, hence the last bits, can differ between runs).
+ * workspace: vpn_feature_pool_bwd_workspace_bytes(B, N) bytes of scratch, reusable for every map. */
+int vpn_feature_pool_bwd_workspace_bytes(int B, int N, size_t* bytes);
+int vpn_feature_pool_bwd_sorted(const float* feat, const float* pts, const float* bounds, const float* range,
+                                const float* grad_out, float* grad_feat, float* grad_grid, void* workspace,
+                                size_t workspace_bytes, int B, int C, int H, int W, int N, int Ctot, int coff, void* stream);
 int vpn_feature_pool_points_bwd(const float* pts, const float* bounds, const float* range, const int* arg,
                                 const float* grad_grid, float* grad_pts, int B, int N, void* stream);
 

@@ -22,13 +22,23 @@ ggrid = torch.zeros(b, n, 2, device=dev)
 coff = 0
 for c, h, w in maps:
     f = torch.randn(b, c, h, w, device=dev); gf = torch.empty_like(f)
-    def run():
+    import ctypes
+    nws = ctypes.c_size_t(0)
+    check(lib.vpn_feature_pool_bwd_workspace_bytes(b, n, ctypes.byref(nws)), "ws")
+    ws = torch.empty(nws.value, dtype=torch.uint8, device=dev)
+    def run_old():
         check(lib.vpn_feature_pool_bwd(ptr(f), ptr(pts), ptr(bounds), ptr(rng), ptr(gout), ptr(gf), ptr(ggrid), b, c, h, w, n, ctot, coff,
                                        stream_ptr(dev)), "bwd")
-    for _ in range(3): run()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); e0.record()
-    for _ in range(20): run()
-    e1.record(); torch.cuda.synchronize()
-    print(f"map {c}x{h}x{w}: bwd {e0.elapsed_time(e1) / 20:.4f} ms  (atomic kernel forced: {os.environ.get('VPN_POOL_BWD_ATOMIC', '0')})", flush=True)
+    def run_new():
+        check(lib.vpn_feature_pool_bwd_sorted(ptr(f), ptr(pts), ptr(bounds), ptr(rng), ptr(gout), ptr(gf), ptr(ggrid), ptr(ws), nws.value,
+                                              b, c, h, w, n, ctot, coff, stream_ptr(dev)), "bwd sorted")
+    res = []
+    for run in (run_old, run_new):
+        for _ in range(3): run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(20): run()
+        e1.record(); torch.cuda.synchronize()
+        res.append(e0.elapsed_time(e1) / 20)
+    print(f"map {c}x{h}x{w}: bwd shared-memory-atomic kernel {res[0]:.4f} ms, cell-sorted kernels {res[1]:.4f} ms", flush=True)
     coff += c

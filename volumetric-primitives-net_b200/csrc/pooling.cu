@@ -284,6 +284,153 @@ feature_pool_bwd_kernel(const float* __restrict__ feat, const float* __restrict_
   for (int i = tid; i < nch * HW; i += kPoolThreads) gb[i] = gpl[(i / HW) * stride + (i % HW)];
 }
 
+// ---- backward, round 2: vertices sorted by bilinear cell, register accumulation per cell --------------------------
+// The first backward (feature_pool_bwd_kernel above, still behind vpn_feature_pool_bwd) spent its time on per-vertex tap broadcasts (16 shuffles), shared-memory float
+// atomics (compare-and-swap loops) and a shuffle reduction per (vertex, 32-channel chunk): ~90 instructions per
+// (vertex, chunk), 1.85 ms at train_gcn's shape.  Here:
+//   feature_pool_sort_kernel   one CTA per sample: the four taps of every vertex and a counting sort of the vertices by
+//                              the bilinear cell (x0, y0) they fall in.  All vertices of a cell share their four texels.
+//   feature_pool_bwd2_kernel   a warp walks a contiguous run of the sorted list with the lanes over channels (32 KCS per
+//                              CTA): per vertex and chunk ONE coalesced 128-byte load of grad_out and 14 FMAs - the
+//                              texel gradients of the current cell accumulate in registers, the cell's features stay in
+//                              registers - and one shuffle reduction per vertex and CTA for the grid gradient.  When the
+//                              cell changes, the four accumulators per channel are flushed with global float atomics
+//                              (single RED instructions) into the zero-filled grad_feat.
+struct __align__(16) PoolRec { int off[4]; float w[4]; float dx[4]; float dy[4]; };
+
+// grid: x = sample; kPoolThreads threads; dynamic smem: (H + 1) (W + 1) + 1 ints
+__global__ void __launch_bounds__(kPoolThreads)
+feature_pool_sort_kernel(const float* __restrict__ pts, const float* __restrict__ bounds, const float* __restrict__ range,
+                         PoolRec* __restrict__ rec, int* __restrict__ key_out, int* __restrict__ vid_out, int H, int W, int N) {
+  extern __shared__ int pool_hist[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int ncell = (H + 1) * (W + 1);
+  for (int i = tid; i <= ncell; i += kPoolThreads) pool_hist[i] = 0;
+  __syncthreads();
+  const float* bnd = bounds + 4 * b;
+  const float* rng = range + 4 * b;
+  int valid_mask = 0;
+  auto cell_of = [&](int n, Taps& t) {
+    float gx, gy;
+    grid_of_vertex(pts + ((size_t)b * N + n) * 3, bnd, rng, gx, gy);
+    make_taps(gx, gy, H, W, t);
+    const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(W - 1));
+    const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(H - 1));
+    // cell (x0, y0) = floor of the pixel coordinates, shifted by one so that the border cells (x0 = -1) get key >= 0;
+    // coordinates outside [-1, W) / NaN share cell 0 - all their taps are invalid anyway
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const bool in = x0 >= -1.f && x0 <= (float)(W - 1) && y0 >= -1.f && y0 <= (float)(H - 1);
+    // which of the four taps (nw, ne, sw, se) lie inside the plane: a property of the cell, kept in the key's top bits
+    // (a tap's coefficients can all vanish for ONE vertex - one that sits exactly on a texel - while the tap is valid)
+    valid_mask = 0;
+    if (in) {
+      const bool xa = x0 >= 0.f, xb = x0 + 1.0f <= (float)(W - 1), ya = y0 >= 0.f, yb = y0 + 1.0f <= (float)(H - 1);
+      valid_mask = (xa && ya ? 1 : 0) | (xb && ya ? 2 : 0) | (xa && yb ? 4 : 0) | (xb && yb ? 8 : 0);
+    }
+    return in ? ((int)y0 + 1) * (W + 1) + ((int)x0 + 1) : 0;
+  };
+  for (int n = tid; n < N; n += kPoolThreads) { Taps t; atomicAdd(&pool_hist[cell_of(n, t) + 1], 1); }
+  __syncthreads();
+  if (tid == 0) { int run = 0; for (int i = 1; i <= ncell; ++i) { run += pool_hist[i]; pool_hist[i] = run; } }      // hist[c] = start of cell c
+  __syncthreads();
+  for (int n = tid; n < N; n += kPoolThreads) {
+    Taps t;
+    const int key = cell_of(n, t);
+    const int slot = atomicAdd(&pool_hist[key], 1);                                // order inside a cell: whichever thread comes first
+    const size_t o = (size_t)b * N + slot;
+    PoolRec r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { r.off[k] = t.off[k]; r.w[k] = t.w[k]; r.dx[k] = t.dx[k]; r.dy[k] = t.dy[k]; }
+    rec[o] = r; key_out[o] = key | (valid_mask << 24); vid_out[o] = n;
+  }
+}
+
+// grid: x = run of the sorted vertex list, y = channel slab (32 KCS channels), z = sample
+template <int KCS>
+__global__ void __launch_bounds__(kPoolThreads)
+feature_pool_bwd2_kernel(const float* __restrict__ feat, const float* __restrict__ gout, const PoolRec* __restrict__ rec,
+                         const int* __restrict__ keys, const int* __restrict__ vids, float* __restrict__ gfeat,
+                         float* __restrict__ ggrid, int C, int H, int W, int N, int Ctot, int coff, int per_cta) {
+  const int b = blockIdx.z, c0 = blockIdx.y * 32 * KCS, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HW = H * W;
+  const int per_warp = (per_cta + kPoolThreads / 32 - 1) / (kPoolThreads / 32);
+  const int p0 = blockIdx.x * per_cta + warp * per_warp;
+  const int p1 = min(min(p0 + per_warp, (int)(blockIdx.x + 1) * per_cta), N);
+  const float mx = 0.5f * (float)(W - 1), my = 0.5f * (float)(H - 1);             // d ix / d grid x (align_corners=True)
+  bool chan[KCS];
+  const float* fch[KCS]; float* gch[KCS];
+#pragma unroll
+  for (int kc = 0; kc < KCS; ++kc) {
+    const int c = c0 + kc * 32 + lane;
+    chan[kc] = c < C;
+    const size_t plane = ((size_t)b * C + (chan[kc] ? c : 0)) * HW;
+    fch[kc] = feat + plane; gch[kc] = gfeat + plane;
+  }
+  float acc[KCS][4], f[KCS][4];
+  int cur_key = -1, cur_off[4] = {0, 0, 0, 0};
+  bool cur_ok[4] = {false, false, false, false};
+  auto flush = [&]() {
+#pragma unroll
+    for (int kc = 0; kc < KCS; ++kc)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (chan[kc] && cur_ok[k] && acc[kc][k] != 0.f) atomicAdd(gch[kc] + cur_off[k], acc[kc][k]);
+  };
+  // two-deep software pipeline: a vertex's record (rec, key, vertex id) is loaded two iterations ahead, its grad_out
+  // words - whose address needs the vertex id - one iteration ahead; a warp walks its run serially, so without this every
+  // vertex paid an L2 round trip plus an HBM round trip
+  PoolRec r0, r1; int key0 = 0, key1 = 0, n0 = 0, n1 = 0;
+  float g0[KCS];
+  auto load_rec = [&](int p, PoolRec& r, int& key, int& n) {
+    const size_t o = (size_t)b * N + p;
+    r = rec[o]; key = keys[o]; n = vids[o];                                         // same address on every lane: broadcast
+  };
+  auto load_g = [&](int n, float (&g)[KCS]) {
+    const float* grow = gout + ((size_t)b * N + n) * Ctot + coff + c0 + lane;
+#pragma unroll
+    for (int kc = 0; kc < KCS; ++kc) g[kc] = chan[kc] ? grow[kc * 32] : 0.f;
+  };
+  if (p0 < p1) { load_rec(p0, r0, key0, n0); load_g(n0, g0); }
+  if (p0 + 1 < p1) load_rec(p0 + 1, r1, key1, n1);
+  for (int p = p0; p < p1; ++p) {
+    const PoolRec r = r0;
+    const int key = key0, n = n0;
+    float g[KCS];
+#pragma unroll
+    for (int kc = 0; kc < KCS; ++kc) g[kc] = g0[kc];
+    if (p + 1 < p1) { r0 = r1; key0 = key1; n0 = n1; load_g(n0, g0); }
+    if (p + 2 < p1) load_rec(p + 2, r1, key1, n1);
+    if (key != cur_key) {
+      if (cur_key >= 0) flush();
+      cur_key = key;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { cur_off[k] = r.off[k]; cur_ok[k] = (key >> (24 + k)) & 1; }      // validity: per cell, in the key
+#pragma unroll
+      for (int kc = 0; kc < KCS; ++kc)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc[kc][k] = 0.f; f[kc][k] = (chan[kc] && cur_ok[k]) ? __ldg(fch[kc] + cur_off[k]) : 0.f; }
+    }
+    float gix = 0.f, giy = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < KCS; ++kc) {
+      float sx = 0.f, sy = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        sx = fmaf(f[kc][k], r.dx[k], sx); sy = fmaf(f[kc][k], r.dy[k], sy);
+        acc[kc][k] = fmaf(g[kc], r.w[k], acc[kc][k]);
+      }
+      gix = fmaf(g[kc], sx, gix); giy = fmaf(g[kc], sy, giy);
+    }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) { gix += __shfl_xor_sync(0xffffffffu, gix, o2); giy += __shfl_xor_sync(0xffffffffu, giy, o2); }
+    if (lane == 0) {
+      atomicAdd(&ggrid[((size_t)b * N + n) * 2], gix * mx);
+      atomicAdd(&ggrid[((size_t)b * N + n) * 2 + 1], giy * my);
+    }
+  }
+  if (cur_key >= 0) flush();
+}
+
 // grad_grid (B, N, 2) -> grad_points (B, N, 3), including the terms that reach the arg-min / arg-max vertices through
 // the range (autograd of gcn.py:146-154: points.max(0) / .min(0) are differentiable).  grid: x = sample
 __global__ void __launch_bounds__(kPoolThreads)
@@ -418,6 +565,56 @@ extern "C" int vpn_feature_pool_bwd(const float* feat, const float* pts, const f
   feature_pool_bwd_kernel<<<grid, kPoolThreads, staged ? (size_t)2 * ch * stride * 4 : 0, (cudaStream_t)stream>>>(
       feat, pts, bounds, range, grad_out, grad_feat, grad_grid, C, H, W, N, Ctot, coff, ch, stride, staged);
   return vpn_check_launch("feature_pool_bwd_kernel");
+}
+
+extern "C" int vpn_feature_pool_bwd_workspace_bytes(int B, int N, size_t* bytes) {
+  if (B < 0 || N <= 0 || !bytes) { vpn_set_error("feature pool bwd workspace: bad arguments"); return VPN_ERR_ARG; }
+  *bytes = (size_t)B * N * (sizeof(PoolRec) + 8) + 256;
+  return VPN_OK;
+}
+
+// Same contract as vpn_feature_pool_bwd (grad_feat fully written, grad_grid ACCUMULATED), through the cell-sorted kernels.
+// workspace: vpn_feature_pool_bwd_workspace_bytes(B, N) bytes of scratch (reused for every map).
+extern "C" int vpn_feature_pool_bwd_sorted(const float* feat, const float* pts, const float* bounds, const float* range,
+                                           const float* grad_out, float* grad_feat, float* grad_grid, void* workspace,
+                                           size_t workspace_bytes, int B, int C, int H, int W, int N, int Ctot, int coff,
+                                           void* stream) {
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0 || N <= 0 || coff < 0 || coff + C > Ctot) { vpn_set_error("feature pool bwd: bad shape"); return VPN_ERR_SHAPE; }
+  if (B == 0) return VPN_OK;
+  if (B > 65535) { vpn_set_error("feature pool bwd: batch > 65535 unsupported"); return VPN_ERR_SHAPE; }
+  if (!feat || !pts || !bounds || !range || !grad_out || !grad_feat || !grad_grid || !workspace) { vpn_set_error("feature pool bwd: null pointer"); return VPN_ERR_ARG; }
+  const size_t need = (size_t)B * N * (sizeof(PoolRec) + 8) + 256;
+  const size_t hist_bytes = ((size_t)(H + 1) * (W + 1) + 1) * sizeof(int);
+  if (workspace_bytes < need) { vpn_set_error("feature pool bwd: workspace too small"); return VPN_ERR_WORKSPACE; }
+  if (hist_bytes > 200 * 1024) { vpn_set_error("feature pool bwd: feature map too large for the cell histogram"); return VPN_ERR_SHAPE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(workspace);
+  PoolRec* rec = reinterpret_cast<PoolRec*>(ws);
+  int* keys = reinterpret_cast<int*>(ws + (((size_t)B * N * sizeof(PoolRec) + 255) & ~(size_t)255));
+  int* vids = keys + (size_t)B * N;
+  if (cudaMemsetAsync(grad_feat, 0, (size_t)B * C * H * W * 4, s) != cudaSuccess) { vpn_set_error("feature pool bwd: memset failed"); return VPN_ERR_CUDA; }
+  static DeviceOnce once;
+  if (hist_bytes > 48 * 1024 && set_dyn_smem(feature_pool_sort_kernel, 200 * 1024, once) != cudaSuccess) {
+    vpn_set_error("feature pool bwd: smem attribute"); return VPN_ERR_CUDA;
+  }
+  feature_pool_sort_kernel<<<B, kPoolThreads, hist_bytes, s>>>(pts, bounds, range, rec, keys, vids, H, W, N);
+  int rc = vpn_check_launch("feature_pool_sort_kernel");
+  if (rc) return rc;
+  // 32 KCS channels per CTA; enough runs of the sorted list for ~4 CTAs per SM, at least 64 vertices per CTA
+  const int kcs = C > 64 ? 4 : (C > 32 ? 2 : 1);
+  const int slabs = (C + 32 * kcs - 1) / (32 * kcs);
+  int runs = (4 * device_sm_count() + slabs * B - 1) / (slabs * B);
+  const int max_runs = (N + 63) / 64;
+  if (runs > max_runs) runs = max_runs;
+  if (runs < 1) runs = 1;
+  const int per_cta = (N + runs - 1) / runs;
+  dim3 grid((N + per_cta - 1) / per_cta, slabs, B);
+  switch (kcs) {
+    case 4:  feature_pool_bwd2_kernel<4><<<grid, kPoolThreads, 0, s>>>(feat, grad_out, rec, keys, vids, grad_feat, grad_grid, C, H, W, N, Ctot, coff, per_cta); break;
+    case 2:  feature_pool_bwd2_kernel<2><<<grid, kPoolThreads, 0, s>>>(feat, grad_out, rec, keys, vids, grad_feat, grad_grid, C, H, W, N, Ctot, coff, per_cta); break;
+    default: feature_pool_bwd2_kernel<1><<<grid, kPoolThreads, 0, s>>>(feat, grad_out, rec, keys, vids, grad_feat, grad_grid, C, H, W, N, Ctot, coff, per_cta); break;
+  }
+  return vpn_check_launch("feature_pool_bwd2_kernel");
 }
 
 extern "C" int vpn_feature_pool_points_bwd(const float* pts, const float* bounds, const float* range, const int* arg,

@@ -56,6 +56,8 @@ _SIGNATURES = {
     "vpn_points_yz_range": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vpn_feature_pool_fwd": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     "vpn_feature_pool_bwd": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_void_p]),
+    "vpn_feature_pool_bwd_workspace_bytes": (c_int, [c_int, c_int, POINTER(c_size_t)]),
+    "vpn_feature_pool_bwd_sorted": (c_int, [c_void_p] * 8 + [c_size_t] + [c_int] * 7 + [c_void_p]),
     "vpn_feature_pool_points_bwd": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),
     "vpn_allreduce_nvls": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "vpn_allreduce_nvls_flag_floats": (c_int, [POINTER(c_size_t)]),

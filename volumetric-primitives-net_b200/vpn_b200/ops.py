@@ -576,12 +576,16 @@ class _FeaturePool(torch.autograd.Function):
         ggrid = torch.zeros((b, n, 2), dtype=f32, device=dev)
         gfeats = []
         coff = 0
+        ws, nws = None, ctypes.c_size_t(0)
+        if b > 0 and n > 0:
+            check(lib.vpn_feature_pool_bwd_workspace_bytes(b, n, ctypes.byref(nws)), "vpn_feature_pool_bwd_workspace_bytes")
+            ws = _scratch_bytes(nws.value, dev)
         for f in feats:
             gf = torch.empty_like(f)
             if b > 0 and n > 0:
-                check(lib.vpn_feature_pool_bwd(ptr(f), ptr(points), ptr(bounds), ptr(rng), ptr(grad_out), ptr(gf), ptr(ggrid), b,
-                                               f.shape[1], f.shape[2], f.shape[3], n, ctot, coff, stream_ptr(dev)),
-                      "vpn_feature_pool_bwd")
+                check(lib.vpn_feature_pool_bwd_sorted(ptr(f), ptr(points), ptr(bounds), ptr(rng), ptr(grad_out), ptr(gf), ptr(ggrid),
+                                                      ptr(ws), nws.value, b, f.shape[1], f.shape[2], f.shape[3], n, ctot, coff,
+                                                      stream_ptr(dev)), "vpn_feature_pool_bwd_sorted")
             else:
                 gf.zero_()
             gfeats.append(gf)
