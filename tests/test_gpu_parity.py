@@ -729,6 +729,60 @@ def test_feature_pooling_vs_oracle(vpn, O, b, n, maps):
     close(pc.grad, po.grad, rtol=1e-3, atol=2e-4 * float(po.grad.abs().max()), what="grad points")
 
 
+def test_feature_pooling_backward_edge_geometry(vpn, O):
+    """The cell-sorted backward on the geometries that stress its cell / tap-validity logic: vertices exactly on texel
+    centres (integer pixel coordinates: a tap's coefficients vanish for that vertex while the tap is valid for its cell
+    mates), image bounds beyond [-1, 1] (taps and whole cells outside the plane), all vertices in one cell, a 1-row
+    map, and the two backward implementations (shared-memory atomics / cell-sorted) against each other and the oracle."""
+    import ctypes
+    from vpn_b200 import _lib
+    from vpn_b200._lib import ptr, stream_ptr, check
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    b, n = 2, 700
+    maps = [(5, 9, 11), (40, 5, 5), (3, 1, 6), (70, 4, 3)]
+    for bounds in (torch.tensor([[-1.0, 1.0, -1.0, 1.0], [-1.0, 1.0, -1.0, 1.0]]),          # exact texel hits with the lattice below
+                   torch.tensor([[-1.6, 1.3, -0.2, 2.0], [0.5, 0.6, -3.0, -1.2]])):         # partly / wholly outside the plane
+        pts = torch.rand(b, n, 3, generator=g)
+        pts[0, :400, 1:] = torch.round(pts[0, :400, 1:] * 10) / 10        # lattice: with bounds +-1 and a 11-wide map -> integer ix
+        pts[1, :, 1:] = 0.5 + 0.01 * torch.rand(n, 2, generator=g)        # everything in one or two cells ...
+        pts[1, 0, 1:] = 0.0; pts[1, 1, 1:] = 1.0                          # ... except the two vertices that set the range
+        feats = [torch.randn(b, c, h, w, generator=g) for c, h, w in maps]
+        fo = [f.clone().requires_grad_() for f in feats]
+        po = pts.clone().requires_grad_()
+        ref = O.perceptual_feature_pooling(fo, po, bounds)
+        up = torch.randn(ref.shape, generator=g)
+        (ref * up).sum().backward()
+        fc = [C(f).requires_grad_() for f in feats]
+        pc = C(pts).requires_grad_()
+        out = vpn.perceptual_feature_pooling(fc, pc, C(bounds))
+        close(out, ref, rtol=RTOL, atol=2e-6, what="pooled")
+        (out * C(up)).sum().backward()
+        for i in range(len(maps)):
+            close(fc[i].grad, fo[i].grad, rtol=RTOL, atol=1e-5 * max(1.0, float(fo[i].grad.abs().max())), what=f"grad feat {i}")
+        close(pc.grad, po.grad, rtol=1e-3, atol=2e-4 * float(po.grad.abs().max()), what="grad points")
+        # old kernel == new kernels, map by map, through the C ABI
+        rng = torch.empty(b, 4, device="cuda"); arg = torch.empty(b, 4, dtype=torch.int32, device="cuda")
+        check(lib.vpn_points_yz_range(ptr(pc.detach()), ptr(rng), ptr(arg), b, n, stream_ptr("cuda")), "range")
+        nws = ctypes.c_size_t(0)
+        check(lib.vpn_feature_pool_bwd_workspace_bytes(b, n, ctypes.byref(nws)), "ws")
+        ws = torch.empty(nws.value, dtype=torch.uint8, device="cuda")
+        ctot, coff = sum(c for c, _, _ in maps), 0
+        gout = C(up).contiguous()
+        bd = C(bounds).contiguous()
+        for (c, h, w), f in zip(maps, feats):
+            fcu = C(f)
+            g_old, g_new = torch.empty_like(fcu), torch.empty_like(fcu)
+            gg_old, gg_new = torch.zeros(b, n, 2, device="cuda"), torch.zeros(b, n, 2, device="cuda")
+            check(lib.vpn_feature_pool_bwd(ptr(fcu), ptr(pc.detach()), ptr(bd), ptr(rng), ptr(gout), ptr(g_old), ptr(gg_old), b, c, h, w, n,
+                                           ctot, coff, stream_ptr("cuda")), "old")
+            check(lib.vpn_feature_pool_bwd_sorted(ptr(fcu), ptr(pc.detach()), ptr(bd), ptr(rng), ptr(gout), ptr(g_new), ptr(gg_new), ptr(ws),
+                                                  nws.value, b, c, h, w, n, ctot, coff, stream_ptr("cuda")), "new")
+            close(g_new, g_old, rtol=RTOL, atol=1e-5 * max(1.0, float(g_old.abs().max())), what=f"map {c}x{h}x{w}: grad_feat old vs sorted")
+            close(gg_new, gg_old, rtol=1e-3, atol=1e-4 * max(1.0, float(gg_old.abs().max())), what=f"map {c}x{h}x{w}: grad_grid old vs sorted")
+            coff += c
+
+
 def test_image_bounds_edge_cases(vpn, O):
     g = torch.Generator().manual_seed(5)
     cases = [torch.zeros(2, 3, 16, 12)]                                        # empty masks: bounds stay (0, w, 0, h)
