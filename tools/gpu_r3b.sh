@@ -1,0 +1,12 @@
+#!/bin/bash
+TAG=${1:-r03b}
+mkdir -p gpurun_out
+timeout 300 python tools/diag_chamfer.py 2>&1 | cut -c1-260 | tail -40
+timeout 900 python -m pytest tests/test_gpu_chamfer_prune.py tests/test_gpu_chamfer_fuzz.py -q -x 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -k "chamfer or end_to_end or step" 2>&1 | tail -3
+timeout 300 python tools/bench_chamfer.py c2 > gpurun_out/bench_chamfer_$TAG.log 2>&1; echo "bench chamfer rc=$?"
+timeout 300 python bench.py --configs c3,c5 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_c2_$TAG.log; echo "bench rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2_$TAG.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --graph off --configs none > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:sort_targets|prune_bounds|recover_rows' -s 6 -c 3 -f -o gpurun_out/prof_prep_$TAG \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --graph off --configs none > gpurun_out/ncu_prep_$TAG.log 2>&1; echo "ncu prep rc=$?"

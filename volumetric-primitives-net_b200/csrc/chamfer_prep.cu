@@ -25,8 +25,8 @@
 namespace vpn {
 
 constexpr int kSortThreads = 1024;
-constexpr int kSortMaxM = 16384;          // 14 index bits in the 32-bit sort key; 64 KB of keys in shared memory
-constexpr int kSortMinKeys = 1024;        // padded key count is at least one key per thread
+constexpr int kSortMaxM = 16384;          // 14 index bits in the 32-bit sort key; two key buffers of 64 KB in shared memory
+constexpr int kSortMinKeys = 1024;        // key count granularity: 32 warps x 32 lanes
 constexpr int kBlk = 128;                 // rows per block = columns per chunk
 
 __device__ __forceinline__ float prep_inf() { return __int_as_float(0x7f800000); }
@@ -42,14 +42,16 @@ __device__ __forceinline__ float prep_d2(float ax, float ay, float az, float bx,
 }
 
 // Box layout: 8 floats per block / chunk: lo.x lo.y lo.z hi.x hi.y hi.z pad pad.  An empty box is (+inf, -inf).
-// grid: x = sample.  dynamic smem: u32 keys[npow2] (npow2 = 0 when the sample is too large to sort: identity order).
-// (Batching each thread's compare-exchanges of a substep - all loads first - was measured slower: 91 vs 62 us.)
+// grid: x = sample.  dynamic smem: u32 keys[2][npad], npad = M rounded up to 1024 (npad = 0 when the sample is too large to
+// sort: identity order).
 __global__ void __launch_bounds__(kSortThreads)
-chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2s, int* __restrict__ perm,
-                            float* __restrict__ cbox, float* __restrict__ tmax, int M, int npow2, int nchunks) {
+chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2s, float4* __restrict__ p2v, int* __restrict__ perm,
+                            float* __restrict__ cbox, float* __restrict__ tmax, int M, int npad, int nchunks) {
   extern __shared__ __align__(16) unsigned char prep_smem[];
   unsigned* keys = reinterpret_cast<unsigned*>(prep_smem);
   __shared__ float red[32][7];
+  __shared__ unsigned hist[64 * 33];
+  __shared__ int wsum[32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* T = p2 + (size_t)b * M * 3;
   float* Ts = p2s + (size_t)b * M * 3;
@@ -93,7 +95,8 @@ chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2
     if (lane == 0) { for (int k = 0; k < 3; ++k) { red[0][k] = lo[k]; red[0][3 + k] = hi[k]; } tmax[b] = am; }
   }
   __syncthreads();
-  if (npow2 > 0) {
+  const unsigned* sorted = keys;
+  if (npad > 0) {
     float q0[3], qs[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -101,7 +104,7 @@ chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2
       const float ext = red[0][3 + k] - red[0][k];
       qs[k] = (ext > 0.f && ext < 1e30f) ? 63.999f / ext : 0.f;
     }
-    for (int i = tid; i < npow2; i += kSortThreads) {
+    for (int i = tid; i < npad; i += kSortThreads) {
       unsigned key = 0xffffffffu;
       if (i < M) {
         unsigned code = 0;
@@ -116,38 +119,75 @@ chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2
       keys[i] = key;
     }
     __syncthreads();
-    // Bitonic sort, ascending; keys are unique (index in the low bits): the order is deterministic.  Warp w owns the
-    // aligned group of G = npow2 / 32 keys [w G, (w + 1) G): every compare-exchange at distance j < G stays inside one
-    // group, so those substeps need no block barrier (28 instead of 91 barriers for 8192 keys).
-    const int G = npow2 >> 5;
-    for (int k = 2; k <= npow2; k <<= 1) {
-      int j = k >> 1;
-      for (; j >= G; j >>= 1) {
-        for (int t = tid; t < (npow2 >> 1); t += kSortThreads) {
-          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-          const unsigned a = keys[i], c = keys[i | j];
-          const bool up = (i & k) == 0;
-          if ((a > c) == up) { keys[i] = c; keys[i | j] = a; }
-        }
-        __syncthreads();
-      }
-      for (; j > 0; j >>= 1) {
-        for (int t = lane; t < (G >> 1); t += 32) {
-          const int i = warp * G + (((t & ~(j - 1)) << 1) | (t & (j - 1)));
-          const unsigned a = keys[i], c = keys[i | j];
-          const bool up = (i & k) == 0;
-          if ((a > c) == up) { keys[i] = c; keys[i | j] = a; }
-        }
+    // LSD radix sort of the 18 code bits, three stable passes of 6 bits.  Keys start in index order and every pass is
+    // stable, so equal codes stay in index order: the same deterministic permutation as sorting the full 32-bit keys
+    // (the bitonic network this replaces: 91 substeps, 62 us for 8192 keys on one SM).  Warp w owns the contiguous
+    // run [w seg, (w + 1) seg) of the pass's input; a round ranks 32 keys with match.any (rank = peers of the same
+    // digit in lower lanes), hist[digit][warp] counted in a first walk and scanned digit-major gives every (digit,
+    // warp) its output offset.  Padding keys (0xffffffff) have digit 63 in every pass and come last in the input: they
+    // stay behind every real key.
+    const int seg = npad >> 5;
+    unsigned* kin = keys; unsigned* kout = keys + npad;
+    for (int pass = 0; pass < 3; ++pass) {
+      const int shift = 14 + 6 * pass;
+      for (int i = tid; i < 64 * 33; i += kSortThreads) hist[i] = 0u;
+      __syncthreads();
+      for (int r = 0; r < seg; r += 32) {
+        const unsigned d = (kin[warp * seg + r + lane] >> shift) & 63u;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if ((peers & ((1u << lane) - 1u)) == 0u) hist[d * 33 + warp] += (unsigned)__popc(peers);
         __syncwarp();
       }
-      if (k >= G) __syncthreads();             // the next level starts with (or this was) a block-wide substep
+      __syncthreads();
+      {                                                              // exclusive scan over (digit, warp), two entries per thread
+        const int l0 = 2 * tid, l1 = 2 * tid + 1;
+        const int p0 = (l0 >> 5) * 33 + (l0 & 31), p1i = (l1 >> 5) * 33 + (l1 & 31);
+        const unsigned a = hist[p0], c = hist[p1i];
+        int inc = (int)(a + c);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+          const int w = wsum[lane];
+          int winc = w;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+          wsum[lane] = winc - w;
+        }
+        __syncthreads();
+        const unsigned off = (unsigned)(wsum[warp] + inc) - (a + c);
+        hist[p0] = off; hist[p1i] = off + a;
+      }
+      __syncthreads();
+      for (int r = 0; r < seg; r += 32) {
+        const unsigned key = kin[warp * seg + r + lane];
+        const unsigned d = (key >> shift) & 63u;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const unsigned base = hist[d * 33 + warp];
+        kout[base + rank] = key;
+        __syncwarp();
+        if (rank == 0) hist[d * 33 + warp] = base + (unsigned)__popc(peers);
+        __syncwarp();
+      }
+      __syncthreads();
+      unsigned* t = kin; kin = kout; kout = t;
     }
-    __syncthreads();
+    sorted = kin;
   }
-  for (int i = tid; i < M; i += kSortThreads) {
-    const int src = npow2 > 0 ? (int)(keys[i] & 0x3fffu) : i;
-    pm[i] = src;
-    Ts[3 * (size_t)i] = T[3 * (size_t)src]; Ts[3 * (size_t)i + 1] = T[3 * (size_t)src + 1]; Ts[3 * (size_t)i + 2] = T[3 * (size_t)src + 2];
+  float4* Tv = p2v + (size_t)b * nchunks * kBlk;
+  for (int i = tid; i < nchunks * kBlk; i += kSortThreads) {
+    if (i < M) {
+      const int src = npad > 0 ? (int)(sorted[i] & 0x3fffu) : i;
+      const float x = T[3 * (size_t)src], y = T[3 * (size_t)src + 1], z = T[3 * (size_t)src + 2];
+      pm[i] = src;
+      Ts[3 * (size_t)i] = x; Ts[3 * (size_t)i + 1] = y; Ts[3 * (size_t)i + 2] = z;
+      Tv[i] = make_float4(x, y, z, __int_as_float(src));            // what the row recovery stages: one 16-byte copy per target
+    } else {
+      const float qnan = __int_as_float(0x7fc00000);
+      Tv[i] = make_float4(qnan, qnan, qnan, __int_as_float(0x7fffffff));
+    }
   }
   __syncthreads();                                                 // the CTA's own global writes are visible to it
   // ---- chunk boxes: one warp per chunk, 4 columns per lane
@@ -308,20 +348,19 @@ chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restric
 
 size_t chamfer_sort_smem_bytes(int M) {
   if (M > kSortMaxM) return 0;
-  int n = kSortMinKeys;
-  while (n < M) n <<= 1;
-  return (size_t)n * 4;
+  const int npad = (M + kSortMinKeys - 1) / kSortMinKeys * kSortMinKeys;     // whole rounds of 32 keys for each of the 32 warps
+  return (size_t)npad * 8;
 }
 
-int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, int* perm, float* cbox, float* rbox, float* rthr,
+int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, float4* p2v, int* perm, float* cbox, float* rbox, float* rthr,
                         float* cub, float* tmax, int B, int P, int M, cudaStream_t s) {
   const int nchunks = (M + kBlk - 1) / kBlk, nrb = (P + kBlk - 1) / kBlk;
   const size_t smem = chamfer_sort_smem_bytes(M);
   static DeviceOnce once;
-  if (set_dyn_smem(chamfer_sort_targets_kernel, kSortMaxM * 4, once) != cudaSuccess) {
+  if (set_dyn_smem(chamfer_sort_targets_kernel, kSortMaxM * 8, once) != cudaSuccess) {
     vpn_set_error("chamfer prep: smem attribute"); return VPN_ERR_CUDA;
   }
-  chamfer_sort_targets_kernel<<<B, kSortThreads, smem, s>>>(p2, p2s, perm, cbox, tmax, M, (int)(smem / 4), nchunks);
+  chamfer_sort_targets_kernel<<<B, kSortThreads, smem, s>>>(p2, p2s, p2v, perm, cbox, tmax, M, (int)(smem / 8), nchunks);
   int rc = vpn_check_launch("chamfer_sort_targets_kernel");
   if (rc) return rc;
   chamfer_row_boxes_kernel<<<dim3(nrb, B), kBlk, 0, s>>>(p1, rbox, P, nrb);

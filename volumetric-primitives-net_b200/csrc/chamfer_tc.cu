@@ -58,13 +58,15 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
 // instruction descriptor (cute::UMMA::InstrDescriptor): D f32, A/B f16, both K-major, N=256, M=128
 constexpr uint32_t kTcIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(2 * kTcBlk >> 3) << 17) | ((uint32_t)(kTcBlk >> 4) << 24);
 
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t accumulate) {
+constexpr uint32_t kTcIdescHalf = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kTcBlk >> 3) << 17) | ((uint32_t)(kTcBlk >> 4) << 24);   // N = 128
+
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t accumulate, uint32_t idesc = kTcIdesc) {
 #if defined(VPN_TC_VARIANT) && VPN_TC_VARIANT == 3       // probe: epilogue alone
   return;
 #endif
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-               :: "r"(d_tmem), "l"(a), "l"(b), "r"(kTcIdesc), "r"(accumulate) : "memory");
+               :: "r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ bool tc_elect() {
   uint32_t pred;
@@ -137,15 +139,17 @@ __device__ __forceinline__ float tc_make_operand(unsigned char* tile, int idx, f
 
 // dynamic shared memory carve-up (NB = row blocks per tile)
 struct TcSmem {
-  unsigned char* rows; unsigned char* cols; float* rs_best; uint32_t* rs_mask; float* colw;
+  unsigned char* rows; unsigned char* cols; float* rs_best; uint4* rs_mask; float* colw;
   u64* bars; float* red; uint32_t* tmem_slot; uint32_t* skip;
 };
-// skip words of a tile: [0,32) phase-0 stage masks per chunk pair (bit r = row block r), [32,96) phase-1 stage masks per
-// chunk (bit rp = row-block pair)
-constexpr int kTcPlanWords = 96;
-constexpr int kTcSkipWords = 128;
+// plan words of a tile (global): [0,64) per chunk c the row blocks r (bit r) whose 128 x 128 block is pruned for the row
+// direction, [64,128) the same for the column direction.  In shared memory the kernel appends the stage masks it derives:
+// [128,160) phase 0, per chunk pair j: bit r set = stage (j, r) pruned (both halves); [160,224) phase 1, per chunk: bit
+// rp set = stage (chunk, row-block pair rp) pruned.
+constexpr int kTcPlanWords = 128;
+constexpr int kTcSkipWords = 224;
 __host__ __device__ inline size_t tc_smem_bytes(int NB) {
-  return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 8 + 2 * (size_t)NB * kTcBlk * 4 + 16 * 8 + 64 * 4 + 16 +
+  return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 20 + 2 * 2 * kTcBlk * 16 + 16 * 8 + 64 * 4 + 16 +
          kTcSkipWords * 4;
 }
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
@@ -153,8 +157,8 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
   s.rows = p; p += (size_t)NB * kTcBlkBytes;
   s.cols = p; p += 4 * kTcBlkBytes;                                   // two buffers of 256 columns
   s.rs_best = reinterpret_cast<float*>(p); p += 2 * (size_t)NB * kTcBlk * 4;      // [column half][row]
-  s.rs_mask = reinterpret_cast<uint32_t*>(p); p += 2 * (size_t)NB * kTcBlk * 4;
-  s.colw = reinterpret_cast<float*>(p); p += 2 * (size_t)NB * kTcBlk * 4;         // [chunk parity][row block][column]
+  s.rs_mask = reinterpret_cast<uint4*>(p); p += 2 * (size_t)NB * kTcBlk * 16;     // [column half][row]: 4 bits per chunk pair (32-column units)
+  s.colw = reinterpret_cast<float*>(p); p += 2 * 2 * kTcBlk * 16;                 // column record exchange: [chunk parity][h][column] float4
   s.bars = reinterpret_cast<u64*>(p); p += 16 * 8;
   s.red = reinterpret_cast<float*>(p); p += 64 * 4;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p); p += 16;
@@ -189,14 +193,43 @@ __device__ __forceinline__ float tc_lane_min128(uint32_t taddr, uint32_t empty_b
   return fminf(m0, m1);
 }
 
-// bit k of x -> bit 2k
-__device__ __forceinline__ u64 tc_spread32(uint32_t v) {
+// The same sweep keeping the minimum of every 32-column UNIT apart (u[0..3]; same FMNMX3 count, four chains instead of
+// two): the row records name candidate units, not whole chunks, so that the exact recovery redoes a quarter of the pairs.
+__device__ __forceinline__ float tc_lane_min4x32(uint32_t taddr, uint32_t empty_bar, int lane, float (&u)[4]) {
+  float v0[32], v1[32], v2[32], v3[32];
+  tc_ld32(taddr, v0); tc_ld32(taddr + 32, v1);
+  tc_wait_ld();
+  float m0 = tc_inf(), m1 = tc_inf(), m2 = tc_inf(), m3 = tc_inf();
+#if defined(VPN_TC_SCHED) && VPN_TC_SCHED == 1
+  // The address of the second half's loads is made to depend on the partly reduced first half (z is always 0: a minimum
+  // is never the all-ones NaN): ptxas otherwise hoists all four loads to the top and nothing overlaps the reduction.
+#pragma unroll
+  for (int k = 0; k < VPN_TC_SPLIT; k += 2) { m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]); }
+  const uint32_t z = (__float_as_uint(m0) == 0xffffffffu) ? 1u : 0u;
+  tc_ld32(taddr + 64 + z, v2); tc_ld32(taddr + 96 + z, v3);
+#pragma unroll
+  for (int k = VPN_TC_SPLIT; k < 32; k += 2) { m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]); }
+#else
+  tc_ld32(taddr + 64, v2); tc_ld32(taddr + 96, v3);
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) { m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]); }
+#endif
+  tc_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) tc_mbar_arrive(empty_bar);
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) { m2 = tc_min3(m2, v2[k], v2[k + 1]); m3 = tc_min3(m3, v3[k], v3[k + 1]); }
+  u[0] = m0; u[1] = m1; u[2] = m2; u[3] = m3;
+  return fminf(tc_min3(m0, m1, m2), m3);
+}
+
+// nibble k of x -> low nibble of byte k
+__device__ __forceinline__ u64 tc_spread_nibbles(uint32_t v) {
   u64 x = v;
   x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
   x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
   x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
-  x = (x | (x << 2)) & 0x3333333333333333ull;
-  x = (x | (x << 1)) & 0x5555555555555555ull;
   return x;
 }
 // squared gap between two axis-aligned boxes (8 floats: lo xyz, hi xyz); an empty box gives +inf
@@ -224,8 +257,9 @@ __device__ __forceinline__ bool tc_pass_needed(bool phase0, int j, int nc, int N
 // then at least sqrt(gap2) apart while T / U are distances the block's rows / the chunk's columns certainly achieve
 // elsewhere (exact arithmetic).  1e-5 relative covers the roundings on both sides (~1e-6); a NaN gap or an infinite
 // bound compares false: not skipped.  Row blocks past the end of the cloud are always prunable.
-// Output per tile: kTcPlanWords mask words + the number of live stages (the tile's work).
+// Output per tile: kTcPlanWords mask words + the number of live 128 x 128 blocks (the tile's work).
 constexpr int kPlanThreads = 128;
+static_assert(kPlanThreads == kTcPlanWords, "one plan word per thread");
 __global__ void __launch_bounds__(kPlanThreads)
 chamfer_tc_plan_kernel(const float* __restrict__ cbox, const float* __restrict__ rbox, const float* __restrict__ rthr,
                        const float* __restrict__ cub, uint32_t* __restrict__ plan_masks, int* __restrict__ plan_work,
@@ -236,7 +270,6 @@ chamfer_tc_plan_kernel(const float* __restrict__ cbox, const float* __restrict__
   const int cta = blockIdx.x;                                         // one CTA per tile (the box loads of its NB x nc pairs in parallel)
   const int tile_i = cta % ntiles, split = (cta / ntiles) % nsplit, b = cta / (ntiles * nsplit);
   const int c_first = split * cps, nc = min(nchunks, c_first + cps) - c_first;
-  const int hc = (nc + 1) >> 1, NP = NB >> 1;
   if (tid < 64) { skipR[tid] = 0u; skipC[tid] = 0u; }
   __syncthreads();
   for (int e = tid; e < NB * nc; e += kPlanThreads) {
@@ -252,22 +285,12 @@ chamfer_tc_plan_kernel(const float* __restrict__ cbox, const float* __restrict__
   }
   __syncthreads();
   uint32_t* out = plan_masks + (size_t)cta * kTcPlanWords;
-  int live = 0;
-  if (tid < 32) {                                                     // phase-0 words (hc <= 32)
-    const int j = tid;
-    uint32_t m = 0xffffffffu;
-    if (j < hc) { m = skipR[2 * j] & ((2 * j + 1 < nc) ? skipR[2 * j + 1] : 0xffffffffu); live += NB - __popc(m & ((1u << NB) - 1u)); }
-    out[j] = m;
-  } else if (tid < 96) {                                              // phase-1 words
-    const int c = tid - 32;
-    uint32_t m = 0xffffffffu;
-    if (c < nc) {
-      const uint32_t both = skipC[c] & (skipC[c] >> 1);              // bit 2 rp: row blocks 2 rp and 2 rp + 1 both prunable
-      m = 0u;
-      for (int rp = 0; rp < NP; ++rp) m |= ((both >> (2 * rp)) & 1u) << rp;
-      live += NP - __popc(m);
-    }
-    out[32 + c] = m;
+  int live = 0;                                                       // work in 128 x 128 blocks (half stages)
+  {
+    const int c = tid & 63;
+    const uint32_t m = (c < nc) ? (tid < 64 ? skipR[c] : skipC[c]) : 0xffffffffu;
+    if (c < nc) live = NB - __popc(m & ((1u << NB) - 1u));
+    out[tid] = m;                                                     // kPlanThreads == kTcPlanWords
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(0xffffffffu, live, o);
@@ -276,9 +299,9 @@ chamfer_tc_plan_kernel(const float* __restrict__ cbox, const float* __restrict__
   if (tid == 0) plan_work[cta] = s_live[0] + s_live[1] + s_live[2] + s_live[3];
 }
 
-// Counting sort of the tiles by work, heaviest first (work <= 1024 stages).  One CTA.  The order among tiles of equal
+// Counting sort of the tiles by work, heaviest first (work <= 2048 blocks).  One CTA.  The order among tiles of equal
 // work depends on atomics; it only affects which SM runs which tile, never a result.
-constexpr int kOrderThreads = 1024, kOrderBins = 1056;
+constexpr int kOrderThreads = 1024, kOrderBins = 2112;
 __global__ void __launch_bounds__(kOrderThreads)
 chamfer_tc_order_kernel(const int* __restrict__ plan_work, int* __restrict__ plan_order, int ncta) {
   __shared__ int hist[kOrderBins];
@@ -312,10 +335,10 @@ chamfer_tc_order_kernel(const int* __restrict__ plan_work, int* __restrict__ pla
 __global__ void __launch_bounds__(kTcThreads, 1)
 chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                   float* __restrict__ rbest, u64* __restrict__ rmask,
-                  float* __restrict__ cbest, unsigned* __restrict__ cmask,
+                  float* __restrict__ cbest, u64* __restrict__ cmask,
                   float2* __restrict__ tslack, int* __restrict__ fallback, const float* __restrict__ tmax,
                   const uint32_t* __restrict__ plan_masks, const int* __restrict__ plan_order, u64* __restrict__ stats,
-                  int ntiles, int nsplit, int P, int M, int NB, int nchunks, int cps) {
+                  int ntiles, int nsplit, int P, int M, int NB, int nchunks, int cps, int whole_stages) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
 #ifdef VPN_TC_COUNTERS
   const long long t_start = clock64();
@@ -402,7 +425,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     if (i < TM) {
       tc_make_operand(sm.rows + (size_t)(i >> 7) * kTcBlkBytes, i & 127, rx[k] * S, ry[k] * S, rz[k] * S, true);
       sm.rs_best[i] = tc_inf(); sm.rs_best[TM + i] = tc_inf();
-      sm.rs_mask[i] = 0u; sm.rs_mask[TM + i] = 0u;
+      sm.rs_mask[i] = make_uint4(0u, 0u, 0u, 0u); sm.rs_mask[TM + i] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   tc_fence_async_smem();                      // operand rows were written with generic stores; the MMA reads them through the async proxy
@@ -421,25 +444,40 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   const int hc = (nc + 1) >> 1;                // chunk pairs (<= 32)
   const int NP = NB >> 1;                      // row-block pairs
   // ---- stage skip masks of this tile (computed by chamfer_tc_plan_kernel).  Without a plan every stage is computed.
-  uint32_t* skip0 = sm.skip; uint32_t* skip1 = sm.skip + 32;
+  const uint32_t* rawR = sm.skip; const uint32_t* rawC = sm.skip + 64;
+  uint32_t* skip0 = sm.skip + 128; uint32_t* skip1 = sm.skip + 160;
   for (int i = tid; i < kTcPlanWords; i += kTcThreads) sm.skip[i] = plan_masks ? plan_masks[(size_t)cta * kTcPlanWords + i] : 0u;
   __syncthreads();
+  if (tid < 32) {
+    const uint32_t a = rawR[2 * tid], bb = (2 * tid + 1 < nc) ? rawR[2 * tid + 1] : 0xffffffffu;
+    skip0[tid] = (tid < hc) ? (a & bb) : 0xffffffffu;
+  } else if (tid < 96) {
+    const int c = tid - 32;
+    const uint32_t both = rawC[c] & (rawC[c] >> 1);                   // bit 2 rp: row blocks 2 rp and 2 rp + 1 both pruned
+    uint32_t m = 0u;
+    for (int rp = 0; rp < 8; ++rp) m |= ((both >> (2 * rp)) & 1u) << rp;
+    skip1[c] = (c < nc) ? m : 0xffffffffu;
+  }
+  __syncthreads();
+  if (whole_stages) {                                                 // probe (vpn_set_tuning("tc_half", 1)): live stages are computed whole
+    for (int i = tid; i < kTcPlanWords; i += kTcThreads) sm.skip[i] = 0u;
+    __syncthreads();
+  }
   // statistics: stats[0] stages, stats[1] stages skipped - counted by the MMA warp's lanes in parallel, two atomics per CTA
   // (thread 0 doing it alone, plus cycle counters, delayed epilogue warp 0 and with it every stage: +3 %).  A probe build
   // (-DVPN_TC_COUNTERS) adds the cycle counters of epilogue warp 0: [2] prologue, [3] row phase, [4] column phase, [5]
   // tail, and [6] / [7] live stages per phase, [8] live chunks, [9] operand passes built.
   if (warp == kTcEpiWarps + 1 && stats != nullptr) {
     unsigned s0 = 0, s1 = 0;
-    for (int j = lane; j < hc; j += 32) s0 += __popc(skip0[j] & ((1u << NB) - 1u));
-    for (int c = lane; c < nc; c += 32) s1 += __popc(skip1[c]);
+    for (int c = lane; c < nc; c += 32) { s0 += __popc(rawR[c] & ((1u << NB) - 1u)); s1 += __popc(rawC[c] & ((1u << NB) - 1u)); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
     if (lane == 0) {
-      atomicAdd(&stats[0], (u64)(hc * NB + nc * NP));
+      atomicAdd(&stats[0], (u64)(2 * nc * NB));                         // 128 x 128 blocks, both directions
       atomicAdd(&stats[1], (u64)(s0 + s1));
 #ifdef VPN_TC_COUNTERS
-      atomicAdd(&stats[6], (u64)(hc * NB - s0));
-      atomicAdd(&stats[7], (u64)(nc * NP - s1));
+      atomicAdd(&stats[6], (u64)(nc * NB - s0));
+      atomicAdd(&stats[7], (u64)(nc * NB - s1));
 #endif
     }
   }
@@ -521,7 +559,11 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
           if (tc_elect()) {
             const uint64_t dr = drows + (uint64_t)(r * (kTcBlkBytes >> 4));
             const uint32_t d = tb + st * 256;
-            tc_mma(d, dr, dcols, 0);                                        // D[row][2 chunks]
+            // a half whose 128 x 128 block is pruned is not computed (N = 128 MMA on the other half's operand and columns)
+            const bool dead0 = (rawR[2 * j] >> r) & 1u, dead1 = (2 * j + 1 < nc) ? ((rawR[2 * j + 1] >> r) & 1u) : true;
+            if (dead0) tc_mma(d + 128, dr, dcols + (uint64_t)(kTcBlkBytes >> 4), 0, kTcIdescHalf);
+            else if (dead1) tc_mma(d, dr, dcols, 0, kTcIdescHalf);
+            else tc_mma(d, dr, dcols, 0);                                   // D[row][2 chunks]
             tc_commit(bar_full + 8 * st);
           }
           __syncwarp();
@@ -539,7 +581,10 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
             if (tc_elect()) {
               const uint64_t dr = drows + (uint64_t)(rp * (2 * kTcBlkBytes >> 4));
               const uint32_t d = tb + st * 256;
-              tc_mma(d, dc, dr, 0);                                         // D[col][2 row blocks]
+              const uint32_t rc = rawC[2 * j + h] >> (2 * rp);
+              if (rc & 1u) tc_mma(d + 128, dc, dr + (uint64_t)(kTcBlkBytes >> 4), 0, kTcIdescHalf);
+              else if (rc & 2u) tc_mma(d, dc, dr, 0, kTcIdescHalf);
+              else tc_mma(d, dc, dr, 0);                                    // D[col][2 row blocks]
               tc_commit(bar_full + 8 * st);
             }
             __syncwarp();
@@ -556,38 +601,52 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + h * 128;
     const int li = q * 32 + lane;                                    // row in block (phase 0) / column in chunk (phase 1)
     uint32_t it = 0;
-    // ---- phase 0: row minima; record (h, row): best value and the mask of chunk pairs j whose chunk may hold the arg-min
+    // ---- phase 0: row minima; record (h, row): best value and, per chunk pair j, four bits naming the 32-column units of
+    // chunk 2 j + h that may hold the arg-min (word j >> 3, nibble j & 7)
     float* my_best = sm.rs_best + (size_t)h * TM;
-    uint32_t* my_mask = sm.rs_mask + (size_t)h * TM;
+    uint4* my_mask = sm.rs_mask + (size_t)h * TM;
     const uint32_t nbmask = (1u << NB) - 1u, npmask = (1u << NP) - 1u;
     for (int j = 0; j < hc; ++j) {
       const bool valid = 2 * j + h < nc;
+      const uint32_t dead = valid ? rawR[2 * j + h] : 0xffffffffu;   // row blocks whose block with MY chunk is pruned
       // only the live stages are visited (a per-stage `if skipped continue` cost as many instructions as the stages left)
       for (uint32_t live = ~skip0[j] & nbmask; live; live &= live - 1) {
         const int r = __ffs((int)live) - 1;
         const uint32_t st = it & 1;
         tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
+        if ((dead >> r) & 1u) {
+          // my half of the stage was not computed: hand the stage back (after its `full`, so that this arrival cannot be
+          // counted for the accumulator's previous use) and leave the issue slots to the other half's warp on this SMSP
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(bar_empty + 8 * st);
+          ++it;
+          continue;
+        }
         tc_fence_after();
-        const float m = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
+        float mu[4];
+        const float m = tc_lane_min4x32(tlane + st * 256, bar_empty + 8 * st, lane, mu);
         ++it;
         const int ri = r * kTcBlk + li;
         const float best = my_best[ri];
         if (valid && m <= tc_thr(best, slack_rel, slack_abs)) {
-          const float tm = tc_thr(m, slack_rel, slack_abs);
-          const uint32_t mask = (tm < best) ? 0u : my_mask[ri];
-          my_mask[ri] = mask | (1u << j);
+          // units within the slack of the best value known now (the final filter uses the final, smaller, best)
+          const float t = tc_thr(fminf(best, m), slack_rel, slack_abs);
+          const uint32_t nib = (mu[0] <= t ? 1u : 0u) | (mu[1] <= t ? 2u : 0u) | (mu[2] <= t ? 4u : 0u) | (mu[3] <= t ? 8u : 0u);
+          if (tc_thr(m, slack_rel, slack_abs) < best) my_mask[ri] = make_uint4(0u, 0u, 0u, 0u);   // everything recorded so far is out
+          reinterpret_cast<uint32_t*>(my_mask + ri)[j >> 3] |= nib << ((j & 7) * 4);
           if (m < best) my_best[ri] = m;
         }
       }
     }
     TC_MARK(3)
-    // ---- phase 1: column minima.  Thread = one column of the chunk; it keeps a running record (best, mask of row
-    // blocks) of the row blocks 2 rp + h it sees, in REGISTERS, with the same update rule as the row records; at the end
-    // of a chunk the two warps of a lane quarter (h = 0 / 1) exchange their records through shared memory (8 bytes per
-    // column) and the warp whose turn it is merges the two and writes the (tile, column) record.  (A per-block value
-    // array in shared memory merged in two passes per chunk cost ~400 clk per chunk on the critical path.)
+    // ---- phase 1: column minima.  Thread = one column of the chunk; it keeps a running record (best, 64-bit mask of the
+    // tile's 32-row UNITS: bit 4 (2 rp + h) + u) of the row blocks 2 rp + h it sees, in REGISTERS, with the same update
+    // rule as the row records; at the end of a chunk the two warps of a lane quarter (h = 0 / 1) exchange their records
+    // through shared memory (16 bytes per column) and the warp whose turn it is merges the two and writes the (tile,
+    // column) record.  (A per-block value array in shared memory merged in two passes per chunk cost ~400 clk per chunk
+    // on the critical path.)
     int cseq = 0;
-    float2* xch = reinterpret_cast<float2*>(sm.colw);                 // [parity][h][128] exchange slots
+    float4* xch = reinterpret_cast<float4*>(sm.colw);                 // [parity][h][128] exchange slots
     for (int j = 0; j < hc; ++j) {
       const int nh = (2 * j + 1 < nc) ? 2 : 1;
       for (int hh = 0; hh < nh; ++hh) {
@@ -596,34 +655,45 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
           // chunk pruned for the whole tile: record (+inf, no candidate) - it is never a candidate in the recovery.  No
           // exchange, no barrier, and it does not take part in the two warps' alternation (cseq counts live chunks).
           const int col = (c_first + 2 * j + hh) * kTcBlk + li;
-          if (h == hh && col < M) { const size_t o = ((size_t)b * ntiles + tile_i) * M + col; cbest[o] = tc_inf(); cmask[o] = 0u; }
+          if (h == hh && col < M) { const size_t o = ((size_t)b * ntiles + tile_i) * M + col; cbest[o] = tc_inf(); cmask[o] = 0ull; }
           continue;
         }
-        float best = tc_inf(); uint32_t mask = 0u;
+        float best = tc_inf(); u64 mask = 0ull;
+        const uint32_t dead = rawC[2 * j + hh] >> h;                 // bit 2 rp: my row block 2 rp + h is pruned for this chunk
         for (uint32_t live = live1; live; live &= live - 1) {
           const int rp = __ffs((int)live) - 1;
           const uint32_t st = it & 1;
           tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
+          if ((dead >> (2 * rp)) & 1u) {
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(bar_empty + 8 * st);
+            ++it;
+            continue;
+          }
           tc_fence_after();
-          const float m = tc_lane_min128(tlane + st * 256, bar_empty + 8 * st, lane);
+          float mu[4];
+          const float m = tc_lane_min4x32(tlane + st * 256, bar_empty + 8 * st, lane, mu);
           ++it;
           if (m <= tc_thr(best, slack_rel, slack_abs)) {
+            const float t = tc_thr(fminf(best, m), slack_rel, slack_abs);
+            const uint32_t nib = (mu[0] <= t ? 1u : 0u) | (mu[1] <= t ? 2u : 0u) | (mu[2] <= t ? 4u : 0u) | (mu[3] <= t ? 8u : 0u);
             const float tm = tc_thr(m, slack_rel, slack_abs);
-            mask = ((tm < best) ? 0u : mask) | (1u << (2 * rp + h));
+            mask = ((tm < best) ? 0ull : mask) | ((u64)nib << (4 * (2 * rp + h)));
             best = fminf(best, m);
           }
         }
-        float2* slot = xch + (size_t)(cseq & 1) * 2 * kTcBlk;
-        slot[h * kTcBlk + li] = make_float2(best, __uint_as_float(mask));
+        float4* slot = xch + (size_t)(cseq & 1) * 2 * kTcBlk;
+        slot[h * kTcBlk + li] = make_float4(best, __uint_as_float((uint32_t)mask), __uint_as_float((uint32_t)(mask >> 32)), 0.f);
         // the two warps of this lane quarter meet once per live chunk; they take turns merging
         asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
         if ((cseq & 1) == h) {
           const int col = (c_first + 2 * j + hh) * kTcBlk + li;
           if (col < M) {
-            const float2 other = slot[(h ^ 1) * kTcBlk + li];
+            const float4 other = slot[(h ^ 1) * kTcBlk + li];
             const float b2 = fminf(best, other.x);
             const float t = tc_thr(b2, slack_rel, slack_abs);
-            const uint32_t m2 = ((best <= t) ? mask : 0u) | ((other.x <= t) ? __float_as_uint(other.y) : 0u);
+            const u64 omask = (u64)__float_as_uint(other.y) | ((u64)__float_as_uint(other.z) << 32);
+            const u64 m2 = ((best <= t) ? mask : 0ull) | ((other.x <= t) ? omask : 0ull);
             const size_t o = ((size_t)b * ntiles + tile_i) * M + col;
             cbest[o] = b2 * invS2; cmask[o] = m2;
           }
@@ -636,16 +706,23 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tbase) : "memory");
+  const size_t mask_plane = (size_t)gridDim.x / ntiles * P;           // B * nsplit * P records per plane
   for (int i = tid; i < TM; i += kTcThreads) {
     const int row = tile_i * TM + i;
     if (row < P) {
       const float b0 = sm.rs_best[i], b1 = sm.rs_best[TM + i];
       const float best = fminf(b0, b1);
       const float t = tc_thr(best, slack_rel, slack_abs);
-      // record (h, row) bit j names chunk 2 j + h of the split: interleave the two 32-bit masks
-      const u64 mask = ((b0 <= t) ? tc_spread32(sm.rs_mask[i]) : 0ull) | ((b1 <= t) ? (tc_spread32(sm.rs_mask[TM + i]) << 1) : 0ull);
+      // record (h, row) nibble j names the units of chunk 2 j + h of the split: unit 4 (2 j + h) + u = bit 8 j + 4 h + u of the
+      // 256-bit row mask, stored as four planes of u64 (plane w = units [64 w, 64 w + 64))
+      const uint4 k0 = sm.rs_mask[i], k1 = sm.rs_mask[TM + i];
+      const bool in0 = b0 <= t, in1 = b1 <= t;
       const size_t o = ((size_t)b * nsplit + split) * P + row;
-      rbest[o] = best * invS2; rmask[o] = mask;
+      rbest[o] = best * invS2;
+      rmask[o] = (in0 ? tc_spread_nibbles(k0.x) : 0ull) | (in1 ? (tc_spread_nibbles(k1.x) << 4) : 0ull);
+      rmask[mask_plane + o] = (in0 ? tc_spread_nibbles(k0.y) : 0ull) | (in1 ? (tc_spread_nibbles(k1.y) << 4) : 0ull);
+      rmask[2 * mask_plane + o] = (in0 ? tc_spread_nibbles(k0.z) : 0ull) | (in1 ? (tc_spread_nibbles(k1.z) << 4) : 0ull);
+      rmask[3 * mask_plane + o] = (in0 ? tc_spread_nibbles(k0.w) : 0ull) | (in1 ? (tc_spread_nibbles(k1.w) << 4) : 0ull);
     }
   }
   TC_MARK(5)
@@ -707,12 +784,13 @@ chamfer_tc_bounds_kernel(const float* __restrict__ p2, float* __restrict__ tmax,
 }
 
 size_t chamfer_tc_smem_bytes(int NB) { return tc_smem_bytes(NB); }
+int chamfer_tc_plan_words() { return kTcPlanWords; }
 
 
 // p2: the targets the filter sweeps (Morton-sorted copy when cbox != NULL); tmax filled by the caller (chamfer_prep_launch)
 // when with_bounds == 0, by chamfer_tc_bounds_kernel here otherwise.
 // cbox != NULL: the pruned sweep; plan_masks (ncta x kTcPlanWords words), plan_work and plan_order (ncta ints) are scratch.
-int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
+int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, u64* cmask,
                       float2* tslack, int* fallback, float* tmax, const float* cbox, const float* rbox, const float* rthr,
                       const float* cub, u64* stats, uint32_t* plan_masks, int* plan_work, int* plan_order, int with_bounds,
                       int B, int P, int M, int NB, int ntiles, int nsplit, int nchunks, int cps, cudaStream_t s) {
@@ -739,7 +817,7 @@ int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask
   }
   chamfer_tc_kernel<<<ncta, kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax,
                                                    cbox ? plan_masks : nullptr, cbox ? plan_order : nullptr, stats,
-                                                   ntiles, nsplit, P, M, NB, nchunks, cps);
+                                                   ntiles, nsplit, P, M, NB, nchunks, cps, tuning_value(kTuneTcHalf) == 1 ? 1 : 0);
   return vpn_check_launch("chamfer_tc_kernel");
 }
 

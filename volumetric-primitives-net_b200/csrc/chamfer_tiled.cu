@@ -34,6 +34,7 @@
 // an add and cannot be contracted.
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include "common.cuh"
 
 namespace vpn {
@@ -282,7 +283,7 @@ chamfer_tiled_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
 // ---------------------------------------------------------------------------------------------
 constexpr int kRecThreads = 1024;
 constexpr int kSegChunks = 64;                       // column chunks resident in shared memory per segment
-constexpr int kItemCap = 4096;
+constexpr int kItemCap = 4096;                      // work items per round: (row, 32-column unit) / (column, row block)
 
 struct ExactBest {
   float d, hi, v; int i;
@@ -357,91 +358,144 @@ __device__ __forceinline__ int block_exclusive_scan(int cnt, int* warp_sums, int
   return off;
 }
 
-// grid: x = block of kRecThreads rows, y = sample.  dynamic smem: float4 cols[min(nchunks,64)*128]
+// 16 chunk bits -> 64 unit bits (bit k -> bits 4k..4k+3): a chunk-granular record names all four units of the chunk
+__device__ __forceinline__ u64 expand_chunk_bits16(unsigned v) {
+  u64 x = v & 0xffffu;
+  x = (x | (x << 24)) & 0x000000ff000000ffull;
+  x = (x | (x << 12)) & 0x000f000f000f000full;
+  x = (x | (x << 6)) & 0x0303030303030303ull;
+  x = (x | (x << 3)) & 0x1111111111111111ull;
+  return x * 0xfull;
+}
+// seg |= w << base over a 256-bit mask held in four words (base may be negative or past the end)
+__device__ __forceinline__ void or_shifted256(u64 (&seg)[4], u64 w, int base) {
+  if (w == 0ull || base >= 256 || base <= -64) return;
+  const int k = base >> 6, sh = base & 63;                     // floor division: base = 64 k + sh
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    if (kk == k) seg[kk] |= w << sh;
+    if (sh != 0 && kk == k + 1) seg[kk] |= w >> (64 - sh);
+  }
+}
+
+// Persistent: grid x = min(#SMs, B * nblk) CTAs, CTA k takes the work items (sample, block of kRecThreads rows)
+// [k per, (k + 1) per) - consecutive items belong to the same sample, whose targets are staged in shared memory ONCE
+// (one CTA per item re-staged 131 KB per 1024 rows: a fifth of the kernel).  dynamic smem: float4 cols[min(nchunks,64)*128].
+// Candidate records: planes == 4: four u64 planes (plane_stride apart) of 32-column UNIT bits (tensor-core filter),
+// planes == 1: one u64 of 128-column chunk bits (CUDA-core filters), expanded to unit bits here.
+// p2v != NULL: the targets as float4 (x, y, z, original index) padded with NaN to whole chunks (stride mpad per sample).
 __global__ void __launch_bounds__(kRecThreads, 1)
-chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
-                            const float* __restrict__ rbest, const u64* __restrict__ rmask,
+chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restrict__ p2, const float4* __restrict__ p2v, int mpad,
+                            const float* __restrict__ rbest, const u64* __restrict__ rmask, int planes, size_t plane_stride,
                             const float2* __restrict__ tslack, float* __restrict__ min1, int* __restrict__ idx1,
                             int P, int M, int nchunks, int nsplit, int cps, int TM, int ntiles,
-                            const int* __restrict__ skip, const int* __restrict__ perm) {
+                            const int* __restrict__ skip, int nblk, int nitems) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  if (skip && skip[blockIdx.y]) return;                  // sample redone by chamfer_flagged_kernel
   float4* cols = reinterpret_cast<float4*>(smem_raw);
-  const int* pm = perm ? perm + (size_t)blockIdx.y * M : nullptr;      // p2 is a permuted copy: sorted position -> original index
   __shared__ float4 rowc[kRecThreads];
   __shared__ u64 key[kRecThreads];
   __shared__ unsigned items[kItemCap];
   __shared__ int warp_sums[33];
-  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-  const int row = blockIdx.x * kRecThreads + tid;
-  const bool valid = row < P;
-  const float* T = p2 + (size_t)b * M * 3;
-  float g = inf_f(), gthr = inf_f();
-  if (valid) {
-    const float* a = p1 + 3 * ((size_t)b * P + row);
-    rowc[tid] = make_float4(a[0], a[1], a[2], 0.f);
-    for (int s = 0; s < nsplit; ++s) g = fminf(g, rbest[((size_t)b * nsplit + s) * P + row]);
-    const float2 sl = tslack[(size_t)b * ntiles + row / TM];
-    gthr = thr_of(g, sl.x, sl.y);
-  }
-  key[tid] = ~0ull;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int per = (nitems + gridDim.x - 1) / gridDim.x;
+  const int w0 = blockIdx.x * per, w1 = min(nitems, w0 + per);
   const int nseg = (nchunks + kSegChunks - 1) / kSegChunks;
   const float qnan = __int_as_float(0x7fc00000);
-  for (int seg = 0; seg < nseg; ++seg) {
-    __syncthreads();
-    const int seg_chunks = min(kSegChunks, nchunks - seg * kSegChunks);
-    for (int i = tid; i < seg_chunks * kCW; i += kRecThreads) {
-      int col = seg * kSegChunks * kCW + i;
-      cols[i] = col < M ? make_float4(T[3 * (size_t)col], T[3 * (size_t)col + 1], T[3 * (size_t)col + 2],
-                                      __int_as_float(pm ? pm[col] : col))
-                        : make_float4(qnan, qnan, qnan, __int_as_float(0x7fffffff));
-    }
-    u64 segmask = 0ull;
+  int staged_b = -1, staged_seg = -1;
+  for (int wi = w0; wi < w1; ++wi) {
+    const int b = wi / nblk;
+    if (skip && skip[b]) continue;                       // sample redone by chamfer_flagged_kernel
+    const int row = (wi - b * nblk) * kRecThreads + tid;
+    const bool valid = row < P;
+    float g = inf_f(), gthr = inf_f();
+    __syncthreads();                                     // the previous item is done with rowc / key / items
     if (valid) {
-      for (int s = 0; s < nsplit; ++s) {
-        const size_t o = ((size_t)b * nsplit + s) * P + row;
-        if (!(rbest[o] <= gthr)) continue;
-        const u64 m = rmask[o];
-        const int rel = s * cps - seg * kSegChunks;
-        if (rel >= 0) { if (rel < 64) segmask |= m << rel; }
-        else if (-rel < 64) segmask |= m >> (-rel);
-      }
-      if (seg_chunks < 64) segmask &= (1ull << seg_chunks) - 1ull;
+      const float* a = p1 + 3 * ((size_t)b * P + row);
+      rowc[tid] = make_float4(a[0], a[1], a[2], 0.f);
+      for (int s = 0; s < nsplit; ++s) g = fminf(g, rbest[((size_t)b * nsplit + s) * P + row]);
+      const float2 sl = tslack[(size_t)b * ntiles + row / TM];
+      gthr = thr_of(g, sl.x, sl.y);
     }
-    int total;
-    const int off = block_exclusive_scan(__popcll(segmask), warp_sums, &total);   // syncs: cols[] is loaded too
-    for (int base = 0; base < total; base += kItemCap) {
-      int j = off;
-      for (u64 mm = segmask; mm; mm &= mm - 1, ++j)
-        if (j >= base && j < base + kItemCap) items[j - base] = ((unsigned)tid << 6) | (unsigned)(__ffsll((long long)mm) - 1);
-      __syncthreads();
-      const int units = min(kItemCap, total - base) * 4;           // 4 sub-units of 32 columns per item
-      for (int it = tid; it < units; it += kRecThreads) {
-        const unsigned item = items[it >> 2];
-        const int r = item >> 6, c = item & 63, quarter = it & 3;
-        const float4 rc = rowc[r];
-        const float4* src = cols + c * kCW + quarter * 32;
-        const int gcol = (seg * kSegChunks + c) * kCW + quarter * 32;
-        float d[32], dm = inf_f();
-#pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-          const float4 q = src[(kk + lane) & 31];
-          d[kk] = exact_d2s(rc.x, rc.y, rc.z, q.x, q.y, q.z);
-          dm = fminf(dm, d[kk]);
+    key[tid] = ~0ull;
+    for (int seg = 0; seg < nseg; ++seg) {
+      const int seg_chunks = min(kSegChunks, nchunks - seg * kSegChunks);
+      if (staged_b != b || staged_seg != seg) {
+        __syncthreads();                                 // everybody is done with the previous contents
+        if (p2v) {
+          const float4* src = p2v + (size_t)b * mpad + (size_t)seg * kSegChunks * kCW;
+          for (int i = tid; i < seg_chunks * kCW; i += kRecThreads) cols[i] = src[i];
+        } else {
+          const float* T = p2 + (size_t)b * M * 3;
+          for (int i = tid; i < seg_chunks * kCW; i += kRecThreads) {
+            const int col = seg * kSegChunks * kCW + i;
+            cols[i] = col < M ? make_float4(T[3 * (size_t)col], T[3 * (size_t)col + 1], T[3 * (size_t)col + 2], __int_as_float(col))
+                              : make_float4(qnan, qnan, qnan, __int_as_float(0x7fffffff));
+          }
         }
-        int at;
-        const int st = unit_scan(d, dm, lane, &at);
-        if (st == 1) atomicMin(&key[r], ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)__float_as_int(src[at].w));
-        else if (st == 2) { const u64 kv = unit_exact_walk(rc.x, rc.y, rc.z, src, gcol, 1); if (kv != ~0ull) atomicMin(&key[r], kv); }
+        staged_b = b; staged_seg = seg;
       }
-      __syncthreads();
+      // this row's candidate units of the segment: 256 bits, unit u of the segment = columns [32 u, 32 u + 32) of cols[]
+      u64 sg[4] = {0ull, 0ull, 0ull, 0ull};
+      if (valid) {
+        for (int s = 0; s < nsplit; ++s) {
+          const size_t o = ((size_t)b * nsplit + s) * P + row;
+          if (!(rbest[o] <= gthr)) continue;
+          const int rel = (s * cps - seg * kSegChunks) * 4;                    // first unit of the split, relative to the segment
+          if (planes == 4) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) or_shifted256(sg, rmask[o + w * plane_stride], rel + 64 * w);
+          } else {
+            const u64 m = rmask[o];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) or_shifted256(sg, expand_chunk_bits16((unsigned)(m >> (16 * w))), rel + 64 * w);
+          }
+        }
+        if (seg_chunks < kSegChunks) {                                         // units past the end of the cloud
+          const int nu = seg_chunks * 4;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int left = nu - 64 * w;
+            if (left <= 0) sg[w] = 0ull; else if (left < 64) sg[w] &= (1ull << left) - 1ull;
+          }
+        }
+      }
+      int total;
+      const int cnt = __popcll(sg[0]) + __popcll(sg[1]) + __popcll(sg[2]) + __popcll(sg[3]);
+      const int off = block_exclusive_scan(cnt, warp_sums, &total);            // syncs: cols[] is staged too
+      for (int base = 0; base < total; base += kItemCap) {
+        int j = off;
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+          for (u64 mm = sg[w]; mm; mm &= mm - 1, ++j)
+            if (j >= base && j < base + kItemCap) items[j - base] = ((unsigned)tid << 8) | (unsigned)(64 * w + __ffsll((long long)mm) - 1);
+        __syncthreads();
+        const int units = min(kItemCap, total - base);
+        for (int it = tid; it < units; it += kRecThreads) {
+          const unsigned item = items[it];
+          const int r = item >> 8, u = item & 255;
+          const float4 rc = rowc[r];
+          const float4* src = cols + u * 32;
+          float d[32], dm = inf_f();
+#pragma unroll
+          for (int kk = 0; kk < 32; ++kk) {
+            const float4 q = src[(kk + lane) & 31];
+            d[kk] = exact_d2s(rc.x, rc.y, rc.z, q.x, q.y, q.z);
+            dm = fminf(dm, d[kk]);
+          }
+          int at;
+          const int st = unit_scan(d, dm, lane, &at);
+          if (st == 1) atomicMin(&key[r], ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)__float_as_int(src[at].w));
+          else if (st == 2) { const u64 kv = unit_exact_walk(rc.x, rc.y, rc.z, src, 0, 1); if (kv != ~0ull) atomicMin(&key[r], kv); }
+        }
+        __syncthreads();
+      }
     }
-  }
-  __syncthreads();
-  if (valid) {
-    const u64 kv = key[tid];
-    min1[(size_t)b * P + row] = __uint_as_float((unsigned)(kv >> 32));
-    idx1[(size_t)b * P + row] = (int)(unsigned)(kv & 0xffffffffu);
+    __syncthreads();
+    if (valid) {
+      const u64 kv = key[tid];
+      min1[(size_t)b * P + row] = __uint_as_float((unsigned)(kv >> 32));
+      idx1[(size_t)b * P + row] = (int)(unsigned)(kv & 0xffffffffu);
+    }
   }
 }
 
@@ -461,19 +515,23 @@ __global__ void chamfer_col_thr_kernel(const float* __restrict__ cbest, const fl
 }
 
 // grid: x = row tile, y = sample.  dynamic smem: float4 rows[TM].  key2 (B,M) u64 pre-filled with 0xFF.
-// Candidate bit k of a (tile, column) record names the rows
-//   TC == false : rows rr * 256 + k * 32 + [0,32), rr = 0..R-1   (warp k of chamfer_tiled_kernel<R>, TM = 256 R)
-//   TC == true  : rows k * 128 + [0,128)                          (row block k of chamfer_tc_kernel, TM = 128 R)
+// Candidate records of a (tile, column):
+//   TC == false : `unsigned`, bit k = rows rr * 256 + k * 32 + [0,32), rr = 0..R-1  (warp k of chamfer_tiled_kernel<R>, TM = 256 R)
+//   TC == true  : u64, bit k = rows 32 k + [0,32) of the tile                        (32-row UNITS, chamfer_tc_kernel, TM = 128 R)
 template <int R, bool TC>
 __global__ void __launch_bounds__(kRecThreads, 1)
 chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
-                            const float* __restrict__ cbest, const unsigned* __restrict__ cmask,
+                            const float* __restrict__ cbest, const void* __restrict__ cmask_,
                             const float* __restrict__ cthr, u64* __restrict__ key2, int P, int M, int ntiles,
                             const int* __restrict__ skip) {
   constexpr int TM = TC ? 128 * R : kTThreads * R;
-  constexpr int kSub = TC ? 4 : ((R >= 4) ? 4 : R);      // sub-units per (column, bit) item
+  constexpr int kSub = TC ? 1 : ((R >= 4) ? 4 : R);      // sub-units per (column, bit) item
   constexpr int kRunsPerSub = TC ? 1 : R / kSub;
-  constexpr unsigned kBitMask = TC ? ((1u << R) - 1u) : 0xffu;
+  constexpr int kPer = TC ? 4 : 8;                       // columns per thread and slab (TC: 64-bit masks, same register count)
+  constexpr int kBitBits = TC ? 6 : 4;
+  using mask_t = typename std::conditional<TC, u64, unsigned>::type;
+  const mask_t* __restrict__ cmask = reinterpret_cast<const mask_t*>(cmask_);
+  const mask_t kBitMask = TC ? (mask_t)((4 * R >= 64) ? ~0ull : ((1ull << (4 * R)) - 1ull)) : (mask_t)0xffu;
   if (skip && skip[blockIdx.y]) return;                  // sample redone by chamfer_flagged_kernel
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* rows = reinterpret_cast<float4*>(smem_raw);
@@ -488,37 +546,38 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
                        : make_float4(qnan, qnan, qnan, 0.f);
   }
   const size_t rec0 = ((size_t)b * ntiles + ti) * M;
-  // columns are visited in slabs of kRecThreads * 8 so that one slab's items normally fit the list
-  for (int slab = 0; slab < M; slab += kRecThreads * 8) {
-    unsigned mk[8];
+  // columns are visited in slabs of kRecThreads * kPer so that one slab's items normally fit the list
+  for (int slab = 0; slab < M; slab += kRecThreads * kPer) {
+    mask_t mk[kPer];
     int cnt = 0;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < kPer; ++u) {
       const int col = slab + u * kRecThreads + tid;
-      mk[u] = 0u;
+      mk[u] = 0;
       if (col < M && cbest[rec0 + col] <= cthr[(size_t)b * M + col]) mk[u] = cmask[rec0 + col] & kBitMask;
-      cnt += __popc(mk[u]);
+      cnt += TC ? __popcll((u64)mk[u]) : __popc((unsigned)mk[u]);
     }
     int total;
     const int off = block_exclusive_scan(cnt, warp_sums, &total);
     for (int base = 0; base < total; base += kItemCap) {
       int j = off;
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        for (unsigned mm = mk[u]; mm; mm &= mm - 1, ++j)
+      for (int u = 0; u < kPer; ++u)
+        for (mask_t mm = mk[u]; mm; mm &= mm - 1, ++j)
           if (j >= base && j < base + kItemCap)
-            items[j - base] = ((unsigned)(u * kRecThreads + tid) << 4) | (unsigned)(__ffs((int)mm) - 1);
+            items[j - base] = ((unsigned)(u * kRecThreads + tid) << kBitBits) |
+                              (unsigned)((TC ? __ffsll((long long)mm) : __ffs((int)mm)) - 1);
       __syncthreads();
       const int units = min(kItemCap, total - base) * kSub;
       for (int it = tid; it < units; it += kRecThreads) {
         const unsigned item = items[it / kSub];
-        const int col = slab + (int)(item >> 4), w = item & 15, sub = it % kSub;
+        const int col = slab + (int)(item >> kBitBits), w = item & ((1u << kBitBits) - 1u), sub = it % kSub;
         const float* t = p2 + 3 * ((size_t)b * M + col);
         const float tx = __ldg(t), ty = __ldg(t + 1), tz = __ldg(t + 2);
         u64 best = ~0ull;
 #pragma unroll 1
         for (int rr = sub * kRunsPerSub; rr < (sub + 1) * kRunsPerSub; ++rr) {
-          const int base_row = TC ? (w * 128 + rr * 32) : (rr * kTThreads + w * 32);
+          const int base_row = TC ? (w * 32) : (rr * kTThreads + w * 32);
           float d[32], dm = inf_f();
 #pragma unroll
           for (int kk = 0; kk < 32; ++kk) {
@@ -560,12 +619,13 @@ struct TiledPlan { int R, ntiles, nchunks, nsplit, cps, tc, TM; };
 
 // chamfer_tc.cu
 size_t chamfer_tc_smem_bytes(int NB);
-int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, unsigned* cmask,
+int chamfer_tc_plan_words();
+int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask, float* cbest, u64* cmask,
                       float2* tslack, int* fallback, float* tmax, const float* cbox, const float* rbox, const float* rthr,
                       const float* cub, u64* stats, unsigned* plan_masks, int* plan_work, int* plan_order, int with_bounds,
                       int B, int P, int M, int NB, int ntiles, int nsplit, int nchunks, int cps, cudaStream_t s);
 // chamfer_prep.cu
-int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, int* perm, float* cbox, float* rbox, float* rthr,
+int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, float4* p2v, int* perm, float* cbox, float* rbox, float* rthr,
                         float* cub, float* tmax, int B, int P, int M, cudaStream_t s);
 int chamfer_flagged_launch(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                            const int* fallback, int B, int P, int M, cudaStream_t s);
@@ -629,29 +689,30 @@ static bool make_plan_tc(int B, int P, int M, int sm_count, TiledPlan& pl) {
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, tmax, cthr, key2, p2s, perm, cbox, rbox, rthr, cub, pmask, pwork, porder, total; };
+struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, tmax, cthr, key2, p2s, p2v, perm, cbox, rbox, rthr, cub, pmask, pwork, porder, total; };
 static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   TiledWs w; size_t o = 0;
   w.rbest = o; o += al256((size_t)B * pl.nsplit * P * 4);
-  w.rmask = o; o += al256((size_t)B * pl.nsplit * P * 8);
+  w.rmask = o; o += al256((size_t)B * pl.nsplit * P * 8 * (pl.tc ? 4 : 1));      // tensor-core filter: four planes of unit bits
   w.cbest = o; o += al256((size_t)B * pl.ntiles * M * 4);
-  w.cmask = o; o += al256((size_t)B * pl.ntiles * M * 4);
+  w.cmask = o; o += al256((size_t)B * pl.ntiles * M * (pl.tc ? 8 : 4));          // tensor-core filter: 64 unit bits
   w.tslack = o; o += al256((size_t)B * pl.ntiles * 8);
   w.fallback = o; o += al256((size_t)B * 4 + 8 + 128);     // + 16 x u64 statistics / cycle counters of the tensor-core filter, zeroed with the flags
   w.tmax = o; o += al256((size_t)B * 4);
   w.cthr = o; o += al256((size_t)B * M * 4);
   w.key2 = o; o += al256((size_t)B * M * 8);
-  w.p2s = w.perm = w.cbox = w.rbox = w.rthr = w.cub = w.pmask = w.pwork = w.porder = 0;
+  w.p2s = w.p2v = w.perm = w.cbox = w.rbox = w.rthr = w.cub = w.pmask = w.pwork = w.porder = 0;
   if (pl.tc) {                                             // spatial preparation of the pruned tensor-core filter (chamfer_prep.cu)
     const size_t nrb = (size_t)(P + 127) / 128;
     w.p2s = o; o += al256((size_t)B * M * 12);
+    w.p2v = o; o += al256((size_t)B * pl.nchunks * kCW * 16);     // (x, y, z, original index), NaN-padded to whole chunks
     w.perm = o; o += al256((size_t)B * M * 4);
     w.cbox = o; o += al256((size_t)B * pl.nchunks * 32);
     w.rbox = o; o += al256((size_t)B * nrb * 32);
     w.rthr = o; o += al256((size_t)B * nrb * 4);
     w.cub = o; o += al256((size_t)B * pl.nchunks * 4);
     const size_t ncta = (size_t)pl.ntiles * pl.nsplit * B;         // tiles of the filter: skip masks, work, run order
-    w.pmask = o; o += al256(ncta * 96 * 4);
+    w.pmask = o; o += al256(ncta * (size_t)chamfer_tc_plan_words() * 4);
     w.pwork = o; o += al256(ncta * 4);
     w.porder = o; o += al256(ncta * 4);
   }
@@ -736,7 +797,7 @@ static int launch_any(int mode, const float* p1, const float* p2, char* ws, cons
 }
 
 template <int R, bool TC>
-static int launch_recover_cols(const float* p1, const float* p2, const float* cb, const unsigned* cmk, const float* cthr,
+static int launch_recover_cols(const float* p1, const float* p2, const float* cb, const void* cmk, const float* cthr,
                                u64* key2, int B, int P, int M, int ntiles, const int* skip, cudaStream_t s) {
   static DeviceOnce once;
   const size_t smem = (size_t)(TC ? 128 * R : kTThreads * R) * sizeof(float4);
@@ -791,6 +852,7 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   }
   const float* p2w = p2;                       // the targets the sweep and the recovery kernels read
   const int* perm = nullptr;                   // sorted position -> original index (tensor-core mode)
+  const float4* p2v = nullptr;                 // the swept targets as (x, y, z, original index) (tensor-core mode, pruned)
   if (mode == MODE_TC) {
     float* p2s = reinterpret_cast<float*>(ws + wl.p2s);
     int* pm = reinterpret_cast<int*>(ws + wl.perm);
@@ -800,11 +862,12 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
     u64* stats = reinterpret_cast<u64*>(ws + wl.fallback + (((size_t)B * 4 + 7) & ~(size_t)7));
     const bool prune = tuning_value(kTuneTcPrune) != 2;                      // vpn_set_tuning("tc_prune", 2): unpruned sweep
     if (prune) {
-      if ((rc = chamfer_prep_launch(p1, p2, p2s, pm, cbox, rbox, rthr, cub, tmax, B, P, M, s))) return rc;
-      p2w = p2s; perm = pm;
+      float4* pv = reinterpret_cast<float4*>(ws + wl.p2v);
+      if ((rc = chamfer_prep_launch(p1, p2, p2s, pv, pm, cbox, rbox, rthr, cub, tmax, B, P, M, s))) return rc;
+      p2w = p2s; perm = pm; p2v = pv;
     }
     rc = chamfer_tc_launch(p1, p2w, reinterpret_cast<float*>(ws + wl.rbest), reinterpret_cast<u64*>(ws + wl.rmask),
-                           reinterpret_cast<float*>(ws + wl.cbest), reinterpret_cast<unsigned*>(ws + wl.cmask),
+                           reinterpret_cast<float*>(ws + wl.cbest), reinterpret_cast<u64*>(ws + wl.cmask),
                            reinterpret_cast<float2*>(ws + wl.tslack), fallback, tmax, prune ? cbox : nullptr, rbox, rthr, cub, stats,
                            reinterpret_cast<unsigned*>(ws + wl.pmask), reinterpret_cast<int*>(ws + wl.pwork),
                            reinterpret_cast<int*>(ws + wl.porder), prune ? 0 : 1, B, P, M, pl.R, pl.ntiles, pl.nsplit, pl.nchunks,
@@ -837,14 +900,19 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
     if (set_dyn_smem(chamfer_recover_rows_kernel, (int)(kSegChunks * kCW * sizeof(float4)), once_rows) != cudaSuccess) {
       vpn_set_error("chamfer tiled: smem attribute (rows recovery)"); return VPN_ERR_CUDA;
     }
-    chamfer_recover_rows_kernel<<<dim3((P + kRecThreads - 1) / kRecThreads, B), kRecThreads, smem_rows, s>>>(
-        p1, p2w, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
-        reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nchunks, pl.nsplit, pl.cps, pl.TM, pl.ntiles, skip, perm);
+    const int nblk = (P + kRecThreads - 1) / kRecThreads;
+    const long long nitems = (long long)nblk * B;
+    if (nitems > 0x7fffffffLL) { vpn_set_error("chamfer tiled: too many row blocks"); return VPN_ERR_SHAPE; }
+    const int sms = device_sm_count();
+    chamfer_recover_rows_kernel<<<(unsigned)(nitems < sms ? nitems : sms), kRecThreads, smem_rows, s>>>(
+        p1, p2w, p2v, pl.nchunks * kCW, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
+        pl.tc ? 4 : 1, (size_t)B * pl.nsplit * P, reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nchunks,
+        pl.nsplit, pl.cps, pl.TM, pl.ntiles, skip, nblk, (int)nitems);
     if ((rc = vpn_check_launch("chamfer_recover_rows_kernel"))) return rc;
   }
   if (ev) cudaEventRecord(ev[3], s);          // with the fork: end of the row recovery; [3]..[4] = what the column chain adds after it
   const float* cb = reinterpret_cast<const float*>(ws + wl.cbest);
-  const unsigned* cmk = reinterpret_cast<const unsigned*>(ws + wl.cmask);
+  const void* cmk = ws + wl.cmask;
   const float2* tsl = reinterpret_cast<const float2*>(ws + wl.tslack);
   float* cthr = reinterpret_cast<float*>(ws + wl.cthr);
   u64* key2 = reinterpret_cast<u64*>(ws + wl.key2);
