@@ -19,7 +19,7 @@ def main():
     lib = vpn_b200._lib.load()
     for name, impl, prune, nb, half in (("tc_pruned", 5, 0, 0, 0), ("tc_pruned_whole_stages", 5, 0, 0, 1), ("tc_pruned_nb8", 5, 0, 8, 0),
                                         ("tc_unpruned", 5, 2, 0, 0), ("exact", 2, 0, 0, 0), ("expand", 4, 0, 0, 0)):
-        lib.vpn_set_tuning(b"tc_prune", prune); lib.vpn_set_tuning(b"tc_nb", nb); lib.vpn_set_tuning(b"tc_half", half)
+        lib.vpn_set_tuning(b"tc_prune", prune); lib.vpn_set_tuning(b"tc_nb", nb)
         vpn_b200.chamfer_nn_stage_ms(pts, s["target"], impl, reps=2)
         st = vpn_b200.chamfer_nn_stage_ms(pts, s["target"], impl, reps=10)
         st["tflops_total"] = flops / (st["total"] * 1e-3) / 1e12
@@ -27,7 +27,7 @@ def main():
         st["frac_total"] = st["tflops_total"] / peak["ffma2"]
         out[name] = st
         print(name, json.dumps(st), flush=True)
-    lib.vpn_set_tuning(b"tc_prune", 0); lib.vpn_set_tuning(b"tc_nb", 0); lib.vpn_set_tuning(b"tc_half", 0)
+    lib.vpn_set_tuning(b"tc_prune", 0); lib.vpn_set_tuning(b"tc_nb", 0)
     # uniform random clouds of the same size (worst case for the expansion filter's slack)
     p1 = torch.rand(b, k * n, 3, device=dev) - 0.5
     for name, impl in (("tc_uniform", 5), ("exact_uniform", 2), ("expand_uniform", 4)):

@@ -21,7 +21,7 @@ def main():
         ref = [t.clone() for t in vpn_b200.chamfer_nn(p1, p2, 1)]
         for prune, half in ((0, 0), (0, 1), (2, 0)):
             for nb in (0, 8, 4):
-                lib.vpn_set_tuning(b"tc_prune", prune); lib.vpn_set_tuning(b"tc_nb", nb); lib.vpn_set_tuning(b"tc_half", half)
+                lib.vpn_set_tuning(b"tc_prune", prune); lib.vpn_set_tuning(b"tc_nb", nb)
                 out = vpn_b200.chamfer_nn(p1, p2, 5)
                 torch.cuda.synchronize()
                 bad = [int((o != r).sum()) if o.dtype != torch.float32 else int((o.view(torch.int32) != r.view(torch.int32)).sum()) for o, r in zip(out, ref)]
@@ -33,7 +33,7 @@ def main():
                     w = (out[3] != ref[3]).nonzero()[:4]
                     line += "  first idx2: " + str([(int(a), int(bb), int(out[3][a, bb]), int(ref[3][a, bb]), float(out[2][a, bb]), float(ref[2][a, bb])) for a, bb in w])
                 print(line, flush=True)
-        lib.vpn_set_tuning(b"tc_prune", 0); lib.vpn_set_tuning(b"tc_nb", 0); lib.vpn_set_tuning(b"tc_half", 0)
+        lib.vpn_set_tuning(b"tc_prune", 0); lib.vpn_set_tuning(b"tc_nb", 0)
 
 if __name__ == "__main__":
     main()

@@ -43,7 +43,7 @@ namespace vpn {
 
 constexpr int kTcBlk = 128;                    // rows per block = columns per chunk = MMA M = MMA N
 constexpr int kTcEpiWarps = 8;
-constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
+constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;       // 8 epilogue warps, the operand builder, one MMA issuer per half
 constexpr int kTcBlkBytes = kTcBlk * 32;       // 128 points x 16 fp16
 constexpr float kTcBig = 1.0e30f;
 
@@ -143,11 +143,9 @@ struct TcSmem {
   u64* bars; float* red; uint32_t* tmem_slot; uint32_t* skip;
 };
 // plan words of a tile (global): [0,64) per chunk c the row blocks r (bit r) whose 128 x 128 block is pruned for the row
-// direction, [64,128) the same for the column direction.  In shared memory the kernel appends the stage masks it derives:
-// [128,160) phase 0, per chunk pair j: bit r set = stage (j, r) pruned (both halves); [160,224) phase 1, per chunk: bit
-// rp set = stage (chunk, row-block pair rp) pruned.
+// direction, [64,128) the same for the column direction.
 constexpr int kTcPlanWords = 128;
-constexpr int kTcSkipWords = 224;
+constexpr int kTcSkipWords = 128;
 __host__ __device__ inline size_t tc_smem_bytes(int NB) {
   return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 20 + 2 * 2 * kTcBlk * 16 + 16 * 8 + 64 * 4 + 16 +
          kTcSkipWords * 4;
@@ -166,62 +164,34 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
   return s;
 }
 
-// Minimum of this thread's TMEM lane over 128 accumulator columns starting at taddr.  The loads of the second
-// half are in flight while the first half is reduced; the stage is handed back to the MMA warp (mbarrier
-// `empty_bar`) as soon as all 128 values are in registers.  (Carrying a prefetched first half of the next stage
-// across loop iterations, and 16 warps x 64 columns, both measured slower: 765 and 631 clk per stage against 580.)
-__device__ __forceinline__ float tc_lane_min128(uint32_t taddr, uint32_t empty_bar, int lane) {
-  float v0[32], v1[32], v2[32], v3[32];
-  tc_ld32(taddr, v0); tc_ld32(taddr + 32, v1);
-  tc_wait_ld();
-  tc_ld32(taddr + 64, v2); tc_ld32(taddr + 96, v3);
-  float m0 = tc_inf(), m1 = tc_inf();
-#if !defined(VPN_TC_VARIANT) || VPN_TC_VARIANT != 1      // probe 1: TMEM reads, no reduction
-#pragma unroll
-  for (int k = 0; k < 32; k += 2) { m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]); }
-#endif
-  tc_wait_ld();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) tc_mbar_arrive(empty_bar);
-#if !defined(VPN_TC_VARIANT) || VPN_TC_VARIANT != 1
-#pragma unroll
-  for (int k = 0; k < 32; k += 2) { m0 = tc_min3(m0, v2[k], v2[k + 1]); m1 = tc_min3(m1, v3[k], v3[k + 1]); }
-#else
-  m0 = v0[1] + v1[2]; m1 = v2[3] + v3[7];
-#endif
-  return fminf(m0, m1);
-}
-
-// The same sweep keeping the minimum of every 32-column UNIT apart (u[0..3]; same FMNMX3 count, four chains instead of
-// two): the row records name candidate units, not whole chunks, so that the exact recovery redoes a quarter of the pairs.
+// Minima of this thread's TMEM lane over the 128 accumulator columns starting at taddr, one per 32-column UNIT (u[0..3]):
+// the records name candidate units, not whole blocks, so that the exact recovery redoes a quarter of the pairs.
 __device__ __forceinline__ float tc_lane_min4x32(uint32_t taddr, uint32_t empty_bar, int lane, float (&u)[4]) {
-  float v0[32], v1[32], v2[32], v3[32];
-  tc_ld32(taddr, v0); tc_ld32(taddr + 32, v1);
-  tc_wait_ld();
-  float m0 = tc_inf(), m1 = tc_inf(), m2 = tc_inf(), m3 = tc_inf();
-#if defined(VPN_TC_SCHED) && VPN_TC_SCHED == 1
-  // The address of the second half's loads is made to depend on the partly reduced first half (z is always 0: a minimum
-  // is never the all-ones NaN): ptxas otherwise hoists all four loads to the top and nothing overlaps the reduction.
-#pragma unroll
-  for (int k = 0; k < VPN_TC_SPLIT; k += 2) { m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]); }
-  const uint32_t z = (__float_as_uint(m0) == 0xffffffffu) ? 1u : 0u;
-  tc_ld32(taddr + 64 + z, v2); tc_ld32(taddr + 96 + z, v3);
-#pragma unroll
-  for (int k = VPN_TC_SPLIT; k < 32; k += 2) { m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]); }
-#else
-  tc_ld32(taddr + 64, v2); tc_ld32(taddr + 96, v3);
-#pragma unroll
-  for (int k = 0; k < 32; k += 2) { m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]); }
-#endif
-  tc_wait_ld();
-  tc_fence_before();
+#if defined(VPN_TC_VARIANT) && VPN_TC_VARIANT == 2       // probe: tensor side alone (no TMEM reads, no reduction)
   __syncwarp();
   if (lane == 0) tc_mbar_arrive(empty_bar);
+  u[0] = u[1] = u[2] = u[3] = __int_as_float(0x7fc00000);   // NaN: no record is ever updated
+  return u[0];
+#else
+  float v0[32], v1[32], v2[32], v3[32];
+  tc_ld32(taddr, v0); tc_ld32(taddr + 32, v1); tc_ld32(taddr + 64, v2); tc_ld32(taddr + 96, v3);
+  tc_wait_ld();                                // tcgen05.wait::ld has no groups: it waits for every load of the thread
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) tc_mbar_arrive(empty_bar);    // the block's accumulator is free again while the minima are taken
+  float m0 = tc_inf(), m1 = tc_inf(), m2 = tc_inf(), m3 = tc_inf();
+#if defined(VPN_TC_VARIANT) && VPN_TC_VARIANT == 1       // probe: TMEM reads, no reduction
+  m0 = v0[1] + v1[2]; m1 = v2[3] + v3[7]; m2 = v0[9] + v2[11]; m3 = v1[30] + v3[31];
+#else
 #pragma unroll
-  for (int k = 0; k < 32; k += 2) { m2 = tc_min3(m2, v2[k], v2[k + 1]); m3 = tc_min3(m3, v3[k], v3[k + 1]); }
+  for (int k = 0; k < 32; k += 2) {
+    m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]);
+    m2 = tc_min3(m2, v2[k], v2[k + 1]); m3 = tc_min3(m3, v3[k], v3[k + 1]);
+  }
+#endif
   u[0] = m0; u[1] = m1; u[2] = m2; u[3] = m3;
   return fminf(tc_min3(m0, m1, m2), m3);
+#endif
 }
 
 // nibble k of x -> low nibble of byte k
@@ -243,12 +213,11 @@ __device__ __forceinline__ float tc_box_gap2(const float* __restrict__ a, const 
   return s;
 }
 
-// Does pass (phase, chunk pair j) contain a stage that is not pruned?  (The operand builder and the MMA issuer must
-// agree on which column buffers exist.)
-__device__ __forceinline__ bool tc_pass_needed(bool phase0, int j, int nc, int NB, const uint32_t* skip0, const uint32_t* skip1) {
-  if (phase0) return ((~skip0[j]) & ((1u << NB) - 1u)) != 0u;
-  const uint32_t both = skip1[2 * j] & ((2 * j + 1 < nc) ? skip1[2 * j + 1] : 0xffffffffu);
-  return ((~both) & ((1u << (NB >> 1)) - 1u)) != 0u;
+// Does pass (phase, chunk pair j) contain a block that is not pruned?  (The operand builder and the MMA issuers must
+// agree on which column buffers exist.)  raw: the plan words of the phase (bit r of word c: block (r, c) pruned).
+__device__ __forceinline__ bool tc_pass_needed(int j, int nc, int NB, const uint32_t* raw) {
+  const uint32_t live = ~raw[2 * j] | ((2 * j + 1 < nc) ? ~raw[2 * j + 1] : 0u);
+  return (live & ((1u << NB) - 1u)) != 0u;
 }
 
 // ---- plan: which stages of which tile are pruned, and the order the tiles are run in ---------------------------------
@@ -338,7 +307,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                   float* __restrict__ cbest, u64* __restrict__ cmask,
                   float2* __restrict__ tslack, int* __restrict__ fallback, const float* __restrict__ tmax,
                   const uint32_t* __restrict__ plan_masks, const int* __restrict__ plan_order, u64* __restrict__ stats,
-                  int ntiles, int nsplit, int P, int M, int NB, int nchunks, int cps, int whole_stages) {
+                  int ntiles, int nsplit, int P, int M, int NB, int nchunks, int cps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
 #ifdef VPN_TC_COUNTERS
   const long long t_start = clock64();
@@ -355,15 +324,18 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   const float* T = p2 + (size_t)b * M * 3;
   const int c_first = split * cps;
   const int c_last = min(nchunks, c_first + cps);
-  // barriers (8 bytes each): +0/+8 stage full, +16/+24 stage empty, +32/+40 column buffer full, +48/+56 column buffer empty
+  // barriers (8 bytes each): +0..+24 accumulator full [half][buffer], +32..+56 accumulator empty [half][buffer], +64/+72
+  // column operand buffer full, +80/+88 column operand buffer empty
   const uint32_t bar0 = tc_smem_u32(sm.bars);
-  const uint32_t bar_full = bar0, bar_empty = bar0 + 16, bar_cfull = bar0 + 32, bar_cempty = bar0 + 48;
+  const uint32_t bar_full = bar0, bar_empty = bar0 + 32, bar_cfull = bar0 + 64, bar_cempty = bar0 + 80;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       tc_mbar_init(bar_full + 8 * i, 1);
-      tc_mbar_init(bar_empty + 8 * i, kTcEpiWarps);                    // every epilogue warp reads every stage
+      tc_mbar_init(bar_empty + 8 * i, kTcEpiWarps / 2);                // the four epilogue warps of the half read every block of it
+    }
+    for (int i = 0; i < 2; ++i) {
       tc_mbar_init(bar_cfull + 8 * i, 1);
-      tc_mbar_init(bar_cempty + 8 * i, 1);
+      tc_mbar_init(bar_cempty + 8 * i, 2);                             // both issuers release a column buffer
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -442,28 +414,11 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
 
   const int nc = c_last - c_first;             // chunks of this split (<= 64)
   const int hc = (nc + 1) >> 1;                // chunk pairs (<= 32)
-  const int NP = NB >> 1;                      // row-block pairs
   // ---- stage skip masks of this tile (computed by chamfer_tc_plan_kernel).  Without a plan every stage is computed.
   const uint32_t* rawR = sm.skip; const uint32_t* rawC = sm.skip + 64;
-  uint32_t* skip0 = sm.skip + 128; uint32_t* skip1 = sm.skip + 160;
   for (int i = tid; i < kTcPlanWords; i += kTcThreads) sm.skip[i] = plan_masks ? plan_masks[(size_t)cta * kTcPlanWords + i] : 0u;
   __syncthreads();
-  if (tid < 32) {
-    const uint32_t a = rawR[2 * tid], bb = (2 * tid + 1 < nc) ? rawR[2 * tid + 1] : 0xffffffffu;
-    skip0[tid] = (tid < hc) ? (a & bb) : 0xffffffffu;
-  } else if (tid < 96) {
-    const int c = tid - 32;
-    const uint32_t both = rawC[c] & (rawC[c] >> 1);                   // bit 2 rp: row blocks 2 rp and 2 rp + 1 both pruned
-    uint32_t m = 0u;
-    for (int rp = 0; rp < 8; ++rp) m |= ((both >> (2 * rp)) & 1u) << rp;
-    skip1[c] = (c < nc) ? m : 0xffffffffu;
-  }
-  __syncthreads();
-  if (whole_stages) {                                                 // probe (vpn_set_tuning("tc_half", 1)): live stages are computed whole
-    for (int i = tid; i < kTcPlanWords; i += kTcThreads) sm.skip[i] = 0u;
-    __syncthreads();
-  }
-  // statistics: stats[0] stages, stats[1] stages skipped - counted by the MMA warp's lanes in parallel, two atomics per CTA
+  // statistics: stats[0] 128 x 128 blocks, stats[1] blocks skipped - counted by an MMA warp's lanes in parallel, two atomics per CTA
   // (thread 0 doing it alone, plus cycle counters, delayed epilogue warp 0 and with it every stage: +3 %).  A probe build
   // (-DVPN_TC_COUNTERS) adds the cycle counters of epilogue warp 0: [2] prologue, [3] row phase, [4] column phase, [5]
   // tail, and [6] / [7] live stages per phase, [8] live chunks, [9] operand passes built.
@@ -485,8 +440,8 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   long long t_mark = 0;
   if (tid == 0 && stats != nullptr) {
     unsigned livechunks = 0, passes = 0;
-    for (int c = 0; c < nc; ++c) livechunks += (skip1[c] != ((1u << NP) - 1u)) ? 1u : 0u;
-    for (int cc = 0; cc < 2 * hc; ++cc) passes += tc_pass_needed(cc < hc, cc < hc ? cc : cc - hc, nc, NB, skip0, skip1) ? 1u : 0u;
+    for (int c = 0; c < nc; ++c) livechunks += ((~rawC[c]) & ((1u << NB) - 1u)) ? 1u : 0u;
+    for (int cc = 0; cc < 2 * hc; ++cc) passes += tc_pass_needed(cc < hc ? cc : cc - hc, nc, NB, cc < hc ? rawR : rawC) ? 1u : 0u;
     atomicAdd(&stats[8], (u64)livechunks);
     atomicAdd(&stats[9], (u64)passes);
     t_mark = clock64();
@@ -503,7 +458,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     // still read it: with most stages pruned a pass is short, and an L2 round trip per pass would set the pace.
     uint32_t seq = 0;
     float tx[8], ty[8], tz[8];
-    auto next_needed = [&](int cc) { while (cc < 2 * hc && !tc_pass_needed(cc < hc, cc < hc ? cc : cc - hc, nc, NB, skip0, skip1)) ++cc; return cc; };
+    auto next_needed = [&](int cc) { while (cc < 2 * hc && !tc_pass_needed(cc < hc ? cc : cc - hc, nc, NB, cc < hc ? rawR : rawC)) ++cc; return cc; };
     auto load_pass = [&](int cc) {
       const int j = cc < hc ? cc : cc - hc;
 #pragma unroll
@@ -535,100 +490,93 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       cc = next_needed(cc + 1);
       if (cc < 2 * hc) load_pass(cc);
     }
-  } else if (warp == kTcEpiWarps + 1) {
-    // ===== MMA issuer: the whole warp walks the loop (warp-uniform operands), one elected lane issues =====
+  } else if (warp > kTcEpiWarps) {
+    // ===== MMA issuer of half g: the whole warp walks the loop (warp-uniform operands), one elected lane issues =====
+    // Work unit = one 128 x 128 block, tcgen05.mma kind::f16 M = 128, N = 128, K = 16 into TMEM columns
+    // [256 st + 128 g, + 128), st = the half's block counter & 1.  Phase 0: blocks (row block r, chunk 2 j + g); phase 1:
+    // blocks (chunk, row block r) with r & 1 == g.
+    const int g = warp - (kTcEpiWarps + 1);
     const uint32_t rows_a = tc_smem_u32(sm.rows), cols_a = tc_smem_u32(sm.cols);
-    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0) + g * 128;
     const uint64_t drows = tc_desc(rows_a);
+    const uint32_t my_full = bar_full + 16 * g, my_empty = bar_empty + 16 * g;
+    const uint32_t nbmask = (1u << NB) - 1u;
     uint32_t it = 0;
     uint32_t seq = 0;
     for (int cc = 0; cc < 2 * hc; ++cc) {
       const int j = cc < hc ? cc : cc - hc;
-      if (!tc_pass_needed(cc < hc, j, nc, NB, skip0, skip1)) continue;
+      if (!tc_pass_needed(j, nc, NB, cc < hc ? rawR : rawC)) continue;
       const int cb = seq & 1, cuse = seq >> 1;
       ++seq;
       tc_mbar_wait(bar_cfull + 8 * cb, cuse & 1);
       tc_fence_after();
       const uint64_t dcols = tc_desc(cols_a + cb * 2 * kTcBlkBytes);
+      uint32_t issued = 0;
       if (cc < hc) {
-        for (uint32_t live = ~skip0[j] & ((1u << NB) - 1u); live; live &= live - 1) {
+        const uint64_t dc = dcols + (uint64_t)(g * (kTcBlkBytes >> 4));
+        for (uint32_t live = (2 * j + g < nc) ? (~rawR[2 * j + g] & nbmask) : 0u; live; live &= live - 1) {
           const int r = __ffs((int)live) - 1;
           const uint32_t st = it & 1;
-          tc_mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
+          tc_mbar_wait(my_empty + 8 * st, ((it >> 1) & 1) ^ 1);
           tc_fence_after();
           if (tc_elect()) {
-            const uint64_t dr = drows + (uint64_t)(r * (kTcBlkBytes >> 4));
-            const uint32_t d = tb + st * 256;
-            // a half whose 128 x 128 block is pruned is not computed (N = 128 MMA on the other half's operand and columns)
-            const bool dead0 = (rawR[2 * j] >> r) & 1u, dead1 = (2 * j + 1 < nc) ? ((rawR[2 * j + 1] >> r) & 1u) : true;
-            if (dead0) tc_mma(d + 128, dr, dcols + (uint64_t)(kTcBlkBytes >> 4), 0, kTcIdescHalf);
-            else if (dead1) tc_mma(d, dr, dcols, 0, kTcIdescHalf);
-            else tc_mma(d, dr, dcols, 0);                                   // D[row][2 chunks]
-            tc_commit(bar_full + 8 * st);
+            tc_mma(tb + st * 256, drows + (uint64_t)(r * (kTcBlkBytes >> 4)), dc, 0, kTcIdescHalf);     // D[row][column of the chunk]
+            tc_commit(my_full + 8 * st);
           }
           __syncwarp();
-          ++it;
+          ++it; ++issued;
         }
       } else {
         const int nh = (2 * j + 1 < nc) ? 2 : 1;
-        for (int h = 0; h < nh; ++h) {
-          const uint64_t dc = dcols + (uint64_t)(h * (kTcBlkBytes >> 4));
-          for (uint32_t live = ~skip1[2 * j + h] & ((1u << NP) - 1u); live; live &= live - 1) {
-            const int rp = __ffs((int)live) - 1;
+        for (int hh = 0; hh < nh; ++hh) {
+          const uint64_t dc = dcols + (uint64_t)(hh * (kTcBlkBytes >> 4));
+          for (uint32_t live = ~rawC[2 * j + hh] & nbmask & (0x55555555u << g); live; live &= live - 1) {
+            const int r = __ffs((int)live) - 1;
             const uint32_t st = it & 1;
-            tc_mbar_wait(bar_empty + 8 * st, ((it >> 1) & 1) ^ 1);
+            tc_mbar_wait(my_empty + 8 * st, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             if (tc_elect()) {
-              const uint64_t dr = drows + (uint64_t)(rp * (2 * kTcBlkBytes >> 4));
-              const uint32_t d = tb + st * 256;
-              const uint32_t rc = rawC[2 * j + h] >> (2 * rp);
-              if (rc & 1u) tc_mma(d + 128, dc, dr + (uint64_t)(kTcBlkBytes >> 4), 0, kTcIdescHalf);
-              else if (rc & 2u) tc_mma(d, dc, dr, 0, kTcIdescHalf);
-              else tc_mma(d, dc, dr, 0);                                    // D[col][2 row blocks]
-              tc_commit(bar_full + 8 * st);
+              tc_mma(tb + st * 256, dc, drows + (uint64_t)(r * (kTcBlkBytes >> 4)), 0, kTcIdescHalf);   // D[column][row of the block]
+              tc_commit(my_full + 8 * st);
             }
             __syncwarp();
-            ++it;
+            ++it; ++issued;
           }
         }
       }
-      if (tc_elect()) tc_commit(bar_cempty + 8 * cb);               // column buffer free once these MMAs retire
+      // column buffer free once this half's MMAs on it retire (a half without a block in the pass just arrives)
+      if (tc_elect()) { if (issued) tc_commit(bar_cempty + 8 * cb); else tc_mbar_arrive(bar_cempty + 8 * cb); }
       __syncwarp();
     }
   } else {
-    // ===== epilogue: warp = 4 h + q reads TMEM lanes [32 q, 32 q + 32), accumulator columns [128 h, 128 h + 128) =====
+    // ===== epilogue: warp = 4 h + q serves half h: TMEM lanes [32 q, 32 q + 32), accumulator columns [128 h, 128 h + 128)
+    // of either buffer.  The two warps of an SMSP (q) belong to different halves, which run independently: while one waits
+    // for its TMEM loads the other reduces (with one 256-column stage shared by both they moved in lock step - both
+    // loading, then both reducing - and the load latency was exposed: 580 clk per stage against 256 of FMNMX3 issue).
     const int q = warp & 3, h = warp >> 2;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + h * 128;
     const int li = q * 32 + lane;                                    // row in block (phase 0) / column in chunk (phase 1)
+    const uint32_t my_full = bar_full + 16 * h, my_empty = bar_empty + 16 * h;
     uint32_t it = 0;
     // ---- phase 0: row minima; record (h, row): best value and, per chunk pair j, four bits naming the 32-column units of
     // chunk 2 j + h that may hold the arg-min (word j >> 3, nibble j & 7)
     float* my_best = sm.rs_best + (size_t)h * TM;
     uint4* my_mask = sm.rs_mask + (size_t)h * TM;
-    const uint32_t nbmask = (1u << NB) - 1u, npmask = (1u << NP) - 1u;
+    const uint32_t nbmask = (1u << NB) - 1u;
     for (int j = 0; j < hc; ++j) {
-      const bool valid = 2 * j + h < nc;
-      const uint32_t dead = valid ? rawR[2 * j + h] : 0xffffffffu;   // row blocks whose block with MY chunk is pruned
-      // only the live stages are visited (a per-stage `if skipped continue` cost as many instructions as the stages left)
-      for (uint32_t live = ~skip0[j] & nbmask; live; live &= live - 1) {
+      if (2 * j + h >= nc) break;
+      // only the live blocks are visited (a per-block `if skipped continue` cost as many instructions as the blocks left)
+      for (uint32_t live = ~rawR[2 * j + h] & nbmask; live; live &= live - 1) {
         const int r = __ffs((int)live) - 1;
         const uint32_t st = it & 1;
-        tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
-        if ((dead >> r) & 1u) {
-          // my half of the stage was not computed: hand the stage back (after its `full`, so that this arrival cannot be
-          // counted for the accumulator's previous use) and leave the issue slots to the other half's warp on this SMSP
-          __syncwarp();
-          if (lane == 0) tc_mbar_arrive(bar_empty + 8 * st);
-          ++it;
-          continue;
-        }
+        tc_mbar_wait(my_full + 8 * st, (it >> 1) & 1);
         tc_fence_after();
         float mu[4];
-        const float m = tc_lane_min4x32(tlane + st * 256, bar_empty + 8 * st, lane, mu);
+        const float m = tc_lane_min4x32(tlane + st * 256, my_empty + 8 * st, lane, mu);
         ++it;
         const int ri = r * kTcBlk + li;
         const float best = my_best[ri];
-        if (valid && m <= tc_thr(best, slack_rel, slack_abs)) {
+        if (m <= tc_thr(best, slack_rel, slack_abs)) {
           // units within the slack of the best value known now (the final filter uses the final, smaller, best)
           const float t = tc_thr(fminf(best, m), slack_rel, slack_abs);
           const uint32_t nib = (mu[0] <= t ? 1u : 0u) | (mu[1] <= t ? 2u : 0u) | (mu[2] <= t ? 4u : 0u) | (mu[3] <= t ? 8u : 0u);
@@ -640,66 +588,56 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     }
     TC_MARK(3)
     // ---- phase 1: column minima.  Thread = one column of the chunk; it keeps a running record (best, 64-bit mask of the
-    // tile's 32-row UNITS: bit 4 (2 rp + h) + u) of the row blocks 2 rp + h it sees, in REGISTERS, with the same update
-    // rule as the row records; at the end of a chunk the two warps of a lane quarter (h = 0 / 1) exchange their records
-    // through shared memory (16 bytes per column) and the warp whose turn it is merges the two and writes the (tile,
-    // column) record.  (A per-block value array in shared memory merged in two passes per chunk cost ~400 clk per chunk
-    // on the critical path.)
+    // tile's 32-row UNITS: bit 4 r + u) of the row blocks r (r & 1 == h) it sees, in REGISTERS, with the same update rule
+    // as the row records; at the end of a chunk the two warps of a lane quarter (h = 0 / 1) exchange their records through
+    // shared memory (16 bytes per column) and the warp whose turn it is merges the two and writes the (tile, column)
+    // record - the one point where the halves meet.  (A per-block value array in shared memory merged in two passes per
+    // chunk cost ~400 clk per chunk on the critical path.)
     int cseq = 0;
     float4* xch = reinterpret_cast<float4*>(sm.colw);                 // [parity][h][128] exchange slots
-    for (int j = 0; j < hc; ++j) {
-      const int nh = (2 * j + 1 < nc) ? 2 : 1;
-      for (int hh = 0; hh < nh; ++hh) {
-        const uint32_t live1 = ~skip1[2 * j + hh] & npmask;          // row-block pairs of this chunk that are computed
-        if (live1 == 0u) {
-          // chunk pruned for the whole tile: record (+inf, no candidate) - it is never a candidate in the recovery.  No
-          // exchange, no barrier, and it does not take part in the two warps' alternation (cseq counts live chunks).
-          const int col = (c_first + 2 * j + hh) * kTcBlk + li;
-          if (h == hh && col < M) { const size_t o = ((size_t)b * ntiles + tile_i) * M + col; cbest[o] = tc_inf(); cmask[o] = 0ull; }
-          continue;
-        }
-        float best = tc_inf(); u64 mask = 0ull;
-        const uint32_t dead = rawC[2 * j + hh] >> h;                 // bit 2 rp: my row block 2 rp + h is pruned for this chunk
-        for (uint32_t live = live1; live; live &= live - 1) {
-          const int rp = __ffs((int)live) - 1;
-          const uint32_t st = it & 1;
-          tc_mbar_wait(bar_full + 8 * st, (it >> 1) & 1);
-          if ((dead >> (2 * rp)) & 1u) {
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive(bar_empty + 8 * st);
-            ++it;
-            continue;
-          }
-          tc_fence_after();
-          float mu[4];
-          const float m = tc_lane_min4x32(tlane + st * 256, bar_empty + 8 * st, lane, mu);
-          ++it;
-          if (m <= tc_thr(best, slack_rel, slack_abs)) {
-            const float t = tc_thr(fminf(best, m), slack_rel, slack_abs);
-            const uint32_t nib = (mu[0] <= t ? 1u : 0u) | (mu[1] <= t ? 2u : 0u) | (mu[2] <= t ? 4u : 0u) | (mu[3] <= t ? 8u : 0u);
-            const float tm = tc_thr(m, slack_rel, slack_abs);
-            mask = ((tm < best) ? 0ull : mask) | ((u64)nib << (4 * (2 * rp + h)));
-            best = fminf(best, m);
-          }
-        }
-        float4* slot = xch + (size_t)(cseq & 1) * 2 * kTcBlk;
-        slot[h * kTcBlk + li] = make_float4(best, __uint_as_float((uint32_t)mask), __uint_as_float((uint32_t)(mask >> 32)), 0.f);
-        // the two warps of this lane quarter meet once per live chunk; they take turns merging
-        asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
-        if ((cseq & 1) == h) {
-          const int col = (c_first + 2 * j + hh) * kTcBlk + li;
-          if (col < M) {
-            const float4 other = slot[(h ^ 1) * kTcBlk + li];
-            const float b2 = fminf(best, other.x);
-            const float t = tc_thr(b2, slack_rel, slack_abs);
-            const u64 omask = (u64)__float_as_uint(other.y) | ((u64)__float_as_uint(other.z) << 32);
-            const u64 m2 = ((best <= t) ? mask : 0ull) | ((other.x <= t) ? omask : 0ull);
-            const size_t o = ((size_t)b * ntiles + tile_i) * M + col;
-            cbest[o] = b2 * invS2; cmask[o] = m2;
-          }
-        }
-        ++cseq;
+    for (int c = 0; c < nc; ++c) {
+      const uint32_t livec = ~rawC[c] & nbmask;                      // row blocks of this chunk that are computed
+      if (livec == 0u) {
+        // chunk pruned for the whole tile: record (+inf, no candidate) - it is never a candidate in the recovery.  No
+        // exchange, no barrier, and it does not take part in the two warps' alternation (cseq counts live chunks).
+        const int col = (c_first + c) * kTcBlk + li;
+        if (h == (c & 1) && col < M) { const size_t o = ((size_t)b * ntiles + tile_i) * M + col; cbest[o] = tc_inf(); cmask[o] = 0ull; }
+        continue;
       }
+      float best = tc_inf(); u64 mask = 0ull;
+      for (uint32_t live = livec & (0x55555555u << h); live; live &= live - 1) {
+        const int r = __ffs((int)live) - 1;
+        const uint32_t st = it & 1;
+        tc_mbar_wait(my_full + 8 * st, (it >> 1) & 1);
+        tc_fence_after();
+        float mu[4];
+        const float m = tc_lane_min4x32(tlane + st * 256, my_empty + 8 * st, lane, mu);
+        ++it;
+        if (m <= tc_thr(best, slack_rel, slack_abs)) {
+          const float t = tc_thr(fminf(best, m), slack_rel, slack_abs);
+          const uint32_t nib = (mu[0] <= t ? 1u : 0u) | (mu[1] <= t ? 2u : 0u) | (mu[2] <= t ? 4u : 0u) | (mu[3] <= t ? 8u : 0u);
+          const float tm = tc_thr(m, slack_rel, slack_abs);
+          mask = ((tm < best) ? 0ull : mask) | ((u64)nib << (4 * r));
+          best = fminf(best, m);
+        }
+      }
+      float4* slot = xch + (size_t)(cseq & 1) * 2 * kTcBlk;
+      slot[h * kTcBlk + li] = make_float4(best, __uint_as_float((uint32_t)mask), __uint_as_float((uint32_t)(mask >> 32)), 0.f);
+      // the two warps of this lane quarter meet once per live chunk; they take turns merging
+      asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
+      if ((cseq & 1) == h) {
+        const int col = (c_first + c) * kTcBlk + li;
+        if (col < M) {
+          const float4 other = slot[(h ^ 1) * kTcBlk + li];
+          const float b2 = fminf(best, other.x);
+          const float t = tc_thr(b2, slack_rel, slack_abs);
+          const u64 omask = (u64)__float_as_uint(other.y) | ((u64)__float_as_uint(other.z) << 32);
+          const u64 m2 = ((best <= t) ? mask : 0ull) | ((other.x <= t) ? omask : 0ull);
+          const size_t o = ((size_t)b * ntiles + tile_i) * M + col;
+          cbest[o] = b2 * invS2; cmask[o] = m2;
+        }
+      }
+      ++cseq;
     }
   }
   TC_MARK(4)
@@ -817,7 +755,7 @@ int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask
   }
   chamfer_tc_kernel<<<ncta, kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax,
                                                    cbox ? plan_masks : nullptr, cbox ? plan_order : nullptr, stats,
-                                                   ntiles, nsplit, P, M, NB, nchunks, cps, tuning_value(kTuneTcHalf) == 1 ? 1 : 0);
+                                                   ntiles, nsplit, P, M, NB, nchunks, cps);
   return vpn_check_launch("chamfer_tc_kernel");
 }
 
