@@ -42,8 +42,8 @@
 namespace vpn {
 
 constexpr int kTcBlk = 128;                    // rows per block = columns per chunk = MMA M = MMA N
-constexpr int kTcEpiWarps = 8;
-constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;       // 8 epilogue warps, the operand builder, one MMA issuer per half
+constexpr int kTcEpiWarps = 16;
+constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;       // 16 epilogue warps, the operand builder, one MMA issuer per half
 constexpr int kTcBlkBytes = kTcBlk * 32;       // 128 points x 16 fp16
 constexpr float kTcBig = 1.0e30f;
 
@@ -147,7 +147,7 @@ struct TcSmem {
 constexpr int kTcPlanWords = 128;
 constexpr int kTcSkipWords = 128;
 __host__ __device__ inline size_t tc_smem_bytes(int NB) {
-  return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 20 + 2 * 2 * kTcBlk * 16 + 16 * 8 + 64 * 4 + 16 +
+  return (size_t)NB * kTcBlkBytes + 4 * kTcBlkBytes + 2 * (size_t)NB * kTcBlk * 20 + 2 * 2 * 2 * kTcBlk * 16 + 16 * 8 + 96 * 4 + 16 +
          kTcSkipWords * 4;
 }
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
@@ -156,9 +156,9 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
   s.cols = p; p += 4 * kTcBlkBytes;                                   // two buffers of 256 columns
   s.rs_best = reinterpret_cast<float*>(p); p += 2 * (size_t)NB * kTcBlk * 4;      // [column half][row]
   s.rs_mask = reinterpret_cast<uint4*>(p); p += 2 * (size_t)NB * kTcBlk * 16;     // [column half][row]: 4 bits per chunk pair (32-column units)
-  s.colw = reinterpret_cast<float*>(p); p += 2 * 2 * kTcBlk * 16;                 // column record exchange: [chunk parity][h][column] float4
+  s.colw = reinterpret_cast<float*>(p); p += 2 * 2 * 2 * kTcBlk * 16;             // column record exchange: [p][turn][h][column] float4
   s.bars = reinterpret_cast<u64*>(p); p += 16 * 8;
-  s.red = reinterpret_cast<float*>(p); p += 64 * 4;
+  s.red = reinterpret_cast<float*>(p); p += 96 * 4;
   s.tmem_slot = reinterpret_cast<uint32_t*>(p); p += 16;
   s.skip = reinterpret_cast<uint32_t*>(p);
   return s;
@@ -166,6 +166,9 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* p, int NB) {
 
 // Minima of this thread's TMEM lane over the 128 accumulator columns starting at taddr, one per 32-column UNIT (u[0..3]):
 // the records name candidate units, not whole blocks, so that the exact recovery redoes a quarter of the pairs.
+// 64 values are live at a time (the kernel runs 19 warps: 104 registers per thread); each unit is reduced as two
+// interleaved chains.  tcgen05.wait::ld has no groups - it waits for every outstanding load of the thread - so a warp
+// cannot overlap its own loads with its own reduction; the overlap comes from the other three epilogue warps of the SMSP.
 __device__ __forceinline__ float tc_lane_min4x32(uint32_t taddr, uint32_t empty_bar, int lane, float (&u)[4]) {
 #if defined(VPN_TC_VARIANT) && VPN_TC_VARIANT == 2       // probe: tensor side alone (no TMEM reads, no reduction)
   __syncwarp();
@@ -173,22 +176,36 @@ __device__ __forceinline__ float tc_lane_min4x32(uint32_t taddr, uint32_t empty_
   u[0] = u[1] = u[2] = u[3] = __int_as_float(0x7fc00000);   // NaN: no record is ever updated
   return u[0];
 #else
-  float v0[32], v1[32], v2[32], v3[32];
-  tc_ld32(taddr, v0); tc_ld32(taddr + 32, v1); tc_ld32(taddr + 64, v2); tc_ld32(taddr + 96, v3);
-  tc_wait_ld();                                // tcgen05.wait::ld has no groups: it waits for every load of the thread
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) tc_mbar_arrive(empty_bar);    // the block's accumulator is free again while the minima are taken
-  float m0 = tc_inf(), m1 = tc_inf(), m2 = tc_inf(), m3 = tc_inf();
+  float va[32], vb[32];
+  tc_ld32(taddr, va); tc_ld32(taddr + 32, vb);
+  tc_wait_ld();
+  float a0 = tc_inf(), a1 = tc_inf(), b0 = tc_inf(), b1 = tc_inf();
 #if defined(VPN_TC_VARIANT) && VPN_TC_VARIANT == 1       // probe: TMEM reads, no reduction
-  m0 = v0[1] + v1[2]; m1 = v2[3] + v3[7]; m2 = v0[9] + v2[11]; m3 = v1[30] + v3[31];
+  a0 = va[1] + vb[2];
 #else
 #pragma unroll
-  for (int k = 0; k < 32; k += 2) {
-    m0 = tc_min3(m0, v0[k], v0[k + 1]); m1 = tc_min3(m1, v1[k], v1[k + 1]);
-    m2 = tc_min3(m2, v2[k], v2[k + 1]); m3 = tc_min3(m3, v3[k], v3[k + 1]);
+  for (int k = 0; k < 16; k += 2) {
+    a0 = tc_min3(a0, va[k], va[k + 1]); a1 = tc_min3(a1, va[16 + k], va[17 + k]);
+    b0 = tc_min3(b0, vb[k], vb[k + 1]); b1 = tc_min3(b1, vb[16 + k], vb[17 + k]);
   }
 #endif
+  const float m0 = fminf(a0, a1), m1 = fminf(b0, b1);
+  tc_ld32(taddr + 64, va); tc_ld32(taddr + 96, vb);
+  tc_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) tc_mbar_arrive(empty_bar);    // the block's accumulator is free again while the last minima are taken
+  a0 = tc_inf(); a1 = tc_inf(); b0 = tc_inf(); b1 = tc_inf();
+#if defined(VPN_TC_VARIANT) && VPN_TC_VARIANT == 1
+  a0 = va[3] + vb[7];
+#else
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    a0 = tc_min3(a0, va[k], va[k + 1]); a1 = tc_min3(a1, va[16 + k], va[17 + k]);
+    b0 = tc_min3(b0, vb[k], vb[k + 1]); b1 = tc_min3(b1, vb[16 + k], vb[17 + k]);
+  }
+#endif
+  const float m2 = fminf(a0, a1), m3 = fminf(b0, b1);
   u[0] = m0; u[1] = m1; u[2] = m2; u[3] = m3;
   return fminf(tc_min3(m0, m1, m2), m3);
 #endif
@@ -324,14 +341,14 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   const float* T = p2 + (size_t)b * M * 3;
   const int c_first = split * cps;
   const int c_last = min(nchunks, c_first + cps);
-  // barriers (8 bytes each): +0..+24 accumulator full [half][buffer], +32..+56 accumulator empty [half][buffer], +64/+72
+  // barriers (8 bytes each): +0..+24 accumulator full [half g][buffer p], +32..+56 accumulator empty [g][p], +64/+72
   // column operand buffer full, +80/+88 column operand buffer empty
   const uint32_t bar0 = tc_smem_u32(sm.bars);
   const uint32_t bar_full = bar0, bar_empty = bar0 + 32, bar_cfull = bar0 + 64, bar_cempty = bar0 + 80;
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
       tc_mbar_init(bar_full + 8 * i, 1);
-      tc_mbar_init(bar_empty + 8 * i, kTcEpiWarps / 2);                // the four epilogue warps of the half read every block of it
+      tc_mbar_init(bar_empty + 8 * i, 4);                              // the four epilogue warps (lane quarters) that read the buffer
     }
     for (int i = 0; i < 2; ++i) {
       tc_mbar_init(bar_cfull + 8 * i, 1);
@@ -365,10 +382,10 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   if (tid < 3) {
     float s = 0.f;
     for (int w = 0; w < kTcThreads / 32; ++w) s += sm.red[w * 4 + tid];
-    sm.red[48 + tid] = s / (float)TM;
+    sm.red[80 + tid] = s / (float)TM;
   }
   __syncthreads();
-  const float cx = sm.red[48], cy = sm.red[49], cz = sm.red[50];
+  const float cx = sm.red[80], cy = sm.red[81], cz = sm.red[82];
   float rho2 = 0.f;
 #pragma unroll
   for (int k = 0; k < kRowsPerThread; ++k) {
@@ -492,17 +509,30 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
     }
   } else if (warp > kTcEpiWarps) {
     // ===== MMA issuer of half g: the whole warp walks the loop (warp-uniform operands), one elected lane issues =====
-    // Work unit = one 128 x 128 block, tcgen05.mma kind::f16 M = 128, N = 128, K = 16 into TMEM columns
-    // [256 st + 128 g, + 128), st = the half's block counter & 1.  Phase 0: blocks (row block r, chunk 2 j + g); phase 1:
-    // blocks (chunk, row block r) with r & 1 == g.
+    // Work unit = one 128 x 128 block, tcgen05.mma kind::f16 M = 128, N = 128, K = 16 into the half's accumulator buffer p
+    // (TMEM columns [256 p + 128 g, + 128)), which belongs to the four epilogue warps (g, ., p).
+    //   phase 0: blocks (row block r, chunk 2 j + g), buffer p = r & 1;
+    //   phase 1: blocks (chunk c, row block r) with r & 1 == g, buffer p = c & 1 - the two chunks of a pass are interleaved.
     const int g = warp - (kTcEpiWarps + 1);
     const uint32_t rows_a = tc_smem_u32(sm.rows), cols_a = tc_smem_u32(sm.cols);
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0) + g * 128;
     const uint64_t drows = tc_desc(rows_a);
     const uint32_t my_full = bar_full + 16 * g, my_empty = bar_empty + 16 * g;
     const uint32_t nbmask = (1u << NB) - 1u;
-    uint32_t it = 0;
+    uint32_t uses[2] = {0u, 0u};                                      // blocks issued into buffer p so far
     uint32_t seq = 0;
+    // one block: wait until the buffer's previous block has been read, issue, signal `full` when the MMA retires
+    auto issue = [&](int p, uint64_t da, uint64_t db) {
+      const uint32_t n = p ? uses[1] : uses[0];
+      tc_mbar_wait(my_empty + 8 * p, (n & 1) ^ 1);
+      tc_fence_after();
+      if (tc_elect()) {
+        tc_mma(tb + p * 256, da, db, 0, kTcIdescHalf);
+        tc_commit(my_full + 8 * p);
+      }
+      __syncwarp();
+      if (p) ++uses[1]; else ++uses[0];
+    };
     for (int cc = 0; cc < 2 * hc; ++cc) {
       const int j = cc < hc ? cc : cc - hc;
       if (!tc_pass_needed(j, nc, NB, cc < hc ? rawR : rawC)) continue;
@@ -516,31 +546,22 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         const uint64_t dc = dcols + (uint64_t)(g * (kTcBlkBytes >> 4));
         for (uint32_t live = (2 * j + g < nc) ? (~rawR[2 * j + g] & nbmask) : 0u; live; live &= live - 1) {
           const int r = __ffs((int)live) - 1;
-          const uint32_t st = it & 1;
-          tc_mbar_wait(my_empty + 8 * st, ((it >> 1) & 1) ^ 1);
-          tc_fence_after();
-          if (tc_elect()) {
-            tc_mma(tb + st * 256, drows + (uint64_t)(r * (kTcBlkBytes >> 4)), dc, 0, kTcIdescHalf);     // D[row][column of the chunk]
-            tc_commit(my_full + 8 * st);
-          }
-          __syncwarp();
-          ++it; ++issued;
+          issue(r & 1, drows + (uint64_t)(r * (kTcBlkBytes >> 4)), dc);                   // D[row][column of the chunk]
+          ++issued;
         }
       } else {
-        const int nh = (2 * j + 1 < nc) ? 2 : 1;
-        for (int hh = 0; hh < nh; ++hh) {
-          const uint64_t dc = dcols + (uint64_t)(hh * (kTcBlkBytes >> 4));
-          for (uint32_t live = ~rawC[2 * j + hh] & nbmask & (0x55555555u << g); live; live &= live - 1) {
-            const int r = __ffs((int)live) - 1;
-            const uint32_t st = it & 1;
-            tc_mbar_wait(my_empty + 8 * st, ((it >> 1) & 1) ^ 1);
-            tc_fence_after();
-            if (tc_elect()) {
-              tc_mma(tb + st * 256, dc, drows + (uint64_t)(r * (kTcBlkBytes >> 4)), 0, kTcIdescHalf);   // D[column][row of the block]
-              tc_commit(my_full + 8 * st);
-            }
-            __syncwarp();
-            ++it; ++issued;
+        uint32_t live0 = ~rawC[2 * j] & nbmask & (0x55555555u << g);
+        uint32_t live1 = (2 * j + 1 < nc) ? (~rawC[2 * j + 1] & nbmask & (0x55555555u << g)) : 0u;
+        while (live0 | live1) {
+          if (live0) {
+            const int r = __ffs((int)live0) - 1; live0 &= live0 - 1;
+            issue(0, dcols, drows + (uint64_t)(r * (kTcBlkBytes >> 4)));                  // D[column][row of the block]
+            ++issued;
+          }
+          if (live1) {
+            const int r = __ffs((int)live1) - 1; live1 &= live1 - 1;
+            issue(1, dcols + (uint64_t)(kTcBlkBytes >> 4), drows + (uint64_t)(r * (kTcBlkBytes >> 4)));
+            ++issued;
           }
         }
       }
@@ -549,30 +570,31 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       __syncwarp();
     }
   } else {
-    // ===== epilogue: warp = 4 h + q serves half h: TMEM lanes [32 q, 32 q + 32), accumulator columns [128 h, 128 h + 128)
-    // of either buffer.  The two warps of an SMSP (q) belong to different halves, which run independently: while one waits
-    // for its TMEM loads the other reduces (with one 256-column stage shared by both they moved in lock step - both
-    // loading, then both reducing - and the load latency was exposed: 580 clk per stage against 256 of FMNMX3 issue).
-    const int q = warp & 3, h = warp >> 2;
-    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + h * 128;
+    // ===== epilogue: warp = 8 p + 4 h + q reads accumulator buffer p of half h: TMEM lanes [32 q, 32 q + 32), columns
+    // [256 p + 128 h, + 128).  The four warps of an SMSP (q) work on four different blocks at any time: while one waits
+    // for its TMEM loads the others reduce.  (With one 256-column stage shared by two warps per SMSP they moved in lock
+    // step - both loading, then both reducing - and the load latency was exposed: 580 clk per stage against 256 of FMNMX3
+    // issue; two independent warps per SMSP: 353 clk per 128 x 128 block, the serial load -> reduce chain of a warp.)
+    const int q = warp & 3, h = (warp >> 2) & 1, p = warp >> 3;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + p * 256 + h * 128;
     const int li = q * 32 + lane;                                    // row in block (phase 0) / column in chunk (phase 1)
-    const uint32_t my_full = bar_full + 16 * h, my_empty = bar_empty + 16 * h;
-    uint32_t it = 0;
+    const uint32_t my_full = bar_full + 16 * h + 8 * p, my_empty = bar_empty + 16 * h + 8 * p;
+    uint32_t it = 0;                                                 // blocks read from my buffer so far
     // ---- phase 0: row minima; record (h, row): best value and, per chunk pair j, four bits naming the 32-column units of
-    // chunk 2 j + h that may hold the arg-min (word j >> 3, nibble j & 7)
+    // chunk 2 j + h that may hold the arg-min (word j >> 3, nibble j & 7).  Row block r belongs to the warps with p = r & 1:
+    // a record has one writer.
     float* my_best = sm.rs_best + (size_t)h * TM;
     uint4* my_mask = sm.rs_mask + (size_t)h * TM;
     const uint32_t nbmask = (1u << NB) - 1u;
     for (int j = 0; j < hc; ++j) {
       if (2 * j + h >= nc) break;
       // only the live blocks are visited (a per-block `if skipped continue` cost as many instructions as the blocks left)
-      for (uint32_t live = ~rawR[2 * j + h] & nbmask; live; live &= live - 1) {
+      for (uint32_t live = ~rawR[2 * j + h] & nbmask & (0x55555555u << p); live; live &= live - 1) {
         const int r = __ffs((int)live) - 1;
-        const uint32_t st = it & 1;
-        tc_mbar_wait(my_full + 8 * st, (it >> 1) & 1);
+        tc_mbar_wait(my_full, it & 1);
         tc_fence_after();
         float mu[4];
-        const float m = tc_lane_min4x32(tlane + st * 256, my_empty + 8 * st, lane, mu);
+        const float m = tc_lane_min4x32(tlane, my_empty, lane, mu);
         ++it;
         const int ri = r * kTcBlk + li;
         const float best = my_best[ri];
@@ -587,31 +609,30 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       }
     }
     TC_MARK(3)
-    // ---- phase 1: column minima.  Thread = one column of the chunk; it keeps a running record (best, 64-bit mask of the
-    // tile's 32-row UNITS: bit 4 r + u) of the row blocks r (r & 1 == h) it sees, in REGISTERS, with the same update rule
-    // as the row records; at the end of a chunk the two warps of a lane quarter (h = 0 / 1) exchange their records through
-    // shared memory (16 bytes per column) and the warp whose turn it is merges the two and writes the (tile, column)
-    // record - the one point where the halves meet.  (A per-block value array in shared memory merged in two passes per
-    // chunk cost ~400 clk per chunk on the critical path.)
+    // ---- phase 1: column minima of the chunks c with c & 1 == p.  Thread = one column of the chunk; it keeps a running
+    // record (best, 64-bit mask of the tile's 32-row UNITS: bit 4 r + u) of the row blocks r (r & 1 == h) it sees, in
+    // REGISTERS, with the same update rule as the row records; at the end of a chunk the two warps (h = 0 / 1) of this lane
+    // quarter and parity exchange their records through shared memory (16 bytes per column) and the warp whose turn it
+    // is merges the two and writes the (tile, column) record.  (A per-block value array in shared memory merged in two
+    // passes per chunk cost ~400 clk per chunk on the critical path.)
     int cseq = 0;
-    float4* xch = reinterpret_cast<float4*>(sm.colw);                 // [parity][h][128] exchange slots
-    for (int c = 0; c < nc; ++c) {
+    float4* xch = reinterpret_cast<float4*>(sm.colw) + (size_t)p * 4 * kTcBlk;       // [turn][h][128] exchange slots of parity p
+    for (int c = p; c < nc; c += 2) {
       const uint32_t livec = ~rawC[c] & nbmask;                      // row blocks of this chunk that are computed
       if (livec == 0u) {
         // chunk pruned for the whole tile: record (+inf, no candidate) - it is never a candidate in the recovery.  No
         // exchange, no barrier, and it does not take part in the two warps' alternation (cseq counts live chunks).
         const int col = (c_first + c) * kTcBlk + li;
-        if (h == (c & 1) && col < M) { const size_t o = ((size_t)b * ntiles + tile_i) * M + col; cbest[o] = tc_inf(); cmask[o] = 0ull; }
+        if (h == 0 && col < M) { const size_t o = ((size_t)b * ntiles + tile_i) * M + col; cbest[o] = tc_inf(); cmask[o] = 0ull; }
         continue;
       }
       float best = tc_inf(); u64 mask = 0ull;
       for (uint32_t live = livec & (0x55555555u << h); live; live &= live - 1) {
         const int r = __ffs((int)live) - 1;
-        const uint32_t st = it & 1;
-        tc_mbar_wait(my_full + 8 * st, (it >> 1) & 1);
+        tc_mbar_wait(my_full, it & 1);
         tc_fence_after();
         float mu[4];
-        const float m = tc_lane_min4x32(tlane + st * 256, my_empty + 8 * st, lane, mu);
+        const float m = tc_lane_min4x32(tlane, my_empty, lane, mu);
         ++it;
         if (m <= tc_thr(best, slack_rel, slack_abs)) {
           const float t = tc_thr(fminf(best, m), slack_rel, slack_abs);
@@ -623,8 +644,8 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       }
       float4* slot = xch + (size_t)(cseq & 1) * 2 * kTcBlk;
       slot[h * kTcBlk + li] = make_float4(best, __uint_as_float((uint32_t)mask), __uint_as_float((uint32_t)(mask >> 32)), 0.f);
-      // the two warps of this lane quarter meet once per live chunk; they take turns merging
-      asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
+      // the two warps (h = 0 / 1) of this lane quarter and parity meet once per live chunk; they take turns merging
+      asm volatile("bar.sync %0, 64;" :: "r"(1 + q + 4 * p) : "memory");
       if ((cseq & 1) == h) {
         const int col = (c_first + c) * kTcBlk + li;
         if (col < M) {
