@@ -10,7 +10,7 @@
 //       largest |coordinate| (the filter's scale).  After sorting a chunk is a compact patch of the target shape.
 //       Predicted points need no sorting: they arrive primitive-major (train.py:119 torch.cat(dim=1)), so 128
 //       consecutive rows are one patch of one primitive.
-//   chamfer_row_boxes_kernel      the box of every 128-row block.
+//       The CTAs past the first B of the same launch compute the box of every 128-row block of the predicted cloud.
 //   chamfer_prune_bounds_kernel   per 128-row block: T_r = max over its rows of an UPPER bound of the row's
 //       nearest-target distance (exact distance, the reference's arithmetic, to 4 representatives of each of the 8 chunks
 //       whose boxes are nearest to the block's box); per 128-column chunk: U_c likewise over 16 row blocks x 2 rows.
@@ -36,6 +36,16 @@ __device__ __forceinline__ unsigned spread6(unsigned x) {       // 6 bits -> eve
   x = (x | (x << 2)) & 0x00009249u;
   return x;
 }
+// lanes of the warp whose 6-bit digit equals this lane's (match.any costs hundreds of cycles on sm_100; six ballots do not)
+__device__ __forceinline__ unsigned peers6(unsigned d) {
+  unsigned m = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+    const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+    m &= ((d >> b) & 1u) ? bal : ~bal;
+  }
+  return m;
+}
 __device__ __forceinline__ float prep_d2(float ax, float ay, float az, float bx, float by, float bz) {
   const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -46,8 +56,41 @@ __device__ __forceinline__ float prep_d2(float ax, float ay, float az, float bx,
 // sort: identity order).
 __global__ void __launch_bounds__(kSortThreads)
 chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2s, float4* __restrict__ p2v, int* __restrict__ perm,
-                            float* __restrict__ cbox, float* __restrict__ tmax, int M, int npad, int nchunks) {
+                            float* __restrict__ cbox, float* __restrict__ tmax, int M, int npad, int nchunks,
+                            const float* __restrict__ p1, float* __restrict__ rbox, int P, int nrb, int B) {
   extern __shared__ __align__(16) unsigned char prep_smem[];
+  if ((int)blockIdx.x >= B) {
+    // ---- CTAs past the first B: boxes of the 128-row blocks of the predicted cloud, one warp per block, 4 rows per lane.
+    // Independent of the sort; sharing its launch lets the two run side by side (the sort occupies B SMs for tens of
+    // microseconds; as a kernel of its own the boxes waited for it in the stream).
+    const int lane = threadIdx.x & 31;
+    const long long blk = ((long long)blockIdx.x - B) * (kSortThreads / 32) + (threadIdx.x >> 5);
+    if (blk >= (long long)nrb * B) return;
+    const int b = (int)(blk / nrb), rb = (int)(blk % nrb);
+    float l[3] = {prep_inf(), prep_inf(), prep_inf()}, h[3] = {-prep_inf(), -prep_inf(), -prep_inf()};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int row = rb * kBlk + u * 32 + lane;
+      if (row < P) {
+        const float* a = p1 + 3 * ((size_t)b * P + row);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float v = a[k]; l[k] = fminf(l[k], v); h[k] = fmaxf(h[k], v); }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        l[k] = fminf(l[k], __shfl_xor_sync(0xffffffffu, l[k], o));
+        h[k] = fmaxf(h[k], __shfl_xor_sync(0xffffffffu, h[k], o));
+      }
+    }
+    if (lane == 0) {
+      float* o = rbox + ((size_t)b * nrb + rb) * 8;
+      o[0] = l[0]; o[1] = l[1]; o[2] = l[2]; o[3] = h[0]; o[4] = h[1]; o[5] = h[2]; o[6] = 0.f; o[7] = 0.f;
+    }
+    return;
+  }
   unsigned* keys = reinterpret_cast<unsigned*>(prep_smem);
   __shared__ float red[32][7];
   __shared__ unsigned hist[64 * 33];
@@ -122,7 +165,7 @@ chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2
     // LSD radix sort of the 18 code bits, three stable passes of 6 bits.  Keys start in index order and every pass is
     // stable, so equal codes stay in index order: the same deterministic permutation as sorting the full 32-bit keys
     // (the bitonic network this replaces: 91 substeps, 62 us for 8192 keys on one SM).  Warp w owns the contiguous
-    // run [w seg, (w + 1) seg) of the pass's input; a round ranks 32 keys with match.any (rank = peers of the same
+    // run [w seg, (w + 1) seg) of the pass's input; a round ranks 32 keys with six ballots (rank = peers of the same
     // digit in lower lanes), hist[digit][warp] counted in a first walk and scanned digit-major gives every (digit,
     // warp) its output offset.  Padding keys (0xffffffff) have digit 63 in every pass and come last in the input: they
     // stay behind every real key.
@@ -134,7 +177,7 @@ chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2
       __syncthreads();
       for (int r = 0; r < seg; r += 32) {
         const unsigned d = (kin[warp * seg + r + lane] >> shift) & 63u;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const unsigned peers = peers6(d);
         if ((peers & ((1u << lane) - 1u)) == 0u) hist[d * 33 + warp] += (unsigned)__popc(peers);
         __syncwarp();
       }
@@ -163,7 +206,7 @@ chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2
       for (int r = 0; r < seg; r += 32) {
         const unsigned key = kin[warp * seg + r + lane];
         const unsigned d = (key >> shift) & 63u;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const unsigned peers = peers6(d);
         const int rank = __popc(peers & ((1u << lane) - 1u));
         const unsigned base = hist[d * 33 + warp];
         kout[base + rank] = key;
@@ -215,36 +258,6 @@ chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2
   }
 }
 
-// ---- boxes of the 128-row blocks -------------------------------------------------------------------------------
-// grid: x = row block, y = sample; 128 threads
-__global__ void __launch_bounds__(kBlk)
-chamfer_row_boxes_kernel(const float* __restrict__ p1, float* __restrict__ rbox, int P, int nrb) {
-  __shared__ float red[4][6];
-  const int b = blockIdx.y, rb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = rb * kBlk + tid;
-  float l[3] = {prep_inf(), prep_inf(), prep_inf()}, h[3] = {-prep_inf(), -prep_inf(), -prep_inf()};
-  if (row < P) {
-    const float* a = p1 + 3 * ((size_t)b * P + row);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { l[k] = fminf(l[k], a[k]); h[k] = fmaxf(h[k], a[k]); }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      l[k] = fminf(l[k], __shfl_xor_sync(0xffffffffu, l[k], o));
-      h[k] = fmaxf(h[k], __shfl_xor_sync(0xffffffffu, h[k], o));
-    }
-  }
-  if (lane == 0) for (int k = 0; k < 3; ++k) { red[warp][k] = l[k]; red[warp][3 + k] = h[k]; }
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < 4; ++w) for (int k = 0; k < 3; ++k) { l[k] = fminf(l[k], red[w][k]); h[k] = fmaxf(h[k], red[w][3 + k]); }
-    float* o = rbox + ((size_t)b * nrb + rb) * 8;
-    o[0] = l[0]; o[1] = l[1]; o[2] = l[2]; o[3] = h[0]; o[4] = h[1]; o[5] = h[2]; o[6] = 0.f; o[7] = 0.f;
-  }
-}
-
 // ---- upper bounds of the nearest-neighbour distances ---------------------------------------------------------------
 // For a block of 128 points of one cloud: pick the kNear blocks of the OTHER cloud whose boxes are closest to this
 // block's box, take kReps points of each as representatives, and give every point of the block the smallest exact
@@ -275,13 +288,13 @@ __global__ void __launch_bounds__(kBoundWarps * 32)
 chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restrict__ p2s,
                             const float* __restrict__ rbox, const float* __restrict__ cbox,
                             float* __restrict__ rthr, float* __restrict__ cub, int P, int M, int nrb, int nchunks) {
-  __shared__ float s_gap[kBoundWarps][kGapCap];
+  __shared__ unsigned s_gap[kBoundWarps][kGapCap];      // (quantised gap bits | candidate index), 0xffffffff = taken
   __shared__ float4 s_reps[kBoundWarps][kMaxReps];
   __shared__ int s_sel[kBoundWarps][kMaxNear];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int id = blockIdx.x * kBoundWarps + warp;
   if (id >= nrb + nchunks) return;                                           // warp-uniform
-  float* gap = s_gap[warp]; float4* reps = s_reps[warp]; int* sel = s_sel[warp];
+  unsigned* gap = s_gap[warp]; float4* reps = s_reps[warp]; int* sel = s_sel[warp];
   const bool is_row = id < nrb;
   const int blk = is_row ? id : id - nrb;
   const int n_mine = is_row ? P : M, n_other = is_row ? M : P;
@@ -303,27 +316,28 @@ chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restric
     if (valid[u]) { x[u] = mine[3 * (size_t)idx]; y[u] = mine[3 * (size_t)idx + 1]; z[u] = mine[3 * (size_t)idx + 2]; }
   }
   const int stride = (nob + kGapCap - 1) / kGapCap, ncand = (nob + stride - 1) / stride;
+  // key = gap^2 with its low 10 mantissa bits replaced by the candidate index: unsigned order = (gap to ~2^-13 relative,
+  // index).  Which near boxes are chosen only affects how tight the bound is, never its validity.
+  unsigned lmin = 0xffffffffu;                                               // smallest key among this lane's candidates
   for (int c = lane; c < ncand; c += 32) {
     const float g = box_gap2(mybox, obox + (size_t)c * stride * 8);
-    gap[c] = (g == g) ? g : prep_inf();                                      // NaN boxes sort last
+    const unsigned k = ((g == g) ? (__float_as_uint(g) & ~0x3ffu) : 0x7f800000u) | (unsigned)c;   // NaN boxes sort last
+    gap[c] = k;
+    lmin = min(lmin, k);
   }
-  __syncwarp();
-  // `near` rounds of arg-min (value, index) with removal; deterministic
+  // `near` rounds of arg-min with removal: one warp reduction per round; only the winner's lane rescans its candidates
   const int nsel = min(near, ncand);
   for (int s = 0; s < nsel; ++s) {
-    float bv = prep_inf(); int bi = 0x7fffffff;
-    for (int c = lane; c < ncand; c += 32) { const float g = gap[c]; if (g < bv || (g == bv && c < bi)) { bv = g; bi = c; } }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    const unsigned w = __reduce_min_sync(0xffffffffu, lmin);
+    const int bi = (w == 0xffffffffu) ? -1 : (int)(w & 0x3ffu);
+    if (lane == 0) sel[s] = bi < 0 ? 0 : bi;
+    if (bi >= 0 && (bi & 31) == lane) {
+      gap[bi] = 0xffffffffu;
+      lmin = 0xffffffffu;
+      for (int c = lane; c < ncand; c += 32) lmin = min(lmin, gap[c]);
     }
-    if (lane == 0) {
-      sel[s] = (bi == 0x7fffffff) ? 0 : bi;
-      if (bi != 0x7fffffff) gap[bi] = __int_as_float(0x7fc00000);            // NaN: never selected again (comparisons false)
-    }
-    __syncwarp();
   }
+  __syncwarp();
   const int nrep = nsel * per;
   if (lane < nrep) {
     const int ob = sel[lane / per] * stride;
@@ -360,11 +374,12 @@ int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, float4* p2
   if (set_dyn_smem(chamfer_sort_targets_kernel, kSortMaxM * 8, once) != cudaSuccess) {
     vpn_set_error("chamfer prep: smem attribute"); return VPN_ERR_CUDA;
   }
-  chamfer_sort_targets_kernel<<<B, kSortThreads, smem, s>>>(p2, p2s, p2v, perm, cbox, tmax, M, (int)(smem / 8), nchunks);
+  const long long box_ctas = ((long long)nrb * B + kSortThreads / 32 - 1) / (kSortThreads / 32);
+  if (B + box_ctas > 0x7fffffffLL) { vpn_set_error("chamfer prep: too many row blocks"); return VPN_ERR_SHAPE; }
+  chamfer_sort_targets_kernel<<<(unsigned)(B + box_ctas), kSortThreads, smem, s>>>(p2, p2s, p2v, perm, cbox, tmax, M, (int)(smem / 8), nchunks,
+                                                                                   p1, rbox, P, nrb, B);
   int rc = vpn_check_launch("chamfer_sort_targets_kernel");
   if (rc) return rc;
-  chamfer_row_boxes_kernel<<<dim3(nrb, B), kBlk, 0, s>>>(p1, rbox, P, nrb);
-  if ((rc = vpn_check_launch("chamfer_row_boxes_kernel"))) return rc;
   chamfer_prune_bounds_kernel<<<dim3((nrb + nchunks + kBoundWarps - 1) / kBoundWarps, B), kBoundWarps * 32, 0, s>>>(
       p1, p2s, rbox, cbox, rthr, cub, P, M, nrb, nchunks);
   return vpn_check_launch("chamfer_prune_bounds_kernel");

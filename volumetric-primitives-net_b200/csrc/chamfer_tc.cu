@@ -296,9 +296,30 @@ chamfer_tc_order_kernel(const int* __restrict__ plan_work, int* __restrict__ pla
   __syncthreads();
   for (int i = tid; i < ncta; i += kOrderThreads) atomicAdd(&hist[min(max(plan_work[i], 0), kOrderBins - 1)], 1);
   __syncthreads();
-  if (tid == 0) {                                                     // exclusive prefix over the bins, heaviest bin first
-    int run = 0;
-    for (int w = kOrderBins - 1; w >= 0; --w) { const int n = hist[w]; hist[w] = run; run += n; }
+  // exclusive prefix over the bins, heaviest bin first: thread t owns the kPer consecutive bins below kOrderBins - t kPer
+  {
+    constexpr int kPer = (kOrderBins + kOrderThreads - 1) / kOrderThreads;
+    __shared__ int wsum[32];
+    const int lane = tid & 31, warp = tid >> 5;
+    int cnt[kPer], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { const int w = kOrderBins - 1 - (tid * kPer + k); cnt[k] = (w >= 0) ? hist[w] : 0; sum += cnt[k]; }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = wsum[lane];
+      int winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+      wsum[lane] = winc - w;
+    }
+    __syncthreads();
+    int run = wsum[warp] + inc - sum;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { const int w = kOrderBins - 1 - (tid * kPer + k); if (w >= 0) hist[w] = run; run += cnt[k]; }
   }
   __syncthreads();
   for (int i = tid; i < ncta; i += kOrderThreads) plan_order[atomicAdd(&hist[min(max(plan_work[i], 0), kOrderBins - 1)], 1)] = i;

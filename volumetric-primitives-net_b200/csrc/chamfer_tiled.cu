@@ -378,9 +378,39 @@ __device__ __forceinline__ void or_shifted256(u64 (&seg)[4], u64 w, int base) {
   }
 }
 
-// Persistent: grid x = min(#SMs, B * nblk) CTAs, CTA k takes the work items (sample, block of kRecThreads rows)
+// exclusive prefix sum of `cnt` over one half of the CTA (kRowGroup threads, named barrier `bar`); *total gets the sum
+constexpr int kRowGroup = kRecThreads / 2;            // the CTA works as two independent groups of 512 threads
+constexpr int kRowItemCap = kItemCap / 2;
+__device__ __forceinline__ void group_sync(int bar) { asm volatile("bar.sync %0, %1;" :: "r"(bar), "n"(kRowGroup) : "memory"); }
+__device__ __forceinline__ int group_exclusive_scan(int cnt, int* warp_sums, int* total, int gt, int bar) {
+  const int lane = gt & 31, warp = gt >> 5;                           // 16 warps
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) warp_sums[warp] = inc;
+  group_sync(bar);
+  if (warp == 0) {
+    int w = lane < kRowGroup / 32 ? warp_sums[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+    if (lane < kRowGroup / 32) warp_sums[lane] = winc - w;
+    if (lane == 31) warp_sums[kRowGroup / 32] = winc;
+  }
+  group_sync(bar);
+  int off = warp_sums[warp] + inc - cnt;
+  *total = warp_sums[kRowGroup / 32];
+  group_sync(bar);
+  return off;
+}
+
+// Persistent: grid x = min(#SMs, B * nblk) CTAs; CTA k takes the work items (sample, block of kRowGroup rows)
 // [k per, (k + 1) per) - consecutive items belong to the same sample, whose targets are staged in shared memory ONCE
-// (one CTA per item re-staged 131 KB per 1024 rows: a fifth of the kernel).  dynamic smem: float4 cols[min(nchunks,64)*128].
+// (one CTA per item re-staged 131 KB per 1024 rows: a fifth of the kernel).  The two halves of the CTA take alternate
+// items and meet only when the staged targets change: while one half waits for its rows' records (a DRAM round trip per
+// item, nothing else to run on an SM that holds a single CTA) the other evaluates units.  dynamic smem: float4
+// cols[min(nchunks,64)*128].  Clouds of more than 64 chunks are swept in segments; the running best of a row then
+// passes from one segment to the next through min1 / idx1.
 // Candidate records: planes == 4: four u64 planes (plane_stride apart) of 32-column UNIT bits (tensor-core filter),
 // planes == 1: one u64 of 128-column chunk bits (CUDA-core filters), expanded to unit bits here.
 // p2v != NULL: the targets as float4 (x, y, z, original index) padded with NaN to whole chunks (stride mpad per sample).
@@ -392,109 +422,109 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
                             const int* __restrict__ skip, int nblk, int nitems) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* cols = reinterpret_cast<float4*>(smem_raw);
-  __shared__ float4 rowc[kRecThreads];
-  __shared__ u64 key[kRecThreads];
-  __shared__ unsigned items[kItemCap];
-  __shared__ int warp_sums[33];
-  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ float4 rowc_[kRecThreads];
+  __shared__ u64 key_[kRecThreads];
+  __shared__ unsigned items_[kItemCap];
+  __shared__ int warp_sums_[2][kRowGroup / 32 + 1];
+  const int tid = threadIdx.x, lane = tid & 31, grp = tid / kRowGroup, gt = tid % kRowGroup, bar = 1 + grp;
+  float4* rowc = rowc_ + grp * kRowGroup; u64* key = key_ + grp * kRowGroup;
+  unsigned* items = items_ + grp * kRowItemCap; int* warp_sums = warp_sums_[grp];
   const int per = (nitems + gridDim.x - 1) / gridDim.x;
   const int w0 = blockIdx.x * per, w1 = min(nitems, w0 + per);
   const int nseg = (nchunks + kSegChunks - 1) / kSegChunks;
   const float qnan = __int_as_float(0x7fc00000);
-  int staged_b = -1, staged_seg = -1;
-  for (int wi = w0; wi < w1; ++wi) {
-    const int b = wi / nblk;
+  for (int b = w0 / nblk; b * nblk < w1; ++b) {
     if (skip && skip[b]) continue;                       // sample redone by chamfer_flagged_kernel
-    const int row = (wi - b * nblk) * kRecThreads + tid;
-    const bool valid = row < P;
-    float g = inf_f(), gthr = inf_f();
-    __syncthreads();                                     // the previous item is done with rowc / key / items
-    if (valid) {
-      const float* a = p1 + 3 * ((size_t)b * P + row);
-      rowc[tid] = make_float4(a[0], a[1], a[2], 0.f);
-      for (int s = 0; s < nsplit; ++s) g = fminf(g, rbest[((size_t)b * nsplit + s) * P + row]);
-      const float2 sl = tslack[(size_t)b * ntiles + row / TM];
-      gthr = thr_of(g, sl.x, sl.y);
-    }
-    key[tid] = ~0ull;
+    const int i0 = max(w0, b * nblk), i1 = min(w1, (b + 1) * nblk);      // this CTA's items of sample b
     for (int seg = 0; seg < nseg; ++seg) {
       const int seg_chunks = min(kSegChunks, nchunks - seg * kSegChunks);
-      if (staged_b != b || staged_seg != seg) {
-        __syncthreads();                                 // everybody is done with the previous contents
-        if (p2v) {
-          const float4* src = p2v + (size_t)b * mpad + (size_t)seg * kSegChunks * kCW;
-          for (int i = tid; i < seg_chunks * kCW; i += kRecThreads) cols[i] = src[i];
-        } else {
-          const float* T = p2 + (size_t)b * M * 3;
-          for (int i = tid; i < seg_chunks * kCW; i += kRecThreads) {
-            const int col = seg * kSegChunks * kCW + i;
-            cols[i] = col < M ? make_float4(T[3 * (size_t)col], T[3 * (size_t)col + 1], T[3 * (size_t)col + 2], __int_as_float(col))
-                              : make_float4(qnan, qnan, qnan, __int_as_float(0x7fffffff));
-          }
-        }
-        staged_b = b; staged_seg = seg;
-      }
-      // this row's candidate units of the segment: 256 bits, unit u of the segment = columns [32 u, 32 u + 32) of cols[]
-      u64 sg[4] = {0ull, 0ull, 0ull, 0ull};
-      if (valid) {
-        for (int s = 0; s < nsplit; ++s) {
-          const size_t o = ((size_t)b * nsplit + s) * P + row;
-          if (!(rbest[o] <= gthr)) continue;
-          const int rel = (s * cps - seg * kSegChunks) * 4;                    // first unit of the split, relative to the segment
-          if (planes == 4) {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) or_shifted256(sg, rmask[o + w * plane_stride], rel + 64 * w);
-          } else {
-            const u64 m = rmask[o];
-#pragma unroll
-            for (int w = 0; w < 4; ++w) or_shifted256(sg, expand_chunk_bits16((unsigned)(m >> (16 * w))), rel + 64 * w);
-          }
-        }
-        if (seg_chunks < kSegChunks) {                                         // units past the end of the cloud
-          const int nu = seg_chunks * 4;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const int left = nu - 64 * w;
-            if (left <= 0) sg[w] = 0ull; else if (left < 64) sg[w] &= (1ull << left) - 1ull;
-          }
+      __syncthreads();                                   // both groups are done with the previous contents
+      if (p2v) {
+        const float4* src = p2v + (size_t)b * mpad + (size_t)seg * kSegChunks * kCW;
+        for (int i = tid; i < seg_chunks * kCW; i += kRecThreads) cols[i] = src[i];
+      } else {
+        const float* T = p2 + (size_t)b * M * 3;
+        for (int i = tid; i < seg_chunks * kCW; i += kRecThreads) {
+          const int col = seg * kSegChunks * kCW + i;
+          cols[i] = col < M ? make_float4(T[3 * (size_t)col], T[3 * (size_t)col + 1], T[3 * (size_t)col + 2], __int_as_float(col))
+                            : make_float4(qnan, qnan, qnan, __int_as_float(0x7fffffff));
         }
       }
-      int total;
-      const int cnt = __popcll(sg[0]) + __popcll(sg[1]) + __popcll(sg[2]) + __popcll(sg[3]);
-      const int off = block_exclusive_scan(cnt, warp_sums, &total);            // syncs: cols[] is staged too
-      for (int base = 0; base < total; base += kItemCap) {
-        int j = off;
+      __syncthreads();
+      for (int wi = i0 + grp; wi < i1; wi += 2) {
+        const int row = (wi - b * nblk) * kRowGroup + gt;
+        const bool valid = row < P;
+        float g = inf_f(), gthr = inf_f();
+        u64 kinit = ~0ull;
+        // this row's candidate units of the segment: 256 bits, unit u of the segment = columns [32 u, 32 u + 32) of cols[]
+        u64 sg[4] = {0ull, 0ull, 0ull, 0ull};
+        if (valid) {
+          const float* a = p1 + 3 * ((size_t)b * P + row);
+          rowc[gt] = make_float4(a[0], a[1], a[2], 0.f);
+          for (int s = 0; s < nsplit; ++s) g = fminf(g, rbest[((size_t)b * nsplit + s) * P + row]);
+          const float2 sl = tslack[(size_t)b * ntiles + row / TM];
+          gthr = thr_of(g, sl.x, sl.y);
+          if (seg > 0) kinit = ((u64)__float_as_uint(min1[(size_t)b * P + row]) << 32) | (unsigned)idx1[(size_t)b * P + row];
+          for (int s = 0; s < nsplit; ++s) {
+            const size_t o = ((size_t)b * nsplit + s) * P + row;
+            if (!(rbest[o] <= gthr)) continue;
+            const int rel = (s * cps - seg * kSegChunks) * 4;                    // first unit of the split, relative to the segment
+            if (planes == 4) {
 #pragma unroll
-        for (int w = 0; w < 4; ++w)
-          for (u64 mm = sg[w]; mm; mm &= mm - 1, ++j)
-            if (j >= base && j < base + kItemCap) items[j - base] = ((unsigned)tid << 8) | (unsigned)(64 * w + __ffsll((long long)mm) - 1);
-        __syncthreads();
-        const int units = min(kItemCap, total - base);
-        for (int it = tid; it < units; it += kRecThreads) {
-          const unsigned item = items[it];
-          const int r = item >> 8, u = item & 255;
-          const float4 rc = rowc[r];
-          const float4* src = cols + u * 32;
-          float d[32], dm = inf_f();
+              for (int w = 0; w < 4; ++w) or_shifted256(sg, rmask[o + w * plane_stride], rel + 64 * w);
+            } else {
+              const u64 m = rmask[o];
 #pragma unroll
-          for (int kk = 0; kk < 32; ++kk) {
-            const float4 q = src[(kk + lane) & 31];
-            d[kk] = exact_d2s(rc.x, rc.y, rc.z, q.x, q.y, q.z);
-            dm = fminf(dm, d[kk]);
+              for (int w = 0; w < 4; ++w) or_shifted256(sg, expand_chunk_bits16((unsigned)(m >> (16 * w))), rel + 64 * w);
+            }
           }
-          int at;
-          const int st = unit_scan(d, dm, lane, &at);
-          if (st == 1) atomicMin(&key[r], ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)__float_as_int(src[at].w));
-          else if (st == 2) { const u64 kv = unit_exact_walk(rc.x, rc.y, rc.z, src, 0, 1); if (kv != ~0ull) atomicMin(&key[r], kv); }
+          if (seg_chunks < kSegChunks) {                                         // units past the end of the cloud
+            const int nu = seg_chunks * 4;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const int left = nu - 64 * w;
+              if (left <= 0) sg[w] = 0ull; else if (left < 64) sg[w] &= (1ull << left) - 1ull;
+            }
+          }
         }
-        __syncthreads();
+        key[gt] = kinit;
+        int total;
+        const int cnt = __popcll(sg[0]) + __popcll(sg[1]) + __popcll(sg[2]) + __popcll(sg[3]);
+        const int off = group_exclusive_scan(cnt, warp_sums, &total, gt, bar);   // syncs the group: rowc / key are written
+        for (int base = 0; base < total; base += kRowItemCap) {
+          int j = off;
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            for (u64 mm = sg[w]; mm; mm &= mm - 1, ++j)
+              if (j >= base && j < base + kRowItemCap) items[j - base] = ((unsigned)gt << 8) | (unsigned)(64 * w + __ffsll((long long)mm) - 1);
+          group_sync(bar);
+          const int units = min(kRowItemCap, total - base);
+          for (int it = gt; it < units; it += kRowGroup) {
+            const unsigned item = items[it];
+            const int r = item >> 8, u = item & 255;
+            const float4 rc = rowc[r];
+            const float4* src = cols + u * 32;
+            float d[32], dm = inf_f();
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) {
+              const float4 q = src[(kk + lane) & 31];
+              d[kk] = exact_d2s(rc.x, rc.y, rc.z, q.x, q.y, q.z);
+              dm = fminf(dm, d[kk]);
+            }
+            int at;
+            const int st = unit_scan(d, dm, lane, &at);
+            if (st == 1) atomicMin(&key[r], ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)__float_as_int(src[at].w));
+            else if (st == 2) { const u64 kv = unit_exact_walk(rc.x, rc.y, rc.z, src, 0, 1); if (kv != ~0ull) atomicMin(&key[r], kv); }
+          }
+          group_sync(bar);
+        }
+        if (valid) {
+          const u64 kv = key[gt];
+          min1[(size_t)b * P + row] = __uint_as_float((unsigned)(kv >> 32));
+          idx1[(size_t)b * P + row] = (int)(unsigned)(kv & 0xffffffffu);
+        }
+        group_sync(bar);                                 // the next item overwrites rowc / key
       }
-    }
-    __syncthreads();
-    if (valid) {
-      const u64 kv = key[tid];
-      min1[(size_t)b * P + row] = __uint_as_float((unsigned)(kv >> 32));
-      idx1[(size_t)b * P + row] = (int)(unsigned)(kv & 0xffffffffu);
     }
   }
 }
@@ -900,7 +930,7 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
     if (set_dyn_smem(chamfer_recover_rows_kernel, (int)(kSegChunks * kCW * sizeof(float4)), once_rows) != cudaSuccess) {
       vpn_set_error("chamfer tiled: smem attribute (rows recovery)"); return VPN_ERR_CUDA;
     }
-    const int nblk = (P + kRecThreads - 1) / kRecThreads;
+    const int nblk = (P + kRowGroup - 1) / kRowGroup;
     const long long nitems = (long long)nblk * B;
     if (nitems > 0x7fffffffLL) { vpn_set_error("chamfer tiled: too many row blocks"); return VPN_ERR_SHAPE; }
     const int sms = device_sm_count();
