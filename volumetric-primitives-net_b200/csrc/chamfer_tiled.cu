@@ -381,6 +381,7 @@ __device__ __forceinline__ void or_shifted256(u64 (&seg)[4], u64 w, int base) {
 // exclusive prefix sum of `cnt` over one half of the CTA (kRowGroup threads, named barrier `bar`); *total gets the sum
 constexpr int kRowGroup = kRecThreads / 2;            // the CTA works as two independent groups of 512 threads
 constexpr int kRowItemCap = kItemCap / 2;
+constexpr size_t kRowsFixedSmem = (size_t)kRecThreads * (16 + 8 + 32 + 4 + 12) + (size_t)kItemCap * 4;    // row recovery: everything but the targets
 __device__ __forceinline__ void group_sync(int bar) { asm volatile("bar.sync %0, %1;" :: "r"(bar), "n"(kRowGroup) : "memory"); }
 __device__ __forceinline__ int group_exclusive_scan(int cnt, int* warp_sums, int* total, int gt, int bar) {
   const int lane = gt & 31, warp = gt >> 5;                           // 16 warps
@@ -408,8 +409,8 @@ __device__ __forceinline__ int group_exclusive_scan(int cnt, int* warp_sums, int
 // [k per, (k + 1) per) - consecutive items belong to the same sample, whose targets are staged in shared memory ONCE
 // (one CTA per item re-staged 131 KB per 1024 rows: a fifth of the kernel).  The two halves of the CTA take alternate
 // items and meet only when the staged targets change: while one half waits for its rows' records (a DRAM round trip per
-// item, nothing else to run on an SM that holds a single CTA) the other evaluates units.  dynamic smem: float4
-// cols[min(nchunks,64)*128].  Clouds of more than 64 chunks are swept in segments; the running best of a row then
+// item, nothing else to run on an SM that holds a single CTA) the other evaluates units.  dynamic smem: kRowsFixedSmem
+// bytes + float4 cols[min(nchunks,64)*128].  Clouds of more than 64 chunks are swept in segments; the running best of a row then
 // passes from one segment to the next through min1 / idx1.
 // Candidate records: planes == 4: four u64 planes (plane_stride apart) of 32-column UNIT bits (tensor-core filter),
 // planes == 1: one u64 of 128-column chunk bits (CUDA-core filters), expanded to unit bits here.
@@ -421,12 +422,31 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
                             int P, int M, int nchunks, int nsplit, int cps, int TM, int ntiles,
                             const int* __restrict__ skip, int nblk, int nitems) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* cols = reinterpret_cast<float4*>(smem_raw);
-  __shared__ float4 rowc_[kRecThreads];
-  __shared__ u64 key_[kRecThreads];
-  __shared__ unsigned items_[kItemCap];
+  // dynamic shared memory: [rowc | key | pre_mask | items | pre_rb | pre_p1] (kRowsFixedSmem bytes) then cols[]
+  float4* rowc_ = reinterpret_cast<float4*>(smem_raw);
+  u64* key_ = reinterpret_cast<u64*>(rowc_ + kRecThreads);
+  u64 (*pre_mask)[kRecThreads] = reinterpret_cast<u64 (*)[kRecThreads]>(key_ + kRecThreads);
+  unsigned* items_ = reinterpret_cast<unsigned*>(pre_mask + 4);
+  float* pre_rb = reinterpret_cast<float*>(items_ + kItemCap);
+  float* pre_p1 = pre_rb + kRecThreads;
+  float4* cols = reinterpret_cast<float4*>(smem_raw + kRowsFixedSmem);
   __shared__ int warp_sums_[2][kRowGroup / 32 + 1];
+  // records of the group's NEXT item, fetched with cp.async while the current item's units are evaluated (one record per
+  // row, i.e. nsplit == 1; a thread only ever touches its own slots, so no barrier is involved)
   const int tid = threadIdx.x, lane = tid & 31, grp = tid / kRowGroup, gt = tid % kRowGroup, bar = 1 + grp;
+  const bool use_pre = (nsplit == 1) && (planes == 4);
+  auto prefetch = [&](int b_, int wi_) {
+    const int row_ = (wi_ - b_ * nblk) * kRowGroup + gt;
+    if (row_ < P) {
+      const size_t o_ = (size_t)b_ * P + row_;
+      cp_async4(&pre_rb[tid], rbest + o_);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) cp_async8(&pre_mask[w][tid], rmask + o_ + w * plane_stride);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cp_async4(&pre_p1[tid * 3 + k], p1 + 3 * o_ + k);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   float4* rowc = rowc_ + grp * kRowGroup; u64* key = key_ + grp * kRowGroup;
   unsigned* items = items_ + grp * kRowItemCap; int* warp_sums = warp_sums_[grp];
   const int per = (nitems + gridDim.x - 1) / gridDim.x;
@@ -451,6 +471,7 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
         }
       }
       __syncthreads();
+      if (use_pre && i0 + grp < i1) prefetch(b, i0 + grp);
       for (int wi = i0 + grp; wi < i1; wi += 2) {
         const int row = (wi - b * nblk) * kRowGroup + gt;
         const bool valid = row < P;
@@ -458,7 +479,31 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
         u64 kinit = ~0ull;
         // this row's candidate units of the segment: 256 bits, unit u of the segment = columns [32 u, 32 u + 32) of cols[]
         u64 sg[4] = {0ull, 0ull, 0ull, 0ull};
-        if (valid) {
+        if (use_pre) {
+          asm volatile("cp.async.wait_all;" ::: "memory");
+          if (valid) {
+            rowc[gt] = make_float4(pre_p1[tid * 3], pre_p1[tid * 3 + 1], pre_p1[tid * 3 + 2], 0.f);
+            g = pre_rb[tid];
+            if (seg > 0) kinit = ((u64)__float_as_uint(min1[(size_t)b * P + row]) << 32) | (unsigned)idx1[(size_t)b * P + row];
+            const int rel = -seg * kSegChunks * 4;                               // first unit of the record, relative to the segment
+            if (rel == 0) {
+#pragma unroll
+              for (int w = 0; w < 4; ++w) sg[w] = pre_mask[w][tid];
+            } else {
+#pragma unroll
+              for (int w = 0; w < 4; ++w) or_shifted256(sg, pre_mask[w][tid], rel + 64 * w);
+            }
+          }
+          if (wi + 2 < i1) prefetch(b, wi + 2);            // my slots are free again: the next item's records start moving
+          if (valid && seg_chunks < kSegChunks) {                                // units past the end of the cloud
+            const int nu = seg_chunks * 4;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const int left = nu - 64 * w;
+              if (left <= 0) sg[w] = 0ull; else if (left < 64) sg[w] &= (1ull << left) - 1ull;
+            }
+          }
+        } else if (valid) {
           const float* a = p1 + 3 * ((size_t)b * P + row);
           rowc[gt] = make_float4(a[0], a[1], a[2], 0.f);
           for (int s = 0; s < nsplit; ++s) g = fminf(g, rbest[((size_t)b * nsplit + s) * P + row]);
@@ -926,8 +971,8 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   }
   {
     static DeviceOnce once_rows;
-    const size_t smem_rows = (size_t)(pl.nchunks < kSegChunks ? pl.nchunks : kSegChunks) * kCW * sizeof(float4);
-    if (set_dyn_smem(chamfer_recover_rows_kernel, (int)(kSegChunks * kCW * sizeof(float4)), once_rows) != cudaSuccess) {
+    const size_t smem_rows = kRowsFixedSmem + (size_t)(pl.nchunks < kSegChunks ? pl.nchunks : kSegChunks) * kCW * sizeof(float4);
+    if (set_dyn_smem(chamfer_recover_rows_kernel, (int)(kRowsFixedSmem + kSegChunks * kCW * sizeof(float4)), once_rows) != cudaSuccess) {
       vpn_set_error("chamfer tiled: smem attribute (rows recovery)"); return VPN_ERR_CUDA;
     }
     const int nblk = (P + kRowGroup - 1) / kRowGroup;
