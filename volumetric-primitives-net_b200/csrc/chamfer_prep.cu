@@ -8,9 +8,13 @@
 //       of the sample's bounding box, index in the low 14 key bits: a deterministic permutation), writes the sorted copy p2s, the
 //       permutation perm (sorted position -> original index), the axis-aligned box of every 128-column chunk, and the
 //       largest |coordinate| (the filter's scale).  After sorting a chunk is a compact patch of the target shape.
-//       Predicted points need no sorting: they arrive primitive-major (train.py:119 torch.cat(dim=1)), so 128
-//       consecutive rows are one patch of one primitive.
-//       The CTAs past the first B of the same launch compute the box of every 128-row block of the predicted cloud.
+//       The CTAs past the first B of the same launch sort the PREDICTED points: they arrive primitive-major
+//       (train.py:119 torch.cat(dim=1)) but in the random order of the surface samples, so 128 consecutive rows cover
+//       whole faces of a primitive.  Every segment of 4096 consecutive rows (one primitive at the training sizes) is
+//       Morton-sorted on its own (12-bit code in the segment's box, 12 index bits): a block of 128 sorted rows is a
+//       compact patch, its box small, and far more stages prune (ideal share of live 128 x 128 blocks on the C2
+//       clouds: 27 % unsorted, 18 % sorted).  Output: the sorted copy p1s, rperm (sorted row -> original row) and the
+//       box of every 128-row block.
 //   chamfer_prune_bounds_kernel   per 128-row block: T_r = max over its rows of an UPPER bound of the row's
 //       nearest-target distance (exact distance, the reference's arithmetic, to 4 representatives of each of the 8 chunks
 //       whose boxes are nearest to the block's box); per 128-column chunk: U_c likewise over 16 row blocks x 2 rows.
@@ -25,8 +29,7 @@
 namespace vpn {
 
 constexpr int kSortThreads = 1024;
-constexpr int kSortMaxM = 16384;          // 14 index bits in the 32-bit sort key; two key buffers of 64 KB in shared memory
-constexpr int kSortMinKeys = 1024;        // key count granularity: 32 warps x 32 lanes
+constexpr int kSortMaxM = 16384;          // targets per sample the sort handles: 16 items per thread, ent[] of 64 KB in shared memory
 constexpr int kBlk = 128;                 // rows per block = columns per chunk
 
 __device__ __forceinline__ float prep_inf() { return __int_as_float(0x7f800000); }
@@ -36,226 +39,358 @@ __device__ __forceinline__ unsigned spread6(unsigned x) {       // 6 bits -> eve
   x = (x | (x << 2)) & 0x00009249u;
   return x;
 }
-// lanes of the warp whose 6-bit digit equals this lane's (match.any costs hundreds of cycles on sm_100; six ballots do not)
-__device__ __forceinline__ unsigned peers6(unsigned d) {
-  unsigned m = 0xffffffffu;
-#pragma unroll
-  for (int b = 0; b < 6; ++b) {
-    const unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
-    m &= ((d >> b) & 1u) ? bal : ~bal;
-  }
-  return m;
-}
 __device__ __forceinline__ float prep_d2(float ax, float ay, float az, float bx, float by, float bz) {
   const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// Box layout: 8 floats per block / chunk: lo.x lo.y lo.z hi.x hi.y hi.z pad pad.  An empty box is (+inf, -inf).
-// grid: x = sample.  dynamic smem: u32 keys[2][npad], npad = M rounded up to 1024 (npad = 0 when the sample is too large to
-// sort: identity order).
-__global__ void __launch_bounds__(kSortThreads)
-chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2s, float4* __restrict__ p2v, int* __restrict__ perm,
-                            float* __restrict__ cbox, float* __restrict__ tmax, int M, int npad, int nchunks,
-                            const float* __restrict__ p1, float* __restrict__ rbox, int P, int nrb, int B) {
-  extern __shared__ __align__(16) unsigned char prep_smem[];
-  if ((int)blockIdx.x >= B) {
-    // ---- CTAs past the first B: boxes of the 128-row blocks of the predicted cloud, one warp per block, 4 rows per lane.
-    // Independent of the sort; sharing its launch lets the two run side by side (the sort occupies B SMs for tens of
-    // microseconds; as a kernel of its own the boxes waited for it in the stream).
-    const int lane = threadIdx.x & 31;
-    const long long blk = ((long long)blockIdx.x - B) * (kSortThreads / 32) + (threadIdx.x >> 5);
-    if (blk >= (long long)nrb * B) return;
-    const int b = (int)(blk / nrb), rb = (int)(blk % nrb);
-    float l[3] = {prep_inf(), prep_inf(), prep_inf()}, h[3] = {-prep_inf(), -prep_inf(), -prep_inf()};
+// warp-wide float min / max in one instruction (redux.sync.f32 is sm_100a; NaN inputs are dropped, like fminf / fmaxf)
+__device__ __forceinline__ float warp_min_f(float v) { float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float warp_max_f(float v) { float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
+
+// Box of the CTA's points from per-thread (lo, hi): warp redux, then warp 0 over the 32 warps.  Result in red[0][0..5];
+// amu (optional, bits of the largest |coordinate|, NaN above everything) likewise in red[0][6].  Two barriers.
+__device__ __forceinline__ void prep_block_box(float (&lo)[3], float (&hi)[3], unsigned amu, float (*red)[7]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int row = rb * kBlk + u * 32 + lane;
-      if (row < P) {
-        const float* a = p1 + 3 * ((size_t)b * P + row);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { const float v = a[k]; l[k] = fminf(l[k], v); h[k] = fmaxf(h[k], v); }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        l[k] = fminf(l[k], __shfl_xor_sync(0xffffffffu, l[k], o));
-        h[k] = fmaxf(h[k], __shfl_xor_sync(0xffffffffu, h[k], o));
-      }
-    }
-    if (lane == 0) {
-      float* o = rbox + ((size_t)b * nrb + rb) * 8;
-      o[0] = l[0]; o[1] = l[1]; o[2] = l[2]; o[3] = h[0]; o[4] = h[1]; o[5] = h[2]; o[6] = 0.f; o[7] = 0.f;
-    }
-    return;
-  }
-  unsigned* keys = reinterpret_cast<unsigned*>(prep_smem);
-  __shared__ float red[32][7];
-  __shared__ unsigned hist[64 * 33];
-  __shared__ int wsum[32];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* T = p2 + (size_t)b * M * 3;
-  float* Ts = p2s + (size_t)b * M * 3;
-  int* pm = perm + (size_t)b * M;
-  // ---- bounding box (finite values only: fminf / fmaxf drop NaN) and the NaN-sticky largest |coordinate|
-  float lo[3] = {prep_inf(), prep_inf(), prep_inf()}, hi[3] = {-prep_inf(), -prep_inf(), -prep_inf()}, am = 0.f;
-  for (int i = tid; i < M; i += kSortThreads) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float v = T[3 * (size_t)i + k];
-      lo[k] = fminf(lo[k], v); hi[k] = fmaxf(hi[k], v);
-      const float a = fabsf(v);
-      am = (a <= am) ? am : a;                                    // NaN sticks
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
-      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
-    }
-    const float x = __shfl_xor_sync(0xffffffffu, am, o);
-    am = (x <= am) ? am : x;
-  }
-  if (lane == 0) { for (int k = 0; k < 3; ++k) { red[warp][k] = lo[k]; red[warp][3 + k] = hi[k]; } red[warp][6] = am; }
+  for (int k = 0; k < 3; ++k) { lo[k] = warp_min_f(lo[k]); hi[k] = warp_max_f(hi[k]); }
+  amu = __reduce_max_sync(0xffffffffu, amu);
+  if (lane == 0) { for (int k = 0; k < 3; ++k) { red[warp][k] = lo[k]; red[warp][3 + k] = hi[k]; } red[warp][6] = __uint_as_float(amu); }
   __syncthreads();
   if (warp == 0) {
-    for (int k = 0; k < 3; ++k) { lo[k] = red[lane][k]; hi[k] = red[lane][3 + k]; }
-    am = red[lane][6];
+    float l[3], h[3];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
-        hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
-      }
-      const float x = __shfl_xor_sync(0xffffffffu, am, o);
-      am = (x <= am) ? am : x;
-    }
-    if (lane == 0) { for (int k = 0; k < 3; ++k) { red[0][k] = lo[k]; red[0][3 + k] = hi[k]; } tmax[b] = am; }
+    for (int k = 0; k < 3; ++k) { l[k] = warp_min_f(red[lane][k]); h[k] = warp_max_f(red[lane][3 + k]); }
+    const unsigned a = __reduce_max_sync(0xffffffffu, __float_as_uint(red[lane][6]));
+    if (lane == 0) { for (int k = 0; k < 3; ++k) { red[0][k] = l[k]; red[0][3 + k] = h[k]; } red[0][6] = __uint_as_float(a); }
   }
   __syncthreads();
-  const unsigned* sorted = keys;
-  if (npad > 0) {
+}
+
+// Morton cell of a point: 16 cells per axis of the cloud's box (q0 = lower corner, qs = 15.999 / extent), 12 bits
+constexpr int kCells = 4096;
+constexpr int kCellCap = 64;              // cells up to this size are put in index order (deterministic permutation)
+__device__ __forceinline__ unsigned prep_cell(float x, float y, float z, const float (&q0)[3], const float (&qs)[3]) {
+  const float fx = (x - q0[0]) * qs[0], fy = (y - q0[1]) * qs[1], fz = (z - q0[2]) * qs[2];
+  const unsigned qx = (fx >= 0.f) ? (unsigned)fminf(fx, 15.f) : 0u, qy = (fy >= 0.f) ? (unsigned)fminf(fy, 15.f) : 0u,
+                 qz = (fz >= 0.f) ? (unsigned)fminf(fz, 15.f) : 0u;                                   // NaN -> 0
+  return spread6(qx) | (spread6(qy) << 1) | (spread6(qz) << 2);
+}
+
+// Counting sort of the CTA's n items (item i = tid + 1024 k, k < K, belongs to this thread; its cell is half k & 1 of
+// pk[k >> 1]) into ent[] (sorted position -> item), ONE pass over the 4096 cells: count with shared-memory reductions,
+// prefix-sum the cells, then every item takes the next free position of its cell (atomic cursor).  The order INSIDE a
+// cell is the order the atomics were served in; with `deterministic` set one thread per cell then puts the cell's items
+// (up to kCellCap of them) in index order, so that the permutation is reproducible - which sorted position an item gets
+// never changes a result (the recovery kernels key on original indices), only which block of 128 a few border points
+// fall into.  The whole CTA (1024 threads) calls it.
+// (History: a bitonic network, 62 us for 8192 keys on one SM; 6-bit radix passes ranked with ballots, 15 us per pass;
+// 4-bit radix passes with shuffle scans, 10 us per pass - an 18-bit code needed 3 to 5 such passes.  With 128 points per
+// block the order inside a cell of 1/16 of the box does not matter, so 12 code bits and one pass are enough.)
+template <int K>
+__device__ __forceinline__ void prep_cell_sort(const unsigned (&pk)[(K + 1) / 2], int n, unsigned* cnt, unsigned* start, unsigned* ent,
+                                               unsigned* wsum, int deterministic) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0u, 0u, 0u, 0u);        // kCells == 4 x 1024
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    if (tid + k * kSortThreads < n) atomicAdd(&cnt[(pk[k >> 1] >> ((k & 1) * 16)) & 0xffffu], 1u);
+  }
+  __syncthreads();
+  {
+    const uint4 v = reinterpret_cast<const uint4*>(cnt)[tid];
+    const unsigned sum = v.x + v.y + v.z + v.w;
+    unsigned inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned w = wsum[lane];
+      unsigned winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+      wsum[lane] = winc - w;
+    }
+    __syncthreads();
+    const unsigned base = wsum[warp] + inc - sum;
+    reinterpret_cast<uint4*>(start)[tid] = make_uint4(base, base + v.x, base + v.x + v.y, base + v.x + v.y + v.z);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int i = tid + k * kSortThreads;
+    if (i < n) ent[atomicAdd(&start[(pk[k >> 1] >> ((k & 1) * 16)) & 0xffffu], 1u)] = (unsigned)i;
+  }
+  __syncthreads();
+  if (deterministic) {                                             // start[c] is now the END of cell c
+#pragma unroll 1
+    for (int c = 4 * tid; c < 4 * tid + 4; ++c) {
+      const unsigned sz = cnt[c];
+      if (sz < 2u || sz > (unsigned)kCellCap) continue;
+      unsigned* e = ent + (start[c] - sz);
+      for (unsigned a = 1; a < sz; ++a) {                          // insertion sort by item index
+        const unsigned v = e[a];
+        unsigned j = a;
+        while (j > 0u && e[j - 1] > v) { e[j] = e[j - 1]; --j; }
+        e[j] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// probe (NULL unless vpn_set_tuning("prep_probe", 1)): clock64 deltas of the phases of CTA 0 (target sort, statistics
+// words 2-6) and CTA B (first row segment, words 7-11)
+struct PrepProbe {
+  unsigned long long* out; long long t; int slot;
+  __device__ __forceinline__ void begin(unsigned long long* probe, bool mine, int first) {
+    out = (probe != nullptr && mine && threadIdx.x == 0) ? probe : nullptr; slot = first; t = out ? clock64() : 0;
+  }
+  __device__ __forceinline__ void mark() {
+    if (out) { const long long n = clock64(); atomicAdd(&out[slot++], (unsigned long long)(n - t)); t = n; }
+  }
+};
+
+// sort of one sample's targets: the sorted copies p2s / p2v, the permutation perm, the chunk boxes, tmax
+template <int K>
+__device__ __forceinline__ void prep_sort_targets(const float* __restrict__ T, float* __restrict__ Ts, float4* __restrict__ Tv,
+                                                  int* __restrict__ pm, float* __restrict__ cb, float* __restrict__ tmax_b,
+                                                  int M, int do_sort, int deterministic, int nchunks, unsigned* cnt, unsigned* start,
+                                                  unsigned* ent, unsigned* wsum, float (*red)[7], PrepProbe& pp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- bounding box (finite values only: fminf / fmaxf drop NaN) and the NaN-sticky largest |coordinate| (as bits: a NaN
+  // compares above every number)
+  float lo[3] = {prep_inf(), prep_inf(), prep_inf()}, hi[3] = {-prep_inf(), -prep_inf(), -prep_inf()};
+  unsigned amu = 0u;
+  for (int i0 = tid; i0 < M; i0 += 4 * kSortThreads) {              // four items per round: twelve loads in flight
+    float v[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kSortThreads;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v[u][k] = (i < M) ? T[3 * (size_t)i + k] : __int_as_float(0x7fc00000);     // NaN: dropped below
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * kSortThreads < M) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          lo[k] = fminf(lo[k], v[u][k]); hi[k] = fmaxf(hi[k], v[u][k]);
+          amu = max(amu, __float_as_uint(fabsf(v[u][k])));
+        }
+      }
+    }
+  }
+  prep_block_box(lo, hi, amu, red);
+  if (tid == 0) *tmax_b = red[0][6];
+  pp.mark();                                                        // target: box
+  if (do_sort) {
     float q0[3], qs[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       q0[k] = red[0][k];
       const float ext = red[0][3 + k] - red[0][k];
-      qs[k] = (ext > 0.f && ext < 1e30f) ? 63.999f / ext : 0.f;
+      qs[k] = (ext > 0.f && ext < 1e30f) ? 15.999f / ext : 0.f;
     }
-    for (int i = tid; i < npad; i += kSortThreads) {
-      unsigned key = 0xffffffffu;
-      if (i < M) {
-        unsigned code = 0;
+    unsigned pk[K / 2];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float f = (T[3 * (size_t)i + k] - q0[k]) * qs[k];
-          const unsigned q = (f >= 0.f) ? (unsigned)fminf(f, 63.f) : 0u;            // NaN -> 0
-          code |= spread6(q) << k;
-        }
-        key = (code << 14) | (unsigned)i;
-      }
-      keys[i] = key;
+    for (int k = 0; k < K; ++k) {
+      const int i = tid + k * kSortThreads;
+      const unsigned c = (i < M) ? prep_cell(T[3 * (size_t)i], T[3 * (size_t)i + 1], T[3 * (size_t)i + 2], q0, qs) : 0u;
+      if (k & 1) pk[k >> 1] |= c << 16; else pk[k >> 1] = c;
     }
-    __syncthreads();
-    // LSD radix sort of the 18 code bits, three stable passes of 6 bits.  Keys start in index order and every pass is
-    // stable, so equal codes stay in index order: the same deterministic permutation as sorting the full 32-bit keys
-    // (the bitonic network this replaces: 91 substeps, 62 us for 8192 keys on one SM).  Warp w owns the contiguous
-    // run [w seg, (w + 1) seg) of the pass's input; a round ranks 32 keys with six ballots (rank = peers of the same
-    // digit in lower lanes), hist[digit][warp] counted in a first walk and scanned digit-major gives every (digit,
-    // warp) its output offset.  Padding keys (0xffffffff) have digit 63 in every pass and come last in the input: they
-    // stay behind every real key.
-    const int seg = npad >> 5;
-    unsigned* kin = keys; unsigned* kout = keys + npad;
-    for (int pass = 0; pass < 3; ++pass) {
-      const int shift = 14 + 6 * pass;
-      for (int i = tid; i < 64 * 33; i += kSortThreads) hist[i] = 0u;
-      __syncthreads();
-      for (int r = 0; r < seg; r += 32) {
-        const unsigned d = (kin[warp * seg + r + lane] >> shift) & 63u;
-        const unsigned peers = peers6(d);
-        if ((peers & ((1u << lane) - 1u)) == 0u) hist[d * 33 + warp] += (unsigned)__popc(peers);
-        __syncwarp();
-      }
-      __syncthreads();
-      {                                                              // exclusive scan over (digit, warp), two entries per thread
-        const int l0 = 2 * tid, l1 = 2 * tid + 1;
-        const int p0 = (l0 >> 5) * 33 + (l0 & 31), p1i = (l1 >> 5) * 33 + (l1 & 31);
-        const unsigned a = hist[p0], c = hist[p1i];
-        int inc = (int)(a + c);
+    pp.mark();                                                      // target: cells
+    prep_cell_sort<K>(pk, M, cnt, start, ent, wsum, deterministic);
+    pp.mark();                                                      // target: sort
+  } else { pp.mark(); pp.mark(); }
+  for (int i0 = tid; i0 < nchunks * kBlk; i0 += 4 * kSortThreads) {       // four items per round: the gathers in flight together
+    int src[4]; float x[4], y[4], z[4];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-          const int w = wsum[lane];
-          int winc = w;
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * kSortThreads; src[u] = (i < M) ? (do_sort ? (int)ent[i] : i) : -1; }
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
-          wsum[lane] = winc - w;
-        }
-        __syncthreads();
-        const unsigned off = (unsigned)(wsum[warp] + inc) - (a + c);
-        hist[p0] = off; hist[p1i] = off + a;
-      }
-      __syncthreads();
-      for (int r = 0; r < seg; r += 32) {
-        const unsigned key = kin[warp * seg + r + lane];
-        const unsigned d = (key >> shift) & 63u;
-        const unsigned peers = peers6(d);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        const unsigned base = hist[d * 33 + warp];
-        kout[base + rank] = key;
-        __syncwarp();
-        if (rank == 0) hist[d * 33 + warp] = base + (unsigned)__popc(peers);
-        __syncwarp();
-      }
-      __syncthreads();
-      unsigned* t = kin; kin = kout; kout = t;
+    for (int u = 0; u < 4; ++u) {
+      x[u] = y[u] = z[u] = __int_as_float(0x7fc00000);
+      if (src[u] >= 0) { x[u] = T[3 * (size_t)src[u]]; y[u] = T[3 * (size_t)src[u] + 1]; z[u] = T[3 * (size_t)src[u] + 2]; }
     }
-    sorted = kin;
-  }
-  float4* Tv = p2v + (size_t)b * nchunks * kBlk;
-  for (int i = tid; i < nchunks * kBlk; i += kSortThreads) {
-    if (i < M) {
-      const int src = npad > 0 ? (int)(sorted[i] & 0x3fffu) : i;
-      const float x = T[3 * (size_t)src], y = T[3 * (size_t)src + 1], z = T[3 * (size_t)src + 2];
-      pm[i] = src;
-      Ts[3 * (size_t)i] = x; Ts[3 * (size_t)i + 1] = y; Ts[3 * (size_t)i + 2] = z;
-      Tv[i] = make_float4(x, y, z, __int_as_float(src));            // what the row recovery stages: one 16-byte copy per target
-    } else {
-      const float qnan = __int_as_float(0x7fc00000);
-      Tv[i] = make_float4(qnan, qnan, qnan, __int_as_float(0x7fffffff));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kSortThreads;
+      if (i < nchunks * kBlk) {
+        if (src[u] >= 0) { pm[i] = src[u]; Ts[3 * (size_t)i] = x[u]; Ts[3 * (size_t)i + 1] = y[u]; Ts[3 * (size_t)i + 2] = z[u]; }
+        // what the row recovery stages: one 16-byte copy per target (NaN padding up to whole chunks)
+        Tv[i] = make_float4(x[u], y[u], z[u], __int_as_float(src[u] >= 0 ? src[u] : 0x7fffffff));
+      }
     }
   }
   __syncthreads();                                                 // the CTA's own global writes are visible to it
+  pp.mark();                                                        // target: sorted copies
   // ---- chunk boxes: one warp per chunk, 4 columns per lane
   for (int c = warp; c < nchunks; c += kSortThreads / 32) {
     float l[3] = {prep_inf(), prep_inf(), prep_inf()}, h[3] = {-prep_inf(), -prep_inf(), -prep_inf()};
+#pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int col = c * kBlk + u * 32 + lane;
       if (col < M) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { const float v = Ts[3 * (size_t)col + k]; l[k] = fminf(l[k], v); h[k] = fmaxf(h[k], v); }
+        const float4 q = Tv[col];
+        l[0] = fminf(l[0], q.x); l[1] = fminf(l[1], q.y); l[2] = fminf(l[2], q.z);
+        h[0] = fmaxf(h[0], q.x); h[1] = fmaxf(h[1], q.y); h[2] = fmaxf(h[2], q.z);
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        l[k] = fminf(l[k], __shfl_xor_sync(0xffffffffu, l[k], o));
-        h[k] = fmaxf(h[k], __shfl_xor_sync(0xffffffffu, h[k], o));
-      }
-    }
+    for (int k = 0; k < 3; ++k) { l[k] = warp_min_f(l[k]); h[k] = warp_max_f(h[k]); }
     if (lane == 0) {
-      float* o = cbox + ((size_t)b * nchunks + c) * 8;
+      float* o = cb + (size_t)c * 8;
       o[0] = l[0]; o[1] = l[1]; o[2] = l[2]; o[3] = h[0]; o[4] = h[1]; o[5] = h[2]; o[6] = 0.f; o[7] = 0.f;
     }
   }
+  __syncthreads();
+  pp.mark();                                                        // target: chunk boxes
+}
+
+// Box layout: 8 floats per block / chunk: lo.x lo.y lo.z hi.x hi.y hi.z pad pad.  An empty box is (+inf, -inf).
+// grid: x = sample [0, B), then (sample, row segment) [B, B + B nseg).  dynamic smem: u32 cnt[4096], start[4096], ent[max(M,
+// 4096)], then (row segments) float sx / sy / sz[4096].  sort_targets = 0 when the sample is too large to sort: identity order.
+constexpr int kRowSeg = 4096;             // rows per independently sorted segment
+constexpr int kRowK = kRowSeg / kSortThreads;
+__global__ void __launch_bounds__(kSortThreads)
+chamfer_sort_targets_kernel(const float* __restrict__ p2, float* __restrict__ p2s, float4* __restrict__ p2v, int* __restrict__ perm,
+                            float* __restrict__ cbox, float* __restrict__ tmax, int M, int sort_targets, int nchunks,
+                            const float* __restrict__ p1, float* __restrict__ p1s, int* __restrict__ rperm,
+                            float* __restrict__ rbox, int P, int nrb, int B, int deterministic,
+                            unsigned long long* __restrict__ probe) {
+  extern __shared__ __align__(16) unsigned char prep_smem[];
+  unsigned* cnt = reinterpret_cast<unsigned*>(prep_smem);
+  unsigned* start = cnt + kCells;
+  unsigned* ent = start + kCells;
+  __shared__ float red[32][7];
+  __shared__ unsigned wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PrepProbe pp;
+  pp.begin(probe, (int)blockIdx.x == 0 || (int)blockIdx.x == B, (int)blockIdx.x == 0 ? 2 : 7);
+  if ((int)blockIdx.x >= B) {
+    // ---- CTAs past the first B: one segment of kRowSeg predicted points each - Morton sort inside the segment's box, the
+    // sorted copy, the permutation and the boxes of its 128-row blocks.  Independent of the target sort; sharing its
+    // launch lets the two run side by side.
+    const int nseg = (P + kRowSeg - 1) / kRowSeg;
+    const int sid = (int)blockIdx.x - B, b = sid / nseg, s0 = (sid % nseg) * kRowSeg;
+    const int n = min(kRowSeg, P - s0);
+    const float* A = p1 + ((size_t)b * P + s0) * 3;
+    // the segment's points are staged in shared memory: the gathers of the sorted copy and of the boxes read them there
+    float* sx = reinterpret_cast<float*>(ent + kRowSeg); float* sy = sx + kRowSeg; float* sz = sy + kRowSeg;
+    float x[kRowK], y[kRowK], z[kRowK];
+    float lo[3] = {prep_inf(), prep_inf(), prep_inf()}, hi[3] = {-prep_inf(), -prep_inf(), -prep_inf()};
+#pragma unroll
+    for (int k = 0; k < kRowK; ++k) {
+      const int i = tid + k * kSortThreads;
+      x[k] = y[k] = z[k] = 0.f;
+      if (i < n) { x[k] = A[3 * (size_t)i]; y[k] = A[3 * (size_t)i + 1]; z[k] = A[3 * (size_t)i + 2]; }
+    }
+#pragma unroll
+    for (int k = 0; k < kRowK; ++k) {
+      const int i = tid + k * kSortThreads;
+      if (i < n) {
+        sx[i] = x[k]; sy[i] = y[k]; sz[i] = z[k];
+        lo[0] = fminf(lo[0], x[k]); lo[1] = fminf(lo[1], y[k]); lo[2] = fminf(lo[2], z[k]);           // NaN dropped
+        hi[0] = fmaxf(hi[0], x[k]); hi[1] = fmaxf(hi[1], y[k]); hi[2] = fmaxf(hi[2], z[k]);
+      }
+    }
+    prep_block_box(lo, hi, 0u, red);
+    pp.mark();                                                      // row: staged + box
+    float q0[3], qs[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      q0[k] = red[0][k];
+      const float ext = red[0][3 + k] - red[0][k];
+      qs[k] = (ext > 0.f && ext < 1e30f) ? 15.999f / ext : 0.f;
+    }
+    unsigned pk[kRowK / 2];
+#pragma unroll
+    for (int k = 0; k < kRowK; ++k) {
+      const unsigned c = (tid + k * kSortThreads < n) ? prep_cell(x[k], y[k], z[k], q0, qs) : 0u;
+      if (k & 1) pk[k >> 1] |= c << 16; else pk[k >> 1] = c;
+    }
+    pp.mark();                                                      // row: cells
+    prep_cell_sort<kRowK>(pk, n, cnt, start, ent, wsum, deterministic);
+    pp.mark();                                                      // row: sort
+    // boxes of the segment's 128-row blocks in both orders: warp w = block w, 4 rows per lane.  The order whose blocks are
+    // more compact (sum of squared box diagonals) is kept: surface samples of a primitive gain a lot from the sort, mesh
+    // vertices that already arrive one small primitive per block (train_gcn.py) would lose.
+    float bl[2][3], bh[2][3], diag[2] = {0.f, 0.f};
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { bl[v][k] = prep_inf(); bh[v][k] = -prep_inf(); }
+    }
+    if (warp * kBlk < n) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = warp * kBlk + u * 32 + lane;
+        if (i < n) {
+          const int src = (int)ent[i];
+          bl[0][0] = fminf(bl[0][0], sx[i]); bl[0][1] = fminf(bl[0][1], sy[i]); bl[0][2] = fminf(bl[0][2], sz[i]);
+          bh[0][0] = fmaxf(bh[0][0], sx[i]); bh[0][1] = fmaxf(bh[0][1], sy[i]); bh[0][2] = fmaxf(bh[0][2], sz[i]);
+          bl[1][0] = fminf(bl[1][0], sx[src]); bl[1][1] = fminf(bl[1][1], sy[src]); bl[1][2] = fminf(bl[1][2], sz[src]);
+          bh[1][0] = fmaxf(bh[1][0], sx[src]); bh[1][1] = fmaxf(bh[1][1], sy[src]); bh[1][2] = fmaxf(bh[1][2], sz[src]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          bl[v][k] = warp_min_f(bl[v][k]); bh[v][k] = warp_max_f(bh[v][k]);
+          const float e = bh[v][k] - bl[v][k];
+          if (e > 0.f) diag[v] = fmaf(e, e, diag[v]);
+        }
+      }
+    }
+    if (lane == 0) { red[warp][0] = diag[0]; red[warp][1] = diag[1]; }       // red[0][0..5] were consumed before the sort's barriers
+    __syncthreads();
+    float dn = 0.f, ds = 0.f;
+    if (warp == 0) {
+      dn = red[lane][0]; ds = red[lane][1];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { dn += __shfl_xor_sync(0xffffffffu, dn, o); ds += __shfl_xor_sync(0xffffffffu, ds, o); }
+      if (lane == 0) wsum[0] = (ds < dn) ? 1u : 0u;                          // NaN sums: natural order
+    }
+    __syncthreads();
+    const bool use_sorted = wsum[0] != 0u;                                   // CTA-uniform
+    pp.mark();                                                      // row: block boxes, both orders
+    float* As = p1s + ((size_t)b * P + s0) * 3;
+    int* rp = rperm + (size_t)b * P + s0;
+#pragma unroll
+    for (int k = 0; k < kRowK; ++k) {
+      const int i = tid + k * kSortThreads;
+      if (i < n) rp[i] = s0 + (use_sorted ? (int)ent[i] : i);
+    }
+#pragma unroll
+    for (int k = 0; k < 3 * kRowK; ++k) {                            // consecutive threads write consecutive floats
+      const int j = tid + k * kSortThreads;
+      if (j < 3 * n) {
+        const int r = j / 3, c = j - 3 * r;
+        const int src = use_sorted ? (int)ent[r] : r;
+        As[j] = (c == 0 ? sx : (c == 1 ? sy : sz))[src];
+      }
+    }
+    if (warp * kBlk < n && lane == 0) {
+      float* o = rbox + ((size_t)b * nrb + s0 / kBlk + warp) * 8;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { o[k] = use_sorted ? bl[1][k] : bl[0][k]; o[3 + k] = use_sorted ? bh[1][k] : bh[0][k]; }
+      o[6] = 0.f; o[7] = 0.f;
+    }
+    __syncthreads();
+    pp.mark();                                                      // row: sorted copy, permutation, boxes
+    return;
+  }
+  const int b = blockIdx.x;
+  const float* T = p2 + (size_t)b * M * 3;
+  float* Ts = p2s + (size_t)b * M * 3;
+  float4* Tv = p2v + (size_t)b * nchunks * kBlk;
+  int* pm = perm + (size_t)b * M;
+  float* cb = cbox + (size_t)b * nchunks * 8;
+  if (M <= 8 * kSortThreads) prep_sort_targets<8>(T, Ts, Tv, pm, cb, tmax + b, M, sort_targets, deterministic, nchunks, cnt, start, ent, wsum, red, pp);
+  else prep_sort_targets<16>(T, Ts, Tv, pm, cb, tmax + b, M, sort_targets, deterministic, nchunks, cnt, start, ent, wsum, red, pp);
 }
 
 // ---- upper bounds of the nearest-neighbour distances ---------------------------------------------------------------
@@ -288,7 +423,8 @@ __device__ __forceinline__ float box_gap2(const float* __restrict__ a, const flo
 __global__ void __launch_bounds__(kBoundWarps * 32)
 chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restrict__ p2s,
                             const float* __restrict__ rbox, const float* __restrict__ cbox,
-                            float* __restrict__ rthr, float* __restrict__ cub, int P, int M, int nrb, int nchunks) {
+                            float* __restrict__ rthr, float* __restrict__ cub, int P, int M, int nrb, int nchunks,
+                            int near_rows, int reps_rows, int near_cols, int reps_cols) {
   __shared__ unsigned s_gap[kBoundWarps][kGapCap];      // (quantised gap bits | candidate index), 0xffffffff = taken
   __shared__ float4 s_reps[kBoundWarps][kMaxReps];
   __shared__ int s_sel[kBoundWarps][kMaxNear];
@@ -303,7 +439,7 @@ chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restric
   const float* other = (is_row ? p2s + (size_t)b * M * 3 : p1 + (size_t)b * P * 3);
   const int nob = is_row ? nchunks : nrb;                                    // blocks of the other cloud
   const float* obox = (is_row ? cbox + (size_t)b * nchunks * 8 : rbox + (size_t)b * nrb * 8);
-  const int near = is_row ? kNearRows : kNearCols, per = is_row ? kRepsRows : kRepsCols;
+  const int near = is_row ? near_rows : near_cols, per = is_row ? reps_rows : reps_cols;
   const float* mb = is_row ? rbox + ((size_t)b * nrb + blk) * 8 : cbox + ((size_t)b * nchunks + blk) * 8;
   float mybox[6];
 #pragma unroll
@@ -361,28 +497,38 @@ chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restric
   if (lane == 0) { if (is_row) rthr[(size_t)b * nrb + blk] = m; else cub[(size_t)b * nchunks + blk] = m; }
 }
 
+int chamfer_row_segment() { return kRowSeg; }
+
 size_t chamfer_sort_smem_bytes(int M) {
   if (M > kSortMaxM) return 0;
-  const int npad = (M + kSortMinKeys - 1) / kSortMinKeys * kSortMinKeys;     // whole rounds of 32 keys for each of the 32 warps
-  return (size_t)npad * 8;
+  return (size_t)kCells * 8 + (((size_t)M * 4 + 15) & ~(size_t)15);         // cnt, start, ent[M]
 }
 
+// p1s / rperm: the predicted points sorted inside segments of kRowSeg rows and the map sorted row -> original row; the
+// bounds, and every later kernel of the forward, work on the sorted copy.
 int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, float4* p2v, int* perm, float* cbox, float* rbox, float* rthr,
-                        float* cub, float* tmax, int B, int P, int M, cudaStream_t s) {
+                        float* cub, float* tmax, float* p1s, int* rperm, unsigned long long* stats, int B, int P, int M, cudaStream_t s) {
   const int nchunks = (M + kBlk - 1) / kBlk, nrb = (P + kBlk - 1) / kBlk;
-  const size_t smem = chamfer_sort_smem_bytes(M);
+  const size_t smem_t = chamfer_sort_smem_bytes(M);
+  const size_t smem_r = (size_t)kCells * 8 + (size_t)kRowSeg * 4 + (size_t)kRowSeg * 12;      // cnt, start, ent + the staged points
+  const size_t smem = smem_t > smem_r ? smem_t : smem_r;
   static DeviceOnce once;
-  if (set_dyn_smem(chamfer_sort_targets_kernel, kSortMaxM * 8, once) != cudaSuccess) {
+  if (set_dyn_smem(chamfer_sort_targets_kernel, kCells * 8 + kSortMaxM * 4 + kRowSeg * 12, once) != cudaSuccess) {
     vpn_set_error("chamfer prep: smem attribute"); return VPN_ERR_CUDA;
   }
-  const long long box_ctas = ((long long)nrb * B + kSortThreads / 32 - 1) / (kSortThreads / 32);
-  if (B + box_ctas > 0x7fffffffLL) { vpn_set_error("chamfer prep: too many row blocks"); return VPN_ERR_SHAPE; }
-  chamfer_sort_targets_kernel<<<(unsigned)(B + box_ctas), kSortThreads, smem, s>>>(p2, p2s, p2v, perm, cbox, tmax, M, (int)(smem / 8), nchunks,
-                                                                                   p1, rbox, P, nrb, B);
+  const long long seg_ctas = (long long)((P + kRowSeg - 1) / kRowSeg) * B;
+  if (B + seg_ctas > 0x7fffffffLL) { vpn_set_error("chamfer prep: too many row segments"); return VPN_ERR_SHAPE; }
+  chamfer_sort_targets_kernel<<<(unsigned)(B + seg_ctas), kSortThreads, smem, s>>>(p2, p2s, p2v, perm, cbox, tmax, M, smem_t > 0 ? 1 : 0, nchunks,
+                                                                                   p1, p1s, rperm, rbox, P, nrb, B,
+                                                                                   tuning_value(kTunePrepDeterministic) == 1 ? 1 : 0,
+                                                                                   tuning_value(kTunePrepProbe) == 1 ? stats : nullptr);
   int rc = vpn_check_launch("chamfer_sort_targets_kernel");
   if (rc) return rc;
+  // vpn_set_tuning("prep_near_rows" / "prep_reps_rows" / "prep_near_cols" / "prep_reps_cols"): probes only (near <= 32, reps 1 / 2 / 4)
+  auto pick = [](int key, int dflt, int cap) { const int v = tuning_value(key); return (v >= 1 && v <= cap && (key == kTunePrepNearRows || key == kTunePrepNearCols || v == 1 || v == 2 || v == 4)) ? v : dflt; };
   chamfer_prune_bounds_kernel<<<dim3((nrb + nchunks + kBoundWarps - 1) / kBoundWarps, B), kBoundWarps * 32, 0, s>>>(
-      p1, p2s, rbox, cbox, rthr, cub, P, M, nrb, nchunks);
+      p1s, p2s, rbox, cbox, rthr, cub, P, M, nrb, nchunks, pick(kTunePrepNearRows, kNearRows, kMaxNear), pick(kTunePrepRepsRows, kRepsRows, 4),
+      pick(kTunePrepNearCols, kNearCols, kMaxNear), pick(kTunePrepRepsCols, kRepsCols, 4));
   return vpn_check_launch("chamfer_prune_bounds_kernel");
 }
 

@@ -420,7 +420,7 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
                             const float* __restrict__ rbest, const u64* __restrict__ rmask, int planes, size_t plane_stride,
                             const float2* __restrict__ tslack, float* __restrict__ min1, int* __restrict__ idx1,
                             int P, int M, int nchunks, int nsplit, int cps, int TM, int ntiles,
-                            const int* __restrict__ skip, int nblk, int nitems) {
+                            const int* __restrict__ skip, int nblk, int nitems, const int* __restrict__ rperm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // dynamic shared memory: [rowc | key | pre_mask | items | pre_rb | pre_p1] (kRowsFixedSmem bytes) then cols[]
   float4* rowc_ = reinterpret_cast<float4*>(smem_raw);
@@ -475,6 +475,9 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
       for (int wi = i0 + grp; wi < i1; wi += 2) {
         const int row = (wi - b * nblk) * kRowGroup + gt;
         const bool valid = row < P;
+        // p1 is the spatially sorted copy when rperm != NULL: the results go to the row's original position (looked up where
+        // it is needed: kept live across the item it costs two registers the kernel does not have)
+        auto orow_of = [&]() { return (size_t)b * P + (rperm ? rperm[(size_t)b * P + row] : row); };
         float g = inf_f(), gthr = inf_f();
         u64 kinit = ~0ull;
         // this row's candidate units of the segment: 256 bits, unit u of the segment = columns [32 u, 32 u + 32) of cols[]
@@ -484,7 +487,7 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
           if (valid) {
             rowc[gt] = make_float4(pre_p1[tid * 3], pre_p1[tid * 3 + 1], pre_p1[tid * 3 + 2], 0.f);
             g = pre_rb[tid];
-            if (seg > 0) kinit = ((u64)__float_as_uint(min1[(size_t)b * P + row]) << 32) | (unsigned)idx1[(size_t)b * P + row];
+            if (seg > 0) { const size_t orow = orow_of(); kinit = ((u64)__float_as_uint(min1[orow]) << 32) | (unsigned)idx1[orow]; }
             const int rel = -seg * kSegChunks * 4;                               // first unit of the record, relative to the segment
             if (rel == 0) {
 #pragma unroll
@@ -509,7 +512,7 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
           for (int s = 0; s < nsplit; ++s) g = fminf(g, rbest[((size_t)b * nsplit + s) * P + row]);
           const float2 sl = tslack[(size_t)b * ntiles + row / TM];
           gthr = thr_of(g, sl.x, sl.y);
-          if (seg > 0) kinit = ((u64)__float_as_uint(min1[(size_t)b * P + row]) << 32) | (unsigned)idx1[(size_t)b * P + row];
+          if (seg > 0) { const size_t orow = orow_of(); kinit = ((u64)__float_as_uint(min1[orow]) << 32) | (unsigned)idx1[orow]; }
           for (int s = 0; s < nsplit; ++s) {
             const size_t o = ((size_t)b * nsplit + s) * P + row;
             if (!(rbest[o] <= gthr)) continue;
@@ -565,8 +568,9 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
         }
         if (valid) {
           const u64 kv = key[gt];
-          min1[(size_t)b * P + row] = __uint_as_float((unsigned)(kv >> 32));
-          idx1[(size_t)b * P + row] = (int)(unsigned)(kv & 0xffffffffu);
+          const size_t orow = orow_of();
+          min1[orow] = __uint_as_float((unsigned)(kv >> 32));
+          idx1[orow] = (int)(unsigned)(kv & 0xffffffffu);
         }
         group_sync(bar);                                 // the next item overwrites rowc / key
       }
@@ -598,7 +602,7 @@ __global__ void __launch_bounds__(kRecThreads, 1)
 chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                             const float* __restrict__ cbest, const void* __restrict__ cmask_,
                             const float* __restrict__ cthr, u64* __restrict__ key2, int P, int M, int ntiles,
-                            const int* __restrict__ skip) {
+                            const int* __restrict__ skip, const int* __restrict__ rperm) {
   constexpr int TM = TC ? 128 * R : kTThreads * R;
   constexpr int kSub = TC ? 1 : ((R >= 4) ? 4 : R);      // sub-units per (column, bit) item
   constexpr int kRunsPerSub = TC ? 1 : R / kSub;
@@ -617,8 +621,10 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
   const float qnan = __int_as_float(0x7fc00000);
   for (int i = tid; i < TM; i += kRecThreads) {
     int rowi = ti * TM + i;
-    rows[i] = rowi < P ? make_float4(A[3 * (size_t)rowi], A[3 * (size_t)rowi + 1], A[3 * (size_t)rowi + 2], 0.f)
-                       : make_float4(qnan, qnan, qnan, 0.f);
+    // w = the row's ORIGINAL index (p1 is the spatially sorted copy when rperm != NULL): ties go to the first original row
+    rows[i] = rowi < P ? make_float4(A[3 * (size_t)rowi], A[3 * (size_t)rowi + 1], A[3 * (size_t)rowi + 2],
+                                     __int_as_float(rperm ? rperm[(size_t)b * P + rowi] : rowi))
+                       : make_float4(qnan, qnan, qnan, __int_as_float(0x7fffffff));
   }
   const size_t rec0 = ((size_t)b * ntiles + ti) * M;
   // columns are visited in slabs of kRecThreads * kPer so that one slab's items normally fit the list
@@ -663,8 +669,8 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
           int at;
           const int st = unit_scan(d, dm, lane, &at);
           u64 kv = ~0ull;
-          if (st == 1) kv = ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)(ti * TM + base_row + at);
-          else if (st == 2) kv = unit_exact_walk(tx, ty, tz, rows + base_row, ti * TM + base_row, 0);
+          if (st == 1) kv = ((u64)__float_as_uint(sqrtf(dm)) << 32) | (unsigned)__float_as_int(rows[base_row + at].w);
+          else if (st == 2) kv = unit_exact_walk(tx, ty, tz, rows + base_row, 0, 1);
           best = kv < best ? kv : best;
         }
         if (best != ~0ull) atomicMin(&key2[(size_t)b * M + col], best);
@@ -701,7 +707,7 @@ int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask
                       int B, int P, int M, int NB, int ntiles, int nsplit, int nchunks, int cps, cudaStream_t s);
 // chamfer_prep.cu
 int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, float4* p2v, int* perm, float* cbox, float* rbox, float* rthr,
-                        float* cub, float* tmax, int B, int P, int M, cudaStream_t s);
+                        float* cub, float* tmax, float* p1s, int* rperm, unsigned long long* stats, int B, int P, int M, cudaStream_t s);
 int chamfer_flagged_launch(const float* p1, const float* p2, float* min1, int* idx1, float* min2, int* idx2,
                            const int* fallback, int B, int P, int M, cudaStream_t s);
 
@@ -764,7 +770,7 @@ static bool make_plan_tc(int B, int P, int M, int sm_count, TiledPlan& pl) {
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, tmax, cthr, key2, p2s, p2v, perm, cbox, rbox, rthr, cub, pmask, pwork, porder, total; };
+struct TiledWs { size_t rbest, rmask, cbest, cmask, tslack, fallback, tmax, cthr, key2, p2s, p2v, perm, cbox, rbox, rthr, cub, pmask, pwork, porder, p1s, rperm, total; };
 static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   TiledWs w; size_t o = 0;
   w.rbest = o; o += al256((size_t)B * pl.nsplit * P * 4);
@@ -776,7 +782,7 @@ static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
   w.tmax = o; o += al256((size_t)B * 4);
   w.cthr = o; o += al256((size_t)B * M * 4);
   w.key2 = o; o += al256((size_t)B * M * 8);
-  w.p2s = w.p2v = w.perm = w.cbox = w.rbox = w.rthr = w.cub = w.pmask = w.pwork = w.porder = 0;
+  w.p2s = w.p2v = w.perm = w.cbox = w.rbox = w.rthr = w.cub = w.pmask = w.pwork = w.porder = w.p1s = w.rperm = 0;
   if (pl.tc) {                                             // spatial preparation of the pruned tensor-core filter (chamfer_prep.cu)
     const size_t nrb = (size_t)(P + 127) / 128;
     w.p2s = o; o += al256((size_t)B * M * 12);
@@ -790,6 +796,8 @@ static TiledWs ws_layout(int B, int P, int M, const TiledPlan& pl) {
     w.pmask = o; o += al256(ncta * (size_t)chamfer_tc_plan_words() * 4);
     w.pwork = o; o += al256(ncta * 4);
     w.porder = o; o += al256(ncta * 4);
+    w.p1s = o; o += al256((size_t)B * P * 12);                     // predicted points, Morton-sorted inside 4096-row segments
+    w.rperm = o; o += al256((size_t)B * P * 4);                    // sorted row -> original row
   }
   w.total = o;
   return w;
@@ -873,13 +881,13 @@ static int launch_any(int mode, const float* p1, const float* p2, char* ws, cons
 
 template <int R, bool TC>
 static int launch_recover_cols(const float* p1, const float* p2, const float* cb, const void* cmk, const float* cthr,
-                               u64* key2, int B, int P, int M, int ntiles, const int* skip, cudaStream_t s) {
+                               u64* key2, int B, int P, int M, int ntiles, const int* skip, const int* rperm, cudaStream_t s) {
   static DeviceOnce once;
   const size_t smem = (size_t)(TC ? 128 * R : kTThreads * R) * sizeof(float4);
   if (set_dyn_smem(chamfer_recover_cols_kernel<R, TC>, (int)smem, once) != cudaSuccess) {
     vpn_set_error("chamfer tiled: smem attribute (cols recovery)"); return VPN_ERR_CUDA;
   }
-  chamfer_recover_cols_kernel<R, TC><<<dim3(ntiles, B), kRecThreads, smem, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, ntiles, skip);
+  chamfer_recover_cols_kernel<R, TC><<<dim3(ntiles, B), kRecThreads, smem, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, ntiles, skip, rperm);
   return vpn_check_launch("chamfer_recover_cols_kernel");
 }
 
@@ -928,6 +936,8 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   const float* p2w = p2;                       // the targets the sweep and the recovery kernels read
   const int* perm = nullptr;                   // sorted position -> original index (tensor-core mode)
   const float4* p2v = nullptr;                 // the swept targets as (x, y, z, original index) (tensor-core mode, pruned)
+  const float* p1w = p1;                       // the predicted points the sweep and the recovery kernels read
+  const int* rperm = nullptr;                  // sorted row -> original row (tensor-core mode, pruned)
   if (mode == MODE_TC) {
     float* p2s = reinterpret_cast<float*>(ws + wl.p2s);
     int* pm = reinterpret_cast<int*>(ws + wl.perm);
@@ -938,10 +948,12 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
     const bool prune = tuning_value(kTuneTcPrune) != 2;                      // vpn_set_tuning("tc_prune", 2): unpruned sweep
     if (prune) {
       float4* pv = reinterpret_cast<float4*>(ws + wl.p2v);
-      if ((rc = chamfer_prep_launch(p1, p2, p2s, pv, pm, cbox, rbox, rthr, cub, tmax, B, P, M, s))) return rc;
-      p2w = p2s; perm = pm; p2v = pv;
+      float* p1s = reinterpret_cast<float*>(ws + wl.p1s);
+      int* rp = reinterpret_cast<int*>(ws + wl.rperm);
+      if ((rc = chamfer_prep_launch(p1, p2, p2s, pv, pm, cbox, rbox, rthr, cub, tmax, p1s, rp, stats, B, P, M, s))) return rc;
+      p2w = p2s; perm = pm; p2v = pv; p1w = p1s; rperm = rp;
     }
-    rc = chamfer_tc_launch(p1, p2w, reinterpret_cast<float*>(ws + wl.rbest), reinterpret_cast<u64*>(ws + wl.rmask),
+    rc = chamfer_tc_launch(p1w, p2w, reinterpret_cast<float*>(ws + wl.rbest), reinterpret_cast<u64*>(ws + wl.rmask),
                            reinterpret_cast<float*>(ws + wl.cbest), reinterpret_cast<u64*>(ws + wl.cmask),
                            reinterpret_cast<float2*>(ws + wl.tslack), fallback, tmax, prune ? cbox : nullptr, rbox, rthr, cub, stats,
                            reinterpret_cast<unsigned*>(ws + wl.pmask), reinterpret_cast<int*>(ws + wl.pwork),
@@ -980,9 +992,9 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
     if (nitems > 0x7fffffffLL) { vpn_set_error("chamfer tiled: too many row blocks"); return VPN_ERR_SHAPE; }
     const int sms = device_sm_count();
     chamfer_recover_rows_kernel<<<(unsigned)(nitems < sms ? nitems : sms), kRecThreads, smem_rows, s>>>(
-        p1, p2w, p2v, pl.nchunks * kCW, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
+        p1w, p2w, p2v, pl.nchunks * kCW, reinterpret_cast<const float*>(ws + wl.rbest), reinterpret_cast<const u64*>(ws + wl.rmask),
         pl.tc ? 4 : 1, (size_t)B * pl.nsplit * P, reinterpret_cast<const float2*>(ws + wl.tslack), min1, idx1, P, M, pl.nchunks,
-        pl.nsplit, pl.cps, pl.TM, pl.ntiles, skip, nblk, (int)nitems);
+        pl.nsplit, pl.cps, pl.TM, pl.ntiles, skip, nblk, (int)nitems, rperm);
     if ((rc = vpn_check_launch("chamfer_recover_rows_kernel"))) return rc;
   }
   if (ev) cudaEventRecord(ev[3], s);          // with the fork: end of the row recovery; [3]..[4] = what the column chain adds after it
@@ -996,15 +1008,15 @@ int chamfer_tiled_fwd(const float* p1, const float* p2, float* min1, int* idx1, 
   if ((rc = vpn_check_launch("chamfer_col_thr_kernel"))) return rc;
   if (pl.tc) {
     switch (pl.R) {
-      case 16: rc = launch_recover_cols<16, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
-      case 8:  rc = launch_recover_cols<8, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
-      default: rc = launch_recover_cols<4, true>(p1, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
+      case 16: rc = launch_recover_cols<16, true>(p1w, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, rperm, sc); break;
+      case 8:  rc = launch_recover_cols<8, true>(p1w, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, rperm, sc); break;
+      default: rc = launch_recover_cols<4, true>(p1w, p2w, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, rperm, sc); break;
     }
   } else {
     switch (pl.R) {
-      case 16: rc = launch_recover_cols<16, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
-      case 8:  rc = launch_recover_cols<8, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
-      default: rc = launch_recover_cols<4, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, sc); break;
+      case 16: rc = launch_recover_cols<16, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, nullptr, sc); break;
+      case 8:  rc = launch_recover_cols<8, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, nullptr, sc); break;
+      default: rc = launch_recover_cols<4, false>(p1, p2, cb, cmk, cthr, key2, B, P, M, pl.ntiles, skip, nullptr, sc); break;
     }
   }
   if (rc) return rc;

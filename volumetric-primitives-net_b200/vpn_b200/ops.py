@@ -246,7 +246,7 @@ def chamfer_nn_stage_ms(points1: torch.Tensor, points2: torch.Tensor, impl: int 
     out["stages"], out["stages_skipped"] = int(stages.value), int(skipped.value)
     cnt = (ctypes.c_ulonglong * 16)()
     check(lib.vpn_chamfer_tc_counters(ptr(ws), b, p, m, impl, cnt, stream_ptr(dev)), "vpn_chamfer_tc_counters")
-    out["tc_counters"] = [int(x) for x in cnt[:10]]
+    out["tc_counters"] = [int(x) for x in cnt[:16]]
     return out
 
 
