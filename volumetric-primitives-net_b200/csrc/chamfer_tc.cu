@@ -59,6 +59,9 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
 constexpr uint32_t kTcIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(2 * kTcBlk >> 3) << 17) | ((uint32_t)(kTcBlk >> 4) << 24);
 
 constexpr uint32_t kTcIdescHalf = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kTcBlk >> 3) << 17) | ((uint32_t)(kTcBlk >> 4) << 24);   // N = 128
+// the same with an FP16 accumulator (c_format = 0): the tensor core accumulates as before and rounds the result once, to
+// nearest (tools/tc_f16acc.cu: f16 result == RN16(f32 result) on every probed tile); TMEM keeps one f16 per 32-bit column
+constexpr uint32_t kTcIdescHalfF16 = (0u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kTcBlk >> 3) << 17) | ((uint32_t)(kTcBlk >> 4) << 24);
 
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t accumulate, uint32_t idesc = kTcIdesc) {
 #if defined(VPN_TC_VARIANT) && VPN_TC_VARIANT == 3       // probe: epilogue alone
@@ -101,6 +104,33 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                : "r"(taddr) : "memory");
+}
+// 64 accumulator columns as 32 registers of two f16 each (column 2k in the low half of register k)
+__device__ __forceinline__ void tc_ld32_pack(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr) : "memory");
+}
+// min of three pairs of 16-bit integers (ptxas fuses the two into one VIMNMX3.S16x2)
+__device__ __forceinline__ uint32_t tc_min3_s16x2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r, t;
+  asm("min.s16x2 %0, %1, %2;" : "=r"(t) : "r"(a), "r"(b));
+  asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(t), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t tc_min_s16x2(uint32_t a, uint32_t b) { uint32_t r; asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t tc_max_s16x2(uint32_t a, uint32_t b) { uint32_t r; asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// min over 16 registers of packed 16-bit values, per half
+__device__ __forceinline__ uint32_t tc_min16_s16x2(const uint32_t* s) {
+  uint32_t x = s[0];
+#pragma unroll
+  for (int k = 1; k < 15; k += 2) x = tc_min3_s16x2(x, s[k], s[k + 1]);
+  return tc_min_s16x2(x, s[15]);
 }
 __device__ __forceinline__ float tc_min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float tc_thr(float x, float rel, float abs_) { return __fadd_ru(__fmaf_ru(fabsf(x), rel, x), abs_); }
@@ -209,6 +239,30 @@ __device__ __forceinline__ float tc_lane_min4x32(uint32_t taddr, uint32_t empty_
   u[0] = m0; u[1] = m1; u[2] = m2; u[3] = m3;
   return fminf(tc_min3(m0, m1, m2), m3);
 #endif
+}
+
+// The same for an FP16 accumulator: 128 columns arrive as 64 registers of two f16, all loaded before the single wait, so
+// the accumulator is released before any reduction.  Non-negative f16 numbers order like their bit patterns as signed
+// 16-bit integers, and the 3-input packed integer min (VIMNMX3.S16x2) reduces 6 values per instruction where FMNMX3
+// reduces 2 (tools/tc_f16acc.cu, 16 epilogue warps: 255 clk per 128 x 128 block per SM against 385; the 3-input half2
+// min VHMNMX: 522).  A negative hot value (a squared distance of ~0 whose rounding errors won) is a negative integer and
+// wins the min, in any order among negatives; it is then clamped to +0, which is at least as close to the true value
+// (>= 0) - the error bound holds for the clamped number.  +inf (overflow: |P - T|^2 >= 65520) is the largest pattern.
+__device__ __forceinline__ float tc_lane_min4x32_h(uint32_t taddr, uint32_t empty_bar, int lane, float (&u)[4]) {
+  uint32_t a[32], b[32];
+  tc_ld32_pack(taddr, a); tc_ld32_pack(taddr + 64, b);
+  tc_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) tc_mbar_arrive(empty_bar);
+  const uint32_t m0 = tc_min16_s16x2(a), m1 = tc_min16_s16x2(a + 16), m2 = tc_min16_s16x2(b), m3 = tc_min16_s16x2(b + 16);
+  // (lo, hi) of two units -> (lo0, lo1) and (hi0, hi1): the min of the two is (u0, u1)
+  uint32_t u01 = tc_min_s16x2(__byte_perm(m0, m1, 0x5410), __byte_perm(m0, m1, 0x7632));
+  uint32_t u23 = tc_min_s16x2(__byte_perm(m2, m3, 0x5410), __byte_perm(m2, m3, 0x7632));
+  u01 = tc_max_s16x2(u01, 0u); u23 = tc_max_s16x2(u23, 0u);
+  const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&u01)), f23 = __half22float2(*reinterpret_cast<const __half2*>(&u23));
+  u[0] = f01.x; u[1] = f01.y; u[2] = f23.x; u[3] = f23.y;
+  return fminf(tc_min3(u[0], u[1], u[2]), u[3]);
 }
 
 // nibble k of x -> low nibble of byte k
@@ -445,8 +499,12 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   // all hot values and thresholds below are in scaled units (x S^2); records are stored unscaled
   // the true arg-min and the best hot value each err by <= max(16 E rho^2, 4 E d): the threshold needs 32 E rho^2 + 8 E |x|
   // = 6.1e-5 rho^2 + 2^-16 |x| at E = 2^-19; both are taken 4 x larger (measured E over random tiles: 2^-19.85)
-  const float slack_rel = 6.103515625e-05f;                       // 2^-14
-  const float slack_abs = __fmaf_ru(2.5e-4f, rho2 * (S * S), 9.5367431640625e-07f);      // + 2^-20: fp16 subnormal low parts
+  // The accumulator is FP16: the hot value h is RN16 of the f32 hot value f (then clamped at 0), |h - f| <= u |f| + s with
+  // u = 2^-11, s = 2^-25 (subnormal range).  If the f32 values satisfy x_f <= b_f (1 + r) + a (the two lines above), then
+  // x_h <= x_f (1 + u) + s and b_f <= (b_h + s) / (1 - u) give x_h <= b_h (1 + r + 2 u + ...) + a (1 + u) + 3 s: the
+  // relative slack grows by 2 u (1 + u + r) < 1.125 x 2^-10, the absolute one by the factor 1.001 and 2^-22.
+  const float slack_rel = 6.103515625e-05f + 1.0986328125e-03f;   // 2^-14 + 1.125 x 2^-10
+  const float slack_abs = __fmaf_ru(2.5025e-4f, rho2 * (S * S), 1.1930e-06f);      // (2.5e-4 rho^2 + 2^-20: fp16 subnormal low parts) x 1.001 + 2^-22
   if (tid == 0 && split == 0) tslack[(size_t)b * ntiles + tile_i] = make_float2(slack_rel, slack_abs * invS2);
   const uint32_t tbase = *sm.tmem_slot;
 
@@ -548,7 +606,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       tc_mbar_wait(my_empty + 8 * p, (n & 1) ^ 1);
       tc_fence_after();
       if (tc_elect()) {
-        tc_mma(tb + p * 256, da, db, 0, kTcIdescHalf);
+        tc_mma(tb + p * 256, da, db, 0, kTcIdescHalfF16);
         tc_commit(my_full + 8 * p);
       }
       __syncwarp();
@@ -615,7 +673,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         tc_mbar_wait(my_full, it & 1);
         tc_fence_after();
         float mu[4];
-        const float m = tc_lane_min4x32(tlane, my_empty, lane, mu);
+        const float m = tc_lane_min4x32_h(tlane, my_empty, lane, mu);
         ++it;
         const int ri = r * kTcBlk + li;
         const float best = my_best[ri];
@@ -653,7 +711,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         tc_mbar_wait(my_full, it & 1);
         tc_fence_after();
         float mu[4];
-        const float m = tc_lane_min4x32(tlane, my_empty, lane, mu);
+        const float m = tc_lane_min4x32_h(tlane, my_empty, lane, mu);
         ++it;
         if (m <= tc_thr(best, slack_rel, slack_abs)) {
           const float t = tc_thr(fminf(best, m), slack_rel, slack_abs);
