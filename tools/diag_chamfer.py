@@ -19,13 +19,13 @@ def main():
             p2 = (torch.rand(b, m, 3, generator=g) - 0.5)
         p1 = p1.to(dev).contiguous(); p2 = p2.to(dev).contiguous()
         ref = [t.clone() for t in vpn_b200.chamfer_nn(p1, p2, 1)]
-        for prune, half in ((0, 0), (0, 1), (2, 0)):
+        for prune, half in ((0, 0), (0, 1), (0, 2), (0, 3), (0, 5), (2, 0)):
             for nb in (0, 8, 4):
-                lib.vpn_set_tuning(b"tc_prune", prune); lib.vpn_set_tuning(b"tc_nb", nb)
+                lib.vpn_set_tuning(b"tc_prune", prune); lib.vpn_set_tuning(b"tc_nb", nb); lib.vpn_set_tuning(b"tc_hunits", half)   # half: 1 + units on the FP16 pipe, 0 = default
                 out = vpn_b200.chamfer_nn(p1, p2, 5)
                 torch.cuda.synchronize()
                 bad = [int((o != r).sum()) if o.dtype != torch.float32 else int((o.view(torch.int32) != r.view(torch.int32)).sum()) for o, r in zip(out, ref)]
-                line = f"{kind} B={b} P={p} M={m} prune={prune} whole={half} nb={nb}: mismatches min1 {bad[0]} idx1 {bad[1]} min2 {bad[2]} idx2 {bad[3]}"
+                line = f"{kind} B={b} P={p} M={m} prune={prune} hunits+1={half} nb={nb}: mismatches min1 {bad[0]} idx1 {bad[1]} min2 {bad[2]} idx2 {bad[3]}"
                 if bad[1]:
                     w = (out[1] != ref[1]).nonzero()[:4]
                     line += "  first idx1: " + str([(int(a), int(bb), int(out[1][a, bb]), int(ref[1][a, bb]), float(out[0][a, bb]), float(ref[0][a, bb])) for a, bb in w])
@@ -33,7 +33,7 @@ def main():
                     w = (out[3] != ref[3]).nonzero()[:4]
                     line += "  first idx2: " + str([(int(a), int(bb), int(out[3][a, bb]), int(ref[3][a, bb]), float(out[2][a, bb]), float(ref[2][a, bb])) for a, bb in w])
                 print(line, flush=True)
-        lib.vpn_set_tuning(b"tc_prune", 0); lib.vpn_set_tuning(b"tc_nb", 0)
+        lib.vpn_set_tuning(b"tc_prune", 0); lib.vpn_set_tuning(b"tc_nb", 0); lib.vpn_set_tuning(b"tc_hunits", 0)
 
 if __name__ == "__main__":
     main()

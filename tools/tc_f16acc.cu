@@ -82,7 +82,23 @@ __device__ __forceinline__ uint32_t min3_s16x2(uint32_t a, uint32_t b, uint32_t 
   asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(t), "r"(c));      // ptxas fuses the pair into VIMNMX3.S16x2
   return r;
 }
-template <int MODE>      // 0: f32 columns + FMNMX3, 1: packed f16 + 3-input half2 min, 2: packed + 3-input s16x2 min, 3: packed loads only, 4: f32 loads only
+__device__ __forceinline__ uint32_t hmin2_(uint32_t a, uint32_t b) { uint32_t r; asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t hmin2n_(uint32_t a, uint32_t b) { uint32_t r; asm("min.NaN.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// 16 packed registers -> 1 with 2-input half2 mins only (alternating NaN modes keep ptxas from fusing them into VHMNMX)
+__device__ __forceinline__ uint32_t hmin16(const uint32_t* v) {
+  const uint32_t t0 = hmin2_(v[0], v[1]), t1 = hmin2_(v[2], v[3]), t2 = hmin2_(v[4], v[5]), t3 = hmin2_(v[6], v[7]);
+  const uint32_t t4 = hmin2_(v[8], v[9]), t5 = hmin2_(v[10], v[11]), t6 = hmin2_(v[12], v[13]), t7 = hmin2_(v[14], v[15]);
+  const uint32_t s0 = hmin2n_(t0, t1), s1 = hmin2n_(t2, t3), s2 = hmin2n_(t4, t5), s3 = hmin2n_(t6, t7);
+  return hmin2n_(hmin2_(s0, s1), hmin2_(s2, s3));
+}
+__device__ __forceinline__ uint32_t imin16(const uint32_t* s) {
+  uint32_t x = s[0];
+#pragma unroll
+  for (int k = 1; k < 15; k += 2) x = min3_s16x2(x, s[k], s[k + 1]);
+  uint32_t r; asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s[15]));
+  return r;
+}
+template <int MODE>      // 5: packed + 2-input HMNMX2 only, 6: units 0,1 VIMNMX3.S16x2 + units 2,3 HMNMX2, 7: three units integer + one half2; 0: f32 columns + FMNMX3, 1: packed f16 + 3-input half2 min, 2: packed + 3-input s16x2 min, 3: packed loads only, 4: f32 loads only
 __global__ void __launch_bounds__(512, 1) rate_kernel(float* __restrict__ out, long long* __restrict__ clk, int iters) {
   __shared__ uint32_t slot;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -125,6 +141,22 @@ __global__ void __launch_bounds__(512, 1) rate_kernel(float* __restrict__ out, l
         const int lo = (int)(short)(m[k] & 0xffffu), hi = (int)(short)(m[k] >> 16);
         const int w = max(min(lo, hi), 0);                                   // negative (tiny) values clamp to +0
         u[k] = __half2float(__ushort_as_half((unsigned short)w));
+      }
+      acc += fminf(tc_min3(u[0], u[1], u[2]), u[3]) + u[1];
+    } else if (MODE == 5 || MODE == 6 || MODE == 7) {
+      uint32_t a[32], b[32];
+      ld32_pack(tl, a); ld32_pack(tl + 64, b);
+      tc_wait_ld();
+      uint32_t m[4];
+      m[0] = (MODE == 5) ? hmin16(a) : imin16(a);
+      m[1] = (MODE == 5) ? hmin16(a + 16) : imin16(a + 16);
+      m[2] = (MODE == 7) ? imin16(b) : hmin16(b);
+      m[3] = hmin16(b + 16);
+      float u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&m[k]));
+        u[k] = fminf(f.x, f.y);
       }
       acc += fminf(tc_min3(u[0], u[1], u[2]), u[3]) + u[1];
     } else if (MODE == 3) {
@@ -224,14 +256,18 @@ int main() {
   // ---- rates
   float* dout; long long* dclk; CK(cudaMalloc(&dout, 148 * 512 * 4)); CK(cudaMalloc(&dclk, 148 * 8));
   const int iters = 2000;
-  const char* names[5] = {"f32 columns + FMNMX3", "packed f16 + 3-input half2 min", "packed f16 + 3-input s16x2 min", "packed loads only", "f32 loads only"};
-  for (int mode = 0; mode < 5; ++mode) {
+  const char* names[8] = {"f32 columns + FMNMX3", "packed f16 + 3-input half2 min", "packed f16 + 3-input s16x2 min", "packed loads only", "f32 loads only",
+                          "packed f16 + 2-input HMNMX2", "packed f16, half VIMNMX3.S16x2 half HMNMX2", "packed f16, 3/4 VIMNMX3.S16x2 1/4 HMNMX2"};
+  for (int mode = 0; mode < 8; ++mode) {
     for (int rep = 0; rep < 2; ++rep) {
       switch (mode) {
         case 0: rate_kernel<0><<<148, 512>>>(dout, dclk, iters); break;
         case 1: rate_kernel<1><<<148, 512>>>(dout, dclk, iters); break;
         case 2: rate_kernel<2><<<148, 512>>>(dout, dclk, iters); break;
         case 3: rate_kernel<3><<<148, 512>>>(dout, dclk, iters); break;
+        case 5: rate_kernel<5><<<148, 512>>>(dout, dclk, iters); break;
+        case 6: rate_kernel<6><<<148, 512>>>(dout, dclk, iters); break;
+        case 7: rate_kernel<7><<<148, 512>>>(dout, dclk, iters); break;
         default: rate_kernel<4><<<148, 512>>>(dout, dclk, iters); break;
       }
       CK(cudaGetLastError()); CK(cudaDeviceSynchronize());

@@ -53,7 +53,7 @@ int vpn::tuning_value(int key) { return (key >= 0 && key < vpn::kTuneCount) ? g_
 // spatial pruning of chamfer_prep.cu), "serial_recovery" (1 = row and column recovery on one stream); value 0 restores the automatic choice.
 extern "C" int vpn_set_tuning(const char* key, int value) {
   static const char* names[vpn::kTuneCount] = {"tiled_r", "tc_nb", "emd_cluster", "tc_prune", "serial_recovery", "ar_variant", "ar_ctas", "ar_threads", "ar_grid_div",
-                                                "prep_near_cols", "prep_reps_cols", "prep_near_rows", "prep_reps_rows", "prep_probe", "prep_deterministic"};
+                                                "prep_near_cols", "prep_reps_cols", "prep_near_rows", "prep_reps_rows", "prep_probe", "prep_deterministic", "tc_hunits"};
   for (int k = 0; key && k < vpn::kTuneCount; ++k)
     if (strcmp(key, names[k]) == 0) { g_tuning[k].store(value, std::memory_order_relaxed); return VPN_OK; }
   vpn_set_error("vpn_set_tuning: unknown key"); return VPN_ERR_ARG;

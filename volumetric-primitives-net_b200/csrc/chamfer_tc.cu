@@ -32,10 +32,14 @@
 // derived once per CTA in the prologue from the per-block boxes and bounds, and the MMA and epilogue warps walk the same
 // bit masks.  The row and the column direction prune independently (phase 0 / phase 1).
 //
-// CTA = 10 warps over one tile of NB x 128 rows, swept twice (D1 stages, then D2 stages): warps 0-7 read the
-// accumulators and keep the per-row candidate records in shared memory / emit the per-column records, warp 8
-// builds the C_j operands of the next 256 columns, warp 9 (one elected lane) issues the MMAs.  TMEM holds two
-// stages; accumulators and column buffers are handed over with mbarriers (tcgen05.commit on the MMA side).
+// CTA = 20 warps over one tile of NB x 128 rows, swept twice (D1 blocks, then D2 blocks): warps 0-15 read the
+// accumulators and keep the per-row candidate records in shared memory / emit the per-column records, warps 16-17
+// build the C_j operands of the next 256 columns (one half each), warps 18-19 (one elected lane each) issue the MMAs of
+// one column half each.  TMEM holds four 128 x 128 accumulators; accumulators and column buffers are handed over with
+// mbarriers (tcgen05.commit on the MMA side).
+// The accumulator is FP16 (round 2): the tensor core accumulates in f32 as before and rounds the result once; the
+// epilogue then reads two values per register and reduces them with packed 16-bit integer mins, 2.6 x fewer ALU cycles
+// per block than f32 + FMNMX3; the filter's slack grows by the rounding (2^-10 relative), the recovery stays exact.
 #include <cuda_fp16.h>
 #include "common.cuh"
 
@@ -43,9 +47,10 @@ namespace vpn {
 
 constexpr int kTcBlk = 128;                    // rows per block = columns per chunk = MMA M = MMA N
 constexpr int kTcEpiWarps = 16;
-constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;       // 16 epilogue warps, the operand builder, one MMA issuer per half
+constexpr int kTcThreads = (kTcEpiWarps + 4) * 32;       // 16 epilogue warps, one operand builder and one MMA issuer per half
 constexpr int kTcBlkBytes = kTcBlk * 32;       // 128 points x 16 fp16
 constexpr float kTcBig = 1.0e30f;
+constexpr int kTcDefaultHunits = 0;            // 32-column units per block reduced on the FP16 pipe (the rest: ALU pipe)
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float tc_inf() { return __int_as_float(0x7f800000); }
@@ -116,7 +121,20 @@ __device__ __forceinline__ void tc_ld32_pack(uint32_t taddr, uint32_t (&r)[32]) 
                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                : "r"(taddr) : "memory");
 }
-// min of three pairs of 16-bit integers (ptxas fuses the two into one VIMNMX3.S16x2)
+// min of two pairs of f16.  The two spellings compute the same for the numbers met here (no NaN: the sums are finite) and
+// alternate along the reduction tree so that ptxas keeps 2-input HMNMX2 instead of fusing pairs into the 3-input VHMNMX,
+// which runs at a fraction of the rate (tools/tc_f16acc.cu, clk per 128 x 128 block per SM with 16 epilogue warps: f32 +
+// FMNMX3 385, VHMNMX 519, 3-input packed integer min VIMNMX3.S16x2 254, HMNMX2 133; TMEM loads alone 65).
+__device__ __forceinline__ uint32_t tc_hmin2(uint32_t a, uint32_t b) { uint32_t r; asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t tc_hmin2n(uint32_t a, uint32_t b) { uint32_t r; asm("min.NaN.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// min over 16 registers of two f16, per half
+__device__ __forceinline__ uint32_t tc_hmin16(const uint32_t* v) {
+  const uint32_t t0 = tc_hmin2(v[0], v[1]), t1 = tc_hmin2(v[2], v[3]), t2 = tc_hmin2(v[4], v[5]), t3 = tc_hmin2(v[6], v[7]);
+  const uint32_t t4 = tc_hmin2(v[8], v[9]), t5 = tc_hmin2(v[10], v[11]), t6 = tc_hmin2(v[12], v[13]), t7 = tc_hmin2(v[14], v[15]);
+  const uint32_t s0 = tc_hmin2n(t0, t1), s1 = tc_hmin2n(t2, t3), s2 = tc_hmin2n(t4, t5), s3 = tc_hmin2n(t6, t7);
+  return tc_hmin2n(tc_hmin2(s0, s1), tc_hmin2(s2, s3));
+}
+// min of three pairs of 16-bit integers (ptxas fuses the two into one VIMNMX3.S16x2, ALU pipe)
 __device__ __forceinline__ uint32_t tc_min3_s16x2(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r, t;
   asm("min.s16x2 %0, %1, %2;" : "=r"(t) : "r"(a), "r"(b));
@@ -126,7 +144,7 @@ __device__ __forceinline__ uint32_t tc_min3_s16x2(uint32_t a, uint32_t b, uint32
 __device__ __forceinline__ uint32_t tc_min_s16x2(uint32_t a, uint32_t b) { uint32_t r; asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t tc_max_s16x2(uint32_t a, uint32_t b) { uint32_t r; asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 // min over 16 registers of packed 16-bit values, per half
-__device__ __forceinline__ uint32_t tc_min16_s16x2(const uint32_t* s) {
+__device__ __forceinline__ uint32_t tc_imin16(const uint32_t* s) {
   uint32_t x = s[0];
 #pragma unroll
   for (int k = 1; k < 15; k += 2) x = tc_min3_s16x2(x, s[k], s[k + 1]);
@@ -135,31 +153,34 @@ __device__ __forceinline__ uint32_t tc_min16_s16x2(const uint32_t* s) {
 __device__ __forceinline__ float tc_min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float tc_thr(float x, float rel, float abs_) { return __fadd_ru(__fmaf_ru(fabsf(x), rel, x), abs_); }
 
-// x = hi + lo with hi, lo fp16 (lo may be subnormal); returned packed as (first, second) halves of a 32-bit word
-__device__ __forceinline__ void tc_split(float x, __half& hi, __half& lo) {
-  hi = __float2half_rn(x);
-  lo = __float2half_rn(x - __half2float(hi));
+// (a, b) -> hi = (f16(a), f16(b)) and lo = (f16(a - hi.a), f16(b - hi.b)), first element in the low half: x = hi + lo with
+// hi, lo fp16 (lo may be subnormal).  One packed conversion per pair (F2FP) instead of two scalar F2F, which run on the
+// slow conversion unit: the operand builders are on the critical path of a pruned sweep.
+__device__ __forceinline__ uint32_t tc_cvt2(float first, float second) {
+  uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first)); return r;
 }
-__device__ __forceinline__ uint32_t tc_pack(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+__device__ __forceinline__ void tc_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = tc_cvt2(a, b);
+  const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = tc_cvt2(a - back.x, b - back.y);
 }
 // X, Y, Z centred and scaled.  Writes the row operand R_i (is_row) or column operand C_j of point `idx` of a
 // 128-point tile: 8-row groups of 256 B, two 128-B core matrices (8 rows x 16 B) per group, k 0-7 and k 8-15.
 // Returns |.|^2 (scaled).
 __device__ __forceinline__ float tc_make_operand(unsigned char* tile, int idx, float x, float y, float z, bool is_row) {
   const float n2 = fmaf(z, z, fmaf(y, y, x * x));
-  __half nh, nl, xh, xl, yh, yl, zh, zl;
-  tc_split(n2, nh, nl);
   if (is_row) { x *= -2.f; y *= -2.f; z *= -2.f; }
-  tc_split(x, xh, xl); tc_split(y, yh, yl); tc_split(z, zh, zl);
-  const __half one = __float2half_rn(1.0f);
+  uint32_t hxy, lxy, hzn, lzn;
+  tc_split2(x, y, hxy, lxy); tc_split2(z, n2, hzn, lzn);
+  const uint32_t ones = 0x3c003c00u;                                 // (1, 1)
   uint4 k0, k1;
-  if (is_row) {
-    k0 = make_uint4(tc_pack(xh, xh), tc_pack(xl, xl), tc_pack(yh, yh), tc_pack(yl, yl));
-    k1 = make_uint4(tc_pack(zh, zh), tc_pack(zl, zl), tc_pack(nh, nl), tc_pack(one, one));
-  } else {
-    k0 = make_uint4(tc_pack(xh, xl), tc_pack(xh, xl), tc_pack(yh, yl), tc_pack(yh, yl));
-    k1 = make_uint4(tc_pack(zh, zl), tc_pack(zh, zl), tc_pack(one, one), tc_pack(nh, nl));
+  if (is_row) {                                                      // [xh xh xl xl  yh yh yl yl] [zh zh zl zl  nh nl 1 1]
+    k0 = make_uint4(__byte_perm(hxy, hxy, 0x1010), __byte_perm(lxy, lxy, 0x1010), __byte_perm(hxy, hxy, 0x3232), __byte_perm(lxy, lxy, 0x3232));
+    k1 = make_uint4(__byte_perm(hzn, hzn, 0x1010), __byte_perm(lzn, lzn, 0x1010), __byte_perm(hzn, lzn, 0x7632), ones);
+  } else {                                                           // [xh xl xh xl  yh yl yh yl] [zh zl zh zl  1 1 nh nl]
+    const uint32_t wx = __byte_perm(hxy, lxy, 0x5410), wy = __byte_perm(hxy, lxy, 0x7632), wz = __byte_perm(hzn, lzn, 0x5410);
+    k0 = make_uint4(wx, wx, wy, wy);
+    k1 = make_uint4(wz, wz, ones, __byte_perm(hzn, lzn, 0x7632));
   }
   unsigned char* base = tile + (idx >> 3) * 256 + (idx & 7) * 16;
   *reinterpret_cast<uint4*>(base) = k0;
@@ -242,12 +263,18 @@ __device__ __forceinline__ float tc_lane_min4x32(uint32_t taddr, uint32_t empty_
 }
 
 // The same for an FP16 accumulator: 128 columns arrive as 64 registers of two f16, all loaded before the single wait, so
-// the accumulator is released before any reduction.  Non-negative f16 numbers order like their bit patterns as signed
-// 16-bit integers, and the 3-input packed integer min (VIMNMX3.S16x2) reduces 6 values per instruction where FMNMX3
-// reduces 2 (tools/tc_f16acc.cu, 16 epilogue warps: 255 clk per 128 x 128 block per SM against 385; the 3-input half2
-// min VHMNMX: 522).  A negative hot value (a squared distance of ~0 whose rounding errors won) is a negative integer and
-// wins the min, in any order among negatives; it is then clamped to +0, which is at least as close to the true value
-// (>= 0) - the error bound holds for the clamped number.  +inf (overflow: |P - T|^2 >= 65520) is the largest pattern.
+// the accumulator is released before any reduction.  The reduction runs on packed pairs, per 32-column unit either
+//   * as 16-bit INTEGERS on the ALU pipe (tc_imin16, 8 VIMNMX3.S16x2): non-negative f16 numbers order like their bit
+//     patterns; a negative hot value (a squared distance of ~0 whose rounding errors won) is a negative integer and wins
+//     the min, in any order among negatives - it is then clamped to +0, which is at least as close to the true value (>= 0),
+//     so the error bound holds for the clamped number; or
+//   * as f16 on the FP16 pipe (tc_hmin16, 15 HMNMX2), negative values ordered as numbers (and clamped all the same).
+// HUNITS of the four units take the second route.  With nothing else running the FP16 pipe is the faster one
+// (tools/tc_f16acc.cu, clk per 128 x 128 block per SM with 16 epilogue warps: all integer 254, all f16 133, two and two
+// 110), but inside the filter, next to the MMAs, every unit moved to it makes the kernel slower (C2 filter stage 0.595 ms
+// with 0 units, 0.610 / 0.625 / 0.645 / 0.674 with 1 / 2 / 3 / 4): the default is all integer.  +inf (overflow: |P - T|^2 >=
+// 65520 in scaled units) is the largest pattern either way.
+template <int HUNITS>
 __device__ __forceinline__ float tc_lane_min4x32_h(uint32_t taddr, uint32_t empty_bar, int lane, float (&u)[4]) {
   uint32_t a[32], b[32];
   tc_ld32_pack(taddr, a); tc_ld32_pack(taddr + 64, b);
@@ -255,8 +282,10 @@ __device__ __forceinline__ float tc_lane_min4x32_h(uint32_t taddr, uint32_t empt
   tc_fence_before();
   __syncwarp();
   if (lane == 0) tc_mbar_arrive(empty_bar);
-  const uint32_t m0 = tc_min16_s16x2(a), m1 = tc_min16_s16x2(a + 16), m2 = tc_min16_s16x2(b), m3 = tc_min16_s16x2(b + 16);
-  // (lo, hi) of two units -> (lo0, lo1) and (hi0, hi1): the min of the two is (u0, u1)
+  const uint32_t m0 = (HUNITS >= 4) ? tc_hmin16(a) : tc_imin16(a), m1 = (HUNITS >= 3) ? tc_hmin16(a + 16) : tc_imin16(a + 16);
+  const uint32_t m2 = (HUNITS >= 2) ? tc_hmin16(b) : tc_imin16(b), m3 = (HUNITS >= 1) ? tc_hmin16(b + 16) : tc_imin16(b + 16);
+  // (even, odd) column minima of two units -> (even0, even1) and (odd0, odd1): the min of the two is (u0, u1).  The integer
+  // min is right for a mixed pair too: both routes leave ordinary f16 bit patterns.
   uint32_t u01 = tc_min_s16x2(__byte_perm(m0, m1, 0x5410), __byte_perm(m0, m1, 0x7632));
   uint32_t u23 = tc_min_s16x2(__byte_perm(m2, m3, 0x5410), __byte_perm(m2, m3, 0x7632));
   u01 = tc_max_s16x2(u01, 0u); u23 = tc_max_s16x2(u23, 0u);
@@ -389,10 +418,11 @@ chamfer_tc_order_kernel(const int* __restrict__ plan_work, int* __restrict__ pla
 //                            half h reduces the 128 values of chunk 2j + h;
 //   phase 1 (column minima): stage (chunk, rp) = C_chunk (128 columns) x [R_2rp R_2rp+1]^T; TMEM lane = column, the
 //                            thread of half h reduces over the 128 rows of block 2 rp + h.
-// Roles: warps 0-7 epilogue (warp = 4 h + q: TMEM lane quarter q, column half h), warp 8 builds the column operands,
-// warp 9 issues the MMAs (one elected lane).
+// Roles: warps 0-15 epilogue (warp = 8 p + 4 h + q: accumulator buffer p, column half h, TMEM lane quarter q), warps 16-17
+// build the column operands of half 0 / 1, warps 18-19 issue the MMAs of half 0 / 1 (one elected lane).
 // Measured (tools/tc_var.cu, clk per stage per SM): tensor side alone 324, epilogue alone 558 (TMEM reads 136 and
 // 128 FMNMX3 = 256 do not overlap: they share the register-file write port), together 580.
+template <int HUNITS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                   float* __restrict__ rbest, u64* __restrict__ rmask,
@@ -426,7 +456,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       tc_mbar_init(bar_empty + 8 * i, 4);                              // the four epilogue warps (lane quarters) that read the buffer
     }
     for (int i = 0; i < 2; ++i) {
-      tc_mbar_init(bar_cfull + 8 * i, 1);
+      tc_mbar_init(bar_cfull + 8 * i, 2);                              // both builders fill a column buffer
       tc_mbar_init(bar_cempty + 8 * i, 2);                             // both issuers release a column buffer
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -438,7 +468,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
 
   // ---- tile centroid, radius and scale (any centre is valid; the centroid keeps the radius, hence the slack, small).
   // Each thread keeps its rows (<= 7 of the 2048) in registers across the three steps.
-  constexpr int kRowsPerThread = (16 * kTcBlk + kTcThreads - 1) / kTcThreads;      // 7
+  constexpr int kRowsPerThread = (16 * kTcBlk + kTcThreads - 1) / kTcThreads;      // 4
   float rx[kRowsPerThread], ry[kRowsPerThread], rz[kRowsPerThread];
   float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll
@@ -478,7 +508,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   for (int w = 1; w < kTcThreads / 32; ++w) rho2 = fmaxf(rho2, sm.red[w * 4 + 3]);
   // scale: |P|, |T| < 128 in scaled units.  |t - c| <= sqrt(3) (max|t_k| + max|c_k|) for every target of the sample.
   float reach = fmaxf(sqrtf(rho2), 1.7320509f * (tmax[b] + fmaxf(fabsf(cx), fmaxf(fabsf(cy), fabsf(cz))))) * 1.001f;
-  if (!(reach < 1.0e15f)) { if (tid == 0) atomicOr(&fallback[b], 1); reach = 1.f; rho2 = 0.f; }
+  if (!(reach < 1.0e15f) || !(tmax[b] < 1.0e15f)) { if (tid == 0) atomicOr(&fallback[b], 1); reach = 1.f; rho2 = 0.f; }      // tmax: NaN if any target coordinate is
   int ex = 0;
   frexpf(reach, &ex);                                               // reach < 2^ex
   ex = max(-40, min(50, ex));
@@ -499,7 +529,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   // all hot values and thresholds below are in scaled units (x S^2); records are stored unscaled
   // the true arg-min and the best hot value each err by <= max(16 E rho^2, 4 E d): the threshold needs 32 E rho^2 + 8 E |x|
   // = 6.1e-5 rho^2 + 2^-16 |x| at E = 2^-19; both are taken 4 x larger (measured E over random tiles: 2^-19.85)
-  // The accumulator is FP16: the hot value h is RN16 of the f32 hot value f (then clamped at 0), |h - f| <= u |f| + s with
+  // The accumulator is FP16: the hot value h is RN16 of the f32 hot value f, |h - f| <= u |f| + s with
   // u = 2^-11, s = 2^-25 (subnormal range).  If the f32 values satisfy x_f <= b_f (1 + r) + a (the two lines above), then
   // x_h <= x_f (1 + u) + s and b_f <= (b_h + s) / (1 - u) give x_h <= b_h (1 + r + 2 u + ...) + a (1 + u) + 3 s: the
   // relative slack grows by 2 u (1 + u + r) < 1.125 x 2^-10, the absolute one by the factor 1.001 and 2^-22.
@@ -518,7 +548,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
   // (thread 0 doing it alone, plus cycle counters, delayed epilogue warp 0 and with it every stage: +3 %).  A probe build
   // (-DVPN_TC_COUNTERS) adds the cycle counters of epilogue warp 0: [2] prologue, [3] row phase, [4] column phase, [5]
   // tail, and [6] / [7] live stages per phase, [8] live chunks, [9] operand passes built.
-  if (warp == kTcEpiWarps + 1 && stats != nullptr) {
+  if (warp == kTcEpiWarps + 2 && stats != nullptr) {
     unsigned s0 = 0, s1 = 0;
     for (int c = lane; c < nc; c += 32) { s0 += __popc(rawR[c] & ((1u << NB) - 1u)); s1 += __popc(rawC[c] & ((1u << NB) - 1u)); }
 #pragma unroll
@@ -547,22 +577,28 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
 #else
 #define TC_MARK(slot)
 #endif
-  if (warp == kTcEpiWarps) {
-    // ===== column-operand builder (one pass per phase) =====
-    // Only passes that contain a live stage are built (buffer = built-pass count & 1).  The 24 coordinate loads of the
-    // NEXT pass are issued before this warp waits for that pass's buffer, so their latency hides behind the MMAs that
-    // still read it: with most stages pruned a pass is short, and an L2 round trip per pass would set the pace.
+  if (warp >= kTcEpiWarps && warp < kTcEpiWarps + 2) {
+    // ===== column-operand builder of half g (one pass per phase): the 128 columns of chunk 2 j + g, 4 per lane =====
+    // Only passes that contain a live stage are built (buffer = built-pass count & 1), and of such a pass only the halves
+    // that have one (the other builder just takes part in the hand-over).  The 12 coordinate loads of the NEXT pass are
+    // issued before this warp waits for that pass's buffer, so their latency hides behind the MMAs that still read it:
+    // with most stages pruned a pass is short, and an L2 round trip per pass would set the pace.  (One warp building both
+    // halves, with scalar f32 -> f16 conversions, took ~1000 clk per pass - as long as the pass's MMAs and epilogues.)
+    const int g = warp - kTcEpiWarps;
     uint32_t seq = 0;
-    float tx[8], ty[8], tz[8];
+    float tx[4], ty[4], tz[4];
+    const uint32_t nbmask = (1u << NB) - 1u;
     auto next_needed = [&](int cc) { while (cc < 2 * hc && !tc_pass_needed(cc < hc ? cc : cc - hc, nc, NB, cc < hc ? rawR : rawC)) ++cc; return cc; };
+    auto half_live = [&](int cc) {
+      const int c = 2 * (cc < hc ? cc : cc - hc) + g;
+      return c < nc && ((~(cc < hc ? rawR : rawC)[c]) & nbmask) != 0u;
+    };
     auto load_pass = [&](int cc) {
-      const int j = cc < hc ? cc : cc - hc;
+      if (!half_live(cc)) return;
+      const int chunk = c_first + 2 * (cc < hc ? cc : cc - hc) + g;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int jj = k * 32 + lane;                               // 0..255: half = jj >> 7
-        int chunk = c_first + 2 * j + (jj >> 7);
-        if (chunk >= c_last) chunk = c_first + 2 * j;               // unpaired last chunk: duplicate, never recorded
-        const int col = min(chunk * kTcBlk + (jj & 127), M - 1);
+      for (int k = 0; k < 4; ++k) {
+        const int col = min(chunk * kTcBlk + k * 32 + lane, M - 1);
         tx[k] = T[3 * (size_t)col]; ty[k] = T[3 * (size_t)col + 1]; tz[k] = T[3 * (size_t)col + 2];
       }
     };
@@ -572,27 +608,28 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
       const int cb = seq & 1, use = seq >> 1;
       ++seq;
       tc_mbar_wait(bar_cempty + 8 * cb, (use & 1) ^ 1);
-      unsigned char* dst = sm.cols + cb * 2 * kTcBlkBytes;
+      if (half_live(cc)) {
+        unsigned char* dst = sm.cols + cb * 2 * kTcBlkBytes + g * kTcBlkBytes;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int jj = k * 32 + lane;
-        const float x = __fsub_rn(tx[k], cx), y = __fsub_rn(ty[k], cy), z = __fsub_rn(tz[k], cz);
-        const float n2 = tc_make_operand(dst + (jj >> 7) * kTcBlkBytes, jj & 127, x * S, y * S, z * S, false);
-        if (!(n2 < 20000.f)) atomicOr(&fallback[b], 1);             // cannot happen for finite targets (|T| < 128)
+        for (int k = 0; k < 4; ++k) {
+          const float x = __fsub_rn(tx[k], cx), y = __fsub_rn(ty[k], cy), z = __fsub_rn(tz[k], cz);
+          const float n2 = tc_make_operand(dst, k * 32 + lane, x * S, y * S, z * S, false);
+          if (!(n2 < 20000.f)) atomicOr(&fallback[b], 1);           // cannot happen for finite targets (|T| < 128)
+        }
+        tc_fence_async_smem();
       }
-      tc_fence_async_smem();
       __syncwarp();
       if (lane == 0) tc_mbar_arrive(bar_cfull + 8 * cb);
       cc = next_needed(cc + 1);
       if (cc < 2 * hc) load_pass(cc);
     }
-  } else if (warp > kTcEpiWarps) {
+  } else if (warp >= kTcEpiWarps + 2) {
     // ===== MMA issuer of half g: the whole warp walks the loop (warp-uniform operands), one elected lane issues =====
     // Work unit = one 128 x 128 block, tcgen05.mma kind::f16 M = 128, N = 128, K = 16 into the half's accumulator buffer p
     // (TMEM columns [256 p + 128 g, + 128)), which belongs to the four epilogue warps (g, ., p).
     //   phase 0: blocks (row block r, chunk 2 j + g), buffer p = r & 1;
     //   phase 1: blocks (chunk c, row block r) with r & 1 == g, buffer p = c & 1 - the two chunks of a pass are interleaved.
-    const int g = warp - (kTcEpiWarps + 1);
+    const int g = warp - (kTcEpiWarps + 2);
     const uint32_t rows_a = tc_smem_u32(sm.rows), cols_a = tc_smem_u32(sm.cols);
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0) + g * 128;
     const uint64_t drows = tc_desc(rows_a);
@@ -673,7 +710,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         tc_mbar_wait(my_full, it & 1);
         tc_fence_after();
         float mu[4];
-        const float m = tc_lane_min4x32_h(tlane, my_empty, lane, mu);
+        const float m = tc_lane_min4x32_h<HUNITS>(tlane, my_empty, lane, mu);
         ++it;
         const int ri = r * kTcBlk + li;
         const float best = my_best[ri];
@@ -711,7 +748,7 @@ chamfer_tc_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
         tc_mbar_wait(my_full, it & 1);
         tc_fence_after();
         float mu[4];
-        const float m = tc_lane_min4x32_h(tlane, my_empty, lane, mu);
+        const float m = tc_lane_min4x32_h<HUNITS>(tlane, my_empty, lane, mu);
         ++it;
         if (m <= tc_thr(best, slack_rel, slack_abs)) {
           const float t = tc_thr(fminf(best, m), slack_rel, slack_abs);
@@ -835,7 +872,13 @@ int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask
   static DeviceOnce once;
   const size_t smem = tc_smem_bytes(NB);
   {
-    cudaError_t e = set_dyn_smem(chamfer_tc_kernel, (int)tc_smem_bytes(16), once);
+    cudaError_t e = set_dyn_smem(chamfer_tc_kernel<0>, (int)tc_smem_bytes(16), once);
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) {
+      void (*kern)(const float*, const float*, float*, u64*, float*, u64*, float2*, int*, const float*, const uint32_t*, const int*, u64*,
+                   int, int, int, int, int, int, int) = k == 0 ? chamfer_tc_kernel<1> : (k == 1 ? chamfer_tc_kernel<2> : (k == 2 ? chamfer_tc_kernel<3> : chamfer_tc_kernel<4>));
+      static DeviceOnce more[4];
+      e = set_dyn_smem(kern, (int)tc_smem_bytes(16), more[k]);
+    }
     if (e != cudaSuccess) { vpn_set_error("chamfer tc: smem attribute: %s", cudaGetErrorString(e)); return VPN_ERR_CUDA; }
   }
   int rc;
@@ -853,9 +896,21 @@ int chamfer_tc_launch(const float* p1, const float* p2, float* rbest, u64* rmask
     chamfer_tc_order_kernel<<<1, kOrderThreads, 0, s>>>(plan_work, plan_order, ncta);
     if ((rc = vpn_check_launch("chamfer_tc_order_kernel"))) return rc;
   }
-  chamfer_tc_kernel<<<ncta, kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax,
-                                                   cbox ? plan_masks : nullptr, cbox ? plan_order : nullptr, stats,
-                                                   ntiles, nsplit, P, M, NB, nchunks, cps);
+  // units (of the four of a 128-column block) reduced on the FP16 pipe, the others on the ALU pipe; vpn_set_tuning("tc_hunits",
+  // 1 + units) overrides the default for probes
+  const int tune_h = tuning_value(kTuneTcHunits);
+  const int hunits = (tune_h >= 1 && tune_h <= 5) ? tune_h - 1 : kTcDefaultHunits;
+#define VPN_TC_LAUNCH(H) chamfer_tc_kernel<H><<<ncta, kTcThreads, smem, s>>>(p1, p2, rbest, rmask, cbest, cmask, tslack, fallback, tmax, \
+                                                   cbox ? plan_masks : nullptr, cbox ? plan_order : nullptr, stats, \
+                                                   ntiles, nsplit, P, M, NB, nchunks, cps)
+  switch (hunits) {
+    case 0: VPN_TC_LAUNCH(0); break;
+    case 1: VPN_TC_LAUNCH(1); break;
+    case 2: VPN_TC_LAUNCH(2); break;
+    case 3: VPN_TC_LAUNCH(3); break;
+    default: VPN_TC_LAUNCH(4); break;
+  }
+#undef VPN_TC_LAUNCH
   return vpn_check_launch("chamfer_tc_kernel");
 }
 

@@ -39,7 +39,7 @@ inline cudaError_t set_dyn_smem(K kernel, int bytes, DeviceOnce& once) {
 int device_sm_count();
 // Tuning overrides set through vpn_set_tuning (tests and probes only; 0 = automatic choice)
 int tuning_value(int key);
-enum { kTuneTiledR = 0, kTuneTcNb = 1, kTuneEmdCluster = 2, kTuneTcPrune = 3, kTuneSerialRecovery = 4, kTuneArVariant = 5, kTuneArCtas = 6, kTuneArThreads = 7, kTuneArGridDiv = 8, kTunePrepNearCols = 9, kTunePrepRepsCols = 10, kTunePrepNearRows = 11, kTunePrepRepsRows = 12, kTunePrepProbe = 13, kTunePrepDeterministic = 14, kTuneCount = 15 };
+enum { kTuneTiledR = 0, kTuneTcNb = 1, kTuneEmdCluster = 2, kTuneTcPrune = 3, kTuneSerialRecovery = 4, kTuneArVariant = 5, kTuneArCtas = 6, kTuneArThreads = 7, kTuneArGridDiv = 8, kTunePrepNearCols = 9, kTunePrepRepsCols = 10, kTunePrepNearRows = 11, kTunePrepRepsRows = 12, kTunePrepProbe = 13, kTunePrepDeterministic = 14, kTuneTcHunits = 15, kTuneCount = 16 };
 
 // Rigid pose of one primitive: row-major rotation R (from the reference's axis/turn-fraction
 // "quaternion"), plus what the backward pass needs to chain dL/dR to dL/dq.
