@@ -39,10 +39,11 @@ __device__ __forceinline__ unsigned spread6(unsigned x) {       // 6 bits -> eve
   x = (x | (x << 2)) & 0x00009249u;
   return x;
 }
-__device__ __forceinline__ float prep_d2(float ax, float ay, float az, float bx, float by, float bz) {
-  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
-  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-}
+__device__ __forceinline__ u64 prep_pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void prep_upk(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 prep_sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 prep_mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 prep_fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 // warp-wide float min / max in one instruction (redux.sync.f32 is sm_100a; NaN inputs are dropped, like fminf / fmaxf)
 __device__ __forceinline__ float warp_min_f(float v) { float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
@@ -420,13 +421,13 @@ __device__ __forceinline__ float box_gap2(const float* __restrict__ a, const flo
 // waiting at barriers for warp 0's selection rounds).
 //   blocks [0, nchunks)             chunk c      : cub[b][c]   = max_j min_rep d2(col j, rep)
 //   blocks [nchunks, nchunks + nrb) row block rb : rthr[b][rb] = max_i min_rep d2(row i, rep)
-__global__ void __launch_bounds__(kBoundWarps * 32)
+__global__ void __launch_bounds__(kBoundWarps * 32, 8)
 chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restrict__ p2s,
                             const float* __restrict__ rbox, const float* __restrict__ cbox,
                             float* __restrict__ rthr, float* __restrict__ cub, int P, int M, int nrb, int nchunks,
                             int near_rows, int reps_rows, int near_cols, int reps_cols) {
   __shared__ unsigned s_gap[kBoundWarps][kGapCap];      // (quantised gap bits | candidate index), 0xffffffff = taken
-  __shared__ float4 s_reps[kBoundWarps][kMaxReps];
+  __shared__ float4 s_reps[kBoundWarps][2 * kMaxReps];   // per representative (x, x, y, y) (z, z, -, -): operands of the packed f32x2 ops
   __shared__ int s_sel[kBoundWarps][kMaxNear];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int id = blockIdx.x * kBoundWarps + warp;
@@ -480,20 +481,31 @@ chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restric
     const int ob = sel[i / per] * stride;
     int o = ob * kBlk + (i % per) * (kBlk / per);
     o = min(o, n_other - 1);                                                 // a clamped duplicate is still a real point of the cloud
-    reps[i] = make_float4(other[3 * (size_t)o], other[3 * (size_t)o + 1], other[3 * (size_t)o + 2], 0.f);
+    const float qx = other[3 * (size_t)o], qy = other[3 * (size_t)o + 1], qz = other[3 * (size_t)o + 2];
+    reps[2 * i] = make_float4(qx, qx, qy, qy); reps[2 * i + 1] = make_float4(qz, qz, 0.f, 0.f);
   }
   __syncwarp();
+  // Two points per packed op (sub / mul / fma .f32x2: 6 ops per two distances where the scalar form needs 16).  The fused
+  // multiply-adds round differently from the reference's separate operations, by ~1e-7 relative: the bound only has to
+  // hold within the 1e-5 margin the plan kernel applies.
+  const u64 x01 = prep_pk(x[0], x[1]), x23 = prep_pk(x[2], x[3]), y01 = prep_pk(y[0], y[1]), y23 = prep_pk(y[2], y[3]),
+            z01 = prep_pk(z[0], z[1]), z23 = prep_pk(z[2], z[3]);
   float ub[4] = {prep_inf(), prep_inf(), prep_inf(), prep_inf()};
   for (int r = 0; r < nrep; ++r) {
-    const float4 q = reps[r];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) ub[u] = fminf(ub[u], prep_d2(x[u], y[u], z[u], q.x, q.y, q.z));   // NaN distances are dropped: +inf -> nothing pruned
+    const ulonglong2 qa = *reinterpret_cast<const ulonglong2*>(&reps[2 * r]);       // (x, x), (y, y)
+    const u64 qz = *reinterpret_cast<const u64*>(&reps[2 * r + 1]);                 // (z, z)
+    const u64 dx0 = prep_sub2(x01, qa.x), dy0 = prep_sub2(y01, qa.y), dz0 = prep_sub2(z01, qz);
+    const u64 dx1 = prep_sub2(x23, qa.x), dy1 = prep_sub2(y23, qa.y), dz1 = prep_sub2(z23, qz);
+    const u64 s0 = prep_fma2(dz0, dz0, prep_fma2(dy0, dy0, prep_mul2(dx0, dx0)));
+    const u64 s1 = prep_fma2(dz1, dz1, prep_fma2(dy1, dy1, prep_mul2(dx1, dx1)));
+    float a, c, e, f;
+    prep_upk(s0, a, c); prep_upk(s1, e, f);
+    ub[0] = fminf(ub[0], a); ub[1] = fminf(ub[1], c); ub[2] = fminf(ub[2], e); ub[3] = fminf(ub[3], f);   // NaN distances are dropped: +inf -> nothing pruned
   }
   float m = 0.f;
 #pragma unroll
   for (int u = 0; u < 4; ++u) if (valid[u]) m = fmaxf(m, ub[u]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  m = warp_max_f(m);
   if (lane == 0) { if (is_row) rthr[(size_t)b * nrb + blk] = m; else cub[(size_t)b * nchunks + blk] = m; }
 }
 
