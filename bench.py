@@ -477,7 +477,7 @@ def measure_workload(B, workload, steps, warmup, chamfer_impl=0, graph="auto", w
                 "peak_nominal": nominal, "frac_of_nominal": executed_tf / nominal, "ms": main_ms,
                 "algorithmic_flops": flops * (1.0 - skipped_share), "traffic": traffic, "traffic_source": tsrc if traffic else None,
                 "pairs_skipped_share": skipped_share,
-                "pairs_skipped_note": "share of the 128 x 256 distance blocks (both directions) the spatial pruning proves "
+                "pairs_skipped_note": "share of the 128 x 128 distance blocks (both directions) the spatial pruning proves "
                                       "irrelevant and never evaluates (csrc/chamfer_prep.cu).  `achieved` / `frac` count 8 flop "
                                       "for the EVALUATED pairs only (the kernel's own work over its time, prep kernels included "
                                       "in the time); `all_pairs` is the same time against the reference's full pair count",
@@ -486,7 +486,7 @@ def measure_workload(B, workload, steps, warmup, chamfer_impl=0, graph="auto", w
                                       "finish in this time; above the FP32 peak because most pairs are never evaluated"},
                 "note": "achieved = 8 flop per (predicted, target) pair / kernel time, against the FP32 FMA peak the "
                         "north star names; chamfer_tc_kernel evaluates the pairs on the tensor cores (fp16-split "
-                        "operands, fp32 accumulate) and is bounded by TMEM reads + FMNMX on the ALU pipe, see DESIGN.md 4.1",
+                        "operands, the fp32 sum rounded once into an fp16 accumulator) and is bounded by the packed integer mins of its epilogue on the ALU pipe, see DESIGN.md 4.1",
                 "forward_total": {"ms": cham_ms, "stages_ms": stage,
                                   "achieved": flops * (1.0 - skipped_share) / (cham_ms * 1e-3) / 1e12,
                                   "frac": flops * (1.0 - skipped_share) / (cham_ms * 1e-3) / 1e12 / peak_tf,
@@ -505,7 +505,7 @@ def measure_workload(B, workload, steps, warmup, chamfer_impl=0, graph="auto", w
         executed = 64.0 * b * (k * n) * m * (1.0 - skipped_share) / (main_ms * 1e-3) / 1e12
         roofline["tensor_executed"] = {"tflops": executed, "peak_dense_16bit": tensor_peak,
                                        "frac": (executed / tensor_peak) if tensor_peak else None,
-                                       "note": "fp16 operands, fp32 accumulate, K = 16; padded tiles not counted"}
+                                       "note": "fp16 operands, fp16 accumulator (fp32 sum rounded once), K = 16; padded tiles not counted"}
     out["roofline"] = roofline
     if not vertex_mode:
         pk = "pose_fwd_kernel"

@@ -5,7 +5,7 @@ timeout 200 python tools/diag_chamfer.py 2>&1 | cut -c1-260 | grep -v "mismatche
 echo "diag rc=$?"
 timeout 600 python -m pytest tests/test_gpu_chamfer_prune.py tests/test_gpu_chamfer_fuzz.py -q -x 2>&1 | tail -15
 timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "chamfer or end_to_end or step" 2>&1 | tail -3
-for w in c2 c5; do timeout 300 python tools/tc_sweep.py $w 2>&1 | tail -8; done
+for w in c2 c3 c5; do timeout 300 python tools/tc_sweep.py $w 2>&1 | tail -4; done
 timeout 300 python bench.py --configs c3,c5 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_c2_$TAG.log; echo "bench rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --graph off --configs none > gpurun_out/ncu_launches_$TAG.log 2>&1; echo "ncu rc=$?"

@@ -14,12 +14,14 @@ def main():
     dev = torch.device("cuda")
     pts, tgt = points_of(wl, dev)
     lib = vpn_b200._lib.load()
-    for h in (1, 2, 3, 4, 5, 1, 3):
-        lib.vpn_set_tuning(b"tc_hunits", h)
+    sweep = ((1, 0), (3, 0), (5, 0)) if (len(sys.argv) > 2 and sys.argv[2] == "hunits") else ((0, 0), (0, 8), (0, 16), (0, 0))
+    for h, nb in sweep:
+        lib.vpn_set_tuning(b"tc_hunits", h); lib.vpn_set_tuning(b"tc_nb", nb)
         vpn_b200.chamfer_nn_stage_ms(pts, tgt, 5, reps=2)
         st = vpn_b200.chamfer_nn_stage_ms(pts, tgt, 5, reps=10)
-        print(wl, "units on the FP16 pipe %d: main %.4f rows %.4f cols %.4f total %.4f" % (h - 1, st["main"], st["rows"], st["cols"], st["total"]), flush=True)
-    lib.vpn_set_tuning(b"tc_hunits", 0)
+        print(wl, "tc_hunits %d tc_nb %d: main %.4f rows %.4f cols %.4f total %.4f skipped %.4f" % (
+            h, nb, st["main"], st["rows"], st["cols"], st["total"], st["stages_skipped"] / max(1, st["stages"])), flush=True)
+    lib.vpn_set_tuning(b"tc_hunits", 0); lib.vpn_set_tuning(b"tc_nb", 0)
 
 
 if __name__ == "__main__":

@@ -335,7 +335,8 @@ __device__ __noinline__ u64 unit_exact_walk(float ax, float ay, float az, const 
   return eb.i != 0x7fffffff ? eb.key() : ~0ull;
 }
 
-// exclusive prefix sum of `cnt` over the CTA (kRecThreads threads); returns the offset, *total gets the sum
+// exclusive prefix sum of `cnt` over the CTA (NT threads, NT / 32 <= 32 warps); returns the offset, *total gets the sum
+template <int NT>
 __device__ __forceinline__ int block_exclusive_scan(int cnt, int* warp_sums, int* total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int inc = cnt;
@@ -344,7 +345,7 @@ __device__ __forceinline__ int block_exclusive_scan(int cnt, int* warp_sums, int
   if (lane == 31) warp_sums[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    int w = warp_sums[lane];                                    // kRecThreads / 32 == 32 warps
+    int w = lane < NT / 32 ? warp_sums[lane] : 0;
     int winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
@@ -597,8 +598,11 @@ __global__ void chamfer_col_thr_kernel(const float* __restrict__ cbest, const fl
 // Candidate records of a (tile, column):
 //   TC == false : `unsigned`, bit k = rows rr * 256 + k * 32 + [0,32), rr = 0..R-1  (warp k of chamfer_tiled_kernel<R>, TM = 256 R)
 //   TC == true  : u64, bit k = rows 32 k + [0,32) of the tile                        (32-row UNITS, chamfer_tc_kernel, TM = 128 R)
-template <int R, bool TC>
-__global__ void __launch_bounds__(kRecThreads, 1)
+// NT threads per CTA: 512 for the tensor-core records (two CTAs per SM: the kernel is a chain of short latency-bound phases -
+// record loads, scan, a few hundred unit evaluations per tile - and a single 1024-thread CTA per SM left the SM idle
+// between them), 1024 otherwise.
+template <int R, bool TC, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT)
 chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                             const float* __restrict__ cbest, const void* __restrict__ cmask_,
                             const float* __restrict__ cthr, u64* __restrict__ key2, int P, int M, int ntiles,
@@ -606,7 +610,7 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
   constexpr int TM = TC ? 128 * R : kTThreads * R;
   constexpr int kSub = TC ? 1 : ((R >= 4) ? 4 : R);      // sub-units per (column, bit) item
   constexpr int kRunsPerSub = TC ? 1 : R / kSub;
-  constexpr int kPer = TC ? 4 : 8;                       // columns per thread and slab (TC: 64-bit masks, same register count)
+  constexpr int kPer = TC ? 4096 / NT : 8;               // columns per thread and slab (4096 columns per slab with the tensor-core records)
   constexpr int kBitBits = TC ? 6 : 4;
   using mask_t = typename std::conditional<TC, u64, unsigned>::type;
   const mask_t* __restrict__ cmask = reinterpret_cast<const mask_t*>(cmask_);
@@ -619,7 +623,7 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
   const int b = blockIdx.y, ti = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const float* A = p1 + (size_t)b * P * 3;
   const float qnan = __int_as_float(0x7fc00000);
-  for (int i = tid; i < TM; i += kRecThreads) {
+  for (int i = tid; i < TM; i += NT) {
     int rowi = ti * TM + i;
     // w = the row's ORIGINAL index (p1 is the spatially sorted copy when rperm != NULL): ties go to the first original row
     rows[i] = rowi < P ? make_float4(A[3 * (size_t)rowi], A[3 * (size_t)rowi + 1], A[3 * (size_t)rowi + 2],
@@ -627,30 +631,30 @@ chamfer_recover_cols_kernel(const float* __restrict__ p1, const float* __restric
                        : make_float4(qnan, qnan, qnan, __int_as_float(0x7fffffff));
   }
   const size_t rec0 = ((size_t)b * ntiles + ti) * M;
-  // columns are visited in slabs of kRecThreads * kPer so that one slab's items normally fit the list
-  for (int slab = 0; slab < M; slab += kRecThreads * kPer) {
+  // columns are visited in slabs of NT * kPer so that one slab's items normally fit the list
+  for (int slab = 0; slab < M; slab += NT * kPer) {
     mask_t mk[kPer];
     int cnt = 0;
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
-      const int col = slab + u * kRecThreads + tid;
+      const int col = slab + u * NT + tid;
       mk[u] = 0;
       if (col < M && cbest[rec0 + col] <= cthr[(size_t)b * M + col]) mk[u] = cmask[rec0 + col] & kBitMask;
       cnt += TC ? __popcll((u64)mk[u]) : __popc((unsigned)mk[u]);
     }
     int total;
-    const int off = block_exclusive_scan(cnt, warp_sums, &total);
+    const int off = block_exclusive_scan<NT>(cnt, warp_sums, &total);
     for (int base = 0; base < total; base += kItemCap) {
       int j = off;
 #pragma unroll
       for (int u = 0; u < kPer; ++u)
         for (mask_t mm = mk[u]; mm; mm &= mm - 1, ++j)
           if (j >= base && j < base + kItemCap)
-            items[j - base] = ((unsigned)(u * kRecThreads + tid) << kBitBits) |
+            items[j - base] = ((unsigned)(u * NT + tid) << kBitBits) |
                               (unsigned)((TC ? __ffsll((long long)mm) : __ffs((int)mm)) - 1);
       __syncthreads();
       const int units = min(kItemCap, total - base) * kSub;
-      for (int it = tid; it < units; it += kRecThreads) {
+      for (int it = tid; it < units; it += NT) {
         const unsigned item = items[it / kSub];
         const int col = slab + (int)(item >> kBitBits), w = item & ((1u << kBitBits) - 1u), sub = it % kSub;
         const float* t = p2 + 3 * ((size_t)b * M + col);
@@ -882,12 +886,21 @@ static int launch_any(int mode, const float* p1, const float* p2, char* ws, cons
 template <int R, bool TC>
 static int launch_recover_cols(const float* p1, const float* p2, const float* cb, const void* cmk, const float* cthr,
                                u64* key2, int B, int P, int M, int ntiles, const int* skip, const int* rperm, cudaStream_t s) {
-  static DeviceOnce once;
+  static DeviceOnce once, once_half;
   const size_t smem = (size_t)(TC ? 128 * R : kTThreads * R) * sizeof(float4);
-  if (set_dyn_smem(chamfer_recover_cols_kernel<R, TC>, (int)smem, once) != cudaSuccess) {
+  // 512-thread CTAs, two per SM, once the grid fills the machine twice (C2: 1024 CTAs, 79 -> 73 us); a grid below that (C5:
+  // 64 CTAs) is faster with all 1024 threads on its few CTAs
+  if (TC && (long long)ntiles * B >= 2LL * device_sm_count()) {
+    if (set_dyn_smem(chamfer_recover_cols_kernel<R, TC, 512>, (int)smem, once_half) != cudaSuccess) {
+      vpn_set_error("chamfer tiled: smem attribute (cols recovery)"); return VPN_ERR_CUDA;
+    }
+    chamfer_recover_cols_kernel<R, TC, 512><<<dim3(ntiles, B), 512, smem, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, ntiles, skip, rperm);
+    return vpn_check_launch("chamfer_recover_cols_kernel");
+  }
+  if (set_dyn_smem(chamfer_recover_cols_kernel<R, TC, kRecThreads>, (int)smem, once) != cudaSuccess) {
     vpn_set_error("chamfer tiled: smem attribute (cols recovery)"); return VPN_ERR_CUDA;
   }
-  chamfer_recover_cols_kernel<R, TC><<<dim3(ntiles, B), kRecThreads, smem, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, ntiles, skip, rperm);
+  chamfer_recover_cols_kernel<R, TC, kRecThreads><<<dim3(ntiles, B), kRecThreads, smem, s>>>(p1, p2, cb, cmk, cthr, key2, P, M, ntiles, skip, rperm);
   return vpn_check_launch("chamfer_recover_cols_kernel");
 }
 
