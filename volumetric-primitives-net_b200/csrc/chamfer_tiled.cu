@@ -382,7 +382,7 @@ __device__ __forceinline__ void or_shifted256(u64 (&seg)[4], u64 w, int base) {
 // exclusive prefix sum of `cnt` over one half of the CTA (kRowGroup threads, named barrier `bar`); *total gets the sum
 constexpr int kRowGroup = kRecThreads / 2;            // the CTA works as two independent groups of 512 threads
 constexpr int kRowItemCap = kItemCap / 2;
-constexpr size_t kRowsFixedSmem = (size_t)kRecThreads * (16 + 8 + 32 + 4 + 12) + (size_t)kItemCap * 4;    // row recovery: everything but the targets
+constexpr size_t kRowsFixedSmem = (size_t)kRecThreads * (16 + 8 + 32 + 4 + 12 + 4) + (size_t)kItemCap * 4;    // row recovery: everything but the targets
 __device__ __forceinline__ void group_sync(int bar) { asm volatile("bar.sync %0, %1;" :: "r"(bar), "n"(kRowGroup) : "memory"); }
 __device__ __forceinline__ int group_exclusive_scan(int cnt, int* warp_sums, int* total, int gt, int bar) {
   const int lane = gt & 31, warp = gt >> 5;                           // 16 warps
@@ -423,13 +423,14 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
                             int P, int M, int nchunks, int nsplit, int cps, int TM, int ntiles,
                             const int* __restrict__ skip, int nblk, int nitems, const int* __restrict__ rperm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // dynamic shared memory: [rowc | key | pre_mask | items | pre_rb | pre_p1] (kRowsFixedSmem bytes) then cols[]
+  // dynamic shared memory: [rowc | key | pre_mask | items | pre_rb | pre_p1 | pre_perm] (kRowsFixedSmem bytes) then cols[]
   float4* rowc_ = reinterpret_cast<float4*>(smem_raw);
   u64* key_ = reinterpret_cast<u64*>(rowc_ + kRecThreads);
   u64 (*pre_mask)[kRecThreads] = reinterpret_cast<u64 (*)[kRecThreads]>(key_ + kRecThreads);
   unsigned* items_ = reinterpret_cast<unsigned*>(pre_mask + 4);
   float* pre_rb = reinterpret_cast<float*>(items_ + kItemCap);
   float* pre_p1 = pre_rb + kRecThreads;
+  int* pre_perm = reinterpret_cast<int*>(pre_p1 + 3 * kRecThreads);
   float4* cols = reinterpret_cast<float4*>(smem_raw + kRowsFixedSmem);
   __shared__ int warp_sums_[2][kRowGroup / 32 + 1];
   // records of the group's NEXT item, fetched with cp.async while the current item's units are evaluated (one record per
@@ -445,6 +446,7 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
       for (int w = 0; w < 4; ++w) cp_async8(&pre_mask[w][tid], rmask + o_ + w * plane_stride);
 #pragma unroll
       for (int k = 0; k < 3; ++k) cp_async4(&pre_p1[tid * 3 + k], p1 + 3 * o_ + k);
+      if (rperm) cp_async4(&pre_perm[tid], rperm + o_);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -478,7 +480,9 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
         const bool valid = row < P;
         // p1 is the spatially sorted copy when rperm != NULL: the results go to the row's original position (looked up where
         // it is needed: kept live across the item it costs two registers the kernel does not have)
-        auto orow_of = [&]() { return (size_t)b * P + (rperm ? rperm[(size_t)b * P + row] : row); };
+        // (prefetched with the records and parked in the unused .w of the row's staged coordinates: loaded just before the
+        // final stores it was 6 % of the kernel's stalls)
+        auto orow_of = [&]() { return (size_t)b * P + (use_pre ? __float_as_int(rowc[gt].w) : (rperm ? rperm[(size_t)b * P + row] : row)); };
         float g = inf_f(), gthr = inf_f();
         u64 kinit = ~0ull;
         // this row's candidate units of the segment: 256 bits, unit u of the segment = columns [32 u, 32 u + 32) of cols[]
@@ -486,7 +490,7 @@ chamfer_recover_rows_kernel(const float* __restrict__ p1, const float* __restric
         if (use_pre) {
           asm volatile("cp.async.wait_all;" ::: "memory");
           if (valid) {
-            rowc[gt] = make_float4(pre_p1[tid * 3], pre_p1[tid * 3 + 1], pre_p1[tid * 3 + 2], 0.f);
+            rowc[gt] = make_float4(pre_p1[tid * 3], pre_p1[tid * 3 + 1], pre_p1[tid * 3 + 2], __int_as_float(rperm ? pre_perm[tid] : row));
             g = pre_rb[tid];
             if (seg > 0) { const size_t orow = orow_of(); kinit = ((u64)__float_as_uint(min1[orow]) << 32) | (unsigned)idx1[orow]; }
             const int rel = -seg * kSegChunks * 4;                               // first unit of the record, relative to the segment
