@@ -205,3 +205,29 @@ def test_reference_derived_test_binaries_build_here():
     # nothing of the reference's text is tracked by git: _ref is ignored
     tracked = subprocess.run(["git", "-C", REPO, "ls-files", "oracle/_ref"], capture_output=True, text=True).stdout.strip()
     assert tracked == ""
+
+
+def test_host_pipeline_orders_results_and_bounds_in_flight():
+    """vpn_b200.HostPipeline (CPU path: same ordering logic, synchronous copies): results come back in submission order,
+    one step late; a third submit without a result() is refused; host outputs of a slot stay valid until two submits later."""
+    import torch
+    import vpn_b200
+    seen = []
+
+    def step(batch):
+        seen.append(float(batch["x"][0]))
+        return batch["x"].sum(), batch["x"] * 2
+
+    pipe = vpn_b200.HostPipeline(step, {"x": torch.zeros(4), "unused": None}, "cpu", pre_step=lambda: seen.append("pre"))
+    batches = [{"x": torch.full((4,), float(i)), "unused": None} for i in range(5)]
+    got = []
+    pipe.submit(batches[0])
+    for b in batches[1:]:
+        pipe.submit(b)
+        got.append([t.clone() for t in pipe.result()])
+    with pytest.raises(AssertionError):
+        pipe.submit(batches[0]); pipe.submit(batches[1])
+    got.append([t.clone() for t in pipe.result()])
+    assert [float(g[0]) for g in got] == [0.0, 4.0, 8.0, 12.0, 16.0]
+    assert [float(g[1][0]) for g in got] == [0.0, 2.0, 4.0, 6.0, 8.0]
+    assert seen[:4] == ["pre", 0.0, "pre", 1.0]

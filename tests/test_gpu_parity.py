@@ -674,6 +674,38 @@ def test_graphed_step_matches_eager(vpn, O):
     assert l1 > 0 and l2 > 0 and l1 != l2                      # a fresh uniform draw every replay
 
 
+def test_host_pipeline_matches_direct_steps(vpn, O):
+    """vpn_b200.HostPipeline (pinned host batches, copies overlapped with the previous step on a copy stream): the same
+    losses and gradients (to the repeatability of the atomics in the backward), in order, as calling the graphed step on device tensors (vertex Chamfer + silhouette: no random
+    draw); six batches through the two staging slots."""
+    g = torch.Generator().manual_seed(11)
+    b, k, m, res = 2, 8, 1024, 32
+    v, q, t = O.synthetic_primitives(b, k); t = t * 0.3
+    cfg = vpn.PrimitiveLossConfig(kind="sphere", l_sil=1.0, vertex_chamfer=True)
+    batches = []
+    for i in range(6):
+        batches.append({"v": (v * (1.0 - 0.05 * i)).contiguous().pin_memory(), "q": q.clone().pin_memory(), "t": (t + 0.01 * i).pin_memory(),
+                        "target": ((torch.rand(b, m, 3, generator=g) - 0.5) * 0.8).pin_memory(),
+                        "sil": (torch.rand(b, 1, res, res, generator=g) > 0.5).float().pin_memory(), "unused": None})
+    d0 = batches[0]
+    gr = vpn.GraphedPrimitiveLoss(cfg, C(d0["v"]), C(d0["q"]), C(d0["t"]), C(d0["target"]), C(d0["sil"]))
+    want = []
+    for bt in batches:
+        outs = gr(C(bt["v"]), C(bt["q"]), C(bt["t"]), C(bt["target"]), C(bt["sil"]))
+        want.append([o.detach().cpu().clone() for o in outs])
+    pipe = vpn.HostPipeline(lambda s: gr(s["v"], s["q"], s["t"], s["target"], s["sil"]), d0, "cuda")
+    got = []
+    pipe.submit(batches[0])
+    for bt in batches[1:]:
+        pipe.submit(bt)
+        got.append([o.clone() for o in pipe.result()])
+    got.append([o.clone() for o in pipe.result()])
+    for w, gg in zip(want, got):                                 # the backward scatters with atomics: not bitwise repeatable
+        close(gg[0], w[0], rtol=1e-6)
+        for a, c in zip(w[1:], gg[1:]):
+            close(c, a, rtol=1e-5, atol=1e-7)
+
+
 # ------------------------------------------------------------------------------------------------
 # GCN vertex-feature pooling (modules/network/gcn.py:84-164; SURVEY.md 8f-4)
 # ------------------------------------------------------------------------------------------------

@@ -220,3 +220,86 @@ class GraphedPrimitiveLoss:
             self.sil.copy_(silhouettes, non_blocking=True)
         self.graph.replay()
         return self.loss, self.gv, self.gq, self.gt
+
+
+class HostPipeline:
+    """Feeds a step with batches that live in (pinned) HOST memory and hands the results back in host memory, with the
+    transfers overlapped with the computation - what a training loop with a pinned-memory loader does.
+
+        pipe = HostPipeline(step, example_batch, device)       # step(device_batch: dict) -> tuple of device tensors
+        pipe.submit(batch0)
+        for batch in batches[1:]:
+            pipe.submit(batch)            # host -> device copy of THIS batch runs while the previous step computes
+            outs = pipe.result()          # results of the PREVIOUS batch (pinned host tensors, valid until two submits later)
+        outs = pipe.result()
+
+    Every batch is copied host -> device and every result device -> host, once per step; nothing is cached.  Two staging
+    slots on the device: the copy stream fills slot i % 2 while the compute stream works on the other; the step for a
+    batch is queued as soon as it is submitted (behind the previous one), so the device never waits for the host between
+    steps, and the host synchronises once per step, on the oldest outstanding result.  `pre_step` (optional) is queued
+    on the compute stream before every step (the bench's L2 flush).  On a CPU device everything runs synchronously (the
+    ordering logic is the same; used by the tests)."""
+
+    def __init__(self, step, example_batch: Dict[str, Optional[torch.Tensor]], device, pre_step=None):
+        self.step, self.pre_step = step, pre_step
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.staging = [{k: (None if v is None else torch.empty(v.shape, dtype=v.dtype, device=self.device))
+                         for k, v in example_batch.items()} for _ in range(2)]
+        self.host_out: list = [None, None]
+        self.submitted = 0
+        self.returned = 0
+        if self.cuda:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+            self.staged = [torch.cuda.Event(), torch.cuda.Event()]
+            self.free = [torch.cuda.Event(), torch.cuda.Event()]
+            self.done = [torch.cuda.Event(), torch.cuda.Event()]
+            self.pre_done = None                                     # end of the most recent submit's pre_step
+            cur = torch.cuda.current_stream(self.device)
+            for e in self.free:
+                e.record(cur)
+
+    def submit(self, batch: Dict[str, Optional[torch.Tensor]]) -> None:
+        assert self.submitted - self.returned < 2, "two batches are already in flight: call result() first"
+        slot = self.submitted % 2
+        st = self.staging[slot]
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(self.free[slot])          # the step that last read this slot has finished
+                if self.pre_done is not None:
+                    # start after the running step's pre_step: a host-to-device copy that overlaps the bench's 256 MB
+                    # flush kernel slowed the loop by 0.14 ms per step (measured, tools/e2e_probe.py)
+                    self.copy_stream.wait_event(self.pre_done)
+                for k, v in batch.items():
+                    if v is not None:
+                        st[k].copy_(v, non_blocking=True)
+                self.staged[slot].record(self.copy_stream)
+            cur.wait_event(self.staged[slot])
+        else:
+            for k, v in batch.items():
+                if v is not None:
+                    st[k].copy_(v)
+        if self.pre_step is not None:
+            self.pre_step()
+            if self.cuda:
+                self.pre_done = torch.cuda.Event()
+                self.pre_done.record(cur)
+        outs = self.step(st)
+        if self.cuda:
+            self.free[slot].record(cur)
+        if self.host_out[slot] is None:
+            self.host_out[slot] = [torch.empty(o.shape, dtype=o.dtype, pin_memory=self.cuda) for o in outs]
+        for h, o in zip(self.host_out[slot], outs):
+            h.copy_(o.detach(), non_blocking=True)
+        if self.cuda:
+            self.done[slot].record(cur)
+        self.submitted += 1
+
+    def result(self):
+        assert self.returned < self.submitted, "nothing in flight"
+        slot = self.returned % 2
+        if self.cuda:
+            self.done[slot].synchronize()
+        self.returned += 1
+        return self.host_out[slot]
