@@ -126,3 +126,35 @@ def test_compact_blocks_keep_their_order(vpn, c_oracle):
     (m1, i1, m2, i2), stages, skipped = stats(vpn, p1.cuda(), p2.cuda())
     np.testing.assert_array_equal(i1.cpu().numpy().astype(np.int64), want[1]); np.testing.assert_array_equal(i2.cpu().numpy().astype(np.int64), want[3])
     assert skipped > 0.6 * stages          # natural order: ~0.65-0.7 (ideal 0.72); the segment sort would leave < 0.57
+
+
+def test_probe_knobs_keep_results_exact(vpn, c_oracle):
+    """The probe knobs of the filter and the prep pass change how the work is done, never a result: epilogue reduction
+    on the FP16 pipe for 0 / 2 / 4 units of a block (tc_hunits), reproducible sort permutation (prep_deterministic),
+    narrower / wider pruning bounds.  With prep_deterministic the pruning statistics repeat exactly."""
+    from vpn_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(21)
+    p1, p2 = primitive_scene(gen, 2, 6, 1500, 3000, lattice=True)
+    want = c_oracle(p1.numpy(), p2.numpy())
+    try:
+        for knobs in ({b"tc_hunits": 1}, {b"tc_hunits": 3}, {b"tc_hunits": 5}, {b"prep_deterministic": 1},
+                      {b"prep_near_rows": 2, b"prep_reps_rows": 1, b"prep_near_cols": 4, b"prep_reps_cols": 2}, {b"prep_probe": 1}):
+            for k, v in knobs.items():
+                _lib.check(lib.vpn_set_tuning(k, v), "tuning")
+            (m1, i1, m2, i2), stages, skipped = stats(vpn, p1.cuda(), p2.cuda())
+            np.testing.assert_array_equal(i1.cpu().numpy().astype(np.int64), want[1]); np.testing.assert_array_equal(i2.cpu().numpy().astype(np.int64), want[3])
+            np.testing.assert_array_equal(m1.cpu().numpy().view(np.int32), want[0].view(np.int32))
+            np.testing.assert_array_equal(m2.cpu().numpy().view(np.int32), want[2].view(np.int32))
+            if b"prep_deterministic" in knobs:                  # continuous coordinates: no cell above the in-order cap
+                q1, q2 = primitive_scene(gen, 2, 6, 1500, 3000)
+                first = stats(vpn, q1.cuda(), q2.cuda())
+                again = stats(vpn, q1.cuda(), q2.cuda())
+                assert (again[1], again[2]) == (first[1], first[2])
+                for a, c in zip(first[0], again[0]):
+                    assert torch.equal(a, c)
+            for k in knobs:
+                lib.vpn_set_tuning(k, 0)
+    finally:
+        for k in (b"tc_hunits", b"prep_deterministic", b"prep_near_rows", b"prep_reps_rows", b"prep_near_cols", b"prep_reps_cols", b"prep_probe"):
+            lib.vpn_set_tuning(k, 0)

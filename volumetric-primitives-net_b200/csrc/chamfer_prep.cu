@@ -1,29 +1,31 @@
 // Spatial preparation for the tensor-core Chamfer filter (chamfer_tc.cu): what lets it SKIP distance blocks.
 //
-// The filter evaluates the (P x M) distance matrix of modules/loss/chamfer_distance.py:14-23 in stages of 128 rows x
-// 256 columns.  A stage cannot hold any row's (column's) nearest neighbour when the two point sets are further apart
+// The filter evaluates the (P x M) distance matrix of modules/loss/chamfer_distance.py:14-23 in blocks of 128 rows x
+// 128 columns.  A block cannot hold any row's (column's) nearest neighbour when the two point sets are further apart
 // than a distance some point of the block is already known to achieve.  Two small kernels provide the ingredients:
 //
-//   chamfer_sort_targets_kernel   one CTA per sample: Morton-sorts the sample's targets (18-bit code, 64 cells per axis
-//       of the sample's bounding box, index in the low 14 key bits: a deterministic permutation), writes the sorted copy p2s, the
-//       permutation perm (sorted position -> original index), the axis-aligned box of every 128-column chunk, and the
-//       largest |coordinate| (the filter's scale).  After sorting a chunk is a compact patch of the target shape.
-//       The CTAs past the first B of the same launch sort the PREDICTED points: they arrive primitive-major
-//       (train.py:119 torch.cat(dim=1)) but in the random order of the surface samples, so 128 consecutive rows cover
-//       whole faces of a primitive.  Every segment of 4096 consecutive rows (one primitive at the training sizes) is
-//       Morton-sorted on its own (12-bit code in the segment's box, 12 index bits): a block of 128 sorted rows is a
-//       compact patch, its box small, and far more stages prune (ideal share of live 128 x 128 blocks on the C2
-//       clouds: 27 % unsorted, 18 % sorted).  Output: the sorted copy p1s, rperm (sorted row -> original row) and the
-//       box of every 128-row block.
+//   chamfer_sort_targets_kernel   puts BOTH clouds in spatial order, one launch.
+//       CTA b < B: sample b's targets by Morton cell (16 cells per axis of the sample's bounding box, 12 bits) with a
+//       single-pass counting sort (prep_cell_sort); writes the sorted copies p2s / p2v, the permutation perm (sorted
+//       position -> original index), the axis-aligned box of every 128-column chunk, and the largest |coordinate| (the
+//       filter's scale; NaN if any coordinate is).  After sorting a chunk is a compact patch of the target shape.
+//       The CTAs after them sort the PREDICTED points: they arrive primitive-major (train.py:119 torch.cat(dim=1)) but
+//       in the random order of the surface samples, so 128 consecutive rows cover whole faces of a primitive.  Every
+//       segment of 4096 consecutive rows (one primitive at the training sizes) is sorted on its own, inside the
+//       segment's box: a block of 128 sorted rows is a compact patch, its box small, and far more blocks prune (ideal
+//       share of live blocks on the C2 clouds: 27 % unsorted, 18 % sorted; measured 32 % -> 22 %).  A segment whose
+//       natural order is already the more compact one (mesh vertices: one small primitive per block) keeps it.
+//       Output: the sorted copy p1s, rperm (sorted row -> original row) and the box of every 128-row block.
 //   chamfer_prune_bounds_kernel   per 128-row block: T_r = max over its rows of an UPPER bound of the row's
-//       nearest-target distance (exact distance, the reference's arithmetic, to 4 representatives of each of the 8 chunks
-//       whose boxes are nearest to the block's box); per 128-column chunk: U_c likewise over 16 row blocks x 2 rows.
+//       nearest-target distance (distance to 4 representatives of each of the 8 chunks whose boxes are nearest to the
+//       block's box); per 128-column chunk: U_c likewise over 32 row blocks x 4 rows.
 //
-// chamfer_tc_kernel skips the stage (row block r, chunk c) for the row direction when gap(box_r, box_c)^2 > T_r and for
-// the column direction when gap^2 > U_c (both with a 1e-5 relative margin): every pair in the stage is then further
+// chamfer_tc_kernel skips the block (row block r, chunk c) for the row direction when gap(box_r, box_c)^2 > T_r and for
+// the column direction when gap^2 > U_c (both with a 1e-5 relative margin): every pair in the block is then further
 // apart than a distance row i (column j) certainly achieves elsewhere, so neither its arg-min nor a tie can be there.
-// Results are unchanged bit for bit (the exact recovery kernels still decide); first-index ties survive the
-// permutation because recovery keys carry the ORIGINAL target index.
+// Results are unchanged bit for bit (the exact recovery kernels still decide); first-index ties survive both
+// permutations because the recovery keys carry the ORIGINAL target / row index, and the row results are written back
+// through rperm.
 #include "common.cuh"
 
 namespace vpn {
@@ -70,7 +72,7 @@ __device__ __forceinline__ void prep_block_box(float (&lo)[3], float (&hi)[3], u
 
 // Morton cell of a point: 16 cells per axis of the cloud's box (q0 = lower corner, qs = 15.999 / extent), 12 bits
 constexpr int kCells = 4096;
-constexpr int kCellCap = 64;              // cells up to this size are put in index order (deterministic permutation)
+constexpr int kCellCap = 64;              // deterministic mode: cells up to this size are insertion-sorted, larger ones heap-sorted
 __device__ __forceinline__ unsigned prep_cell(float x, float y, float z, const float (&q0)[3], const float (&qs)[3]) {
   const float fx = (x - q0[0]) * qs[0], fy = (y - q0[1]) * qs[1], fz = (z - q0[2]) * qs[2];
   const unsigned qx = (fx >= 0.f) ? (unsigned)fminf(fx, 15.f) : 0u, qy = (fy >= 0.f) ? (unsigned)fminf(fy, 15.f) : 0u,
@@ -81,10 +83,10 @@ __device__ __forceinline__ unsigned prep_cell(float x, float y, float z, const f
 // Counting sort of the CTA's n items (item i = tid + 1024 k, k < K, belongs to this thread; its cell is half k & 1 of
 // pk[k >> 1]) into ent[] (sorted position -> item), ONE pass over the 4096 cells: count with shared-memory reductions,
 // prefix-sum the cells, then every item takes the next free position of its cell (atomic cursor).  The order INSIDE a
-// cell is the order the atomics were served in; with `deterministic` set one thread per cell then puts the cell's items
-// (up to kCellCap of them) in index order, so that the permutation is reproducible - which sorted position an item gets
-// never changes a result (the recovery kernels key on original indices), only which block of 128 a few border points
-// fall into.  The whole CTA (1024 threads) calls it.
+// cell is the order the atomics were served in; with `deterministic` set (a test / debugging knob) one thread per cell
+// then puts the cell's items in index order (insertion sort up to kCellCap items, heapsort for a crowded cell), so that
+// the permutation is reproducible - which sorted position an item gets never changes a result (the recovery kernels key
+// on original indices), only which block of 128 a few border points fall into.  The whole CTA (1024 threads) calls it.
 // (History: a bitonic network, 62 us for 8192 keys on one SM; 6-bit radix passes ranked with ballots, 15 us per pass;
 // 4-bit radix passes with shuffle scans, 10 us per pass - an 18-bit code needed 3 to 5 such passes.  With 128 points per
 // block the order inside a cell of 1/16 of the box does not matter, so 12 code bits and one pass are enough.)
@@ -129,13 +131,31 @@ __device__ __forceinline__ void prep_cell_sort(const unsigned (&pk)[(K + 1) / 2]
 #pragma unroll 1
     for (int c = 4 * tid; c < 4 * tid + 4; ++c) {
       const unsigned sz = cnt[c];
-      if (sz < 2u || sz > (unsigned)kCellCap) continue;
+      if (sz < 2u) continue;
       unsigned* e = ent + (start[c] - sz);
-      for (unsigned a = 1; a < sz; ++a) {                          // insertion sort by item index
-        const unsigned v = e[a];
-        unsigned j = a;
-        while (j > 0u && e[j - 1] > v) { e[j] = e[j - 1]; --j; }
-        e[j] = v;
+      if (sz <= (unsigned)kCellCap) {
+        for (unsigned a = 1; a < sz; ++a) {                        // insertion sort by item index
+          const unsigned v = e[a];
+          unsigned j = a;
+          while (j > 0u && e[j - 1] > v) { e[j] = e[j - 1]; --j; }
+          e[j] = v;
+        }
+      } else {                                                     // a crowded cell (coincident points): heapsort, O(n log n)
+        auto sift = [&](unsigned root, unsigned end) {
+          for (;;) {
+            unsigned child = 2u * root + 1u;
+            if (child >= end) break;
+            if (child + 1u < end && e[child] < e[child + 1u]) ++child;
+            if (e[root] >= e[child]) break;
+            const unsigned t = e[root]; e[root] = e[child]; e[child] = t;
+            root = child;
+          }
+        };
+        for (unsigned st = sz / 2u; st-- > 0u;) sift(st, sz);
+        for (unsigned end = sz - 1u; end > 0u; --end) {
+          const unsigned t = e[0]; e[0] = e[end]; e[end] = t;
+          sift(0u, end);
+        }
       }
     }
     __syncthreads();
