@@ -217,20 +217,22 @@ __device__ __forceinline__ void pixel_coords(const RasterParams& rp, int w, int 
   Y = __fmul_rn(__fdiv_rn(rp.mult, (float)rp.H), (float)(rp.H - 2 * h - 1));
 }
 
-// Per-tile candidate lists in dynamic shared memory, [k][pixel] so that a pixel's thread writes conflict free:
-//   cand  u16 [kKnumMax][256]  face index of the pixel's k-th soft candidate (F <= 65535)
-//   fac   f32 [kKnumMax][256]  forward: 1 - prob; backward: prob
-//   which u8  [kKnumMax][256]  backward: winning distance case
+// Per-tile candidate lists in dynamic shared memory, [k][pixel] so that a pixel's thread writes conflict free, sized by the
+// call's knum (30 in DIB-R: 53.8 KB for the backward - four CTAs per SM where kKnumMax rows allowed three):
+//   backward  fac f32 [knum][256] prob, cand u16 [knum][256] face index of the pixel's k-th soft candidate (F <= 65535),
+//             which u8 [knum][256] winning distance case
+//   forward   ONE u32 [knum][256]: the face index until the item has been evaluated, then the bits of 1 - prob (the lane
+//             that evaluates an item is the only one to read its face index): 30 KB, five CTAs per SM
 struct TileLists { unsigned short* cand; float* fac; unsigned char* which; };
-__device__ __forceinline__ TileLists tile_lists(unsigned char* p) {
+__device__ __forceinline__ TileLists tile_lists(unsigned char* p, int knum) {
   TileLists t;
-  t.fac = reinterpret_cast<float*>(p); p += kKnumMax * kRThreads * sizeof(float);
-  t.cand = reinterpret_cast<unsigned short*>(p); p += kKnumMax * kRThreads * sizeof(unsigned short);
+  t.fac = reinterpret_cast<float*>(p); p += (size_t)knum * kRThreads * sizeof(float);
+  t.cand = reinterpret_cast<unsigned short*>(p); p += (size_t)knum * kRThreads * sizeof(unsigned short);
   t.which = p;
   return t;
 }
-constexpr size_t kTileListBytesFwd = kKnumMax * kRThreads * (sizeof(float) + sizeof(unsigned short));
-constexpr size_t kTileListBytesBwd = kTileListBytesFwd + kKnumMax * kRThreads;
+__host__ __device__ inline size_t tile_list_bytes_fwd(int knum) { return (size_t)knum * kRThreads * sizeof(unsigned); }
+__host__ __device__ inline size_t tile_list_bytes_bwd(int knum) { return (size_t)knum * kRThreads * (sizeof(float) + sizeof(unsigned short) + 1); }
 
 // Exclusive prefix sum of cnt over the warp's 32 pixels; *total = sum.
 __device__ __forceinline__ int warp_offsets(int cnt, int* total) {
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kRThreads)
 sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restrict__ box_all, float* __restrict__ alpha,
                       unsigned char* __restrict__ covered_out, RasterParams rp) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  const TileLists tl = tile_lists(s_dyn);
+  unsigned* slot = reinterpret_cast<unsigned*>(s_dyn);           // [k][pixel]: face index, then the bits of 1 - prob
   const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
   int px, py; tile_px(tid, px, py);
   const int w = blockIdx.x * kTile + px, h = blockIdx.y * kTile + py;
@@ -283,7 +285,7 @@ sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
     if (!(X >= __fsub_rn(txmin, em) && X < __fadd_rn(txmax, em) && Y >= __fsub_rn(tymin, em) && Y < __fadd_rn(tymax, em))) return;
     // coverage (hard pass): front faces only.  A back face that holds the pixel is an ordinary soft candidate.
     if (r.front > 0.5f && X >= txmin && X < txmax && Y >= tymin && Y < tymax && inside_tri(r, X, Y, rp.eps)) { covered = true; return; }
-    if (cnt < rp.knum) { tl.cand[cnt * kRThreads + tid] = (unsigned short)f; ++cnt; }
+    if (cnt < rp.knum) { slot[cnt * kRThreads + tid] = (unsigned)f; ++cnt; }
   });
   const int mine = (in_img && !covered) ? cnt : 0;
   int total;
@@ -295,17 +297,17 @@ sil_raster_fwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restr
     const int k = it - __shfl_sync(0xffffffffu, off, pl);
     const float PX = __shfl_sync(0xffffffffu, X, pl), PY = __shfl_sync(0xffffffffu, Y, pl);
     if (on) {
-      const FaceRec r = rec[tl.cand[k * kRThreads + wbase + pl]];
+      const FaceRec r = rec[slot[k * kRThreads + wbase + pl]];
       int which;
       const float d2 = tri_dist2(r, PX, PY, rp.mult, rp.eps, which);
       const float z = __fdiv_rn(__fdiv_rn(__fmul_rn(rp.delta, d2), rp.mult), rp.mult);
-      tl.fac[k * kRThreads + wbase + pl] = __fsub_rn(1.0f, expf(-z));
+      slot[k * kRThreads + wbase + pl] = __float_as_uint(__fsub_rn(1.0f, expf(-z)));
     }
   }
   __syncwarp();
   if (in_img) {
     float prod = 1.0f;
-    for (int k = 0; k < mine; ++k) prod = __fmul_rn(prod, tl.fac[k * kRThreads + tid]);
+    for (int k = 0; k < mine; ++k) prod = __fmul_rn(prod, __uint_as_float(slot[k * kRThreads + tid]));
     const size_t o = ((size_t)b * rp.H + h) * rp.W + w;
     alpha[o] = covered ? 1.0f : __fsub_rn(1.0f, prod);
     covered_out[o] = covered ? 1 : 0;
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(kRThreads)
 sil_raster_bwd_kernel(const FaceRec* __restrict__ rec_all, const float4* __restrict__ box_all, const float* __restrict__ galpha,
                       const unsigned char* __restrict__ covered_in, float* __restrict__ gface, RasterParams rp) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  const TileLists tl = tile_lists(s_dyn);
+  const TileLists tl = tile_lists(s_dyn, rp.knum);
   const int b = blockIdx.z, tid = threadIdx.x, lane = tid & 31, wbase = tid & ~31;
   int px, py; tile_px(tid, px, py);
   const int w = blockIdx.x * kTile + px, h = blockIdx.y * kTile + py;
@@ -490,10 +492,10 @@ extern "C" int vpn_silhouette_fwd(const float* verts, const int* faces, const fl
   RasterParams rp{H, W, F, knum, expand, multiplier, delta, 1e-15f, soft_cull_backfaces ? 1 : 0};
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
   static DeviceOnce once_fwd;
-  if (set_dyn_smem(sil_raster_fwd_kernel, (int)kTileListBytesFwd, once_fwd) != cudaSuccess) {
+  if (set_dyn_smem(sil_raster_fwd_kernel, (int)tile_list_bytes_fwd(kKnumMax), once_fwd) != cudaSuccess) {
     vpn_set_error("silhouette fwd: smem attribute"); return VPN_ERR_CUDA;
   }
-  sil_raster_fwd_kernel<<<grid, kRThreads, kTileListBytesFwd, s>>>(rec, boxes, alpha, covered, rp);
+  sil_raster_fwd_kernel<<<grid, kRThreads, tile_list_bytes_fwd(knum), s>>>(rec, boxes, alpha, covered, rp);
   return vpn_check_launch("sil_raster_fwd_kernel");
 }
 
@@ -521,10 +523,10 @@ extern "C" int vpn_silhouette_bwd(const int* faces, const float* cam_rot, float 
   RasterParams rp{H, W, F, knum, expand, multiplier, delta, 1e-15f, soft_cull_backfaces ? 1 : 0};
   dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B);
   static DeviceOnce once_bwd;
-  if (set_dyn_smem(sil_raster_bwd_kernel, (int)kTileListBytesBwd, once_bwd) != cudaSuccess) {
+  if (set_dyn_smem(sil_raster_bwd_kernel, (int)tile_list_bytes_bwd(kKnumMax), once_bwd) != cudaSuccess) {
     vpn_set_error("silhouette bwd: smem attribute"); return VPN_ERR_CUDA;
   }
-  sil_raster_bwd_kernel<<<grid, kRThreads, kTileListBytesBwd, s>>>(rec, reinterpret_cast<const float4*>(ws + wl.box), grad_alpha, covered, gface, rp);
+  sil_raster_bwd_kernel<<<grid, kRThreads, tile_list_bytes_bwd(knum), s>>>(rec, reinterpret_cast<const float4*>(ws + wl.box), grad_alpha, covered, gface, rp);
   if ((rc = vpn_check_launch("sil_raster_bwd_kernel"))) return rc;
   sil_face_to_vertex_kernel<<<dim3((F + 255) / 256, B), 256, 0, s>>>(gface, faces, cam, cam_rot, proj_x, proj_y, proj_z,
                                                                       multiplier, grad_verts, V, F);
