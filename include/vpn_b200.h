@@ -42,8 +42,14 @@ int vpn_abi_version(void);
 int vpn_device_info(int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
 /* kernels launched by this library in this process so far (bench.py reports the per-step delta) */
 unsigned long long vpn_launch_count(void);
-/* Test / probe hook: force a launch-plan choice.  key "tiled_r" | "tc_nb" (4, 8, 16), "emd_cluster" (1, 2, 4, 8);
- * value 0 restores the automatic choice.  Results never depend on it (tests check exactly that). */
+/* Test / probe hook: force a launch-plan choice.  key "tiled_r" | "tc_nb" (4, 8, 16), "emd_cluster" (1, 2, 4, 8),
+ * "tc_prune" (2 = tensor-core Chamfer filter without the spatial pruning), "tc_hunits" (1 + the 32-column units of a
+ * block reduced on the FP16 pipe, 1..5), "serial_recovery" (1 = row and column recovery on one stream),
+ * "prep_near_rows" | "prep_near_cols" (1..32) and "prep_reps_rows" | "prep_reps_cols" (1, 2, 4): near blocks and
+ * representatives of the pruning bounds, "prep_deterministic" (1 = reproducible sort permutation), "prep_probe" (1 =
+ * phase timers of the sort kernel in the statistics words), "ar_variant" | "ar_ctas" | "ar_threads" | "ar_grid_div"
+ * (all-reduce launch shape); value 0 restores the automatic choice.  Results never depend on it (tests check exactly
+ * that); unknown keys return VPN_ERR_ARG. */
 int vpn_set_tuning(const char* key, int value);
 
 /* ---- primitive instantiation: canonical sample -> scale -> rotate -> translate, one kernel ------------
