@@ -445,14 +445,16 @@ __global__ void __launch_bounds__(kBoundWarps * 32, 8)
 chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restrict__ p2s,
                             const float* __restrict__ rbox, const float* __restrict__ cbox,
                             float* __restrict__ rthr, float* __restrict__ cub, int P, int M, int nrb, int nchunks,
-                            int near_rows, int reps_rows, int near_cols, int reps_cols) {
-  __shared__ unsigned s_gap[kBoundWarps][kGapCap];      // (quantised gap bits | candidate index), 0xffffffff = taken
+                            int near_rows, int reps_rows, int near_cols, int reps_cols, int gap_cap) {
+  // (quantised gap bits | candidate index), 0xffffffff = taken: gap_cap entries per warp, dynamic - sized by the larger
+  // block count of the two clouds (<= kGapCap), so that the C2 shape keeps 8 CTAs per SM instead of 6
+  extern __shared__ unsigned s_gap[];
   __shared__ float4 s_reps[kBoundWarps][2 * kMaxReps];   // per representative (x, x, y, y) (z, z, -, -): operands of the packed f32x2 ops
   __shared__ int s_sel[kBoundWarps][kMaxNear];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int id = blockIdx.x * kBoundWarps + warp;
   if (id >= nrb + nchunks) return;                                           // warp-uniform
-  unsigned* gap = s_gap[warp]; float4* reps = s_reps[warp]; int* sel = s_sel[warp];
+  unsigned* gap = s_gap + warp * gap_cap; float4* reps = s_reps[warp]; int* sel = s_sel[warp];
   const bool is_row = id >= nchunks;                                         // the chunks (4 x the work of a row block) are dispatched first
   const int blk = is_row ? id - nchunks : id;
   const int n_mine = is_row ? P : M, n_other = is_row ? M : P;
@@ -558,9 +560,12 @@ int chamfer_prep_launch(const float* p1, const float* p2, float* p2s, float4* p2
   if (rc) return rc;
   // vpn_set_tuning("prep_near_rows" / "prep_reps_rows" / "prep_near_cols" / "prep_reps_cols"): probes only (near <= 32, reps 1 / 2 / 4)
   auto pick = [](int key, int dflt, int cap) { const int v = tuning_value(key); return (v >= 1 && v <= cap && (key == kTunePrepNearRows || key == kTunePrepNearCols || v == 1 || v == 2 || v == 4)) ? v : dflt; };
-  chamfer_prune_bounds_kernel<<<dim3((nrb + nchunks + kBoundWarps - 1) / kBoundWarps, B), kBoundWarps * 32, 0, s>>>(
+  const int most = nrb > nchunks ? nrb : nchunks;
+  const int gap_cap = most >= kGapCap ? kGapCap : ((most + 31) & ~31);      // candidates per block are min(blocks of the other cloud, kGapCap)
+  chamfer_prune_bounds_kernel<<<dim3((nrb + nchunks + kBoundWarps - 1) / kBoundWarps, B), kBoundWarps * 32,
+                                (size_t)kBoundWarps * gap_cap * sizeof(unsigned), s>>>(
       p1s, p2s, rbox, cbox, rthr, cub, P, M, nrb, nchunks, pick(kTunePrepNearRows, kNearRows, kMaxNear), pick(kTunePrepRepsRows, kRepsRows, 4),
-      pick(kTunePrepNearCols, kNearCols, kMaxNear), pick(kTunePrepRepsCols, kRepsCols, 4));
+      pick(kTunePrepNearCols, kNearCols, kMaxNear), pick(kTunePrepRepsCols, kRepsCols, 4), gap_cap);
   return vpn_check_launch("chamfer_prune_bounds_kernel");
 }
 
