@@ -335,22 +335,46 @@ chamfer_tc_plan_kernel(const float* __restrict__ cbox, const float* __restrict__
                        int ncta, int ntiles, int nsplit, int nrb_total, int NB, int nchunks, int cps) {
   __shared__ uint32_t skipR[64], skipC[64];
   __shared__ int s_live[kPlanThreads / 32];
+  __shared__ float4 s_rbox[16][2];                                    // the tile's row-block boxes (8 floats each) and bounds
+  __shared__ float s_rthr[16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cta = blockIdx.x;                                         // one CTA per tile (the box loads of its NB x nc pairs in parallel)
+  const int cta = blockIdx.x;                                         // one CTA per tile
   const int tile_i = cta % ntiles, split = (cta / ntiles) % nsplit, b = cta / (ntiles * nsplit);
   const int c_first = split * cps, nc = min(nchunks, c_first + cps) - c_first;
   if (tid < 64) { skipR[tid] = 0u; skipC[tid] = 0u; }
+  if (tid < 2 * NB) {
+    const int r = tid >> 1, rb = tile_i * NB + r;
+    if (rb < nrb_total) s_rbox[r][tid & 1] = reinterpret_cast<const float4*>(rbox + ((size_t)b * nrb_total + rb) * 8)[tid & 1];
+  } else if (tid >= 32 && tid < 32 + NB) {
+    const int r = tid - 32, rb = tile_i * NB + r;
+    s_rthr[r] = (rb < nrb_total) ? __fmul_ru(rthr[(size_t)b * nrb_total + rb], 1.00001f) : 0.f;
+  }
   __syncthreads();
-  for (int e = tid; e < NB * nc; e += kPlanThreads) {
-    const int r = e % NB, c = e / NB, rb = tile_i * NB + r;
-    bool pr = true, pc = true;
-    if (rb < nrb_total) {
-      const float gap2 = tc_box_gap2(rbox + ((size_t)b * nrb_total + rb) * 8, cbox + ((size_t)b * nchunks + c_first + c) * 8);
-      pr = gap2 > __fmul_ru(rthr[(size_t)b * nrb_total + rb], 1.00001f);
-      pc = gap2 > __fmul_ru(cub[(size_t)b * nchunks + c_first + c], 1.00001f);
+  // thread = (chunk c, half of the row blocks): the chunk's box stays in registers (two 16-byte loads), the row boxes are
+  // broadcast reads of shared memory.  (One (r, c) pair per thread and turn with twelve scalar global loads per pair: 11 us.)
+  {
+    const int c = tid & 63, r0 = (tid >> 6) * (NB / 2);
+    if (c < nc) {
+      const float4 c0 = reinterpret_cast<const float4*>(cbox + ((size_t)b * nchunks + c_first + c) * 8)[0];
+      const float4 c1 = reinterpret_cast<const float4*>(cbox + ((size_t)b * nchunks + c_first + c) * 8)[1];
+      const float cb8[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      const float ub = __fmul_ru(cub[(size_t)b * nchunks + c_first + c], 1.00001f);
+      uint32_t mr = 0u, mc = 0u;
+      for (int r = r0; r < r0 + NB / 2; ++r) {
+        bool pr = true, pc = true;
+        if (tile_i * NB + r < nrb_total) {
+          const float4 a0 = s_rbox[r][0], a1 = s_rbox[r][1];
+          const float rb8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float gap2 = tc_box_gap2(rb8, cb8);
+          pr = gap2 > s_rthr[r];
+          pc = gap2 > ub;
+        }
+        mr |= pr ? (1u << r) : 0u;
+        mc |= pc ? (1u << r) : 0u;
+      }
+      atomicOr(&skipR[c], mr);
+      atomicOr(&skipC[c], mc);
     }
-    if (pr) atomicOr(&skipR[c], 1u << r);
-    if (pc) atomicOr(&skipC[c], 1u << r);
   }
   __syncthreads();
   uint32_t* out = plan_masks + (size_t)cta * kTcPlanWords;
