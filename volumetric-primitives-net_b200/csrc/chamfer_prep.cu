@@ -480,7 +480,10 @@ chamfer_prune_bounds_kernel(const float* __restrict__ p1, const float* __restric
   // index).  Which near boxes are chosen only affects how tight the bound is, never its validity.
   unsigned lmin = 0xffffffffu;                                               // smallest key among this lane's candidates
   for (int c = lane; c < ncand; c += 32) {
-    const float g = box_gap2(mybox, obox + (size_t)c * stride * 8);
+    const float4* ob = reinterpret_cast<const float4*>(obox + (size_t)c * stride * 8);      // 32-byte box records: two 16-byte loads
+    const float4 o0 = ob[0], o1 = ob[1];
+    const float other_box[6] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y};
+    const float g = box_gap2(mybox, other_box);
     const unsigned k = ((g == g) ? (__float_as_uint(g) & ~0x3ffu) : 0x7f800000u) | (unsigned)c;   // NaN boxes sort last
     gap[c] = k;
     lmin = min(lmin, k);
